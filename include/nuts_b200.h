@@ -1,0 +1,256 @@
+/* nuts_b200.h — C ABI of libnuts_b200.so: the B200 (sm_100a) many-chain NUTS hot path.
+ *
+ * This is the drop-in boundary for ONE path of pymc-devs/nuts-rs: leapfrog + logp/grad inside the
+ * NUTS tree-doubling loop, plus the per-draw diagonal mass-matrix / dual-averaging adaptation.
+ * The reference keeps that path behind `pub trait Math` (reference src/math/math.rs:15-314), one
+ * instance per chain, one `faer::Col<f64>` per vector.  Here every object is BATCHED over chains:
+ * a "plane" is a device-resident [nchains x dim] f64 matrix (row = chain), i.e. `nchains` Math::Vector's.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in any signature (cudaStream_t is passed as void*).
+ *   - every function returns 0 on success, <0 on a fatal error (text via nuts_last_error()).
+ *   - per-chain recoverable conditions are reported through int32 status arrays:
+ *       0 ok, 1 divergent (energy error), 2 divergent (non-finite logp/grad, "recoverable logp error"),
+ *       3 fatal / bad initial point (NutsError::BadInitGrad, reference src/nuts.rs:14-23).
+ *   - all host pointers may be pageable or pinned; device pointers are never exposed except through
+ *     nuts_plane_device_ptr (for callers that already own CUDA memory, e.g. torch tensors).
+ *   - threading contract = the reference's `&mut self`: one ctx / sampler is driven by one host thread;
+ *     different ctx's (one per GPU) may be driven concurrently.
+ *   - there is NO CPU fallback: every entry point fails with NUTS_ERR_NO_DEVICE when no sm_100 GPU exists.
+ */
+#ifndef NUTS_B200_H
+#define NUTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NUTS_OK 0
+#define NUTS_ERR_INVALID -1
+#define NUTS_ERR_CUDA -2
+#define NUTS_ERR_NO_DEVICE -3
+#define NUTS_ERR_UNSUPPORTED -4
+
+#define NUTS_STATUS_OK 0
+#define NUTS_STATUS_DIVERGENT_ENERGY 1
+#define NUTS_STATUS_DIVERGENT_LOGP 2
+#define NUTS_STATUS_FATAL 3
+
+typedef struct nuts_ctx nuts_ctx_t;
+typedef struct nuts_plane nuts_plane_t;     /* [nchains x dim] f64 on the device */
+typedef struct nuts_point nuts_point_t;     /* batched TransformedPoint (reference src/dynamics/transformed_hamiltonian.rs:56-77) */
+typedef struct nuts_sampler nuts_sampler_t; /* batched NutsChain (reference src/chain.rs:44-61) */
+
+/* ---- device-side log densities: stand-ins for CpuLogpFunc::logp (reference src/math/cpu_math.rs:885-970) ---- */
+enum {
+  NUTS_LOGP_GAUSS_ISO = 0,   /* logp = -sum (x-mu)^2/2          reference src/math/test_logps.rs:49-58, benches/sample.rs:49-62 */
+  NUTS_LOGP_GAUSS_DIAG = 1,  /* logp = -sum (x-mu_i)^2/(2 s_i^2) diagonal generalisation of the above                           */
+  NUTS_LOGP_GAUSS_RANK1 = 2, /* Sigma = I + s*11^T              reference tests/sample_normal.rs:29-96                           */
+  NUTS_LOGP_FUNNEL = 3       /* Neal's funnel: x0=v~N(0,fs^2), x_i~N(0,e^v)  (BASELINE.json config 3; not in the reference)      */
+};
+
+typedef struct {
+  int32_t kind;
+  int32_t _pad;
+  double mu_scalar;     /* mean used for every coordinate when `mu` is NULL */
+  const double* mu;     /* optional host pointer [dim] */
+  const double* sigma;  /* GAUSS_DIAG: host pointer [dim] of standard deviations (required) */
+  double rank1_scale;   /* GAUSS_RANK1: s */
+  double funnel_scale;  /* FUNNEL: prior sd of v (3.0 in BASELINE) */
+} nuts_logp_desc_t;
+
+/* ---- settings: NutsSettings<EuclideanAdaptOptions<DiagAdaptExpSettings>> field for field --------------------
+ * reference src/sampler.rs:199-239 (NutsSettings), src/adapt_strategy.rs:41-69 (EuclideanAdaptOptions),
+ * src/stepsize/adapt.rs:308-329 (StepSizeSettings), :21-49 (StepSizeAdaptOptions / Method),
+ * src/stepsize/dual_avg.rs:11-31 (DualAverageOptions), src/transform/adapt/diagonal.rs:93-106 (DiagAdaptExpSettings). */
+enum { NUTS_STEPSIZE_DUAL_AVERAGE = 0, NUTS_STEPSIZE_FIXED = 2 /* Adam (1) is out of scope */ };
+enum { NUTS_KINETIC_EUCLIDEAN = 0 /* ExactNormal / Microcanonical are out of scope */ };
+
+typedef struct {
+  double k, t0, gamma, max_step_size;
+} nuts_dual_average_options_t;
+
+typedef struct {
+  int32_t method;    /* NUTS_STEPSIZE_* */
+  int32_t _pad;
+  double fixed_step; /* StepSizeAdaptMethod::Fixed(val) */
+  nuts_dual_average_options_t dual_average;
+} nuts_step_size_adapt_options_t;
+
+typedef struct {
+  double target_accept;
+  double initial_step;
+  int32_t has_jitter; /* Option<f64>: 0 = None */
+  int32_t _pad;
+  double jitter;
+  nuts_step_size_adapt_options_t adapt_options;
+} nuts_step_size_settings_t;
+
+typedef struct {
+  int32_t store_mass_matrix;
+  int32_t use_grad_based_estimate;
+} nuts_diag_adapt_settings_t;
+
+typedef struct {
+  nuts_step_size_settings_t step_size_settings;
+  nuts_diag_adapt_settings_t mass_matrix_options;
+  double early_window;
+  double step_size_window;
+  uint64_t mass_matrix_switch_freq;
+  uint64_t early_mass_matrix_switch_freq;
+  uint64_t mass_matrix_update_freq;
+  double mass_matrix_window_growth;
+} nuts_euclidean_adapt_options_t;
+
+typedef struct {
+  uint64_t num_tune;
+  uint64_t num_draws;
+  uint64_t maxdepth;
+  uint64_t mindepth;
+  int32_t store_gradient;
+  int32_t store_unconstrained;
+  int32_t store_transformed;
+  int32_t store_divergences;
+  double max_energy_error;
+  nuts_euclidean_adapt_options_t adapt_options;
+  int32_t check_turning;
+  int32_t has_target_integration_time; /* Option<f64> */
+  double target_integration_time;
+  int32_t trajectory_kind; /* NUTS_KINETIC_EUCLIDEAN */
+  int32_t _pad;
+  uint64_t num_chains;
+  uint64_t seed;
+  uint64_t extra_doublings;
+} nuts_settings_t;
+
+/* DiagNutsSettings::default()  (reference src/sampler.rs:507-531,630-634). */
+void nuts_settings_default(nuts_settings_t* s);
+
+/* Per-draw sampler statistics, SoA, each a HOST array [n_draws x nchains] (draw-major) or NULL to skip.
+ * Names follow the reference's stat schema: NutsStats (src/chain.rs:215-231), stepsize Stats
+ * (src/stepsize/adapt.rs:274-281), PointStats (src/dynamics/transformed_hamiltonian.rs:96-112),
+ * HamiltonianStats (:497-505), GlobalStrategyStats (src/adapt_strategy.rs:248-257), Progress (src/sampler.rs:165-174). */
+typedef struct {
+  uint64_t* depth;
+  uint8_t* maxdepth_reached;
+  int64_t* index_in_trajectory;
+  double* logp;
+  double* energy;
+  double* energy_error;
+  uint8_t* diverging;
+  double* step_size;            /* step size AFTER this draw's adaptation, like HamiltonianStats.step_size */
+  double* step_size_bar;
+  double* mean_tree_accept;
+  double* mean_tree_accept_sym;
+  uint64_t* n_steps;
+  double* max_energy_error;
+  uint8_t* tuning;
+  double* fisher_distance;
+} nuts_stats_t;
+
+const char* nuts_last_error(void);
+/* 0 when a usable sm_100 device is visible, NUTS_ERR_NO_DEVICE otherwise. */
+int nuts_device_available(void);
+
+/* ===================== Tier 0: lifecycle (Math::new_array / read_from_slice / write_to_slice, math.rs:24,94-105) */
+int nuts_ctx_create(nuts_ctx_t** ctx, int device_id, uint64_t nchains, uint64_t dim, const nuts_logp_desc_t* model);
+int nuts_ctx_destroy(nuts_ctx_t* ctx);
+int nuts_ctx_synchronize(nuts_ctx_t* ctx);
+uint64_t nuts_ctx_nchains(const nuts_ctx_t* ctx);
+uint64_t nuts_ctx_dim(const nuts_ctx_t* ctx); /* Math::dim, math.rs:69 */
+void* nuts_ctx_stream(nuts_ctx_t* ctx);       /* the cudaStream_t every call on this ctx is ordered on */
+int nuts_plane_alloc(nuts_ctx_t* ctx, nuts_plane_t** plane);                     /* new_array (zero filled) */
+int nuts_plane_free(nuts_ctx_t* ctx, nuts_plane_t* plane);
+int nuts_plane_read_from_host(nuts_ctx_t* ctx, nuts_plane_t* dst, const double* src /*[N*d]*/); /* read_from_slice */
+int nuts_plane_write_to_host(nuts_ctx_t* ctx, const nuts_plane_t* src, double* dst /*[N*d]*/);  /* write_to_slice / box_array */
+double* nuts_plane_device_ptr(nuts_plane_t* plane, uint64_t* row_stride_elems);
+
+/* ===================== Tier 1: batched Math-trait ops, 1:1 names (math.rs line cited per op) ===================
+ * `a` is a HOST array [N] of per-chain scalars, or NULL with `a_bcast` used for every chain.
+ * `active` is an optional HOST uint8 [N] mask (NULL = all chains). Reductions write HOST arrays [N]. */
+int nuts_axpy(nuts_ctx_t*, const nuts_plane_t* x, nuts_plane_t* y, const double* a, double a_bcast, const uint8_t* active);                 /* :99  y = a*x + y (FMA) */
+int nuts_axpy_out(nuts_ctx_t*, const nuts_plane_t* x, const nuts_plane_t* y, const double* a, double a_bcast, nuts_plane_t* out, const uint8_t* active); /* :98 */
+int nuts_array_mult(nuts_ctx_t*, const nuts_plane_t* a1, const nuts_plane_t* a2, nuts_plane_t* dest);    /* :123 */
+int nuts_array_mult_inplace(nuts_ctx_t*, nuts_plane_t* a1, const nuts_plane_t* a2);                      /* :124 */
+int nuts_array_recip(nuts_ctx_t*, const nuts_plane_t* a, nuts_plane_t* dest);                            /* :125 */
+int nuts_fill_array(nuts_ctx_t*, nuts_plane_t* a, double val);                                           /* :119 */
+int nuts_copy_into(nuts_ctx_t*, const nuts_plane_t* src, nuts_plane_t* dst);                             /* :97  */
+int nuts_array_vector_dot(nuts_ctx_t*, const nuts_plane_t* a1, const nuts_plane_t* a2, double* out);     /* :212 */
+int nuts_scalar_prods3(nuts_ctx_t*, const nuts_plane_t* positive1, const nuts_plane_t* negative1, const nuts_plane_t* positive2,
+                       const nuts_plane_t* x, const nuts_plane_t* y, double* out1, double* out2);        /* :75-82 */
+int nuts_scalar_prods2(nuts_ctx_t*, const nuts_plane_t* positive1, const nuts_plane_t* positive2,
+                       const nuts_plane_t* x, const nuts_plane_t* y, double* out1, double* out2);        /* :84-90 */
+int nuts_sq_norm_sum(nuts_ctx_t*, const nuts_plane_t* x, const nuts_plane_t* y, double* out);            /* :92  sum (x+y)^2 */
+int nuts_array_all_finite(nuts_ctx_t*, const nuts_plane_t* a, uint8_t* out);                             /* :121 */
+int nuts_array_all_finite_and_nonzero(nuts_ctx_t*, const nuts_plane_t* a, uint8_t* out);                 /* :122 */
+int nuts_array_sum_ln(nuts_ctx_t*, const nuts_plane_t* a, double* out);                                  /* :113-117 */
+/* dest[c,i] = stds[c,i] * normal(seed, stream = chain_offset + c + 1, counter..)  (:213-218); advances nothing:
+ * the caller owns the counter; consumes ceil(dim/2) counter values starting at `counter`. */
+int nuts_array_gaussian(nuts_ctx_t*, nuts_plane_t* dest, const nuts_plane_t* stds, uint64_t seed, uint64_t chain_offset, uint64_t counter);
+int nuts_array_update_variance(nuts_ctx_t*, nuts_plane_t* mean, nuts_plane_t* variance, const nuts_plane_t* value,
+                               const double* diff_scale /*[N] host, or NULL*/, double diff_scale_bcast);  /* :227-233 */
+int nuts_array_update_var_inv_std_draw(nuts_ctx_t*, nuts_plane_t* inv_std, nuts_plane_t* std, const nuts_plane_t* draw_var,
+                                       double scale, int has_fill, double fill_invalid, double clamp_lo, double clamp_hi);        /* :234-242 */
+int nuts_array_update_var_inv_std_draw_grad(nuts_ctx_t*, nuts_plane_t* inv_std, nuts_plane_t* std, const nuts_plane_t* draw_var,
+                                            const nuts_plane_t* grad_var, int has_fill, double fill_invalid, double clamp_lo, double clamp_hi); /* :243-251 */
+int nuts_array_update_var_inv_std_grad(nuts_ctx_t*, nuts_plane_t* inv_std, nuts_plane_t* std, const nuts_plane_t* gradient,
+                                       double fill_invalid, double clamp_lo, double clamp_hi);                                    /* :253-260 */
+/* logp_array (:46-50): gradient plane written, logp[N] + status[N] to host. */
+int nuts_logp_array(nuts_ctx_t*, const nuts_plane_t* position, nuts_plane_t* gradient, double* logp, int32_t* status);
+
+/* ===================== Tier 2: fused Hamiltonian ops (reference src/dynamics/hamiltonian.rs:145-258) ============
+ * A nuts_point_t is N TransformedPoints: 5 planes + per-chain scalars.  The diagonal transformation
+ * (DiagMassMatrix, reference src/transform/diagonal.rs:9-17) lives in the ctx: stds, inv_stds, mean, logdet, id. */
+int nuts_point_alloc(nuts_ctx_t*, nuts_point_t** point);
+int nuts_point_free(nuts_ctx_t*, nuts_point_t* point);
+/* which: 0 untransformed_position, 1 untransformed_gradient, 2 transformed_position, 3 transformed_gradient, 4 velocity */
+nuts_plane_t* nuts_point_plane(nuts_point_t* point, int which);
+/* scalars, HOST arrays [N] (any may be NULL) */
+int nuts_point_get_scalars(nuts_ctx_t*, const nuts_point_t*, int64_t* index_in_trajectory, double* logp, double* logdet,
+                           double* kinetic_energy, double* initial_energy, int64_t* transform_id);
+int nuts_point_set_scalars(nuts_ctx_t*, nuts_point_t*, const int64_t* index_in_trajectory, const double* logp, const double* logdet,
+                           const double* kinetic_energy, const double* initial_energy, const int64_t* transform_id);
+/* DiagMassMatrix::set_transform (diagonal.rs:156-162): stds/mean HOST [N*d]; bumps id, recomputes inv_stds + logdet. */
+int nuts_set_transform(nuts_ctx_t*, const double* stds, const double* mean);
+int nuts_get_transform(nuts_ctx_t*, double* stds, double* inv_stds, double* mean, double* logdet /*[N]*/, int64_t* id /*[N]*/);
+/* Hamiltonian::init_state (transformed_hamiltonian.rs:640-661): x -> logp, grad, z, grad_z; status 3 when check_all fails. */
+int nuts_init_state(nuts_ctx_t*, nuts_point_t* point, const double* position /*HOST [N*d]*/, int32_t* status);
+/* Hamiltonian::initialize_trajectory (:687-736): resample velocity from (seed, chain_offset+c+1, counter), re-whiten when the
+ * transformation id changed, kinetic energy, index=0, initial_energy. */
+int nuts_initialize_trajectory(nuts_ctx_t*, nuts_point_t* point, int resample_velocity, uint64_t seed, uint64_t chain_offset, uint64_t counter);
+/* Hamiltonian::leapfrog (:524-615), Euclidean: eps[c] = dir[c] * step_size[c] (* step_size_factor = 1).
+ * step_size HOST [N] or NULL+bcast; dir HOST int8 [N] (+1/-1) or NULL (= +1); energy_baseline HOST [N] or NULL (= start.initial_energy).
+ * Writes `out` for every active chain (also divergent ones) and status[N] (0 ok / 1 / 2); energy_error[N] optional. */
+int nuts_leapfrog(nuts_ctx_t*, const nuts_point_t* start, nuts_point_t* out, const double* step_size, double step_size_bcast,
+                  const int8_t* dir, const double* energy_baseline, double max_energy_error, const uint8_t* active,
+                  int32_t* status, double* energy_error);
+/* Hamiltonian::is_turning (:617-638) */
+int nuts_is_turning(nuts_ctx_t*, const nuts_point_t* state1, const nuts_point_t* state2, uint8_t* turning);
+
+/* ===================== Tier 3: whole draws (Chain::set_position / Chain::draw, reference src/chain.rs:137-188) == */
+int nuts_sampler_create(nuts_ctx_t*, nuts_sampler_t** sampler, const nuts_settings_t* settings, uint64_t seed, uint64_t chain_id_offset);
+int nuts_sampler_destroy(nuts_sampler_t* sampler);
+/* Chain::set_position for every chain: position HOST [N*d]; status[N] (0 ok, 3 bad initial point). */
+int nuts_set_position(nuts_sampler_t*, const double* position, int32_t* status);
+/* n_draws x Chain::draw for every chain.  draws_out: HOST [n_draws x N x d] (may be NULL); stats: HOST SoA (may be NULL).
+ * Returns after the stream is synchronised. */
+int nuts_draw(nuts_sampler_t*, uint64_t n_draws, double* draws_out, const nuts_stats_t* stats);
+/* Same, but draws stay on the device: draws_dev is a DEVICE pointer [n_draws x N x d] (may be NULL). Asynchronous on the ctx stream. */
+int nuts_draw_device(nuts_sampler_t*, uint64_t n_draws, double* draws_dev);
+/* total leapfrog steps (sum over chains, incl. init searches and divergent steps) and draws done so far. */
+int nuts_sampler_counters(nuts_sampler_t*, uint64_t* total_leapfrogs, uint64_t* draws_done);
+/* milliseconds spent inside the draw kernel during the last nuts_draw / nuts_draw_device call (CUDA events on the ctx stream),
+ * and the number of kernel launches it made. */
+int nuts_sampler_last_timing(nuts_sampler_t*, double* kernel_ms, uint64_t* launches);
+/* white-box access used by the parity tests: HOST arrays, any may be NULL.
+ * position [N*d], step_size [N], stds [N*d], mean [N*d], rng_counter [N]. */
+int nuts_sampler_get_state(nuts_sampler_t*, double* position, double* step_size, double* stds, double* mean, uint64_t* rng_counter);
+int nuts_sampler_set_step_size(nuts_sampler_t*, const double* step_size /*[N]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUTS_B200_H */

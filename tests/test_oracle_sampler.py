@@ -1,0 +1,173 @@
+"""Pins the oracle's chain / tree / adaptation restatement against the reference's behavioural tests
+(no golden trajectories exist in the reference; these are its own acceptance bounds):
+  src/nuts.rs:399-419             N(3,1)^10 from 0: not diverging after 11 draws
+  src/adapt_strategy.rs:367-435   N(30,1)^10 from 1.5, 100 tune: every coordinate within 5 of 30 afterwards, no divergence
+  src/sampler.rs:1662-1692        Progress bookkeeping: tuning flips after num_tune draws
+  tests/sample_normal.rs:205-226  100-dim N(0.5,1), 6 chains, defaults: completes
+  tests/sample_normal.rs:320-356  rank-1 correlated Gaussian model (logp/grad identity check)
+plus structural invariants of the tree (n_steps vs depth) and of the window schedule."""
+import numpy as np
+
+from nuts_rs_b200 import _abi
+
+
+def test_no_divergence_after_10_draws(orc):
+    m = orc.Model(_abi.NUTS_LOGP_GAUSS_ISO, 10, mu=3.0)
+    s = _abi.default_settings()
+    S = orc.Sampler(m, s, seed=0, nchains=1)
+    assert S.set_position(np.zeros((1, 10)))[0] == 0
+    _, st = S.draw(11)
+    assert not st["diverging"][-1, 0]
+
+
+def test_sample_normal_30(orc):
+    m = orc.Model(_abi.NUTS_LOGP_GAUSS_ISO, 10, mu=30.0)
+    s = _abi.default_settings()
+    s.num_tune = 100
+    S = orc.Sampler(m, s, seed=42, nchains=1)
+    assert S.set_position(np.full((1, 10), 1.5))[0] == 0
+    S.draw(1)
+    draws, st = S.draw(200)
+    assert np.all(np.abs(draws[100:] - 30.0) < 5.0)
+    assert not st["diverging"][100:].any()
+
+
+def test_progress_bookkeeping(orc):
+    m = orc.Model(_abi.NUTS_LOGP_GAUSS_ISO, 10, mu=3.0)
+    s = _abi.default_settings()
+    s.num_tune = 20
+    S = orc.Sampler(m, s, seed=3, nchains=2)
+    S.set_position(np.zeros((2, 10)))
+    _, st = S.draw(30)
+    # `tuning` is reported true for draws 0..num_tune-1 and false from draw == num_tune on (adapt_strategy.rs:133-138)
+    assert st["tuning"][:20].all() and not st["tuning"][20:].any()
+    assert (st["n_steps"] >= 1).all()
+
+
+def test_run_100_dim_6_chains(orc):
+    d = 100
+    m = orc.Model(_abi.NUTS_LOGP_GAUSS_ISO, d, mu=0.5)
+    s = _abi.default_settings()
+    s.num_tune = 200
+    rng = np.random.default_rng(0)
+    S = orc.Sampler(m, s, seed=42, nchains=6, nthreads=6)
+    assert (S.set_position(rng.normal(size=(6, d))) == 0).all()
+    S.draw(200)
+    draws, st = S.draw(300)
+    assert abs(draws.mean() - 0.5) < 0.05
+    assert abs(draws.std() - 1.0) < 0.05
+    assert st["diverging"].sum() == 0
+    # adapted step size for a 100-d standard normal at target_accept 0.8 is O(1)
+    assert 0.3 < np.median(st["step_size"]) < 1.5
+
+
+def test_tree_invariants(orc):
+    m = orc.Model(_abi.NUTS_LOGP_GAUSS_ISO, 10, mu=0.0)
+    s = _abi.default_settings()
+    s.num_tune = 50
+    s.maxdepth = 6
+    S = orc.Sampler(m, s, seed=11, nchains=4)
+    S.set_position(np.full((4, 10), 0.3))
+    _, st = S.draw(150)
+    depth, n_steps = st["depth"], st["n_steps"]
+    assert depth.max() <= 6
+    # a finished tree of depth k has 2^k - 1 leapfrogs; an aborted extension adds at most 2^k more
+    assert (n_steps >= 2.0 ** depth - 1).all()
+    assert (n_steps <= 2.0 ** (depth + 1) - 1).all()
+    md = st["maxdepth_reached"].astype(bool)
+    assert (depth[md] == 6).all() and (n_steps[md] == 63).all()
+    assert (np.abs(st["index_in_trajectory"]) <= n_steps).all()
+    # mean_tree_accept in [0,1]
+    assert ((st["mean_tree_accept"] >= 0) & (st["mean_tree_accept"] <= 1)).all()
+
+
+def test_fixed_step_no_jitter_is_deterministic_and_exact_for_maxdepth(orc):
+    # check_turning off via mindepth = maxdepth => exactly 2^maxdepth - 1 leapfrogs per draw
+    m = orc.Model(_abi.NUTS_LOGP_GAUSS_ISO, 5, mu=0.0)
+    s = _abi.default_settings()
+    s.num_tune = 0
+    s.maxdepth = 4
+    s.mindepth = 4
+    ss = s.adapt_options.step_size_settings
+    ss.adapt_options.method = _abi.NUTS_STEPSIZE_FIXED
+    ss.adapt_options.fixed_step = 0.05
+    ss.has_jitter = 0
+    S = orc.Sampler(m, s, seed=5, nchains=3)
+    S.set_position(np.full((3, 5), 0.7))
+    d1, st = S.draw(20)
+    assert (st["n_steps"] == 15).all() and (st["depth"] == 4).all() and st["maxdepth_reached"].all()
+    assert (st["step_size"] == 0.05).all()
+    S2 = orc.Sampler(m, s, seed=5, nchains=3)
+    S2.set_position(np.full((3, 5), 0.7))
+    d2, _ = S2.draw(20)
+    np.testing.assert_array_equal(d1, d2)
+    # chains use distinct streams
+    assert not np.array_equal(d1[:, 0], d1[:, 1])
+    # chain_id_offset shifts the streams: chain 1 of offset 0 == chain 0 of offset 1
+    S3 = orc.Sampler(m, s, seed=5, nchains=1, chain_id_offset=1)
+    S3.set_position(np.full((1, 5), 0.7))
+    d3, _ = S3.draw(20)
+    np.testing.assert_array_equal(d3[:, 0], d1[:, 1])
+
+
+def test_models_gradients(orc):
+    rng = np.random.default_rng(0)
+
+    def fd(model, x, h=1e-6):
+        g = np.zeros_like(x)
+        for i in range(len(x)):
+            xp, xm = x.copy(), x.copy()
+            xp[i] += h
+            xm[i] -= h
+            g[i] = (model.logp(xp)[0] - model.logp(xm)[0]) / (2 * h)
+        return g
+
+    d = 7
+    models = [
+        orc.Model(_abi.NUTS_LOGP_GAUSS_ISO, d, mu=0.5),
+        orc.Model(_abi.NUTS_LOGP_GAUSS_DIAG, d, mu=rng.normal(size=d), sigma=np.exp(rng.normal(size=d))),
+        orc.Model(_abi.NUTS_LOGP_GAUSS_RANK1, d, mu=0.0, rank1_scale=0.5),
+        orc.Model(_abi.NUTS_LOGP_FUNNEL, d, funnel_scale=3.0),
+    ]
+    for m in models:
+        x = rng.normal(size=d)
+        lp, g = m.logp(x)
+        np.testing.assert_allclose(g, fd(m, x), rtol=1e-5, atol=1e-6)
+    # rank-1 model equals the dense Gaussian with Sigma = I + s*11^T (tests/sample_normal.rs:20-27)
+    x = rng.normal(size=d)
+    Sigma = np.eye(d) + 0.5 * np.ones((d, d))
+    lp, g = models[2].logp(x)
+    np.testing.assert_allclose(lp, -0.5 * x @ np.linalg.solve(Sigma, x), rtol=1e-12)
+    np.testing.assert_allclose(g, -np.linalg.solve(Sigma, x), rtol=1e-12)
+
+
+def test_diag_adaptation_recovers_scales(orc):
+    # 20-dim diagonal Gaussian with sigma from 0.1 to 10: after warmup stds^2 ~ sigma (mass = (var_x/var_g)^(1/2) = sigma^2)
+    d = 20
+    sigma = np.exp(np.linspace(np.log(0.1), np.log(10), d))
+    m = orc.Model(_abi.NUTS_LOGP_GAUSS_DIAG, d, mu=0.5, sigma=sigma)
+    s = _abi.default_settings()
+    s.num_tune = 300
+    S = orc.Sampler(m, s, seed=1, nchains=4, nthreads=4)
+    rng = np.random.default_rng(1)
+    assert (S.set_position(rng.normal(size=(4, d))) == 0).all()
+    S.draw(300)
+    stt = S.state()
+    ratio = stt["stds"] / sigma[None, :]
+    assert np.all((ratio > 0.6) & (ratio < 1.6)), ratio
+    draws, st = S.draw(400)
+    z = (draws - 0.5) / sigma
+    assert abs(z.mean()) < 0.1 and abs(z.std() - 1) < 0.1
+    assert st["diverging"].sum() == 0
+
+
+def test_funnel_produces_divergences_and_depth_spread(orc):
+    m = orc.Model(_abi.NUTS_LOGP_FUNNEL, 10, funnel_scale=3.0)
+    s = _abi.default_settings()
+    s.num_tune = 200
+    S = orc.Sampler(m, s, seed=2, nchains=8, nthreads=8)
+    rng = np.random.default_rng(2)
+    assert (S.set_position(rng.normal(size=(8, 10))) == 0).all()
+    _, st = S.draw(400)
+    assert st["diverging"].sum() > 0
+    assert st["depth"].max() - st["depth"].min() >= 3
