@@ -1,0 +1,962 @@
+// capi.cu — host side of libnuts_b200.so: the C ABI declared in include/nuts_b200.h.
+// No torch, no CPU fallback: every entry point needs an sm_100 device and fails loudly otherwise.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nuts_b200.h"
+#include "chain_engine.cuh"
+#include "plane_kernels.cuh"
+
+using namespace nb;
+
+// ---- per-configuration launchers (engine_inst.cu) ----
+#define NB_DECL(TPC, EPT)                                                                                  \
+  extern "C" cudaError_t nb_launch_chain_##TPC##_##EPT(const EngineParams* p, int grid, cudaStream_t s);   \
+  extern "C" cudaError_t nb_occupancy_chain_##TPC##_##EPT(int* blocks_per_sm, int* cta_threads);
+NB_DECL(32, 1)
+NB_DECL(32, 2)
+NB_DECL(32, 4)
+NB_DECL(64, 4)
+NB_DECL(128, 4)
+NB_DECL(128, 8)
+NB_DECL(256, 8)
+NB_DECL(512, 8)
+NB_DECL(1024, 8)
+NB_DECL(1024, 10)
+NB_DECL(1024, 16)
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) return fail(NUTS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct EngineConfig {
+  int tpc, ept, max_d;
+  cudaError_t (*launch)(const EngineParams*, int, cudaStream_t);
+  cudaError_t (*occupancy)(int*, int*);
+};
+#define NB_CFG(TPC, EPT) \
+  { TPC, EPT, TPC * EPT, nb_launch_chain_##TPC##_##EPT, nb_occupancy_chain_##TPC##_##EPT }
+const EngineConfig kConfigs[] = {NB_CFG(32, 1),  NB_CFG(32, 2),  NB_CFG(32, 4),   NB_CFG(64, 4),    NB_CFG(128, 4),  NB_CFG(128, 8),
+                                 NB_CFG(256, 8), NB_CFG(512, 8), NB_CFG(1024, 8), NB_CFG(1024, 10), NB_CFG(1024, 16)};
+
+}  // namespace
+
+struct nuts_plane {
+  double* ptr;
+};
+
+struct nuts_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t N = 0, d = 0, ld = 0;
+  int num_sms = 0;
+  ModelDev model{};
+  double* d_model_mu = nullptr;
+  double* d_model_prec = nullptr;
+  // Tier-2 transformation (one DiagMassMatrix per chain)
+  TransformDev T{};
+  // scratch
+  double* d_dense = nullptr;    // [N*d] staging for host <-> plane packing
+  double* d_sc[4] = {nullptr, nullptr, nullptr, nullptr};  // [N] f64 scratch
+  uint8_t* d_u8 = nullptr;      // [N]
+  int8_t* d_i8 = nullptr;       // [N]
+  int* d_i32 = nullptr;         // [N]
+  long long* d_i64 = nullptr;   // [N]
+  RowArgs row_args() const { return RowArgs{(int)N, (int)d, (int)ld}; }
+};
+
+struct nuts_point {
+  nuts_plane planes[5];
+  PointDev dev{};
+};
+
+struct nuts_sampler {
+  nuts_ctx* ctx = nullptr;
+  nuts_settings_t settings{};
+  EngineParams P{};
+  const EngineConfig* cfg = nullptr;
+  int grid = 0;
+  std::vector<void*> allocations;
+  double* d_init = nullptr;
+  int* d_status = nullptr;
+  // device stats buffers (grown on demand)
+  uint64_t stats_capacity = 0;  // in draws
+  StatsDev d_stats{};
+  double* d_draws = nullptr;
+  uint64_t draws_capacity = 0;  // in draws
+  double* h_pinned = nullptr;   // pinned staging for D2H of draws
+  uint64_t pinned_bytes = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_kernel_ms = 0.0;
+  uint64_t last_launches = 0;
+  uint64_t draws_done = 0;
+  bool positioned = false;
+};
+
+namespace {
+
+int check_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(NUTS_ERR_NO_DEVICE, "no CUDA device visible (%s); libnuts_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  return NUTS_OK;
+}
+
+template <class T>
+int dev_alloc(T** p, size_t count) {
+  CUDA_TRY(cudaMalloc((void**)p, count * sizeof(T)));
+  CUDA_TRY(cudaMemset(*p, 0, count * sizeof(T)));
+  return NUTS_OK;
+}
+
+int upload_mask(nuts_ctx* ctx, const uint8_t* active, const uint8_t** out) {
+  *out = nullptr;
+  if (!active) return NUTS_OK;
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_u8, active, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+  *out = ctx->d_u8;
+  return NUTS_OK;
+}
+int upload_f64(nuts_ctx* ctx, const double* host, int slot, const double** out) {
+  *out = nullptr;
+  if (!host) return NUTS_OK;
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_sc[slot], host, ctx->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  *out = ctx->d_sc[slot];
+  return NUTS_OK;
+}
+int download_f64(nuts_ctx* ctx, int slot, double* host) {
+  if (!host) return NUTS_OK;
+  CUDA_TRY(cudaMemcpyAsync(host, ctx->d_sc[slot], ctx->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return NUTS_OK;
+}
+int sync(nuts_ctx* ctx) {
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return NUTS_OK;
+}
+#define TRY(expr)            \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != NUTS_OK) return _r; \
+  } while (0)
+#define CHECK_LAUNCH() CUDA_TRY(cudaGetLastError())
+
+template <class T>
+int grow(T** p, size_t count) {
+  if (*p) CUDA_TRY(cudaFree(*p));
+  *p = nullptr;
+  CUDA_TRY(cudaMalloc((void**)p, count * sizeof(T)));
+  return NUTS_OK;
+}
+
+
+}  // namespace
+
+extern "C" {
+
+const char* nuts_last_error(void) { return g_last_error.c_str(); }
+
+int nuts_device_available(void) {
+  int r = check_device();
+  if (r != NUTS_OK) return r;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, 0) != cudaSuccess) return fail(NUTS_ERR_NO_DEVICE, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(NUTS_ERR_NO_DEVICE, "device 0 is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  return NUTS_OK;
+}
+
+void nuts_settings_default(nuts_settings_t* s) {
+  // DiagNutsSettings::default(): reference src/sampler.rs:507-531 (num_tune 400, num_chains 6, max_energy_error 1000 at :630-634)
+  std::memset(s, 0, sizeof(*s));
+  s->num_tune = 400;
+  s->num_draws = 1000;
+  s->maxdepth = 10;
+  s->mindepth = 0;
+  s->max_energy_error = 1000.0;
+  s->check_turning = 1;
+  s->num_chains = 6;
+  s->seed = 0;
+  s->extra_doublings = 0;
+  s->trajectory_kind = NUTS_KINETIC_EUCLIDEAN;
+  nuts_euclidean_adapt_options_t& a = s->adapt_options;  // src/adapt_strategy.rs:56-69
+  a.early_window = 0.3;
+  a.step_size_window = 0.15;
+  a.mass_matrix_switch_freq = 80;
+  a.early_mass_matrix_switch_freq = 10;
+  a.mass_matrix_update_freq = 1;
+  a.mass_matrix_window_growth = 1.5;
+  a.mass_matrix_options.store_mass_matrix = 0;  // src/transform/adapt/diagonal.rs:99-106
+  a.mass_matrix_options.use_grad_based_estimate = 1;
+  a.step_size_settings.target_accept = 0.8;  // src/stepsize/adapt.rs:320-329
+  a.step_size_settings.initial_step = 0.1;
+  a.step_size_settings.has_jitter = 1;
+  a.step_size_settings.jitter = 0.1;
+  a.step_size_settings.adapt_options.method = NUTS_STEPSIZE_DUAL_AVERAGE;
+  a.step_size_settings.adapt_options.dual_average = {0.75, 10., 0.05, 3.14159265358979323846};  // src/stepsize/dual_avg.rs:22-31
+}
+
+// ============================================================ Tier 0
+int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t dim, const nuts_logp_desc_t* model) {
+  TRY(check_device());
+  if (!out || !model || nchains == 0 || dim == 0) return fail(NUTS_ERR_INVALID, "nuts_ctx_create: bad arguments");
+  if (nchains > (1ull << 30) || dim > (1ull << 24)) return fail(NUTS_ERR_INVALID, "nuts_ctx_create: nchains/dim too large");
+  CUDA_TRY(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) return fail(NUTS_ERR_NO_DEVICE, "device %d is sm_%d%d; libnuts_b200 is built for sm_100a only", device_id, prop.major, prop.minor);
+  nuts_ctx* ctx = new nuts_ctx();
+  ctx->device = device_id;
+  ctx->N = nchains;
+  ctx->d = dim;
+  ctx->ld = (dim + 15) / 16 * 16;  // rows start on 128-byte boundaries
+  ctx->num_sms = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  // model parameters
+  std::vector<double> mu(ctx->ld, 0.0), prec(ctx->ld, 0.0);
+  for (uint64_t i = 0; i < dim; ++i) mu[i] = model->mu ? model->mu[i] : model->mu_scalar;
+  ctx->model.kind = model->kind;
+  ctx->model.dim = (int)dim;
+  switch (model->kind) {
+    case NUTS_LOGP_GAUSS_ISO:
+      break;
+    case NUTS_LOGP_GAUSS_DIAG:
+      if (!model->sigma) {
+        delete ctx;
+        return fail(NUTS_ERR_INVALID, "GAUSS_DIAG needs sigma");
+      }
+      for (uint64_t i = 0; i < dim; ++i) prec[i] = 1.0 / (model->sigma[i] * model->sigma[i]);
+      break;
+    case NUTS_LOGP_GAUSS_RANK1:
+      ctx->model.rank1_coeff = model->rank1_scale / (1.0 + model->rank1_scale * (double)dim);  // tests/sample_normal.rs:36
+      break;
+    case NUTS_LOGP_FUNNEL:
+      ctx->model.funnel_inv_var = 1.0 / (model->funnel_scale * model->funnel_scale);
+      break;
+    default:
+      delete ctx;
+      return fail(NUTS_ERR_INVALID, "unknown logp kind %d", model->kind);
+  }
+  TRY(dev_alloc(&ctx->d_model_mu, ctx->ld));
+  TRY(dev_alloc(&ctx->d_model_prec, ctx->ld));
+  CUDA_TRY(cudaMemcpy(ctx->d_model_mu, mu.data(), ctx->ld * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(ctx->d_model_prec, prec.data(), ctx->ld * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->model.mu = ctx->d_model_mu;
+  ctx->model.prec = ctx->d_model_prec;
+  // transformation planes: DiagMassMatrix::new (diagonal.rs:73-83): zero vectors, logdet 0, id -1
+  const size_t plane = nchains * ctx->ld;
+  TRY(dev_alloc(&ctx->T.stds, plane));
+  TRY(dev_alloc(&ctx->T.inv_stds, plane));
+  TRY(dev_alloc(&ctx->T.mean, plane));
+  TRY(dev_alloc(&ctx->T.logdet, nchains));
+  TRY(dev_alloc(&ctx->T.id, nchains));
+  CUDA_TRY(cudaMemset(ctx->T.id, 0xff, nchains * sizeof(long long)));  // -1
+  TRY(dev_alloc(&ctx->d_dense, nchains * dim));
+  for (int k = 0; k < 4; ++k) TRY(dev_alloc(&ctx->d_sc[k], nchains));
+  TRY(dev_alloc(&ctx->d_u8, nchains));
+  TRY(dev_alloc(&ctx->d_i8, nchains));
+  TRY(dev_alloc(&ctx->d_i32, nchains));
+  TRY(dev_alloc(&ctx->d_i64, nchains));
+  *out = ctx;
+  return NUTS_OK;
+}
+
+int nuts_ctx_destroy(nuts_ctx_t* ctx) {
+  if (!ctx) return NUTS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_model_mu);
+  cudaFree(ctx->d_model_prec);
+  cudaFree(ctx->T.stds);
+  cudaFree(ctx->T.inv_stds);
+  cudaFree(ctx->T.mean);
+  cudaFree(ctx->T.logdet);
+  cudaFree(ctx->T.id);
+  cudaFree(ctx->d_dense);
+  for (int k = 0; k < 4; ++k) cudaFree(ctx->d_sc[k]);
+  cudaFree(ctx->d_u8);
+  cudaFree(ctx->d_i8);
+  cudaFree(ctx->d_i32);
+  cudaFree(ctx->d_i64);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NUTS_OK;
+}
+int nuts_ctx_synchronize(nuts_ctx_t* ctx) { return sync(ctx); }
+uint64_t nuts_ctx_nchains(const nuts_ctx_t* ctx) { return ctx->N; }
+uint64_t nuts_ctx_dim(const nuts_ctx_t* ctx) { return ctx->d; }
+void* nuts_ctx_stream(nuts_ctx_t* ctx) { return (void*)ctx->stream; }
+
+int nuts_plane_alloc(nuts_ctx_t* ctx, nuts_plane_t** plane) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  nuts_plane* p = new nuts_plane();
+  int r = dev_alloc(&p->ptr, ctx->N * ctx->ld);
+  if (r != NUTS_OK) {
+    delete p;
+    return r;
+  }
+  *plane = p;
+  return NUTS_OK;
+}
+int nuts_plane_free(nuts_ctx_t* ctx, nuts_plane_t* plane) {
+  if (!plane) return NUTS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(plane->ptr);
+  delete plane;
+  return NUTS_OK;
+}
+static int plane_from_host(nuts_ctx* ctx, double* plane, const double* src) {
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_dense, src, ctx->N * ctx->d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  k_pack<<<(unsigned)ctx->N, PK_THREADS, 0, ctx->stream>>>(ctx->row_args(), ctx->d_dense, plane);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+static int plane_to_host(nuts_ctx* ctx, const double* plane, double* dst) {
+  k_unpack<<<(unsigned)ctx->N, PK_THREADS, 0, ctx->stream>>>(ctx->row_args(), plane, ctx->d_dense);
+  CHECK_LAUNCH();
+  CUDA_TRY(cudaMemcpyAsync(dst, ctx->d_dense, ctx->N * ctx->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
+}
+int nuts_plane_read_from_host(nuts_ctx_t* ctx, nuts_plane_t* dst, const double* src) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return plane_from_host(ctx, dst->ptr, src);
+}
+int nuts_plane_write_to_host(nuts_ctx_t* ctx, const nuts_plane_t* src, double* dst) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return plane_to_host(ctx, src->ptr, dst);
+}
+double* nuts_plane_device_ptr(nuts_plane_t* plane, uint64_t* row_stride_elems) {
+  (void)row_stride_elems;
+  return plane->ptr;
+}
+
+// ============================================================ Tier 1
+#define GRID (unsigned)ctx->N, PK_THREADS, 0, ctx->stream
+
+int nuts_axpy(nuts_ctx_t* ctx, const nuts_plane_t* x, nuts_plane_t* y, const double* a, double a_bcast, const uint8_t* active) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const double* da;
+  const uint8_t* dm;
+  TRY(upload_f64(ctx, a, 0, &da));
+  TRY(upload_mask(ctx, active, &dm));
+  k_axpy<<<GRID>>>(ctx->row_args(), x->ptr, y->ptr, da, a_bcast, dm);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_axpy_out(nuts_ctx_t* ctx, const nuts_plane_t* x, const nuts_plane_t* y, const double* a, double a_bcast, nuts_plane_t* out,
+                  const uint8_t* active) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const double* da;
+  const uint8_t* dm;
+  TRY(upload_f64(ctx, a, 0, &da));
+  TRY(upload_mask(ctx, active, &dm));
+  k_axpy_out<<<GRID>>>(ctx->row_args(), x->ptr, y->ptr, da, a_bcast, out->ptr, dm);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_array_mult(nuts_ctx_t* ctx, const nuts_plane_t* a1, const nuts_plane_t* a2, nuts_plane_t* dest) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_mult<<<GRID>>>(ctx->row_args(), a1->ptr, a2->ptr, dest->ptr);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_array_mult_inplace(nuts_ctx_t* ctx, nuts_plane_t* a1, const nuts_plane_t* a2) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_mult<<<GRID>>>(ctx->row_args(), a2->ptr, a1->ptr, a1->ptr);  // out = x * out (util.rs:94-97)
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_array_recip(nuts_ctx_t* ctx, const nuts_plane_t* a, nuts_plane_t* dest) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_recip<<<GRID>>>(ctx->row_args(), a->ptr, dest->ptr);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_fill_array(nuts_ctx_t* ctx, nuts_plane_t* a, double val) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_fill<<<GRID>>>(ctx->row_args(), a->ptr, val);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_copy_into(nuts_ctx_t* ctx, const nuts_plane_t* src, nuts_plane_t* dst) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_copy<<<GRID>>>(ctx->row_args(), src->ptr, dst->ptr);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+static int reduce1(nuts_ctx* ctx, int op, const double* x, const double* y, double* out_f64, uint8_t* out_u8) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_reduce1<<<GRID>>>(ctx->row_args(), op, x, y, ctx->d_sc[0]);
+  CHECK_LAUNCH();
+  if (out_f64) {
+    TRY(download_f64(ctx, 0, out_f64));
+    return sync(ctx);
+  }
+  std::vector<double> tmp(ctx->N);
+  TRY(download_f64(ctx, 0, tmp.data()));
+  TRY(sync(ctx));
+  for (uint64_t c = 0; c < ctx->N; ++c) out_u8[c] = tmp[c] != 0.0;
+  return NUTS_OK;
+}
+int nuts_array_vector_dot(nuts_ctx_t* ctx, const nuts_plane_t* a1, const nuts_plane_t* a2, double* out) {
+  return reduce1(ctx, 0, a1->ptr, a2->ptr, out, nullptr);
+}
+int nuts_sq_norm_sum(nuts_ctx_t* ctx, const nuts_plane_t* x, const nuts_plane_t* y, double* out) {
+  return reduce1(ctx, 1, x->ptr, y->ptr, out, nullptr);
+}
+int nuts_array_sum_ln(nuts_ctx_t* ctx, const nuts_plane_t* a, double* out) { return reduce1(ctx, 2, a->ptr, nullptr, out, nullptr); }
+int nuts_array_all_finite(nuts_ctx_t* ctx, const nuts_plane_t* a, uint8_t* out) { return reduce1(ctx, 3, a->ptr, nullptr, nullptr, out); }
+int nuts_array_all_finite_and_nonzero(nuts_ctx_t* ctx, const nuts_plane_t* a, uint8_t* out) {
+  return reduce1(ctx, 4, a->ptr, nullptr, nullptr, out);
+}
+int nuts_scalar_prods3(nuts_ctx_t* ctx, const nuts_plane_t* positive1, const nuts_plane_t* negative1, const nuts_plane_t* positive2,
+                       const nuts_plane_t* x, const nuts_plane_t* y, double* out1, double* out2) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_scalar_prods<<<GRID>>>(ctx->row_args(), positive1->ptr, negative1->ptr, positive2->ptr, x->ptr, y->ptr, ctx->d_sc[0], ctx->d_sc[1]);
+  CHECK_LAUNCH();
+  TRY(download_f64(ctx, 0, out1));
+  TRY(download_f64(ctx, 1, out2));
+  return sync(ctx);
+}
+int nuts_scalar_prods2(nuts_ctx_t* ctx, const nuts_plane_t* positive1, const nuts_plane_t* positive2, const nuts_plane_t* x,
+                       const nuts_plane_t* y, double* out1, double* out2) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_scalar_prods<<<GRID>>>(ctx->row_args(), positive1->ptr, nullptr, positive2->ptr, x->ptr, y->ptr, ctx->d_sc[0], ctx->d_sc[1]);
+  CHECK_LAUNCH();
+  TRY(download_f64(ctx, 0, out1));
+  TRY(download_f64(ctx, 1, out2));
+  return sync(ctx);
+}
+int nuts_array_gaussian(nuts_ctx_t* ctx, nuts_plane_t* dest, const nuts_plane_t* stds, uint64_t seed, uint64_t chain_offset, uint64_t counter) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_gaussian<<<GRID>>>(ctx->row_args(), dest->ptr, stds->ptr, seed, chain_offset, counter);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_array_update_variance(nuts_ctx_t* ctx, nuts_plane_t* mean, nuts_plane_t* variance, const nuts_plane_t* value,
+                               const double* diff_scale, double diff_scale_bcast) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const double* ds;
+  TRY(upload_f64(ctx, diff_scale, 0, &ds));
+  k_update_variance<<<GRID>>>(ctx->row_args(), mean->ptr, variance->ptr, value->ptr, ds, diff_scale_bcast);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_array_update_var_inv_std_draw(nuts_ctx_t* ctx, nuts_plane_t* inv_std, nuts_plane_t* std_, const nuts_plane_t* draw_var,
+                                       double scale, int has_fill, double fill_invalid, double clamp_lo, double clamp_hi) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_update_var_inv_std<<<GRID>>>(ctx->row_args(), 0, inv_std->ptr, std_->ptr, draw_var->ptr, nullptr, scale, has_fill, fill_invalid, clamp_lo,
+                                 clamp_hi);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_array_update_var_inv_std_draw_grad(nuts_ctx_t* ctx, nuts_plane_t* inv_std, nuts_plane_t* std_, const nuts_plane_t* draw_var,
+                                            const nuts_plane_t* grad_var, int has_fill, double fill_invalid, double clamp_lo,
+                                            double clamp_hi) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_update_var_inv_std<<<GRID>>>(ctx->row_args(), 1, inv_std->ptr, std_->ptr, draw_var->ptr, grad_var->ptr, 0.0, has_fill, fill_invalid,
+                                 clamp_lo, clamp_hi);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_array_update_var_inv_std_grad(nuts_ctx_t* ctx, nuts_plane_t* inv_std, nuts_plane_t* std_, const nuts_plane_t* gradient,
+                                       double fill_invalid, double clamp_lo, double clamp_hi) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_update_var_inv_std<<<GRID>>>(ctx->row_args(), 2, inv_std->ptr, std_->ptr, gradient->ptr, nullptr, 0.0, 1, fill_invalid, clamp_lo, clamp_hi);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_logp_array(nuts_ctx_t* ctx, const nuts_plane_t* position, nuts_plane_t* gradient, double* logp, int32_t* status) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_logp_array<<<GRID>>>(ctx->row_args(), ctx->model, position->ptr, gradient->ptr, ctx->d_sc[0], ctx->d_i32);
+  CHECK_LAUNCH();
+  TRY(download_f64(ctx, 0, logp));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, ctx->d_i32, ctx->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
+}
+
+// ============================================================ Tier 2
+int nuts_point_alloc(nuts_ctx_t* ctx, nuts_point_t** point) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  nuts_point* p = new nuts_point();
+  const size_t plane = ctx->N * ctx->ld;
+  for (int k = 0; k < 5; ++k) TRY(dev_alloc(&p->planes[k].ptr, plane));
+  p->dev.x = p->planes[0].ptr;
+  p->dev.gx = p->planes[1].ptr;
+  p->dev.z = p->planes[2].ptr;
+  p->dev.gz = p->planes[3].ptr;
+  p->dev.v = p->planes[4].ptr;
+  TRY(dev_alloc(&p->dev.idx, ctx->N));
+  TRY(dev_alloc(&p->dev.logp, ctx->N));
+  TRY(dev_alloc(&p->dev.logdet, ctx->N));
+  TRY(dev_alloc(&p->dev.ke, ctx->N));
+  TRY(dev_alloc(&p->dev.e0, ctx->N));
+  TRY(dev_alloc(&p->dev.tid, ctx->N));
+  CUDA_TRY(cudaMemset(p->dev.tid, 0xff, ctx->N * sizeof(long long)));  // transform_id = -1 (transformed_hamiltonian.rs:376)
+  *point = p;
+  return NUTS_OK;
+}
+int nuts_point_free(nuts_ctx_t* ctx, nuts_point_t* p) {
+  if (!p) return NUTS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int k = 0; k < 5; ++k) cudaFree(p->planes[k].ptr);
+  cudaFree(p->dev.idx);
+  cudaFree(p->dev.logp);
+  cudaFree(p->dev.logdet);
+  cudaFree(p->dev.ke);
+  cudaFree(p->dev.e0);
+  cudaFree(p->dev.tid);
+  delete p;
+  return NUTS_OK;
+}
+nuts_plane_t* nuts_point_plane(nuts_point_t* point, int which) {
+  if (which < 0 || which > 4) return nullptr;
+  return &point->planes[which];
+}
+int nuts_point_get_scalars(nuts_ctx_t* ctx, const nuts_point_t* p, int64_t* idx, double* logp, double* logdet, double* ke, double* e0,
+                           int64_t* tid) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t n8 = ctx->N * 8;
+  if (idx) CUDA_TRY(cudaMemcpyAsync(idx, p->dev.idx, n8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (logp) CUDA_TRY(cudaMemcpyAsync(logp, p->dev.logp, n8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (logdet) CUDA_TRY(cudaMemcpyAsync(logdet, p->dev.logdet, n8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ke) CUDA_TRY(cudaMemcpyAsync(ke, p->dev.ke, n8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (e0) CUDA_TRY(cudaMemcpyAsync(e0, p->dev.e0, n8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (tid) CUDA_TRY(cudaMemcpyAsync(tid, p->dev.tid, n8, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
+}
+int nuts_point_set_scalars(nuts_ctx_t* ctx, nuts_point_t* p, const int64_t* idx, const double* logp, const double* logdet, const double* ke,
+                           const double* e0, const int64_t* tid) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t n8 = ctx->N * 8;
+  if (idx) CUDA_TRY(cudaMemcpyAsync(p->dev.idx, idx, n8, cudaMemcpyHostToDevice, ctx->stream));
+  if (logp) CUDA_TRY(cudaMemcpyAsync(p->dev.logp, logp, n8, cudaMemcpyHostToDevice, ctx->stream));
+  if (logdet) CUDA_TRY(cudaMemcpyAsync(p->dev.logdet, logdet, n8, cudaMemcpyHostToDevice, ctx->stream));
+  if (ke) CUDA_TRY(cudaMemcpyAsync(p->dev.ke, ke, n8, cudaMemcpyHostToDevice, ctx->stream));
+  if (e0) CUDA_TRY(cudaMemcpyAsync(p->dev.e0, e0, n8, cudaMemcpyHostToDevice, ctx->stream));
+  if (tid) CUDA_TRY(cudaMemcpyAsync(p->dev.tid, tid, n8, cudaMemcpyHostToDevice, ctx->stream));
+  return sync(ctx);
+}
+int nuts_set_transform(nuts_ctx_t* ctx, const double* stds, const double* mean) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(plane_from_host(ctx, ctx->T.stds, stds));
+  TRY(plane_from_host(ctx, ctx->T.mean, mean));
+  k_set_transform<<<GRID>>>(ctx->row_args(), ctx->T);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_get_transform(nuts_ctx_t* ctx, double* stds, double* inv_stds, double* mean, double* logdet, int64_t* id) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (stds) TRY(plane_to_host(ctx, ctx->T.stds, stds));
+  if (inv_stds) TRY(plane_to_host(ctx, ctx->T.inv_stds, inv_stds));
+  if (mean) TRY(plane_to_host(ctx, ctx->T.mean, mean));
+  if (logdet) CUDA_TRY(cudaMemcpyAsync(logdet, ctx->T.logdet, ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (id) CUDA_TRY(cudaMemcpyAsync(id, ctx->T.id, ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
+}
+int nuts_init_state(nuts_ctx_t* ctx, nuts_point_t* point, const double* position, int32_t* status) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(plane_from_host(ctx, point->dev.x, position));
+  k_init_state<<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, point->dev, ctx->d_i32);
+  CHECK_LAUNCH();
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, ctx->d_i32, ctx->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
+}
+int nuts_initialize_trajectory(nuts_ctx_t* ctx, nuts_point_t* point, int resample_velocity, uint64_t seed, uint64_t chain_offset,
+                               uint64_t counter) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_initialize_trajectory<<<GRID>>>(ctx->row_args(), ctx->T, point->dev, resample_velocity, seed, chain_offset, counter);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_leapfrog(nuts_ctx_t* ctx, const nuts_point_t* start, nuts_point_t* out, const double* step_size, double step_size_bcast,
+                  const int8_t* dir, const double* energy_baseline, double max_energy_error, const uint8_t* active, int32_t* status,
+                  double* energy_error) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (start == out) return fail(NUTS_ERR_INVALID, "nuts_leapfrog: out must not alias start");
+  const double *dstep, *dbase;
+  const uint8_t* dm;
+  TRY(upload_f64(ctx, step_size, 0, &dstep));
+  TRY(upload_f64(ctx, energy_baseline, 1, &dbase));
+  TRY(upload_mask(ctx, active, &dm));
+  const int8_t* ddir = nullptr;
+  if (dir) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_i8, dir, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    ddir = ctx->d_i8;
+  }
+  CUDA_TRY(cudaMemsetAsync(ctx->d_i32, 0, ctx->N * sizeof(int), ctx->stream));
+  k_leapfrog<<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, start->dev, out->dev, dstep, step_size_bcast, ddir, dbase, max_energy_error, dm,
+                       ctx->d_i32, ctx->d_sc[2]);
+  CHECK_LAUNCH();
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, ctx->d_i32, ctx->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(download_f64(ctx, 2, energy_error));
+  return sync(ctx);
+}
+int nuts_is_turning(nuts_ctx_t* ctx, const nuts_point_t* state1, const nuts_point_t* state2, uint8_t* turning) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_is_turning<<<GRID>>>(ctx->row_args(), state1->dev, state2->dev, ctx->d_u8);
+  CHECK_LAUNCH();
+  CUDA_TRY(cudaMemcpyAsync(turning, ctx->d_u8, ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
+}
+
+// ============================================================ Tier 3
+static int sampler_alloc(nuts_sampler* s, void** p, size_t bytes) {
+  CUDA_TRY(cudaMalloc(p, bytes));
+  CUDA_TRY(cudaMemset(*p, 0, bytes));
+  s->allocations.push_back(*p);
+  return NUTS_OK;
+}
+
+int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settings_t* st, uint64_t seed, uint64_t chain_id_offset) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!st) return fail(NUTS_ERR_INVALID, "nuts_sampler_create: settings is NULL");
+  if (st->trajectory_kind != NUTS_KINETIC_EUCLIDEAN) return fail(NUTS_ERR_UNSUPPORTED, "only KineticEnergyKind::Euclidean is supported");
+  const int method = st->adapt_options.step_size_settings.adapt_options.method;
+  if (method != NUTS_STEPSIZE_DUAL_AVERAGE && method != NUTS_STEPSIZE_FIXED)
+    return fail(NUTS_ERR_UNSUPPORTED, "step size method %d not supported (DualAverage and Fixed only)", method);
+  if (st->maxdepth + st->extra_doublings > (uint64_t)MAX_DOUBLING_DEPTH)
+    return fail(NUTS_ERR_UNSUPPORTED, "maxdepth + extra_doublings must be <= %d", MAX_DOUBLING_DEPTH);
+  if (st->adapt_options.mass_matrix_window_growth < 1.0) return fail(NUTS_ERR_INVALID, "mass_matrix_window_growth must be >= 1");
+  const EngineConfig* cfg = nullptr;
+  for (const EngineConfig& c : kConfigs)
+    if ((uint64_t)c.max_d >= ctx->d) {
+      cfg = &c;
+      break;
+    }
+  if (!cfg) return fail(NUTS_ERR_UNSUPPORTED, "dim %llu exceeds the largest register-resident configuration (16384)", (unsigned long long)ctx->d);
+
+  nuts_sampler* s = new nuts_sampler();
+  s->ctx = ctx;
+  s->settings = *st;
+  s->cfg = cfg;
+  EngineParams& P = s->P;
+  P.N = (int)ctx->N;
+  P.d = (int)ctx->d;
+  P.ld = (int)ctx->ld;
+  P.P = (int)std::min<uint64_t>(MAX_SLOTS, 3 * (st->maxdepth + st->extra_doublings) + 4);
+  P.model = ctx->model;
+  P.seed = seed;
+  P.chain_offset = chain_id_offset;
+  SettingsDev& S = P.s;
+  S.num_tune = st->num_tune;
+  S.maxdepth = st->maxdepth;
+  S.mindepth = st->mindepth;
+  S.extra_doublings = st->extra_doublings;
+  S.max_energy_error = st->max_energy_error;
+  S.check_turning = st->check_turning;
+  S.has_target_time = st->has_target_integration_time;
+  S.target_time = st->target_integration_time;
+  const nuts_euclidean_adapt_options_t& a = st->adapt_options;
+  S.target_accept = a.step_size_settings.target_accept;
+  S.initial_step = a.step_size_settings.initial_step;
+  S.has_jitter = a.step_size_settings.has_jitter;
+  S.jitter = a.step_size_settings.jitter;
+  S.method = method;
+  S.fixed_step = a.step_size_settings.adapt_options.fixed_step;
+  S.da_k = a.step_size_settings.adapt_options.dual_average.k;
+  S.da_t0 = a.step_size_settings.adapt_options.dual_average.t0;
+  S.da_gamma = a.step_size_settings.adapt_options.dual_average.gamma;
+  S.da_max_step = a.step_size_settings.adapt_options.dual_average.max_step_size;
+  S.use_grad_based = a.mass_matrix_options.use_grad_based_estimate;
+  // GlobalStrategy::new (adapt_strategy.rs:77-98)
+  const double num_tune_f = (double)st->num_tune;
+  const uint64_t step_size_window = (uint64_t)(a.step_size_window * num_tune_f);
+  S.early_end = (uint64_t)(a.early_window * num_tune_f);
+  S.final_step_size_window = st->num_tune >= step_size_window ? st->num_tune - step_size_window : 0;
+  if (st->num_tune > 0 && !(S.early_end < st->num_tune)) {
+    delete s;
+    return fail(NUTS_ERR_INVALID, "early_window must leave early_end < num_tune");
+  }
+  S.mm_switch_freq = a.mass_matrix_switch_freq;
+  S.early_mm_switch_freq = a.early_mass_matrix_switch_freq;
+  S.mm_update_freq = a.mass_matrix_update_freq;
+  S.mm_window_growth = a.mass_matrix_window_growth;
+
+  const size_t plane = ctx->N * ctx->ld * sizeof(double);
+  int r = NUTS_OK;
+  auto A = [&](void** p, size_t bytes) {
+    if (r == NUTS_OK) r = sampler_alloc(s, p, bytes);
+  };
+  A((void**)&P.x, plane);
+  A((void**)&P.gx, plane);
+  A((void**)&P.z, plane);
+  A((void**)&P.gz, plane);
+  A((void**)&P.v0, plane);
+  A((void**)&P.stds, plane);
+  A((void**)&P.inv_stds, plane);
+  A((void**)&P.mean, plane);
+  A((void**)&P.est, plane * 8);
+  A((void**)&P.slots, plane * 2 * (size_t)P.P);
+  A((void**)&P.ends, plane * 6);
+  A((void**)&P.cs, ctx->N * sizeof(ChainState));
+  A((void**)&P.queue, sizeof(unsigned int));
+  A((void**)&s->d_init, ctx->N * ctx->d * sizeof(double));
+  A((void**)&s->d_status, ctx->N * sizeof(int));
+  if (r != NUTS_OK) {
+    nuts_sampler_destroy(s);
+    return r;
+  }
+  // chain scalars at construction: Strategy::new -> DualAverage::new(initial_step) (stepsize/adapt.rs:67-89),
+  // DiagMassMatrix id -1 (diagonal.rs:81), GlobalStrategy flags (adapt_strategy.rs:87-97)
+  std::vector<ChainState> cs(ctx->N);
+  for (auto& c : cs) {
+    std::memset(&c, 0, sizeof(c));
+    c.step_size = 0.0;
+    c.pt_transform_id = -1;
+    c.mm_id = -1;
+    c.da_log_step = std::log(S.initial_step);
+    c.da_log_step_adapted = std::log(S.initial_step);
+    c.da_hbar = 0.0;
+    c.da_mu = std::log(10.0 * S.initial_step);
+    c.da_count = 1;
+    c.tuning = 1;
+    c.has_initial_mass_matrix = 1;
+    c.current_window_size = S.mm_switch_freq;
+    c.is_good = 1;
+    c.alive = 0;
+  }
+  CUDA_TRY(cudaMemcpy(P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice));
+  // persistent grid: one wave of resident CTAs
+  int blocks_per_sm = 0, cta_threads = 0;
+  CUDA_TRY(cfg->occupancy(&blocks_per_sm, &cta_threads));
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  const int teams_per_cta = cta_threads / cfg->tpc;
+  const uint64_t ctas_needed = (ctx->N + teams_per_cta - 1) / teams_per_cta;
+  s->grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)blocks_per_sm * ctx->num_sms);
+  CUDA_TRY(cudaEventCreate(&s->ev0));
+  CUDA_TRY(cudaEventCreate(&s->ev1));
+  *out = s;
+  return NUTS_OK;
+}
+
+int nuts_sampler_destroy(nuts_sampler_t* s) {
+  if (!s) return NUTS_OK;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  for (void* p : s->allocations) cudaFree(p);
+  auto F = [](void* p) {
+    if (p) cudaFree(p);
+  };
+  F(s->d_stats.depth);
+  F(s->d_stats.maxdepth_reached);
+  F(s->d_stats.index_in_trajectory);
+  F(s->d_stats.logp);
+  F(s->d_stats.energy);
+  F(s->d_stats.energy_error);
+  F(s->d_stats.diverging);
+  F(s->d_stats.step_size);
+  F(s->d_stats.step_size_bar);
+  F(s->d_stats.mean_tree_accept);
+  F(s->d_stats.mean_tree_accept_sym);
+  F(s->d_stats.n_steps);
+  F(s->d_stats.max_energy_error);
+  F(s->d_stats.tuning);
+  F(s->d_stats.fisher_distance);
+  F(s->d_draws);
+  if (s->h_pinned) cudaFreeHost(s->h_pinned);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  delete s;
+  return NUTS_OK;
+}
+
+static int launch_engine(nuts_sampler* s) {
+  nuts_ctx* ctx = s->ctx;
+  CUDA_TRY(cudaMemsetAsync(s->P.queue, 0, sizeof(unsigned int), ctx->stream));
+  CUDA_TRY(cudaEventRecord(s->ev0, ctx->stream));
+  CUDA_TRY(s->cfg->launch(&s->P, s->grid, ctx->stream));
+  CUDA_TRY(cudaEventRecord(s->ev1, ctx->stream));
+  s->last_launches += 1;
+  return NUTS_OK;
+}
+
+int nuts_set_position(nuts_sampler_t* s, const double* position, int32_t* status) {
+  nuts_ctx* ctx = s->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!position) return fail(NUTS_ERR_INVALID, "nuts_set_position: position is NULL");
+  CUDA_TRY(cudaMemcpyAsync(s->d_init, position, ctx->N * ctx->d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  s->P.mode = 0;
+  s->P.init_position = s->d_init;
+  s->P.status_out = s->d_status;
+  s->P.n_draws = 0;
+  s->P.draws_out = nullptr;
+  s->P.stats = StatsDev{};
+  s->last_launches = 0;
+  TRY(launch_engine(s));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, s->d_status, ctx->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(sync(ctx));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  s->last_kernel_ms = ms;
+  s->positioned = true;
+  return NUTS_OK;
+}
+
+static int ensure_stats(nuts_sampler* s, uint64_t n_draws) {
+  if (n_draws <= s->stats_capacity) return NUTS_OK;
+  const size_t n = n_draws * s->ctx->N;
+  StatsDev& d = s->d_stats;
+  TRY(grow(&d.depth, n));
+  TRY(grow(&d.maxdepth_reached, n));
+  TRY(grow(&d.index_in_trajectory, n));
+  TRY(grow(&d.logp, n));
+  TRY(grow(&d.energy, n));
+  TRY(grow(&d.energy_error, n));
+  TRY(grow(&d.diverging, n));
+  TRY(grow(&d.step_size, n));
+  TRY(grow(&d.step_size_bar, n));
+  TRY(grow(&d.mean_tree_accept, n));
+  TRY(grow(&d.mean_tree_accept_sym, n));
+  TRY(grow(&d.n_steps, n));
+  TRY(grow(&d.max_energy_error, n));
+  TRY(grow(&d.tuning, n));
+  TRY(grow(&d.fisher_distance, n));
+  s->stats_capacity = n_draws;
+  return NUTS_OK;
+}
+
+static int run_draws(nuts_sampler* s, uint64_t n_draws, double* draws_dev, bool want_stats) {
+  nuts_ctx* ctx = s->ctx;
+  if (!s->positioned) return fail(NUTS_ERR_INVALID, "nuts_draw: call nuts_set_position first");
+  if (want_stats) TRY(ensure_stats(s, n_draws));
+  s->P.mode = 1;
+  s->P.init_position = nullptr;
+  s->P.status_out = nullptr;
+  s->P.n_draws = n_draws;
+  s->P.draws_out = draws_dev;
+  s->P.stats = want_stats ? s->d_stats : StatsDev{};
+  TRY(launch_engine(s));
+  s->draws_done += n_draws;
+  (void)ctx;
+  return NUTS_OK;
+}
+
+int nuts_draw_device(nuts_sampler_t* s, uint64_t n_draws, double* draws_dev) {
+  CUDA_TRY(cudaSetDevice(s->ctx->device));
+  s->last_launches = 0;
+  return run_draws(s, n_draws, draws_dev, false);
+}
+
+int nuts_draw(nuts_sampler_t* s, uint64_t n_draws, double* draws_out, const nuts_stats_t* stats) {
+  nuts_ctx* ctx = s->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (n_draws == 0) return NUTS_OK;
+  s->last_launches = 0;
+  const size_t per_draw = ctx->N * ctx->d;
+  if (draws_out && n_draws > s->draws_capacity) {
+    TRY(grow(&s->d_draws, n_draws * per_draw));
+    s->draws_capacity = n_draws;
+  }
+  if (draws_out) CUDA_TRY(cudaMemsetAsync(s->d_draws, 0xff, n_draws * per_draw * sizeof(double), ctx->stream));  // NaN for dead chains
+  TRY(run_draws(s, n_draws, draws_out ? s->d_draws : nullptr, stats != nullptr));
+  if (draws_out)
+    CUDA_TRY(cudaMemcpyAsync(draws_out, s->d_draws, n_draws * per_draw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (stats) {
+    const size_t n = n_draws * ctx->N;
+    const StatsDev& d = s->d_stats;
+#define COPY_STAT(name) \
+  if (stats->name) CUDA_TRY(cudaMemcpyAsync(stats->name, d.name, n * sizeof(*stats->name), cudaMemcpyDeviceToHost, ctx->stream));
+    COPY_STAT(depth)
+    COPY_STAT(maxdepth_reached)
+    COPY_STAT(index_in_trajectory)
+    COPY_STAT(logp)
+    COPY_STAT(energy)
+    COPY_STAT(energy_error)
+    COPY_STAT(diverging)
+    COPY_STAT(step_size)
+    COPY_STAT(step_size_bar)
+    COPY_STAT(mean_tree_accept)
+    COPY_STAT(mean_tree_accept_sym)
+    COPY_STAT(n_steps)
+    COPY_STAT(max_energy_error)
+    COPY_STAT(tuning)
+    COPY_STAT(fisher_distance)
+#undef COPY_STAT
+  }
+  TRY(sync(ctx));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  s->last_kernel_ms = ms;
+  return NUTS_OK;
+}
+
+int nuts_sampler_counters(nuts_sampler_t* s, uint64_t* total_leapfrogs, uint64_t* draws_done) {
+  nuts_ctx* ctx = s->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  std::vector<ChainState> cs(ctx->N);
+  CUDA_TRY(cudaMemcpyAsync(cs.data(), s->P.cs, cs.size() * sizeof(ChainState), cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(sync(ctx));
+  uint64_t tot = 0;
+  for (auto& c : cs) tot += c.total_leapfrogs;
+  if (total_leapfrogs) *total_leapfrogs = tot;
+  if (draws_done) *draws_done = s->draws_done;
+  return NUTS_OK;
+}
+
+int nuts_sampler_last_timing(nuts_sampler_t* s, double* kernel_ms, uint64_t* launches) {
+  CUDA_TRY(cudaSetDevice(s->ctx->device));
+  if (s->ev1) {
+    CUDA_TRY(cudaEventSynchronize(s->ev1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_kernel_ms = ms;
+  }
+  if (kernel_ms) *kernel_ms = s->last_kernel_ms;
+  if (launches) *launches = s->last_launches;
+  return NUTS_OK;
+}
+
+int nuts_sampler_get_state(nuts_sampler_t* s, double* position, double* step_size, double* stds, double* mean, uint64_t* rng_counter) {
+  nuts_ctx* ctx = s->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (position) TRY(plane_to_host(ctx, s->P.x, position));
+  if (stds) TRY(plane_to_host(ctx, s->P.stds, stds));
+  if (mean) TRY(plane_to_host(ctx, s->P.mean, mean));
+  if (step_size || rng_counter) {
+    std::vector<ChainState> cs(ctx->N);
+    CUDA_TRY(cudaMemcpyAsync(cs.data(), s->P.cs, cs.size() * sizeof(ChainState), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync(ctx));
+    for (uint64_t c = 0; c < ctx->N; ++c) {
+      if (step_size) step_size[c] = cs[c].step_size;
+      if (rng_counter) rng_counter[c] = cs[c].rng_counter;
+    }
+  }
+  return NUTS_OK;
+}
+
+int nuts_sampler_set_step_size(nuts_sampler_t* s, const double* step_size) {
+  nuts_ctx* ctx = s->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  std::vector<ChainState> cs(ctx->N);
+  CUDA_TRY(cudaMemcpyAsync(cs.data(), s->P.cs, cs.size() * sizeof(ChainState), cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(sync(ctx));
+  for (uint64_t c = 0; c < ctx->N; ++c) cs[c].step_size = step_size[c];
+  CUDA_TRY(cudaMemcpyAsync(s->P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice, ctx->stream));
+  return sync(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,986 @@
+// chain_engine.cuh — the whole-draw NUTS engine: one TEAM of TPC threads owns one chain for a whole
+// nuts_draw() call (n_draws transitions incl. adaptation) with the phase-space point (z, v, grad_z) and the
+// chain's diagonal mass matrix (sigma, mu) held in REGISTERS, EPT elements per thread.
+//
+// What it replaces in the reference (per chain, on one CPU core):
+//   Chain::draw / set_position          src/chain.rs:137-188
+//   nuts::draw, NutsTree::extend/...    src/nuts.rs:94-388           (recursion -> iterative binary counter, see extend())
+//   TransformedHamiltonian::leapfrog,
+//     is_turning, initialize_trajectory src/dynamics/transformed_hamiltonian.rs:524-736
+//   DiagMassMatrix transform + updates  src/transform/diagonal.rs:85-265
+//   AcceptanceRateCollector, DualAverage src/stepsize/dual_avg.rs:33-166
+//   stepsize::Strategy (init search, jitter) src/stepsize/adapt.rs:91-267
+//   RunningVariance / DiagAdaptStrategy src/transform/adapt/diagonal.rs:17-231
+//   GlobalStrategy::adapt schedule      src/adapt_strategy.rs:121-222
+//
+// Execution model (B200-first, not a translation):
+//   * chains are independent (reference src/sampler.rs:1094-1126), so there is no lock-step between chains at all:
+//     a persistent grid pulls chain ids from an atomic queue; a team that finishes its chain takes the next one,
+//     i.e. the "active mask" of the north star degenerates to "a finished chain frees its SM slice immediately".
+//   * per leapfrog the state never leaves the register file; the only memory traffic is the 16*d-byte checkpoint
+//     (z, v) of the new leaf and the checkpoint reads of the U-turn checks (served by L2 for the low tree levels).
+//   * every vector (planes, checkpoints, estimators) uses the same element -> thread mapping (i = tid + j*TPC), so a
+//     thread only ever re-reads global addresses it wrote itself: no barrier or fence is needed around checkpoints.
+//   * all scalar tree / adaptation logic is executed redundantly by every thread of the team on bit-identical
+//     reduction results (see TeamReduce), so no broadcast or extra barrier is ever needed.
+#pragma once
+#include "device_common.cuh"
+
+namespace nb {
+
+constexpr int MAX_DOUBLING_DEPTH = 20;  // deepest new half has 2^20 leaves
+constexpr int MAX_SLOTS = 64;
+
+struct SettingsDev {
+  uint64_t num_tune, maxdepth, mindepth, extra_doublings;
+  double max_energy_error;
+  int check_turning, has_target_time;
+  double target_time;
+  double target_accept, initial_step;
+  int has_jitter, method;  // method: 0 dual average, 2 fixed
+  double jitter, fixed_step;
+  double da_k, da_t0, da_gamma, da_max_step;
+  int use_grad_based, _pad;
+  uint64_t early_end, final_step_size_window, mm_switch_freq, early_mm_switch_freq, mm_update_freq;
+  double mm_window_growth;
+};
+
+// per-chain scalar state that survives between kernel launches
+struct ChainState {
+  double step_size;
+  uint64_t rng_counter;
+  uint64_t draw_count;
+  double logp, pt_logdet;
+  long long pt_transform_id;
+  double mm_logdet;
+  long long mm_id;
+  double da_log_step, da_log_step_adapted, da_hbar, da_mu;
+  uint64_t da_count;
+  int tuning, has_initial_mass_matrix;
+  uint64_t last_update, current_window_size;
+  uint64_t fg_count, bg_count;
+  int fg_set, is_good;
+  double last_mean_tree_accept, last_sym_mean_tree_accept, last_max_energy_error;
+  uint64_t last_n_steps;
+  int alive, _pad;
+  uint64_t total_leapfrogs, tree_leapfrogs;
+};
+
+struct StatsDev {  // device SoA, each [n_draws x N]
+  uint64_t* depth;
+  uint8_t* maxdepth_reached;
+  long long* index_in_trajectory;
+  double* logp;
+  double* energy;
+  double* energy_error;
+  uint8_t* diverging;
+  double* step_size;
+  double* step_size_bar;
+  double* mean_tree_accept;
+  double* mean_tree_accept_sym;
+  uint64_t* n_steps;
+  double* max_energy_error;
+  uint8_t* tuning;
+  double* fisher_distance;
+};
+
+struct EngineParams {
+  int N, d, ld, P;
+  ModelDev model;
+  SettingsDev s;
+  uint64_t seed, chain_offset;
+  double *x, *gx, *z, *gz, *v0;     // chain point planes [N][ld]
+  double *stds, *inv_stds, *mean;   // DiagMassMatrix planes [N][ld]
+  double* est;                      // [N][2 sets][4: draw_mean, draw_var, grad_mean, grad_var][ld]
+  double* slots;                    // [N][P][2: z, v][ld]   leaf checkpoints of the half under construction
+  double* ends;                     // [N][2: left,right][3: z, v, grad_z][ld]   main-tree endpoints
+  ChainState* cs;
+  unsigned int* queue;              // persistent chain queue
+  // mode 0: set_position ; mode 1: draw
+  int mode, _pad;
+  const double* init_position;      // [N][d] device
+  int* status_out;                  // [N]
+  uint64_t n_draws;
+  double* draws_out;                // [n_draws][N][d] device (may be null)
+  StatsDev stats;
+  uint64_t stats_offset;            // unused draws before this call inside the stats arrays (always 0 for now)
+};
+
+enum { EXT_OK = 0, EXT_TURNING = 1, EXT_DIVERGING = 2 };
+
+template <int TPC, int EPT>
+struct Engine {
+  const EngineParams& P;
+  const int chain;
+  const int tid;  // thread index inside the team
+  TeamReduce<TPC> red;
+  const int d;
+  const size_t row;  // chain * ld
+
+  // ---- register-resident vectors ----
+  double z[EPT], v[EPT], g[EPT];  // current phase-space point (whitened position, velocity, whitened gradient)
+  double sig[EPT], mu[EPT];       // this chain's DiagMassMatrix: stds, mean
+
+  ChainState cs;
+  uint64_t stream;
+
+  // ---- per-draw collector (AcceptanceRateCollector, dual_avg.rs:112-166) ----
+  double E0, acc_sum, acc_sym_sum, max_energy_error;
+  uint64_t acc_count;
+
+  // ---- main tree ----
+  double ls_main;
+  int depth;
+  int idx_end[2];
+  bool end_is_init[2], reg_holds[2];
+  int draw_slot;  // -1: the draw is the initial point
+  double draw_energy;
+  int draw_idx;
+
+  // ---- pending sub-trees of the half under construction, one per level ----
+  double A_ls[MAX_DOUBLING_DEPTH], A_draw_energy[MAX_DOUBLING_DEPTH];
+  int A_draw_idx[MAX_DOUBLING_DEPTH];
+  signed char A_first[MAX_DOUBLING_DEPTH], A_last[MAX_DOUBLING_DEPTH], A_draw[MAX_DOUBLING_DEPTH];
+  unsigned char rc[MAX_SLOTS];
+  uint64_t free_mask;
+
+  __device__ Engine(const EngineParams& p, int chain_, int tid_, double* scratch)
+      : P(p), chain(chain_), tid(tid_), red(scratch), d(p.d), row((size_t)chain_ * p.ld) {
+    stream = p.chain_offset + (uint64_t)chain_ + 1;  // reference src/sampler.rs:1106 set_stream(chain_id + 1)
+  }
+
+  // ------------------------------------------------------------------ vector helpers
+  __device__ __forceinline__ void load(const double* __restrict__ src, double (&a)[EPT]) const {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      a[j] = i < d ? src[i] : 0.0;
+    }
+  }
+  __device__ __forceinline__ void store(double* __restrict__ dst, const double (&a)[EPT]) const {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      if (i < d) dst[i] = a[j];
+    }
+  }
+  __device__ __forceinline__ double* slot_ptr(int s, int which) const {
+    return P.slots + (((size_t)chain * P.P + s) * 2 + which) * P.ld;
+  }
+  __device__ __forceinline__ double* end_ptr(int dir, int which) const {
+    return P.ends + (((size_t)chain * 2 + dir) * 3 + which) * P.ld;
+  }
+  __device__ __forceinline__ double* est_ptr(int set, int which) const {
+    return P.est + (((size_t)chain * 2 + set) * 4 + which) * P.ld;
+  }
+
+  // ------------------------------------------------------------------ random stream
+  __device__ __forceinline__ bool rng_bool() { return stream_bool(P.seed, stream, cs.rng_counter++); }
+  __device__ __forceinline__ double rng_f64() { return stream_f64(P.seed, stream, cs.rng_counter++); }
+  // array_gaussian(rng, v, ones): v[i] = 1.0 * normal   (cpu_math.rs:561-577)
+  __device__ __forceinline__ void sample_velocity() {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      v[j] = i < d ? 1.0 * stream_normal(P.seed, stream, cs.rng_counter, (uint32_t)i) : 0.0;
+    }
+    cs.rng_counter += (uint64_t)((d + 1) / 2);
+  }
+
+  // ------------------------------------------------------------------ log density
+  // (logp, grad) at x; `extra` rides along in the final reduction (used for the kinetic energy).
+  // Elementwise formulas match oracle/nuts_oracle.hpp (GaussIso, GaussDiag, GaussRank1, Funnel).
+  __device__ __forceinline__ void model_phase_a(const double (&x)[EPT], double& a0, double& a1) {
+    const ModelDev& m = P.model;
+    a0 = 0.0;
+    a1 = 0.0;
+    if (m.kind == LOGP_GAUSS_RANK1) {
+      double s[1] = {0.0};
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        if (i < d) s[0] += x[j] - m.mu[i];
+      }
+      red.allreduce(s);
+      a0 = m.rank1_coeff * s[0];  // rank1_term
+    } else if (m.kind == LOGP_FUNNEL) {
+      double s[2] = {0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        if (i < d) {
+          if (i == 0) s[1] = x[j];
+          else s[0] = fma(x[j], x[j], s[0]);
+        }
+      }
+      red.allreduce(s);
+      a0 = s[1];  // v
+      a1 = s[0];  // S
+    }
+  }
+  // elementwise gradient; returns this thread's partial of logp (sum-type models)
+  __device__ __forceinline__ double model_phase_b(const double (&x)[EPT], double (&gx)[EPT], double a0, double a1, double& ev_out) {
+    const ModelDev& m = P.model;
+    double lp = 0.0;
+    ev_out = 0.0;
+    if (m.kind == LOGP_GAUSS_ISO) {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        gx[j] = 0.0;
+        if (i < d) {
+          double diff = x[j] - m.mu[i];
+          lp -= diff * diff / 2.;
+          gx[j] = -diff;
+        }
+      }
+    } else if (m.kind == LOGP_GAUSS_DIAG) {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        gx[j] = 0.0;
+        if (i < d) {
+          double diff = x[j] - m.mu[i];
+          double pd = diff * m.prec[i];
+          lp -= diff * pd / 2.;
+          gx[j] = -pd;
+        }
+      }
+    } else if (m.kind == LOGP_GAUSS_RANK1) {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        gx[j] = 0.0;
+        if (i < d) {
+          double diff = x[j] - m.mu[i];
+          double ptd = diff - a0;
+          gx[j] = -ptd;
+          lp -= 0.5 * diff * ptd;
+        }
+      }
+    } else {  // funnel
+      double vv = a0;
+      double ev = exp(-vv);
+      ev_out = ev;
+      double nm1 = (double)(d - 1);
+      double half_ev_S = 0.5 * ev * a1;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        gx[j] = 0.0;
+        if (i < d) {
+          if (i == 0) gx[j] = -vv * m.funnel_inv_var - 0.5 * nm1 + half_ev_S;
+          else gx[j] = -x[j] * ev;
+        }
+      }
+    }
+    return lp;
+  }
+  __device__ __forceinline__ double model_finish(double lp_sum, double a0, double a1, double ev) const {
+    const ModelDev& m = P.model;
+    if (m.kind == LOGP_FUNNEL) {
+      double nm1 = (double)(d - 1);
+      double half_ev_S = 0.5 * ev * a1;
+      return -0.5 * a0 * a0 * m.funnel_inv_var - 0.5 * nm1 * a0 - half_ev_S;
+    }
+    return lp_sum;
+  }
+
+  // ------------------------------------------------------------------ leapfrog (transformed_hamiltonian.rs:524-615, Euclidean)
+  // (z, v, g) <- one velocity-Verlet step of size eps in the whitened space; returns logp' and kinetic energy'.
+  __device__ __forceinline__ void leapfrog(double eps, double& logp_out, double& ke_out) {
+    const double eps_half = eps / 2.;
+    double x[EPT], gx[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      v[j] = fma(eps_half, g[j], v[j]);  // first_velocity_halfstep :178-184  axpy_out(grad, v, eps/2)
+      z[j] = fma(eps, v[j], z[j]);       // position_step :220-225            axpy_out(v', z, eps)
+      double t = z[j] * sig[j];          // compute_untransformed_position    diagonal.rs:253-255  multiply, then axpy(mean, x, 1)
+      x[j] = fma(1.0, mu[j], t);
+    }
+    double a0, a1, ev;
+    model_phase_a(x, a0, a1);
+    double part[2];
+    part[0] = model_phase_b(x, gx, a0, a1, ev);
+    part[1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      g[j] = gx[j] * sig[j];             // compute_transformed_gradient      diagonal.rs:258-265
+      v[j] = fma(eps_half, g[j], v[j]);  // second_velocity_halfstep :245-247 axpy(grad', v, eps/2)
+      part[1] = fma(v[j], v[j], part[1]);  // update_kinetic_energy :260-262
+    }
+    red.allreduce(part);
+    logp_out = model_finish(part[0], a0, a1, ev);
+    ke_out = 0.5 * part[1];
+    cs.total_leapfrogs += 1;
+  }
+
+  // logp + gradient at the x plane -> gx plane; returns logp (Math::logp_array)
+  __device__ __forceinline__ double eval_at_position(double (&x)[EPT], double (&gx)[EPT]) {
+    double a0, a1, ev;
+    model_phase_a(x, a0, a1);
+    double part[1];
+    part[0] = model_phase_b(x, gx, a0, a1, ev);
+    red.allreduce(part);
+    return model_finish(part[0], a0, a1, ev);
+  }
+
+  __device__ __forceinline__ void load_mass_matrix() {
+    load(P.stds + row, sig);
+    load(P.mean + row, mu);
+  }
+
+  // compute_transformed_position / _gradient (diagonal.rs:233-246, 258-265) of the chain point from the x, gx planes
+  // into the z, g registers; also refreshes the z / gz planes.  Returns check_all() (transformed_hamiltonian.rs:310-324).
+  __device__ __forceinline__ bool whiten_from_planes() {
+    double x[EPT], gx[EPT], is[EPT];
+    load(P.x + row, x);
+    load(P.gx + row, gx);
+    load(P.inv_stds + row, is);
+    double bad[1] = {0.0};
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      double t = fma(-1.0, mu[j], x[j]);  // axpy_out(mean, x, -1)
+      z[j] = is[j] * t;                   // multiply_inplace(z, inv_stds): out = x*out
+      g[j] = gx[j] * sig[j];
+      if (i < d) {
+        bool ok = isfinite(z[j]) && isfinite(g[j]) && (g[j] != 0.0) && isfinite(gx[j]) && isfinite(x[j]);
+        if (!ok) bad[0] = 1.0;
+      } else {
+        z[j] = 0.0;
+        g[j] = 0.0;
+      }
+    }
+    store(P.z + row, z);
+    store(P.gz + row, g);
+    red.allreduce(bad);
+    return bad[0] == 0.0;
+  }
+
+  // ------------------------------------------------------------------ slot pool
+  __device__ __forceinline__ int alloc_slot() {
+    int s = __ffsll((long long)free_mask) - 1;
+    free_mask &= ~(1ull << s);
+    rc[s] = 0;
+    return s;
+  }
+  __device__ __forceinline__ void ref(int s) { rc[s] += 1; }
+  __device__ __forceinline__ void unref(int s) {
+    rc[s] -= 1;
+    if (rc[s] == 0) free_mask |= (1ull << s);
+  }
+
+  // ------------------------------------------------------------------ U-turn products (is_turning :617-638 -> scalar_prods3)
+  // pair (P = earlier built, Q = later built): delta = zQ - zP ; sP = delta . vP ; sQ = delta . vQ.
+  // Forward: turning <=> sP < 0 | sQ < 0.  Backward the reference orders the pair the other way round, which negates
+  // delta exactly, so turning <=> sP > 0 | sQ > 0.  NaN never turns (reference :637).
+  __device__ __forceinline__ bool turn_eval(double sP, double sQ, int dir) const {
+    return dir ? ((sP < 0.) | (sQ < 0.)) : ((sP > 0.) | (sQ > 0.));
+  }
+  // checks of one merge: (Af, cur) always; when `full` also (Al, cur) and (Af, Bf).   cur = registers.
+  __device__ __forceinline__ bool merge_turning(const double* Afz, const double* Afv, const double* Alz, const double* Alv,
+                                                const double* Bfz, const double* Bfv, bool full, int dir) {
+    if (!full) {
+      double s[2] = {0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        if (i < d) {
+          double delta = (z[j] + 0.0) - Afz[i];
+          s[0] = fma(delta, Afv[i], s[0]);
+          s[1] = fma(delta, v[j], s[1]);
+        }
+      }
+      red.allreduce(s);
+      return turn_eval(s[0], s[1], dir);
+    }
+    double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      if (i < d) {
+        double afz = Afz[i], afv = Afv[i], alz = Alz[i], alv = Alv[i], bfz = Bfz[i], bfv = Bfv[i];
+        double d1 = (z[j] + 0.0) - afz;
+        s[0] = fma(d1, afv, s[0]);
+        s[1] = fma(d1, v[j], s[1]);
+        double d2 = (z[j] + 0.0) - alz;
+        s[2] = fma(d2, alv, s[2]);
+        s[3] = fma(d2, v[j], s[3]);
+        double d3 = (bfz + 0.0) - afz;
+        s[4] = fma(d3, afv, s[4]);
+        s[5] = fma(d3, bfv, s[5]);
+      }
+    }
+    red.allreduce(s);
+    return turn_eval(s[0], s[1], dir) | turn_eval(s[2], s[3], dir) | turn_eval(s[4], s[5], dir);
+  }
+
+  // ------------------------------------------------------------------ AcceptanceRateCollector::register_leapfrog (dual_avg.rs:131-158)
+  __device__ __forceinline__ void register_leapfrog(double energy, bool divergent) {
+    if (divergent) {
+      max_energy_error = -INFINITY;
+    } else {
+      double diff = E0 - energy;
+      double e = exp(fmin(diff, 0.));
+      acc_sum += e;
+      acc_sym_sum += 2. * e / (1. + exp(diff));
+      if (fabs(diff) > fabs(max_energy_error)) max_energy_error = diff;
+    }
+    acc_count += 1;
+  }
+
+  // ------------------------------------------------------------------ NutsTree::extend for the MAIN tree (nuts.rs:108-170)
+  // The reference recursion builds the new half leaf by leaf and merges equal-depth sub-trees in post-order; that is
+  // a binary counter: after leaf i (0-based) merge levels 0..t-1, t = number of trailing one bits of i.  Every merge
+  // of (A = earlier built, B = later built) checks the span (A.first, B.last) and, when A.depth > 0, (A.last, B.last)
+  // and (A.first, B.first) (nuts.rs:143-161), and ALWAYS runs merge_into before the verdict (nuts.rs:163-169), which
+  // is also the reference's RNG order.  An inner Turning / Diverging discards the whole half (nuts.rs:131-136).
+  __device__ int extend(int dir, bool check) {
+    const int D = depth;
+    const uint32_t nleaf = 1u << D;
+    const double eps = dir ? cs.step_size : -cs.step_size;
+    const int sign = dir ? 1 : -1;
+    free_mask = P.P >= 64 ? ~0ull : ((1ull << P.P) - 1ull);
+    if (draw_slot >= 0) {
+      free_mask &= ~(1ull << draw_slot);
+      rc[draw_slot] = 1;
+    }
+    // start state = the end of the main tree in direction dir
+    const double* nearZ = end_is_init[dir] ? P.z + row : end_ptr(dir, 0);
+    const double* nearV = end_is_init[dir] ? P.v0 + row : end_ptr(dir, 1);
+    const double* farZ = end_is_init[1 - dir] ? P.z + row : end_ptr(1 - dir, 0);
+    const double* farV = end_is_init[1 - dir] ? P.v0 + row : end_ptr(1 - dir, 1);
+    if (!reg_holds[dir]) {
+      load(nearZ, z);
+      load(nearV, v);
+      load(end_is_init[dir] ? P.gz + row : end_ptr(dir, 2), g);
+    }
+    reg_holds[0] = reg_holds[1] = false;
+    int idx_cur = idx_end[dir];
+    // the sub-tree B that the newest leaf belongs to
+    int B_first = -1, B_draw = -1, B_draw_idx = 0;
+    double B_ls = 0., B_draw_energy = 0.;
+
+    for (uint32_t i = 0; i < nleaf; ++i) {
+      // single_step (nuts.rs:209-245): one leapfrog from the previous leaf; baseline = initial energy
+      double logp_new, ke_new;
+      leapfrog(eps, logp_new, ke_new);
+      cs.tree_leapfrogs += 1;
+      double energy = ke_new - (logp_new + cs.pt_logdet);
+      double energy_error = energy - E0;
+      bool divergent = (energy_error > P.s.max_energy_error) | !isfinite(energy_error);
+      register_leapfrog(energy, divergent);
+      if (divergent) return EXT_DIVERGING;
+      idx_cur += sign;
+      int s = alloc_slot();
+      store(slot_ptr(s, 0), z);
+      store(slot_ptr(s, 1), v);
+      rc[s] = 2;  // roles: first-of-B, draw-of-B
+      B_first = s;
+      B_draw = s;
+      B_ls = -energy_error;
+      B_draw_energy = energy;
+      B_draw_idx = idx_cur;
+      int t = __ffs(~i) - 1;  // trailing ones of i
+      if (t > D) t = D;
+      for (int l = 0; l < t; ++l) {
+        const int Af = A_first[l], Al = A_last[l];
+        bool turning = false;
+        if (check) {
+          turning = merge_turning(slot_ptr(Af, 0), slot_ptr(Af, 1), slot_ptr(Al, 0), slot_ptr(Al, 1), slot_ptr(B_first, 0),
+                                  slot_ptr(B_first, 1), l > 0, dir);
+        }
+        // merge_into, non-main (nuts.rs:172-207): self_log_size = log_size of the merged tree
+        double total = logaddexp(A_ls[l], B_ls);
+        bool take_B = (B_ls >= total) || (rng_f64() < exp(B_ls - total));
+        if (take_B) {
+          unref(A_draw[l]);
+        } else {
+          unref(B_draw);
+          B_draw = A_draw[l];
+          B_draw_energy = A_draw_energy[l];
+          B_draw_idx = A_draw_idx[l];
+        }
+        unref(B_first);
+        B_first = Af;
+        unref(Al);
+        B_ls = total;
+        if (turning) return EXT_TURNING;  // inner turn: the old tree is returned unchanged (nuts.rs:131-133)
+      }
+      if (i + 1 < nleaf) {
+        A_first[t] = (signed char)B_first;
+        A_last[t] = (signed char)s;
+        ref(s);
+        A_ls[t] = B_ls;
+        A_draw[t] = (signed char)B_draw;
+        A_draw_energy[t] = B_draw_energy;
+        A_draw_idx[t] = B_draw_idx;
+      }
+    }
+    // top-level merge of the main tree (A) with the finished half (B)
+    bool turning = false;
+    if (check) {
+      turning = merge_turning(farZ, farV, nearZ, nearV, slot_ptr(B_first, 0), slot_ptr(B_first, 1), D > 0, dir);
+    }
+    double total = logaddexp(ls_main, B_ls);
+    bool take = (B_ls >= ls_main) || (rng_f64() < exp(B_ls - ls_main));  // is_main: self_log_size = old log_size
+    if (take) {
+      draw_slot = B_draw;
+      draw_energy = B_draw_energy;
+      draw_idx = B_draw_idx;
+    }
+    ls_main = total;
+    depth += 1;
+    store(end_ptr(dir, 0), z);
+    store(end_ptr(dir, 1), v);
+    store(end_ptr(dir, 2), g);
+    idx_end[dir] = idx_cur;
+    end_is_init[dir] = false;
+    reg_holds[dir] = true;
+    return turning ? EXT_TURNING : EXT_OK;
+  }
+
+  // ------------------------------------------------------------------ DualAverage (dual_avg.rs:33-81)
+  __device__ __forceinline__ void da_new(double initial_step) {
+    cs.da_log_step = log(initial_step);
+    cs.da_log_step_adapted = log(initial_step);
+    cs.da_hbar = 0.;
+    cs.da_mu = log(10. * initial_step);
+    cs.da_count = 1;
+  }
+  __device__ __forceinline__ void da_advance(double accept_stat) {
+    if (P.s.method != 0) return;
+    double cnt = (double)cs.da_count;
+    double w = 1. / (cnt + P.s.da_t0);
+    cs.da_hbar = (1. - w) * cs.da_hbar + w * (P.s.target_accept - accept_stat);
+    cs.da_log_step = cs.da_mu - cs.da_hbar * sqrt(cnt) / P.s.da_gamma;
+    cs.da_log_step = fmin(cs.da_log_step, log(P.s.da_max_step));
+    double mk = pow(cnt, -P.s.da_k);
+    cs.da_log_step_adapted = mk * cs.da_log_step + (1. - mk) * cs.da_log_step_adapted;
+    cs.da_count += 1;
+  }
+  // Strategy::update_stepsize (stepsize/adapt.rs:235-267)
+  __device__ __forceinline__ void update_stepsize(bool use_best_guess) {
+    double step = P.s.method != 0 ? P.s.fixed_step : (use_best_guess ? exp(cs.da_log_step_adapted) : exp(cs.da_log_step));
+    if (P.s.has_jitter) {
+      double lo = 1.0 - P.s.jitter, hi = 1.0 + P.s.jitter;
+      double j = fma(hi - lo, rng_f64(), lo);
+      cs.step_size = step * j;
+    } else {
+      cs.step_size = step;
+    }
+  }
+
+  // ------------------------------------------------------------------ Strategy::init (stepsize/adapt.rs:91-199)
+  // Doubling / halving search from the chain's current position (x, gx planes, cs.logp).  Returns false when
+  // init_state fails check_all (NutsError::BadInitGrad).  Uses the ends[0] buffers as scratch for the start state.
+  __device__ bool stepsize_search() {
+    if (P.s.method != 0) {
+      cs.step_size = P.s.fixed_step;
+      return true;
+    }
+    load_mass_matrix();
+    if (!whiten_from_planes()) return false;  // init_state: same x => same logp / gradient, new whitening
+    const double logdet = cs.mm_logdet;
+    sample_velocity();  // initialize_trajectory(resample = true)
+    double ke[1] = {0.0};
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) ke[0] = fma(v[j], v[j], ke[0]);
+    red.allreduce(ke);
+    const double e0 = 0.5 * ke[0] - (cs.logp + logdet);
+    double* sz = end_ptr(0, 0);
+    double* sv = end_ptr(0, 1);
+    double* sg = end_ptr(0, 2);
+    store(sz, z);
+    store(sv, v);
+    store(sg, g);
+    cs.step_size = P.s.initial_step;
+    double lp, k;
+    leapfrog(cs.step_size, lp, k);
+    double ee = (k - (lp + logdet)) - e0;
+    if ((ee > 1000.0) | !isfinite(ee)) return true;
+    double accept = exp(fmin(e0 - (k - (lp + logdet)), 0.)) / 1.0;
+    const bool forward = accept > P.s.target_accept;
+    for (int it = 0; it < 100; ++it) {
+      load(sz, z);
+      load(sv, v);
+      load(sg, g);
+      leapfrog(forward ? cs.step_size : -cs.step_size, lp, k);
+      double en = k - (lp + logdet);
+      ee = en - e0;
+      if ((ee > 1000.0) | !isfinite(ee)) {
+        cs.step_size = P.s.initial_step;
+        return true;
+      }
+      accept = exp(fmin(e0 - en, 0.));
+      if (forward) {
+        if ((accept <= P.s.target_accept) | (cs.step_size > 1e5)) {
+          da_new(cs.step_size);
+          return true;
+        }
+        cs.step_size *= 2.;
+      } else {
+        if ((accept >= P.s.target_accept) | (cs.step_size < 1e-10)) {
+          da_new(cs.step_size);
+          return true;
+        }
+        cs.step_size /= 2.;
+      }
+    }
+    cs.step_size = P.s.initial_step;
+    return true;
+  }
+
+  // ------------------------------------------------------------------ RunningVariance::add_sample x4 (transform/adapt/diagonal.rs:32-44,134-141)
+  __device__ __forceinline__ void add_sample_set(int set, uint64_t new_count, const double (&x)[EPT], const double (&gx)[EPT]) {
+    double* dm = est_ptr(set, 0);
+    double* dv = est_ptr(set, 1);
+    double* gm = est_ptr(set, 2);
+    double* gv = est_ptr(set, 3);
+    if (new_count == 1) {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        if (i < d) {
+          dm[i] = x[j];
+          dv[i] = 0.0;
+          gm[i] = gx[j];
+          gv[i] = 0.0;
+        }
+      }
+    } else {
+      const double scale = 1.0 / (double)new_count;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        if (i < d) {
+          // array_update_variance (cpu_math.rs:605-631): both terms use the OLD mean
+          double m0 = dm[i], diff = x[j] - m0;
+          dm[i] = m0 + diff * scale;
+          dv[i] = dv[i] + diff * diff;
+          double m1 = gm[i], diff1 = gx[j] - m1;
+          gm[i] = m1 + diff1 * scale;
+          gv[i] = gv[i] + diff1 * diff1;
+        }
+      }
+    }
+  }
+
+  // Strategy::adapt (transform/adapt/diagonal.rs:161-196) -> DiagMassMatrix::update_diag_draw_grad / update_diag_draw
+  __device__ bool mass_matrix_adapt() {
+    if (cs.fg_count < 3) return false;
+    const int set = cs.fg_set;
+    const double* dm = est_ptr(set, 0);
+    const double* dv = est_ptr(set, 1);
+    const double* gm = est_ptr(set, 2);
+    const double* gv = est_ptr(set, 3);
+    double* sd = P.stds + row;
+    double* isd = P.inv_stds + row;
+    double* mn = P.mean + row;
+    double ld[1] = {0.0};
+    const double scale = 1.0 / (double)cs.fg_count;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      if (i < d) {
+        double s_old = sd[i], is_old = isd[i];
+        double s_new = s_old, is_new = is_old;
+        double val = P.s.use_grad_based ? sqrt(dv[i] / gv[i]) : dv[i] * scale;  // cpu_math.rs:695 / :658
+        if (!((!isfinite(val)) | (val == 0.0))) {                               // fill_invalid = None: leave untouched
+          val = clampd(val, 1e-20, 1e20);
+          s_new = sqrt(val);
+          is_new = sqrt(1.0 / val);
+        }
+        sd[i] = s_new;
+        isd[i] = is_new;
+        if (P.s.use_grad_based) {
+          double var = s_new * s_new;       // array_mult(stds, stds, var)
+          double m = var * gm[i];           // array_mult(var, grad_mean, mean)
+          mn[i] = fma(1.0, dm[i], m);       // axpy(draw_mean, mean, 1.0)
+        } else {
+          mn[i] = dm[i];
+        }
+        ld[0] += log(is_new);               // array_sum_ln(inv_stds)
+      }
+    }
+    red.allreduce(ld);
+    cs.mm_logdet = ld[0];
+    cs.mm_id += 1;
+    return true;
+  }
+
+  // ------------------------------------------------------------------ GlobalStrategy::adapt (adapt_strategy.rs:121-222)
+  __device__ bool adapt(uint64_t draw) {
+    // Strategy::update (stepsize/adapt.rs:201-209)
+    cs.last_mean_tree_accept = acc_sum / (double)acc_count;
+    cs.last_sym_mean_tree_accept = acc_sym_sum / (double)acc_count;
+    cs.last_n_steps = acc_count;
+    cs.last_max_energy_error = max_energy_error;
+    const SettingsDev& S = P.s;
+    if (draw >= S.num_tune) {
+      update_stepsize(true);
+      cs.tuning = 0;
+      return true;
+    }
+    if (draw < S.final_step_size_window) {
+      const bool is_early = draw < S.early_end;
+      if (!is_early && draw == S.early_end) cs.current_window_size = max(cs.current_window_size, cs.bg_count);
+      const uint64_t switch_freq = is_early ? S.early_mm_switch_freq : cs.current_window_size;
+      if (cs.is_good) {  // update_estimators
+        double x[EPT], gx[EPT];
+        load(P.x + row, x);
+        load(P.gx + row, gx);
+        cs.fg_count += 1;
+        cs.bg_count += 1;
+        add_sample_set(cs.fg_set, cs.fg_count, x, gx);
+        add_sample_set(1 - cs.fg_set, cs.bg_count, x, gx);
+      }
+      const bool could_switch = cs.bg_count >= switch_freq;
+      const uint64_t next_window_size =
+          is_early ? S.early_mm_switch_freq
+                   : max(cs.current_window_size + 1, (uint64_t)round((double)cs.current_window_size * S.mm_window_growth));
+      const bool is_late = next_window_size + draw > S.final_step_size_window;
+      bool force_update = false;
+      if (could_switch && !is_late) {
+        cs.fg_set = 1 - cs.fg_set;  // Strategy::switch: foreground <- background, background <- empty
+        cs.fg_count = cs.bg_count;
+        cs.bg_count = 0;
+        force_update = true;
+        if (!is_early) cs.current_window_size = next_window_size;
+      }
+      bool did_change = false;
+      if (force_update | (draw - cs.last_update >= S.mm_update_freq)) did_change = mass_matrix_adapt();
+      if (did_change) cs.last_update = draw;
+      if (is_late) da_advance(cs.last_sym_mean_tree_accept);
+      else da_advance(cs.last_mean_tree_accept);
+      if (did_change & (cs.has_initial_mass_matrix != 0)) {
+        cs.has_initial_mass_matrix = 0;
+        return stepsize_search();
+      }
+      update_stepsize(false);
+      return true;
+    }
+    da_advance(cs.last_sym_mean_tree_accept);
+    update_stepsize(draw == S.num_tune - 1);
+    return true;
+  }
+
+  // ------------------------------------------------------------------ Chain::draw (chain.rs:151-188) + nuts::draw (nuts.rs:281-388)
+  __device__ void run_draw(uint64_t t) {
+    const SettingsDev& S = P.s;
+    const size_t N = (size_t)P.N;
+    // ---- initialize_trajectory (transformed_hamiltonian.rs:687-736)
+    load_mass_matrix();
+    if (cs.mm_id != cs.pt_transform_id) {
+      whiten_from_planes();  // inv_transform_normalize: no logp evaluation
+      cs.pt_logdet = cs.mm_logdet;
+      cs.pt_transform_id = cs.mm_id;
+    } else {
+      load(P.z + row, z);
+      load(P.gz + row, g);
+    }
+    sample_velocity();
+    store(P.v0 + row, v);
+    double ke[1] = {0.0};
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) ke[0] = fma(v[j], v[j], ke[0]);
+    red.allreduce(ke);
+    E0 = 0.5 * ke[0] - (cs.logp + cs.pt_logdet);
+    // collector.register_init (dual_avg.rs:160-165)
+    acc_sum = 0.;
+    acc_sym_sum = 0.;
+    acc_count = 0;
+    max_energy_error = 0.;
+    // NutsTree::new (nuts.rs:94-105)
+    ls_main = 0.;
+    depth = 0;
+    idx_end[0] = idx_end[1] = 0;
+    end_is_init[0] = end_is_init[1] = true;
+    reg_holds[0] = reg_holds[1] = true;
+    draw_slot = -1;
+    draw_energy = E0;
+    draw_idx = 0;
+    uint64_t mindepth = S.mindepth, maxdepth = S.maxdepth;
+    if (S.has_target_time) {  // nuts.rs:300-320
+      uint64_t max_steps = (uint64_t)ceil(S.target_time / cs.step_size);
+      mindepth = max((uint64_t)floor(log2((double)max_steps)), S.mindepth);
+      maxdepth = min(max((uint64_t)ceil(log2((double)max_steps)), mindepth), S.maxdepth);
+    }
+    bool diverging = false, reached_maxdepth = true;
+    while ((uint64_t)depth < maxdepth) {
+      const int dir = rng_bool() ? 1 : 0;  // hamiltonian.rs:111-119: true => Forward
+      const bool check = S.check_turning && !((uint64_t)depth < mindepth);
+      int r = extend(dir, check);
+      if (r == EXT_OK) continue;
+      reached_maxdepth = false;
+      if (r == EXT_TURNING) {
+        for (uint64_t k = 0; k < S.extra_doublings; ++k) {  // nuts.rs:349-374
+          if (extend(dir, false) == EXT_DIVERGING) {
+            diverging = true;
+            break;
+          }
+        }
+      } else {
+        diverging = true;
+      }
+      break;
+    }
+    // ---- register_draw (transform/adapt/diagonal.rs:74-83)
+    cs.is_good = diverging ? (abs(draw_idx) > 4) : (draw_idx != 0);
+    // ---- materialise the selected draw: the chain point becomes (x, gx, z, gz, logp) of that leaf.
+    // z is read back from its checkpoint; x / logp / gradient are recomputed by the same instruction sequence the
+    // leaf used, hence bit-identical to what the leapfrog produced.
+    double fisher[1] = {0.0};
+    if (draw_slot >= 0) {
+      double x[EPT], gx[EPT];
+      load(slot_ptr(draw_slot, 0), z);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        double tt = z[j] * sig[j];
+        x[j] = fma(1.0, mu[j], tt);
+      }
+      cs.logp = eval_at_position(x, gx);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) g[j] = gx[j] * sig[j];
+      store(P.x + row, x);
+      store(P.gx + row, gx);
+      store(P.z + row, z);
+      store(P.gz + row, g);
+      if (P.draws_out) store(P.draws_out + (t * N + chain) * (size_t)d, x);
+    } else {
+      load(P.z + row, z);
+      load(P.gz + row, g);
+      if (P.draws_out) {
+        double x[EPT];
+        load(P.x + row, x);
+        store(P.draws_out + (t * N + chain) * (size_t)d, x);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) fisher[0] += (z[j] + g[j]) * (z[j] + g[j]);  // sq_norm_sum (cpu_math.rs:235-243)
+    red.allreduce(fisher);
+    const double pt_energy = draw_energy;
+    const double pt_energy_error = draw_energy - E0;
+    // ---- adaptation
+    const uint64_t draw = cs.draw_count;
+    bool ok = adapt(draw);
+    cs.draw_count += 1;
+    if (!ok) cs.alive = 0;
+    if (tid == 0) {
+      const StatsDev& st = P.stats;
+      const size_t k = (size_t)t * N + chain;
+      if (st.depth) st.depth[k] = (uint64_t)depth;
+      if (st.maxdepth_reached) st.maxdepth_reached[k] = reached_maxdepth ? 1 : 0;
+      if (st.index_in_trajectory) st.index_in_trajectory[k] = draw_idx;
+      if (st.logp) st.logp[k] = cs.logp;
+      if (st.energy) st.energy[k] = pt_energy;
+      if (st.energy_error) st.energy_error[k] = pt_energy_error;
+      if (st.diverging) st.diverging[k] = diverging ? 1 : 0;
+      if (st.step_size) st.step_size[k] = cs.step_size;
+      if (st.step_size_bar) st.step_size_bar[k] = P.s.method != 0 ? P.s.fixed_step : exp(cs.da_log_step_adapted);
+      if (st.mean_tree_accept) st.mean_tree_accept[k] = cs.last_mean_tree_accept;
+      if (st.mean_tree_accept_sym) st.mean_tree_accept_sym[k] = cs.last_sym_mean_tree_accept;
+      if (st.n_steps) st.n_steps[k] = cs.last_n_steps;
+      if (st.max_energy_error) st.max_energy_error[k] = cs.last_max_energy_error;
+      if (st.tuning) st.tuning[k] = cs.tuning ? 1 : 0;
+      if (st.fisher_distance) st.fisher_distance[k] = fisher[0];
+    }
+  }
+
+  // ------------------------------------------------------------------ Chain::set_position (chain.rs:137-149)
+  __device__ int run_set_position() {
+    double x[EPT], gx[EPT];
+    load(P.init_position + (size_t)chain * d, x);
+    // GlobalStrategy::init -> init_state_untransformed (transformed_hamiltonian.rs:663-685)
+    cs.logp = eval_at_position(x, gx);
+    double bad[1] = {0.0};
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      if (i < d && !(isfinite(x[j]) && isfinite(gx[j]))) bad[0] = 1.0;
+    }
+    red.allreduce(bad);
+    if (bad[0] != 0.0) return 3;
+    store(P.x + row, x);
+    store(P.gx + row, gx);
+    // mass_matrix_adapt.init (transform/adapt/diagonal.rs:209-231): seed all four estimators, update_diag_grad
+    cs.fg_set = 0;
+    cs.fg_count = 1;
+    cs.bg_count = 1;
+    add_sample_set(0, 1, x, gx);
+    add_sample_set(1, 1, x, gx);
+    double ld[1] = {0.0};
+    {
+      double* sd = P.stds + row;
+      double* isd = P.inv_stds + row;
+      double* mn = P.mean + row;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        if (i < d) {
+          double val = 1.0 / clampd(fabs(gx[j]), 1e-20, 1e20);  // cpu_math.rs:710-738
+          if (!isfinite(val)) val = 1.0;
+          double s_new = sqrt(val), is_new = sqrt(1.0 / val);
+          sd[i] = s_new;
+          isd[i] = is_new;
+          double var = s_new * s_new;
+          double m = var * gx[j];
+          mn[i] = fma(1.0, x[j], m);
+          ld[0] += log(is_new);
+        }
+      }
+    }
+    red.allreduce(ld);
+    cs.mm_logdet = ld[0];
+    cs.mm_id += 1;
+    // step_size.init
+    if (P.s.method == 0) {
+      if (!stepsize_search()) return 3;
+    } else {
+      cs.step_size = P.s.fixed_step;
+    }
+    // self.state = hamiltonian.init_state(position) (transformed_hamiltonian.rs:640-661)
+    load_mass_matrix();
+    if (!whiten_from_planes()) return 3;
+    cs.pt_logdet = cs.mm_logdet;
+    cs.pt_transform_id = cs.mm_id;
+    return 0;
+  }
+};
+
+// One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).
+template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(const __grid_constant__ EngineParams P) {
+  constexpr int TEAMS = CTA_THREADS / TPC;
+  __shared__ double scratch[TPC > 32 ? 2 * 32 * REDUCE_MAXK : 1];
+  __shared__ int next_chain[TEAMS];
+  const int team = threadIdx.x / TPC;
+  const int tid = threadIdx.x % TPC;
+  for (;;) {
+    if (tid == 0) next_chain[team] = (int)atomicAdd(P.queue, 1u);
+    if (TPC > 32) __syncthreads();
+    else __syncwarp();
+    const int chain = next_chain[team];
+    if (TPC > 32) __syncthreads();
+    else __syncwarp();
+    if (chain >= P.N) break;
+    Engine<TPC, EPT> E(P, chain, tid, scratch);
+    E.cs = P.cs[chain];
+    if (P.mode == 0) {
+      int st = E.run_set_position();
+      E.cs.alive = st == 0 ? 1 : 0;
+      if (tid == 0 && P.status_out) P.status_out[chain] = st;
+    } else if (E.cs.alive) {
+      for (uint64_t t = 0; t < P.n_draws; ++t) {
+        E.run_draw(t);
+        if (!E.cs.alive) break;
+      }
+    }
+    if (TPC > 32) __syncthreads();
+    else __syncwarp();
+    if (tid == 0) P.cs[chain] = E.cs;
+  }
+}
+
+}  // namespace nb

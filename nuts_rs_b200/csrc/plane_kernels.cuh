@@ -1,0 +1,404 @@
+// plane_kernels.cuh — Tier 1 (batched Math-trait ops) and Tier 2 (fused Hamiltonian ops) kernels over
+// [nchains x dim] f64 planes.  One CTA of PK_THREADS threads per chain row, strided over dim (any dim);
+// these kernels stream their operands from HBM once (coalesced 8-byte loads, 256 B per warp instruction).
+// Reference semantics: src/math/math.rs (trait), src/math/cpu_math.rs + src/math/util.rs (CPU implementation).
+#pragma once
+#include "device_common.cuh"
+
+namespace nb {
+
+constexpr int PK_THREADS = 256;
+
+struct RowArgs {
+  int N, d, ld;
+};
+
+#define NB_ROW_PROLOGUE                                       \
+  const int c = blockIdx.x;                                   \
+  if (c >= A.N) return;                                       \
+  if (active && !active[c]) return;                           \
+  const size_t row = (size_t)c * A.ld;                        \
+  (void)row;
+
+// ---------------------------------------------------------------- elementwise
+__global__ void __launch_bounds__(PK_THREADS) k_axpy(RowArgs A, const double* __restrict__ x, double* __restrict__ y,
+                                                      const double* __restrict__ a, double a_bcast, const uint8_t* active) {
+  NB_ROW_PROLOGUE
+  const double av = a ? a[c] : a_bcast;
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) y[row + i] = fma(av, x[row + i], y[row + i]);  // util.rs:426-437
+}
+__global__ void __launch_bounds__(PK_THREADS) k_axpy_out(RowArgs A, const double* __restrict__ x, const double* __restrict__ y,
+                                                          const double* __restrict__ a, double a_bcast, double* __restrict__ out,
+                                                          const uint8_t* active) {
+  NB_ROW_PROLOGUE
+  const double av = a ? a[c] : a_bcast;
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) out[row + i] = fma(av, x[row + i], y[row + i]);  // util.rs:472-495
+}
+__global__ void __launch_bounds__(PK_THREADS) k_mult(RowArgs A, const double* x, const double* y, double* out) {
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) out[row + i] = x[row + i] * y[row + i];  // util.rs:46-49 (plain product)
+}
+__global__ void __launch_bounds__(PK_THREADS) k_recip(RowArgs A, const double* x, double* out) {
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) out[row + i] = 1.0 / x[row + i];  // cpu_math.rs:328-330
+}
+__global__ void __launch_bounds__(PK_THREADS) k_fill(RowArgs A, double* x, double val) {
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) x[row + i] = val;
+}
+__global__ void __launch_bounds__(PK_THREADS) k_copy(RowArgs A, const double* src, double* dst) {
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) dst[row + i] = src[row + i];
+}
+// host [N*d] <-> plane [N][ld]
+__global__ void __launch_bounds__(PK_THREADS) k_pack(RowArgs A, const double* dense, double* plane) {
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) plane[row + i] = dense[(size_t)c * A.d + i];
+}
+__global__ void __launch_bounds__(PK_THREADS) k_unpack(RowArgs A, const double* plane, double* dense) {
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) dense[(size_t)c * A.d + i] = plane[row + i];
+}
+__global__ void __launch_bounds__(PK_THREADS) k_gaussian(RowArgs A, double* dest, const double* stds, uint64_t seed,
+                                                          uint64_t chain_offset, uint64_t counter) {
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  const uint64_t stream = chain_offset + (uint64_t)c + 1;
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS)
+    dest[row + i] = stds[row + i] * stream_normal(seed, stream, counter, (uint32_t)i);  // cpu_math.rs:561-577
+}
+__global__ void __launch_bounds__(PK_THREADS) k_update_variance(RowArgs A, double* mean, double* var, const double* value,
+                                                                 const double* scale, double scale_bcast) {
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  const double sc = scale ? scale[c] : scale_bcast;
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {  // cpu_math.rs:625-629
+    double diff = value[row + i] - mean[row + i];
+    mean[row + i] += diff * sc;
+    var[row + i] += diff * diff;
+  }
+}
+// mode 0: draw (cpu_math.rs:633-669), 1: draw_grad (:671-708), 2: grad (:710-738)
+__global__ void __launch_bounds__(PK_THREADS) k_update_var_inv_std(RowArgs A, int mode, double* inv_std, double* std_, const double* a,
+                                                                    const double* b, double scale, int has_fill, double fill,
+                                                                    double lo, double hi) {
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
+    if (mode == 2) {
+      double val = 1.0 / clampd(fabs(a[row + i]), lo, hi);
+      if (!isfinite(val)) val = fill;
+      std_[row + i] = sqrt(val);
+      inv_std[row + i] = sqrt(1.0 / val);
+    } else {
+      double val = mode == 0 ? a[row + i] * scale : sqrt(a[row + i] / b[row + i]);
+      if ((!isfinite(val)) | (val == 0.0)) {
+        if (has_fill) {
+          std_[row + i] = sqrt(fill);
+          inv_std[row + i] = sqrt(1.0 / fill);
+        }
+      } else {
+        val = clampd(val, lo, hi);
+        std_[row + i] = sqrt(val);
+        inv_std[row + i] = sqrt(1.0 / val);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- per-chain reductions -> out[N] (device)
+// op 0: dot(x,y)  1: sq_norm_sum (x+y)^2  2: sum ln(x)  3: all finite  4: all finite and nonzero
+__global__ void __launch_bounds__(PK_THREADS) k_reduce1(RowArgs A, int op, const double* x, const double* y, double* out) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  double s[1] = {0.0};
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
+    double xv = x[row + i];
+    if (op == 0) s[0] = fma(xv, y[row + i], s[0]);
+    else if (op == 1) s[0] += (xv + y[row + i]) * (xv + y[row + i]);
+    else if (op == 2) s[0] += log(xv);
+    else if (op == 3) s[0] += isfinite(xv) ? 0.0 : 1.0;
+    else s[0] += (isfinite(xv) & (xv != 0.0)) ? 0.0 : 1.0;
+  }
+  red.allreduce(s);
+  if (threadIdx.x == 0) out[c] = (op >= 3) ? (s[0] == 0.0 ? 1.0 : 0.0) : s[0];
+}
+// scalar_prods3 (util.rs:221-347): ((p1 + p2) - n1).x and .y ;  n1 == nullptr gives scalar_prods2 (util.rs:114-219)
+__global__ void __launch_bounds__(PK_THREADS) k_scalar_prods(RowArgs A, const double* p1, const double* n1, const double* p2,
+                                                              const double* x, const double* y, double* out1, double* out2) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  double s[2] = {0.0, 0.0};
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
+    double sum = p1[row + i] + p2[row + i];
+    if (n1) sum = sum - n1[row + i];
+    s[0] = fma(sum, x[row + i], s[0]);
+    s[1] = fma(sum, y[row + i], s[1]);
+  }
+  red.allreduce(s);
+  if (threadIdx.x == 0) {
+    out1[c] = s[0];
+    out2[c] = s[1];
+  }
+}
+
+// ---------------------------------------------------------------- log density over planes (Math::logp_array)
+struct PointDev {  // batched TransformedPoint (transformed_hamiltonian.rs:56-77)
+  double *x, *gx, *z, *gz, *v;
+  long long* idx;
+  double *logp, *logdet, *ke, *e0;
+  long long* tid;
+};
+struct TransformDev {  // batched DiagMassMatrix (transform/diagonal.rs:9-17)
+  double *stds, *inv_stds, *mean;
+  double* logdet;
+  long long* id;
+};
+
+// strided model evaluation at x (row pointer): writes gx, returns logp to every thread
+__device__ __forceinline__ double model_eval_row(const ModelDev& m, int d, const double* x, double* gx, TeamReduce<PK_THREADS>& red) {
+  double a0 = 0.0, a1 = 0.0;
+  if (m.kind == LOGP_GAUSS_RANK1) {
+    double s[1] = {0.0};
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) s[0] += x[i] - m.mu[i];
+    red.allreduce(s);
+    a0 = m.rank1_coeff * s[0];
+  } else if (m.kind == LOGP_FUNNEL) {
+    double s[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      if (i == 0) s[1] = x[i];
+      else s[0] = fma(x[i], x[i], s[0]);
+    }
+    red.allreduce(s);
+    a0 = s[1];
+    a1 = s[0];
+  }
+  double lp[1] = {0.0};
+  if (m.kind == LOGP_FUNNEL) {
+    double ev = exp(-a0), nm1 = (double)(d - 1), half_ev_S = 0.5 * ev * a1;
+    for (int i = threadIdx.x; i < d; i += PK_THREADS)
+      gx[i] = i == 0 ? (-a0 * m.funnel_inv_var - 0.5 * nm1 + half_ev_S) : (-x[i] * ev);
+    return -0.5 * a0 * a0 * m.funnel_inv_var - 0.5 * nm1 * a0 - half_ev_S;
+  }
+  for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+    double diff = x[i] - m.mu[i];
+    if (m.kind == LOGP_GAUSS_ISO) {
+      lp[0] -= diff * diff / 2.;
+      gx[i] = -diff;
+    } else if (m.kind == LOGP_GAUSS_DIAG) {
+      double pd = diff * m.prec[i];
+      lp[0] -= diff * pd / 2.;
+      gx[i] = -pd;
+    } else {
+      double ptd = diff - a0;
+      gx[i] = -ptd;
+      lp[0] -= 0.5 * diff * ptd;
+    }
+  }
+  red.allreduce(lp);
+  return lp[0];
+}
+
+__global__ void __launch_bounds__(PK_THREADS) k_logp_array(RowArgs A, ModelDev m, const double* x, double* gx, double* logp, int* status) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  double lp = model_eval_row(m, A.d, x + row, gx + row, red);
+  double bad[1] = {0.0};
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS)
+    if (!isfinite(gx[row + i])) bad[0] = 1.0;
+  red.allreduce(bad);
+  if (threadIdx.x == 0) {
+    logp[c] = lp;
+    if (status) status[c] = (bad[0] != 0.0 || !isfinite(lp)) ? 2 : 0;
+  }
+}
+
+// DiagMassMatrix::set_transform (diagonal.rs:156-162): stds/mean already written; inv_stds, logdet, id
+__global__ void __launch_bounds__(PK_THREADS) k_set_transform(RowArgs A, TransformDev T) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  double s[1] = {0.0};
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
+    double is = 1.0 / T.stds[row + i];
+    T.inv_stds[row + i] = is;
+    s[0] += log(is);
+  }
+  red.allreduce(s);
+  if (threadIdx.x == 0) {
+    T.logdet[c] = s[0];
+    T.id[c] += 1;
+  }
+}
+
+// Hamiltonian::init_state (transformed_hamiltonian.rs:640-661): x plane given
+__global__ void __launch_bounds__(PK_THREADS) k_init_state(RowArgs A, ModelDev m, TransformDev T, PointDev p, int* status) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  double lp = model_eval_row(m, A.d, p.x + row, p.gx + row, red);
+  double bad[1] = {0.0};
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
+    double xv = p.x[row + i], gxv = p.gx[row + i];
+    double t = fma(-1.0, T.mean[row + i], xv);
+    double zv = T.inv_stds[row + i] * t;
+    double gv = gxv * T.stds[row + i];
+    p.z[row + i] = zv;
+    p.gz[row + i] = gv;
+    if (!(isfinite(zv) && isfinite(gv) && (gv != 0.0) && isfinite(gxv) && isfinite(xv))) bad[0] = 1.0;
+  }
+  red.allreduce(bad);
+  if (threadIdx.x == 0) {
+    p.logp[c] = lp;
+    p.logdet[c] = T.logdet[c];
+    p.tid[c] = T.id[c];
+    if (status) status[c] = bad[0] != 0.0 ? 3 : 0;
+  }
+}
+
+// Hamiltonian::initialize_trajectory (transformed_hamiltonian.rs:687-736)
+__global__ void __launch_bounds__(PK_THREADS) k_initialize_trajectory(RowArgs A, TransformDev T, PointDev p, int resample, uint64_t seed,
+                                                                       uint64_t chain_offset, uint64_t counter) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  const uint64_t stream = chain_offset + (uint64_t)c + 1;
+  const bool rewhiten = T.id[c] != p.tid[c];
+  double s[1] = {0.0};
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
+    double vv = resample ? 1.0 * stream_normal(seed, stream, counter, (uint32_t)i) : p.v[row + i];
+    if (resample) p.v[row + i] = vv;
+    if (rewhiten) {
+      double t = fma(-1.0, T.mean[row + i], p.x[row + i]);
+      p.z[row + i] = T.inv_stds[row + i] * t;
+      p.gz[row + i] = p.gx[row + i] * T.stds[row + i];
+    }
+    s[0] = fma(vv, vv, s[0]);
+  }
+  red.allreduce(s);
+  if (threadIdx.x == 0) {
+    if (rewhiten) {
+      p.logdet[c] = T.logdet[c];
+      p.tid[c] = T.id[c];
+    }
+    double ke = 0.5 * s[0];
+    p.ke[c] = ke;
+    p.idx[c] = 0;
+    p.e0[c] = ke - (p.logp[c] + p.logdet[c]);
+  }
+}
+
+// Hamiltonian::leapfrog (transformed_hamiltonian.rs:524-615), Euclidean, all chains in one launch.
+// HBM traffic per chain: reads z, v, gz, stds, mean (40*d B) ; writes z', v', x', gx', gz' (40*d B).
+__global__ void __launch_bounds__(PK_THREADS) k_leapfrog(RowArgs A, ModelDev m, TransformDev T, PointDev s, PointDev o,
+                                                          const double* step_size, double step_bcast, const int8_t* dir,
+                                                          const double* baseline, double max_energy_error, const uint8_t* active,
+                                                          int* status, double* energy_error_out) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  NB_ROW_PROLOGUE
+  const int d = A.d;
+  const int sign = dir ? (int)dir[c] : 1;
+  const double eps = (double)sign * (step_size ? step_size[c] : step_bcast) * 1.0;
+  const double eps_half = eps / 2.;
+  double part[2] = {0.0, 0.0};
+  double lp;
+  const bool single_pass = (m.kind == LOGP_GAUSS_ISO) | (m.kind == LOGP_GAUSS_DIAG);
+  if (single_pass) {
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      double sg = T.stds[row + i];
+      double vh = fma(eps_half, s.gz[row + i], s.v[row + i]);
+      double zn = fma(eps, vh, s.z[row + i]);
+      double t = zn * sg;
+      double xn = fma(1.0, T.mean[row + i], t);
+      double diff = xn - m.mu[i];
+      double gxn;
+      if (m.kind == LOGP_GAUSS_ISO) {
+        part[0] -= diff * diff / 2.;
+        gxn = -diff;
+      } else {
+        double pd = diff * m.prec[i];
+        part[0] -= diff * pd / 2.;
+        gxn = -pd;
+      }
+      double gn = gxn * sg;
+      double vn = fma(eps_half, gn, vh);
+      part[1] = fma(vn, vn, part[1]);
+      o.z[row + i] = zn;
+      o.x[row + i] = xn;
+      o.gx[row + i] = gxn;
+      o.gz[row + i] = gn;
+      o.v[row + i] = vn;
+    }
+    red.allreduce(part);
+    lp = part[0];
+  } else {
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      double vh = fma(eps_half, s.gz[row + i], s.v[row + i]);
+      double zn = fma(eps, vh, s.z[row + i]);
+      double t = zn * T.stds[row + i];
+      o.v[row + i] = vh;
+      o.z[row + i] = zn;
+      o.x[row + i] = fma(1.0, T.mean[row + i], t);
+    }
+    lp = model_eval_row(m, d, o.x + row, o.gx + row, red);
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      double gn = o.gx[row + i] * T.stds[row + i];
+      double vn = fma(eps_half, gn, o.v[row + i]);
+      o.gz[row + i] = gn;
+      o.v[row + i] = vn;
+      part[1] = fma(vn, vn, part[1]);
+    }
+    red.allreduce(part);
+  }
+  if (threadIdx.x == 0) {
+    double ke = 0.5 * part[1];
+    double logdet = T.logdet[c];
+    o.logp[c] = lp;
+    o.logdet[c] = logdet;
+    o.ke[c] = ke;
+    o.e0[c] = s.e0[c];
+    o.tid[c] = T.id[c];
+    o.idx[c] = s.idx[c] + sign;
+    double base = baseline ? baseline[c] : s.e0[c];
+    double ee = (ke - (lp + logdet)) - base;
+    if (energy_error_out) energy_error_out[c] = ee;
+    if (status) status[c] = ((ee > max_energy_error) | !isfinite(ee)) ? 1 : 0;
+  }
+}
+
+// Hamiltonian::is_turning (transformed_hamiltonian.rs:617-638)
+__global__ void __launch_bounds__(PK_THREADS) k_is_turning(RowArgs A, PointDev s1, PointDev s2, uint8_t* turning) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  const bool first_is_start = s1.idx[c] < s2.idx[c];
+  const PointDev& st = first_is_start ? s1 : s2;
+  const PointDev& en = first_is_start ? s2 : s1;
+  double s[2] = {0.0, 0.0};
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
+    double sum = (en.z[row + i] + 0.0) - st.z[row + i];
+    s[0] = fma(sum, st.v[row + i], s[0]);
+    s[1] = fma(sum, en.v[row + i], s[1]);
+  }
+  red.allreduce(s);
+  if (threadIdx.x == 0) turning[c] = ((s[0] < 0.) | (s[1] < 0.)) ? 1 : 0;
+}
+
+}  // namespace nb

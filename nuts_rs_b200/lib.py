@@ -1,0 +1,453 @@
+"""ctypes loader + thin host-side mirror of the reference's interface for the accelerated path.
+
+Names follow nuts-rs: `CudaMath` plays the role of a `Math` implementation (reference src/math/math.rs:15-314,
+batched over chains), `DiagNutsSettings` is `nuts_rs::DiagNutsSettings` (src/sampler.rs:241-244), `Sampler.set_position`
+/ `Sampler.draw` are `Chain::set_position` / `Chain::draw` (src/chain.rs:137-188) for every chain at once.
+Everything goes through the C ABI of include/nuts_b200.h; there is no CPU fallback — a missing library or GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import c_double_p as dp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnuts_b200.so")
+_LIB = None
+
+EXPORTED_SYMBOLS = [
+    "nuts_last_error", "nuts_device_available", "nuts_settings_default",
+    "nuts_ctx_create", "nuts_ctx_destroy", "nuts_ctx_synchronize", "nuts_ctx_nchains", "nuts_ctx_dim", "nuts_ctx_stream",
+    "nuts_plane_alloc", "nuts_plane_free", "nuts_plane_read_from_host", "nuts_plane_write_to_host", "nuts_plane_device_ptr",
+    "nuts_axpy", "nuts_axpy_out", "nuts_array_mult", "nuts_array_mult_inplace", "nuts_array_recip", "nuts_fill_array",
+    "nuts_copy_into", "nuts_array_vector_dot", "nuts_scalar_prods3", "nuts_scalar_prods2", "nuts_sq_norm_sum",
+    "nuts_array_all_finite", "nuts_array_all_finite_and_nonzero", "nuts_array_sum_ln", "nuts_array_gaussian",
+    "nuts_array_update_variance", "nuts_array_update_var_inv_std_draw", "nuts_array_update_var_inv_std_draw_grad",
+    "nuts_array_update_var_inv_std_grad", "nuts_logp_array",
+    "nuts_point_alloc", "nuts_point_free", "nuts_point_plane", "nuts_point_get_scalars", "nuts_point_set_scalars",
+    "nuts_set_transform", "nuts_get_transform", "nuts_init_state", "nuts_initialize_trajectory", "nuts_leapfrog", "nuts_is_turning",
+    "nuts_sampler_create", "nuts_sampler_destroy", "nuts_set_position", "nuts_draw", "nuts_draw_device",
+    "nuts_sampler_counters", "nuts_sampler_last_timing", "nuts_sampler_get_state", "nuts_sampler_set_step_size",
+]
+
+
+class NutsError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libnuts_b200.so (built by `make -C nuts_rs_b200/csrc` / __graft_entry__.build())."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise NutsError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.nuts_last_error.restype = C.c_char_p
+    L.nuts_ctx_nchains.restype = C.c_uint64
+    L.nuts_ctx_dim.restype = C.c_uint64
+    L.nuts_ctx_stream.restype = vp
+    L.nuts_plane_device_ptr.restype = vp
+    L.nuts_point_plane.restype = vp
+    L.nuts_settings_default.restype = None
+    L.nuts_settings_default.argtypes = [C.POINTER(_abi.NutsSettings)]
+    L.nuts_ctx_create.argtypes = [C.POINTER(vp), C.c_int, C.c_uint64, C.c_uint64, C.POINTER(_abi.LogpDesc)]
+    L.nuts_ctx_destroy.argtypes = [vp]
+    L.nuts_ctx_synchronize.argtypes = [vp]
+    L.nuts_ctx_nchains.argtypes = [vp]
+    L.nuts_ctx_dim.argtypes = [vp]
+    L.nuts_ctx_stream.argtypes = [vp]
+    L.nuts_plane_alloc.argtypes = [vp, C.POINTER(vp)]
+    L.nuts_plane_free.argtypes = [vp, vp]
+    L.nuts_plane_read_from_host.argtypes = [vp, vp, dp]
+    L.nuts_plane_write_to_host.argtypes = [vp, vp, dp]
+    L.nuts_plane_device_ptr.argtypes = [vp, _abi.c_u64_p]
+    L.nuts_axpy.argtypes = [vp, vp, vp, dp, C.c_double, _abi.c_u8_p]
+    L.nuts_axpy_out.argtypes = [vp, vp, vp, dp, C.c_double, vp, _abi.c_u8_p]
+    L.nuts_array_mult.argtypes = [vp, vp, vp, vp]
+    L.nuts_array_mult_inplace.argtypes = [vp, vp, vp]
+    L.nuts_array_recip.argtypes = [vp, vp, vp]
+    L.nuts_fill_array.argtypes = [vp, vp, C.c_double]
+    L.nuts_copy_into.argtypes = [vp, vp, vp]
+    L.nuts_array_vector_dot.argtypes = [vp, vp, vp, dp]
+    L.nuts_scalar_prods3.argtypes = [vp, vp, vp, vp, vp, vp, dp, dp]
+    L.nuts_scalar_prods2.argtypes = [vp, vp, vp, vp, vp, dp, dp]
+    L.nuts_sq_norm_sum.argtypes = [vp, vp, vp, dp]
+    L.nuts_array_all_finite.argtypes = [vp, vp, _abi.c_u8_p]
+    L.nuts_array_all_finite_and_nonzero.argtypes = [vp, vp, _abi.c_u8_p]
+    L.nuts_array_sum_ln.argtypes = [vp, vp, dp]
+    L.nuts_array_gaussian.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.nuts_array_update_variance.argtypes = [vp, vp, vp, vp, dp, C.c_double]
+    L.nuts_array_update_var_inv_std_draw.argtypes = [vp, vp, vp, vp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
+    L.nuts_array_update_var_inv_std_draw_grad.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_double, C.c_double, C.c_double]
+    L.nuts_array_update_var_inv_std_grad.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, C.c_double]
+    L.nuts_logp_array.argtypes = [vp, vp, vp, dp, _abi.c_i32_p]
+    L.nuts_point_alloc.argtypes = [vp, C.POINTER(vp)]
+    L.nuts_point_free.argtypes = [vp, vp]
+    L.nuts_point_plane.argtypes = [vp, C.c_int]
+    L.nuts_point_get_scalars.argtypes = [vp, vp, _abi.c_i64_p, dp, dp, dp, dp, _abi.c_i64_p]
+    L.nuts_point_set_scalars.argtypes = [vp, vp, _abi.c_i64_p, dp, dp, dp, dp, _abi.c_i64_p]
+    L.nuts_set_transform.argtypes = [vp, dp, dp]
+    L.nuts_get_transform.argtypes = [vp, dp, dp, dp, dp, _abi.c_i64_p]
+    L.nuts_init_state.argtypes = [vp, vp, dp, _abi.c_i32_p]
+    L.nuts_initialize_trajectory.argtypes = [vp, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.nuts_leapfrog.argtypes = [vp, vp, vp, dp, C.c_double, _abi.c_i8_p, dp, C.c_double, _abi.c_u8_p, _abi.c_i32_p, dp]
+    L.nuts_is_turning.argtypes = [vp, vp, vp, _abi.c_u8_p]
+    L.nuts_sampler_create.argtypes = [vp, C.POINTER(vp), C.POINTER(_abi.NutsSettings), C.c_uint64, C.c_uint64]
+    L.nuts_sampler_destroy.argtypes = [vp]
+    L.nuts_set_position.argtypes = [vp, dp, _abi.c_i32_p]
+    L.nuts_draw.argtypes = [vp, C.c_uint64, dp, C.POINTER(_abi.Stats)]
+    L.nuts_draw_device.argtypes = [vp, C.c_uint64, vp]
+    L.nuts_sampler_counters.argtypes = [vp, _abi.c_u64_p, _abi.c_u64_p]
+    L.nuts_sampler_last_timing.argtypes = [vp, dp, _abi.c_u64_p]
+    L.nuts_sampler_get_state.argtypes = [vp, dp, dp, dp, dp, _abi.c_u64_p]
+    L.nuts_sampler_set_step_size.argtypes = [vp, dp]
+    _LIB = L
+    return L
+
+
+def device_available() -> bool:
+    return load().nuts_device_available() == 0
+
+
+def _check(rc):
+    if rc != 0:
+        raise NutsError(f"libnuts_b200 error {rc}: {load().nuts_last_error().decode()}")
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+def DiagNutsSettings(**overrides) -> _abi.NutsSettings:
+    """`DiagNutsSettings::default()` from the library itself, with top-level field overrides (num_tune=..., maxdepth=...)."""
+    s = _abi.NutsSettings()
+    load().nuts_settings_default(C.byref(s))
+    for k, v in overrides.items():
+        setattr(s, k, v)
+    return s
+
+
+class Plane:
+    """`nchains` x Math::Vector on the device."""
+
+    def __init__(self, math, handle=None, owned=True):
+        self.math = math
+        self.owned = owned
+        if handle is None:
+            h = C.c_void_p()
+            _check(load().nuts_plane_alloc(math.h, C.byref(h)))
+            handle = h
+        self.h = handle
+
+    def read_from_slice(self, src):
+        src = _f64(src).reshape(self.math.nchains, self.math.dim)
+        _check(load().nuts_plane_read_from_host(self.math.h, self.h, _p(src)))
+        return self
+
+    def box_array(self):
+        out = np.empty((self.math.nchains, self.math.dim))
+        _check(load().nuts_plane_write_to_host(self.math.h, self.h, _p(out)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "owned", False) and getattr(self, "h", None) and self.math.h:
+            load().nuts_plane_free(self.math.h, self.h)
+            self.h = None
+
+
+class Point:
+    """`nchains` x TransformedPoint (reference src/dynamics/transformed_hamiltonian.rs:56-77)."""
+
+    X, GX, Z, GZ, V = range(5)
+
+    def __init__(self, math):
+        self.math = math
+        h = C.c_void_p()
+        _check(load().nuts_point_alloc(math.h, C.byref(h)))
+        self.h = h
+
+    def plane(self, which):
+        return Plane(self.math, C.c_void_p(load().nuts_point_plane(self.h, which)), owned=False)
+
+    def vec(self, which):
+        return self.plane(which).box_array()
+
+    def set_vec(self, which, v):
+        self.plane(which).read_from_slice(v)
+
+    def scalars(self):
+        N = self.math.nchains
+        idx, tid = np.zeros(N, dtype=np.int64), np.zeros(N, dtype=np.int64)
+        logp, logdet, ke, e0 = (np.zeros(N) for _ in range(4))
+        _check(load().nuts_point_get_scalars(self.math.h, self.h, idx.ctypes.data_as(_abi.c_i64_p), _p(logp), _p(logdet), _p(ke), _p(e0),
+                                             tid.ctypes.data_as(_abi.c_i64_p)))
+        return dict(index_in_trajectory=idx, logp=logp, logdet=logdet, kinetic_energy=ke, initial_energy=e0, transform_id=tid)
+
+    def set_scalars(self, index_in_trajectory=None, logp=None, logdet=None, kinetic_energy=None, initial_energy=None, transform_id=None):
+        N = self.math.nchains
+
+        def f(a):
+            return None if a is None else _f64(np.broadcast_to(a, (N,)))
+
+        def i(a):
+            return None if a is None else np.ascontiguousarray(np.broadcast_to(a, (N,)), dtype=np.int64)
+
+        idx, tid = i(index_in_trajectory), i(transform_id)
+        a = [f(logp), f(logdet), f(kinetic_energy), f(initial_energy)]
+        _check(load().nuts_point_set_scalars(self.math.h, self.h, None if idx is None else idx.ctypes.data_as(_abi.c_i64_p), *map(_p, a),
+                                             None if tid is None else tid.ctypes.data_as(_abi.c_i64_p)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.math.h:
+            load().nuts_point_free(self.math.h, self.h)
+            self.h = None
+
+
+class CudaMath:
+    """Batched `Math` backend on one B200: `nchains` independent chains of dimension `dim` with a device-side logp."""
+
+    def __init__(self, nchains, dim, kind, mu=None, sigma=None, rank1_scale=0.0, funnel_scale=3.0, device=0):
+        self.h = None
+        self.nchains = int(nchains)
+        self._dim = int(dim)
+        self.desc, self._keep = _abi.make_logp_desc(kind, dim, mu, sigma, rank1_scale, funnel_scale)
+        h = C.c_void_p()
+        _check(load().nuts_ctx_create(C.byref(h), device, nchains, dim, C.byref(self.desc)))
+        self.h = h
+
+    @property
+    def dim(self):
+        return self._dim
+
+    def new_array(self):
+        return Plane(self)
+
+    def from_host(self, a):
+        return Plane(self).read_from_slice(a)
+
+    # -- Tier 1 --
+    def _mask(self, active):
+        if active is None:
+            return None, None
+        m = np.ascontiguousarray(active, dtype=np.uint8)
+        return m, m.ctypes.data_as(_abi.c_u8_p)
+
+    def _scal(self, a):
+        if np.isscalar(a):
+            return None, None, float(a)
+        arr = _f64(a)
+        return arr, _p(arr), 0.0
+
+    def axpy(self, x, y, a, active=None):
+        keep, ap, ab = self._scal(a)
+        m, mp = self._mask(active)
+        _check(load().nuts_axpy(self.h, x.h, y.h, ap, ab, mp))
+
+    def axpy_out(self, x, y, a, out, active=None):
+        keep, ap, ab = self._scal(a)
+        m, mp = self._mask(active)
+        _check(load().nuts_axpy_out(self.h, x.h, y.h, ap, ab, out.h, mp))
+
+    def array_mult(self, a1, a2, dest):
+        _check(load().nuts_array_mult(self.h, a1.h, a2.h, dest.h))
+
+    def array_mult_inplace(self, a1, a2):
+        _check(load().nuts_array_mult_inplace(self.h, a1.h, a2.h))
+
+    def array_recip(self, a, dest):
+        _check(load().nuts_array_recip(self.h, a.h, dest.h))
+
+    def fill_array(self, a, val):
+        _check(load().nuts_fill_array(self.h, a.h, val))
+
+    def copy_into(self, src, dst):
+        _check(load().nuts_copy_into(self.h, src.h, dst.h))
+
+    def _red(self, fn, *planes):
+        out = np.empty(self.nchains)
+        _check(fn(self.h, *[p.h for p in planes], _p(out)))
+        return out
+
+    def array_vector_dot(self, a1, a2):
+        return self._red(load().nuts_array_vector_dot, a1, a2)
+
+    def sq_norm_sum(self, x, y):
+        return self._red(load().nuts_sq_norm_sum, x, y)
+
+    def array_sum_ln(self, a):
+        return self._red(load().nuts_array_sum_ln, a)
+
+    def scalar_prods3(self, positive1, negative1, positive2, x, y):
+        o1, o2 = np.empty(self.nchains), np.empty(self.nchains)
+        _check(load().nuts_scalar_prods3(self.h, positive1.h, negative1.h, positive2.h, x.h, y.h, _p(o1), _p(o2)))
+        return o1, o2
+
+    def scalar_prods2(self, positive1, positive2, x, y):
+        o1, o2 = np.empty(self.nchains), np.empty(self.nchains)
+        _check(load().nuts_scalar_prods2(self.h, positive1.h, positive2.h, x.h, y.h, _p(o1), _p(o2)))
+        return o1, o2
+
+    def array_all_finite(self, a):
+        out = np.zeros(self.nchains, dtype=np.uint8)
+        _check(load().nuts_array_all_finite(self.h, a.h, out.ctypes.data_as(_abi.c_u8_p)))
+        return out.astype(bool)
+
+    def array_all_finite_and_nonzero(self, a):
+        out = np.zeros(self.nchains, dtype=np.uint8)
+        _check(load().nuts_array_all_finite_and_nonzero(self.h, a.h, out.ctypes.data_as(_abi.c_u8_p)))
+        return out.astype(bool)
+
+    def array_gaussian(self, dest, stds, seed, chain_offset, counter):
+        _check(load().nuts_array_gaussian(self.h, dest.h, stds.h, seed, chain_offset, counter))
+
+    def array_update_variance(self, mean, variance, value, diff_scale):
+        keep, ap, ab = self._scal(diff_scale)
+        _check(load().nuts_array_update_variance(self.h, mean.h, variance.h, value.h, ap, ab))
+
+    def array_update_var_inv_std_draw(self, inv_std, std, draw_var, scale, fill_invalid, clamp):
+        _check(load().nuts_array_update_var_inv_std_draw(self.h, inv_std.h, std.h, draw_var.h, scale, fill_invalid is not None,
+                                                         fill_invalid or 0.0, clamp[0], clamp[1]))
+
+    def array_update_var_inv_std_draw_grad(self, inv_std, std, draw_var, grad_var, fill_invalid, clamp):
+        _check(load().nuts_array_update_var_inv_std_draw_grad(self.h, inv_std.h, std.h, draw_var.h, grad_var.h, fill_invalid is not None,
+                                                              fill_invalid or 0.0, clamp[0], clamp[1]))
+
+    def array_update_var_inv_std_grad(self, inv_std, std, gradient, fill_invalid, clamp):
+        _check(load().nuts_array_update_var_inv_std_grad(self.h, inv_std.h, std.h, gradient.h, fill_invalid, clamp[0], clamp[1]))
+
+    def logp_array(self, position, gradient):
+        logp = np.empty(self.nchains)
+        status = np.zeros(self.nchains, dtype=np.int32)
+        _check(load().nuts_logp_array(self.h, position.h, gradient.h, _p(logp), status.ctypes.data_as(_abi.c_i32_p)))
+        return logp, status
+
+    # -- Tier 2 (Hamiltonian) --
+    def new_point(self):
+        return Point(self)
+
+    def set_transform(self, stds, mean):
+        stds = _f64(np.broadcast_to(stds, (self.nchains, self.dim)))
+        mean = _f64(np.broadcast_to(mean, (self.nchains, self.dim)))
+        _check(load().nuts_set_transform(self.h, _p(stds), _p(mean)))
+
+    def transform(self):
+        N, d = self.nchains, self.dim
+        stds, inv, mean = np.empty((N, d)), np.empty((N, d)), np.empty((N, d))
+        logdet = np.empty(N)
+        tid = np.empty(N, dtype=np.int64)
+        _check(load().nuts_get_transform(self.h, _p(stds), _p(inv), _p(mean), _p(logdet), tid.ctypes.data_as(_abi.c_i64_p)))
+        return dict(stds=stds, inv_stds=inv, mean=mean, logdet=logdet, id=tid)
+
+    def init_state(self, position):
+        p = Point(self)
+        position = _f64(position).reshape(self.nchains, self.dim)
+        status = np.zeros(self.nchains, dtype=np.int32)
+        _check(load().nuts_init_state(self.h, p.h, _p(position), status.ctypes.data_as(_abi.c_i32_p)))
+        return p, status
+
+    def initialize_trajectory(self, point, resample, seed, chain_offset, counter):
+        _check(load().nuts_initialize_trajectory(self.h, point.h, int(resample), seed, chain_offset, counter))
+
+    def leapfrog(self, start, step_size, direction=None, energy_baseline=None, max_energy_error=1000.0, active=None, out=None):
+        out = out or Point(self)
+        keep, sp, sb = self._scal(step_size)
+        d8 = None if direction is None else np.ascontiguousarray(np.broadcast_to(direction, (self.nchains,)), dtype=np.int8)
+        base = None if energy_baseline is None else _f64(np.broadcast_to(energy_baseline, (self.nchains,)))
+        m, mp = self._mask(active)
+        status = np.zeros(self.nchains, dtype=np.int32)
+        ee = np.empty(self.nchains)
+        _check(load().nuts_leapfrog(self.h, start.h, out.h, sp, sb, None if d8 is None else d8.ctypes.data_as(_abi.c_i8_p), _p(base),
+                                    max_energy_error, mp, status.ctypes.data_as(_abi.c_i32_p), _p(ee)))
+        return out, status, ee
+
+    def is_turning(self, p1, p2):
+        out = np.zeros(self.nchains, dtype=np.uint8)
+        _check(load().nuts_is_turning(self.h, p1.h, p2.h, out.ctypes.data_as(_abi.c_u8_p)))
+        return out.astype(bool)
+
+    def synchronize(self):
+        _check(load().nuts_ctx_synchronize(self.h))
+
+    def close(self):
+        if self.h:
+            load().nuts_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        pass  # explicit close(); planes / points may outlive python GC order
+
+
+def alloc_stats(n_draws, nchains, names=None):
+    st = _abi.Stats()
+    arrays = {}
+    ftypes = dict(st._fields_)
+    for name, dt in _abi.STAT_DTYPES.items():
+        if names is not None and name not in names:
+            continue
+        a = np.zeros((n_draws, nchains), dtype=dt)
+        arrays[name] = a
+        setattr(st, name, a.ctypes.data_as(ftypes[name]))
+    return st, arrays
+
+
+class Sampler:
+    """All chains of one GPU: `settings.new_chain(...)` + `Chain::set_position` / `Chain::draw` for each of them."""
+
+    def __init__(self, math, settings, seed, chain_id_offset=0):
+        self.math = math
+        self.nchains, self.dim = math.nchains, math.dim
+        self.settings = settings
+        h = C.c_void_p()
+        _check(load().nuts_sampler_create(math.h, C.byref(h), C.byref(settings), seed, chain_id_offset))
+        self.h = h
+
+    def set_position(self, position):
+        position = _f64(position).reshape(self.nchains, self.dim)
+        status = np.zeros(self.nchains, dtype=np.int32)
+        _check(load().nuts_set_position(self.h, _p(position), status.ctypes.data_as(_abi.c_i32_p)))
+        return status
+
+    def draw(self, n_draws, want_draws=True, stats=True, out=None):
+        draws = None
+        if want_draws:
+            draws = out if out is not None else np.empty((n_draws, self.nchains, self.dim))
+        st, arrays = (alloc_stats(n_draws, self.nchains) if stats else (None, {}))
+        _check(load().nuts_draw(self.h, n_draws, _p(draws), C.byref(st) if stats else None))
+        return draws, arrays
+
+    def draw_device(self, n_draws, draws_dev_ptr=None):
+        _check(load().nuts_draw_device(self.h, n_draws, draws_dev_ptr))
+
+    def counters(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(load().nuts_sampler_counters(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def last_timing(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _check(load().nuts_sampler_last_timing(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def state(self):
+        N, d = self.nchains, self.dim
+        pos, eps, stds, mean = np.empty((N, d)), np.empty(N), np.empty((N, d)), np.empty((N, d))
+        ctr = np.empty(N, dtype=np.uint64)
+        _check(load().nuts_sampler_get_state(self.h, _p(pos), _p(eps), _p(stds), _p(mean), ctr.ctypes.data_as(_abi.c_u64_p)))
+        return dict(position=pos, step_size=eps, stds=stds, mean=mean, rng_counter=ctr)
+
+    def set_step_size(self, eps):
+        eps = _f64(np.broadcast_to(eps, (self.nchains,)))
+        _check(load().nuts_sampler_set_step_size(self.h, _p(eps)))
+
+    def close(self):
+        if self.h:
+            load().nuts_sampler_destroy(self.h)
+            self.h = None

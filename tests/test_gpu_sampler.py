@@ -1,0 +1,200 @@
+"""GPU parity, Tier 3: whole draws (Chain::set_position + n x Chain::draw incl. adaptation) of the register-resident
+engine against the CPU oracle on the same seeds, through nuts_set_position / nuts_draw.
+
+Tolerance: 1e-9 relative on every draw and float statistic (BASELINE.json north_star), with tree depth, number of
+leapfrogs, divergence flags and index_in_trajectory identical.  Each dimension below selects a different
+(threads-per-chain, elements-per-thread) instantiation of the engine."""
+import numpy as np
+import pytest
+
+from nuts_rs_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def L():
+    from nuts_rs_b200 import lib
+
+    assert lib.device_available(), lib.load().nuts_last_error()
+    return lib
+
+
+def _settings(L, **kw):
+    step = kw.pop("step", None)
+    s = L.DiagNutsSettings(**kw)
+    if step is not None:
+        ss = s.adapt_options.step_size_settings
+        for k, v in step.items():
+            obj = ss
+            parts = k.split(".")
+            for p in parts[:-1]:
+                obj = getattr(obj, p)
+            setattr(obj, parts[-1], v)
+    return s
+
+
+def _model_kwargs(kind, d):
+    if kind == _abi.NUTS_LOGP_GAUSS_ISO:
+        return dict(mu=3.0)
+    if kind == _abi.NUTS_LOGP_GAUSS_DIAG:
+        return dict(mu=0.5, sigma=np.exp(np.linspace(-1, 1, d)))
+    if kind == _abi.NUTS_LOGP_GAUSS_RANK1:
+        return dict(mu=0.0, rank1_scale=0.5)
+    return dict(funnel_scale=3.0)
+
+
+def compare_run(L, orc, kind, N, d, settings, n_draws, seed=42, x0=None, chain_offset=0, rtol=RTOL, prefix_only=False):
+    kw = _model_kwargs(kind, d)
+    if x0 is None:
+        x0 = np.random.default_rng(seed).normal(size=(N, d))
+    math = L.CudaMath(N, d, kind, **kw)
+    s = L.Sampler(math, settings, seed=seed, chain_id_offset=chain_offset)
+    st = s.set_position(x0)
+    om = orc.Model(kind, d, **kw)
+    osamp = orc.Sampler(om, settings, seed=seed, nchains=N, chain_id_offset=chain_offset, nthreads=8)
+    ost = osamp.set_position(x0)
+    np.testing.assert_array_equal(st, ost)
+    g0, o0 = s.state(), osamp.state()
+    np.testing.assert_allclose(g0["step_size"], o0["step_size"], rtol=rtol)
+    np.testing.assert_allclose(g0["stds"], o0["stds"], rtol=rtol)
+    np.testing.assert_allclose(g0["mean"], o0["mean"], rtol=rtol, atol=1e-300)
+    np.testing.assert_array_equal(g0["rng_counter"], o0["rng_counter"])
+    draws, stats = s.draw(n_draws)
+    odraws, ostats = osamp.draw(n_draws)
+    alive = st == 0
+    n_cmp = n_draws
+    if prefix_only:
+        # chaotic targets: compare the longest common prefix of identical tree shapes, require it to be substantial
+        same = (stats["n_steps"] == ostats["n_steps"])[:, alive].all(axis=1)
+        n_cmp = int(np.argmin(same)) if not same.all() else n_draws
+        assert n_cmp >= prefix_only, f"trajectories decorrelated after {n_cmp} draws"
+    sl = slice(0, n_cmp)
+    for name in ("depth", "n_steps", "diverging", "maxdepth_reached", "index_in_trajectory", "tuning"):
+        np.testing.assert_array_equal(stats[name][sl][:, alive], ostats[name][sl][:, alive], err_msg=name)
+    scale = np.maximum(1.0, np.abs(odraws[sl][:, alive]))
+    err = np.max(np.abs(draws[sl][:, alive] - odraws[sl][:, alive]) / scale)
+    assert err < rtol, f"draws differ: {err}"
+    for name in ("logp", "energy", "energy_error", "step_size", "step_size_bar", "mean_tree_accept", "mean_tree_accept_sym",
+                 "max_energy_error"):
+        a, b = stats[name][sl][:, alive], ostats[name][sl][:, alive]
+        fin = np.isfinite(b)
+        np.testing.assert_array_equal(np.isfinite(a), fin, err_msg=name)
+        tol = rtol * np.maximum(1.0, np.abs(b[fin]))
+        if name in ("energy_error", "max_energy_error"):
+            tol = tol * 1e3  # differences of O(d) energies
+        assert (np.abs(a[fin] - b[fin]) <= tol).all(), (name, np.max(np.abs(a[fin] - b[fin])))
+    # fisher_distance is a sum of squares of O(1) numbers
+    np.testing.assert_allclose(stats["fisher_distance"][sl][:, alive], ostats["fisher_distance"][sl][:, alive], rtol=1e-6, atol=1e-9)
+    g1, o1 = s.state(), osamp.state()
+    if n_cmp == n_draws:
+        np.testing.assert_array_equal(g1["rng_counter"][alive], o1["rng_counter"][alive])
+        np.testing.assert_allclose(g1["stds"][alive], o1["stds"][alive], rtol=1e-8)
+    total, done = s.counters()
+    assert done == n_draws
+    s.close()
+    math.close()
+    return stats, ostats
+
+
+def test_c1_reference_bench_shape(L, orc):
+    """BASELINE config 1: 10-dim isotropic Gaussian, 4 chains, maxdepth=3, num_tune=1000, start 3.5 (benches/sample.rs:76-98)."""
+    s = _settings(L, num_tune=1000, maxdepth=3)
+    compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_ISO, 4, 10, s, 1000, x0=np.full((4, 10), 3.5))
+
+
+def test_c1_default_depth_with_adaptation(L, orc):
+    s = _settings(L, num_tune=300)
+    stats, _ = compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_ISO, 6, 10, s, 500)
+    assert not stats["tuning"][300:].any() and stats["tuning"][:300].all()
+
+
+@pytest.mark.parametrize("d,N,draws", [(1, 4, 60), (2, 4, 60), (33, 5, 60), (64, 3, 60), (100, 6, 80), (129, 3, 60), (256, 3, 60),
+                                       (400, 3, 50), (1000, 4, 50), (1025, 2, 40), (2048, 2, 30), (3000, 2, 30), (5000, 2, 24),
+                                       (10000, 2, 20), (12000, 2, 16)])
+def test_every_engine_configuration_diag_gaussian(L, orc, d, N, draws):
+    """One run per register-tiling of the engine (32x1 ... 1024x16), diagonal Gaussian with warmup inside the run."""
+    s = _settings(L, num_tune=draws // 2, maxdepth=6)
+    compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_DIAG, N, d, s, draws, seed=d)
+
+
+@pytest.mark.parametrize("kind", [_abi.NUTS_LOGP_GAUSS_RANK1, _abi.NUTS_LOGP_GAUSS_ISO])
+def test_rank1_and_iso_100d(L, orc, kind):
+    s = _settings(L, num_tune=100, maxdepth=8)
+    compare_run(L, orc, kind, 8, 100, s, 160, seed=3)
+
+
+def test_funnel_divergences_match(L, orc):
+    """Neal's funnel: divergences, depth spread and the energy-error divergence test (chaotic target => prefix compare)."""
+    s = _settings(L, num_tune=100, maxdepth=8)
+    stats, ostats = compare_run(L, orc, _abi.NUTS_LOGP_FUNNEL, 16, 10, s, 200, seed=5, prefix_only=30, rtol=1e-7)
+    assert stats["diverging"].sum() > 0
+
+
+def test_fixed_step_no_turn_checks_exact_leapfrog_count(L, orc):
+    """mindepth = maxdepth disables the U-turn checks: exactly 2^maxdepth - 1 leapfrogs per draw, fixed step, no jitter."""
+    s = _settings(L, num_tune=0, maxdepth=5, mindepth=5,
+                  step={"adapt_options.method": _abi.NUTS_STEPSIZE_FIXED, "adapt_options.fixed_step": 0.05, "has_jitter": 0})
+    stats, _ = compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_DIAG, 8, 50, s, 40, seed=8)
+    assert (stats["n_steps"] == 31).all() and (stats["depth"] == 5).all() and stats["maxdepth_reached"].all()
+    assert (stats["step_size"] == 0.05).all()
+
+
+def test_extra_doublings_and_target_time(L, orc):
+    s = _settings(L, num_tune=40, maxdepth=6, extra_doublings=1)
+    compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_ISO, 4, 20, s, 80, seed=9)
+    s = _settings(L, num_tune=40, maxdepth=7, has_target_integration_time=1, target_integration_time=3.0)
+    compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_ISO, 4, 20, s, 80, seed=10)
+
+
+def test_draw_variance_estimator_option(L, orc):
+    s = _settings(L, num_tune=80, maxdepth=6)
+    s.adapt_options.mass_matrix_options.use_grad_based_estimate = 0
+    compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_DIAG, 4, 30, s, 120, seed=11)
+
+
+def test_bad_initial_points_are_reported_and_skipped(L, orc):
+    N, d = 4, 10
+    x0 = np.random.default_rng(0).normal(size=(N, d))
+    x0[1, 3] = np.nan
+    x0[2, :] = 3.0  # exactly at the mode: zero gradient => BadInitGrad (reference transformed_hamiltonian.rs:314)
+    s = _settings(L, num_tune=20, maxdepth=4)
+    math = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_ISO, mu=3.0)
+    samp = L.Sampler(math, s, seed=1)
+    st = samp.set_position(x0)
+    om = orc.Model(_abi.NUTS_LOGP_GAUSS_ISO, d, mu=3.0)
+    osamp = orc.Sampler(om, s, seed=1, nchains=N)
+    np.testing.assert_array_equal(st, osamp.set_position(x0))
+    np.testing.assert_array_equal(st, [0, 3, 3, 0])
+    draws, stats = samp.draw(10)
+    odraws, _ = osamp.draw(10)
+    assert np.isnan(draws[:, 1]).all() and np.isnan(draws[:, 2]).all()
+    np.testing.assert_allclose(draws[:, [0, 3]], odraws[:, [0, 3]], rtol=1e-9)
+    samp.close()
+    math.close()
+
+
+def test_chain_offset_invariance_and_split_draw_calls(L, orc):
+    """Streams are keyed by the GLOBAL chain id (reference set_stream(chain_id+1), src/sampler.rs:1106): a shard that starts
+    at chain_id_offset=k reproduces chains k.. of the unsharded run; and draw(a)+draw(b) == draw(a+b)."""
+    N, d = 6, 20
+    s = _settings(L, num_tune=30, maxdepth=5)
+    x0 = np.random.default_rng(1).normal(size=(N, d))
+    kw = _model_kwargs(_abi.NUTS_LOGP_GAUSS_DIAG, d)
+    m_all = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_DIAG, **kw)
+    s_all = L.Sampler(m_all, s, seed=77)
+    s_all.set_position(x0)
+    d_all, st_all = s_all.draw(50)
+    m_sh = L.CudaMath(3, d, _abi.NUTS_LOGP_GAUSS_DIAG, **kw)
+    s_sh = L.Sampler(m_sh, s, seed=77, chain_id_offset=3)
+    s_sh.set_position(x0[3:])
+    d1, st1 = s_sh.draw(20)
+    d2, st2 = s_sh.draw(30)
+    np.testing.assert_array_equal(np.concatenate([d1, d2]), d_all[:, 3:])
+    np.testing.assert_array_equal(np.concatenate([st1["n_steps"], st2["n_steps"]]), st_all["n_steps"][:, 3:])
+    for x in (s_all, s_sh):
+        x.close()
+    for x in (m_all, m_sh):
+        x.close()
