@@ -476,7 +476,7 @@ struct Engine {
       int s = alloc_slot();
       store(slot_ptr(s, 0), z);
       store(slot_ptr(s, 1), v);
-      rc[s] = 2;  // roles: first-of-B, draw-of-B
+      rc[s] = 3;  // roles: first-of-B, draw-of-B, last-of-B (the newest leaf)
       B_first = s;
       B_draw = s;
       B_ls = -energy_error;
@@ -510,8 +510,7 @@ struct Engine {
       }
       if (i + 1 < nleaf) {
         A_first[t] = (signed char)B_first;
-        A_last[t] = (signed char)s;
-        ref(s);
+        A_last[t] = (signed char)s;  // the last-of-B reference moves to the pending sub-tree
         A_ls[t] = B_ls;
         A_draw[t] = (signed char)B_draw;
         A_draw_energy[t] = B_draw_energy;

@@ -231,6 +231,9 @@ def test_leapfrog_parity(L, orc, name, spec, d):
     N = 3
     kw = _model_kwargs(spec, d)
     kind = kw.pop("kind")
+    # the funnel gradient of x0 cancels O(d) terms (-(d-1)/2 + exp(-v)*S/2): summation-order noise is amplified, so it gets
+    # the north-star trajectory tolerance (1e-9); the Gaussian targets stay at 1e-11
+    tol = 1e-9 if name == "funnel" else 1e-11
     rng = np.random.default_rng(7 * d)
     m = L.CudaMath(N, d, kind, **kw)
     stds, mean = np.exp(0.3 * rng.normal(size=(N, d))), 0.1 * rng.normal(size=(N, d))
@@ -258,12 +261,12 @@ def test_leapfrog_parity(L, orc, name, spec, d):
                 onxt, ost2, oee = h.leapfrog(ocur, eps[c], direction)
                 assert st[c] == ost2
                 for which in range(5):
-                    assert rel_err(nxt.vec(which)[c], onxt.vec(which)) < 1e-11, (which, step)
+                    assert rel_err(nxt.vec(which)[c], onxt.vec(which)) < tol, (which, step)
                 s1, s2 = nxt.scalars(), onxt.scalars()
                 assert s1["index_in_trajectory"][c] == s2["index_in_trajectory"] == direction * (step + 1)
                 for key in ("logp", "kinetic_energy", "logdet", "initial_energy"):
-                    assert abs(s1[key][c] - s2[key]) <= 1e-11 * max(1.0, abs(s2[key])), key
-                assert abs(ee[c] - oee) <= 1e-9 * max(1.0, abs(oee))
+                    assert abs(s1[key][c] - s2[key]) <= tol * max(1.0, abs(s2[key])), key
+                assert abs(ee[c] - oee) <= 1e-9 * max(1.0, abs(oee), abs(s2["initial_energy"]))
                 # is_turning agrees for (start, current)
                 assert m.is_turning(p, nxt)[c] == h.is_turning(op, onxt)
                 cur, ocur = nxt, onxt
