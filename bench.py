@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — leapfrog-steps/sec of the many-chain NUTS hot path on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[1] — 1000-dim diagonal Gaussian (sigma_i = exp(lin(-1,1)), mu = 0.5),
+1024 chains per GPU, maxdepth = 10, DiagNutsSettings defaults (num_tune = 400), seed 42, x0 ~ N(0,1).
+Setup (untimed): nuts_set_position + the 400 tuning draws.  A "step" = one nuts_draw call of DRAWS_PER_STEP post-warmup
+draws for every chain.  `value` = leapfrogs / device time of the draw kernel with the draws written to an HBM buffer;
+`e2e` = the same steps through nuts_draw with pinned HOST buffers (D2H of every draw + all sampler statistics inside the
+timed region; the chain state is resident between calls exactly like the reference's Chain, so there is no per-step H2D).
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1, one rank per GPU, weak scaling)
+  python bench.py --impl reference ...                     (the CPU oracle = C++ restatement of nuts-rs on all host cores)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM = 1000
+CHAINS_PER_GPU = 1024
+MAXDEPTH = 10
+NUM_TUNE = 400
+SEED = 42
+DRAWS_PER_STEP = 10
+METRIC = "leapfrog-steps/sec (all chains)"
+UNIT = "leapfrog-steps/s"
+WORKLOAD = "configs[1]: 1000-dim diagonal Gaussian, 1024 chains per GPU, maxdepth=10, num_tune=400 (untimed), post-warmup draws"
+
+
+def model_sigma():
+    return np.exp(np.linspace(-1.0, 1.0, DIM))
+
+
+def initial_positions(nchains, chain_offset):
+    # one stream of N(0,1) rows keyed by the global chain id, so shards of a multi-GPU run see the rows of the unsharded run
+    rng = np.random.default_rng(SEED)
+    x = rng.normal(size=(chain_offset + nchains, DIM))
+    return np.ascontiguousarray(x[chain_offset:])
+
+
+def settings():
+    from nuts_rs_b200 import _abi
+
+    s = _abi.default_settings()
+    s.num_tune = NUM_TUNE
+    s.maxdepth = MAXDEPTH
+    s.seed = SEED
+    return s
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index):
+        self.rows = []
+        self.stop = False
+        self.idx = device_index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                              timeout=5).decode().strip()
+                self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows),
+                "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def cpu_oracle_throughput(max_seconds, nthreads):
+    """The oracle (C++ restatement of nuts-rs's CPU path, one chain per thread like the reference's rayon pool,
+    src/sampler.rs:1287-1326) on a bounded sample of the same workload: `4 x cores` chains, 400 tuning draws (untimed),
+    then post-warmup draws for ~max_seconds."""
+    from nuts_rs_b200 import _abi
+    from oracle import oracle as O
+
+    nchains = 4 * nthreads
+    model = O.Model(_abi.NUTS_LOGP_GAUSS_DIAG, DIM, mu=0.5, sigma=model_sigma())
+    samp = O.Sampler(model, settings(), seed=SEED, nchains=nchains, nthreads=nthreads)
+    st = samp.set_position(initial_positions(nchains, 0))
+    assert (st == 0).all()
+    samp.draw(NUM_TUNE, want_draws=False)
+    total, elapsed, ndraws = 0, 0.0, 0
+    block = 10
+    while elapsed < max_seconds:
+        t0 = time.perf_counter()
+        _, arr = samp.draw(block, want_draws=True)
+        elapsed += time.perf_counter() - t0
+        total += int(arr["n_steps"].sum())
+        ndraws += block
+    return {"value": total / elapsed, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": f"{nchains} chains x {ndraws} post-warmup draws of the same workload ({total} leapfrogs in {elapsed:.1f} s), "
+                      f"oracle built -O3 -march=native, one chain per thread"}, total, elapsed
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    nthreads = os.cpu_count() or 1
+    per_step_seconds = max(1.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    from nuts_rs_b200 import _abi
+    from oracle import oracle as O
+
+    nchains = 4 * nthreads
+    model = O.Model(_abi.NUTS_LOGP_GAUSS_DIAG, DIM, mu=0.5, sigma=model_sigma())
+    samp = O.Sampler(model, settings(), seed=SEED, nchains=nchains, nthreads=nthreads)
+    samp.set_position(initial_positions(nchains, 0))
+    samp.draw(NUM_TUNE, want_draws=False)
+    # size a step so that it lasts about per_step_seconds
+    t0 = time.perf_counter()
+    _, arr = samp.draw(2, want_draws=True)
+    dt = (time.perf_counter() - t0) / 2
+    draws_per_step = max(1, int(per_step_seconds / max(dt, 1e-6)))
+    for _ in range(args.warmup):
+        samp.draw(draws_per_step, want_draws=True)
+    total, t0 = 0, time.perf_counter()
+    for _ in range(args.steps):
+        _, arr = samp.draw(draws_per_step, want_draws=True)
+        total += int(arr["n_steps"].sum())
+    elapsed = time.perf_counter() - t0
+    value = total / elapsed
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU arm: nuts-rs itself cannot be built here (Rust, no cargo in the image); this is the C++ "
+                   "restatement of its CPU path (oracle/), one chain per host thread"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
+                         "sample": f"{nchains} chains x {draws_per_step} post-warmup draws per step, {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--draws-per-step", type=int, default=DRAWS_PER_STEP)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from nuts_rs_b200 import _abi, lib
+
+    if not lib.device_available():
+        raise SystemExit("bench.py: no sm_100 GPU / libnuts_b200.so not usable: " + lib.load().nuts_last_error().decode())
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dps = args.draws_per_step
+    N = CHAINS_PER_GPU
+    chain_offset = rank * N  # global chain id => RNG stream (reference set_stream(chain_id + 1)); weak scaling: 1024 chains per GPU
+
+    math = lib.CudaMath(N, DIM, _abi.NUTS_LOGP_GAUSS_DIAG, mu=0.5, sigma=model_sigma(), device=local_rank)
+    samp = lib.Sampler(math, settings(), seed=SEED, chain_id_offset=chain_offset)
+    x0 = initial_positions(N, chain_offset)
+    t0 = time.perf_counter()
+    status = samp.set_position(x0)
+    assert (status == 0).all()
+    samp.draw_device(NUM_TUNE)  # tuning phase, untimed
+    math.synchronize()
+    tune_wall = time.perf_counter() - t0
+    tune_ms, _ = samp.last_timing()
+    tune_leapfrogs, _ = samp.counters()
+
+    dev_draws = torch.empty((dps, N, DIM), dtype=torch.float64, device="cuda")
+    host_draws = torch.empty((dps, N, DIM), dtype=torch.float64).pin_memory().numpy()
+    stats_struct, stats_arrays = lib.alloc_stats(dps, N)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: `value`
+    for _ in range(args.warmup):
+        samp.draw_device(dps, dev_draws.data_ptr())
+    math.synchronize()
+    lf0, _ = samp.counters()
+    barrier()
+    kernel_ms, launches = 0.0, 0
+    with ClockSampler(local_rank) as clocks:
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            samp.draw_device(dps, dev_draws.data_ptr())
+            ms, n = samp.last_timing()  # CUDA events around the kernel on the launching stream (waits for the kernel)
+            kernel_ms += ms
+            launches += n
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - w0)
+    lf1, _ = samp.counters()
+    steps_dev = lf1 - lf0
+
+    # ---------------- end-to-end arm through nuts_draw with host buffers: `e2e`
+    import ctypes as C
+
+    def e2e_step():
+        lib._check(lib.load().nuts_draw(samp.h, dps, host_draws.ctypes.data_as(_abi.c_double_p), C.byref(stats_struct)))
+        return int(stats_arrays["n_steps"].sum())
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    steps_e2e = 0
+    for _ in range(args.steps):
+        steps_e2e += e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    d2h = host_draws.nbytes + sum(a.nbytes for a in stats_arrays.values())
+
+    # ---------------- reduce over ranks: max time, summed work
+    t = torch.tensor([kernel_ms, wall_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    w = torch.tensor([float(steps_dev), float(steps_e2e)], dtype=torch.float64, device="cuda")
+    gather_ms = None
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        # the only exchange of the path: gather the draws of the last step on every rank (NCCL over NVLink), timed on its own
+        out = [torch.empty_like(dev_draws) for _ in range(world)]
+        torch.cuda.synchronize()
+        g0 = torch.cuda.Event(enable_timing=True)
+        g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather(out, dev_draws)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+    kernel_ms_max, wall_ms_max, e2e_ms_max = (float(v) for v in t.tolist())
+    steps_dev_all, steps_e2e_all = (float(v) for v in w.tolist())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        value = steps_dev_all / (kernel_ms_max * 1e-3)
+        alg_bytes_per_step = 48 * DIM  # read z, v, grad_z + write z', v', grad_z' per leapfrog per chain
+        per_gpu_steps_per_launch = steps_dev / max(1, launches)
+        avg_launch_ms = kernel_ms / max(1, launches)
+        achieved = per_gpu_steps_per_launch * alg_bytes_per_step / (avg_launch_ms * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu, _, _ = cpu_oracle_throughput(args.cpu_seconds, os.cpu_count() or 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "chains_per_gpu": N, "dim": DIM, "draws_per_step": dps,
+                       "leapfrogs_per_step_all_gpus": steps_dev_all / args.steps,
+                       "cache": "inputs larger than L2: per-GPU checkpoint pool 1024 x 34 x 16 kB = 557 MB vs 126 MB L2; no flush between steps",
+                       "timing": "CUDA events around the draw kernel on the launching stream, summed over K steps, max over ranks",
+                       "wall_ms_per_step_incl_launch": wall_ms_max / args.steps,
+                       "tuning_phase": {"draws": NUM_TUNE, "kernel_ms": tune_ms, "wall_s": tune_wall, "leapfrogs": tune_leapfrogs,
+                                        "leapfrogs_per_s": tune_leapfrogs / max(tune_ms * 1e-3, 1e-9)}},
+            "e2e": {"value": steps_e2e_all / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
+                    "note": "nuts_draw with pinned host buffers: every draw [draws x chains x dim] f64 and all 15 statistics copied D2H inside "
+                            "the timed region; chain state stays resident between calls like the reference's Chain (initial positions: one "
+                            f"{x0.nbytes}-byte H2D in nuts_set_position, outside the steps)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_kind,
+                         "note": "achieved = leapfrogs per launch x 48*dim algorithmic bytes / launch duration; the engine keeps z, v, grad in "
+                                 "registers across leapfrogs, so algorithmic bytes are NOT DRAM bytes (frac > 1 is possible); see DESIGN.md"},
+            "cpu_baseline": cpu,
+        }
+        if gather_ms is not None:
+            line["config"]["nccl_all_gather_last_step_ms"] = gather_ms
+        print(json.dumps(line), flush=True)
+    samp.close()
+    math.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,20 +15,26 @@
 using namespace nb;
 
 // ---- per-configuration launchers (engine_inst.cu) ----
-#define NB_DECL(TPC, EPT)                                                                                  \
-  extern "C" cudaError_t nb_launch_chain_##TPC##_##EPT(const EngineParams* p, int grid, cudaStream_t s);   \
-  extern "C" cudaError_t nb_occupancy_chain_##TPC##_##EPT(int* blocks_per_sm, int* cta_threads);
-NB_DECL(32, 1)
-NB_DECL(32, 2)
-NB_DECL(32, 4)
-NB_DECL(64, 4)
-NB_DECL(128, 4)
-NB_DECL(128, 8)
-NB_DECL(256, 8)
-NB_DECL(512, 8)
-NB_DECL(1024, 8)
-NB_DECL(1024, 10)
-NB_DECL(1024, 16)
+#define NB_DECL(TPC, EPT, MINB)                                                                                     \
+  extern "C" cudaError_t nb_launch_chain_##TPC##_##EPT##_##MINB(const EngineParams* p, int grid, cudaStream_t s);   \
+  extern "C" cudaError_t nb_occupancy_chain_##TPC##_##EPT##_##MINB(int* blocks_per_sm, int* cta_threads);
+NB_DECL(32, 1, 16)
+NB_DECL(32, 2, 16)
+NB_DECL(32, 4, 16)
+NB_DECL(32, 8, 12)
+NB_DECL(32, 16, 8)
+NB_DECL(32, 32, 8)
+NB_DECL(64, 16, 4)
+NB_DECL(64, 16, 6)
+NB_DECL(64, 16, 7)
+NB_DECL(128, 8, 4)
+NB_DECL(128, 8, 5)
+NB_DECL(128, 8, 7)
+NB_DECL(256, 8, 2)
+NB_DECL(512, 8, 1)
+NB_DECL(1024, 8, 1)
+NB_DECL(1024, 10, 1)
+NB_DECL(1024, 16, 1)
 
 namespace {
 
@@ -50,14 +57,18 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 struct EngineConfig {
-  int tpc, ept, max_d;
+  int tpc, ept, minb, max_d;
   cudaError_t (*launch)(const EngineParams*, int, cudaStream_t);
   cudaError_t (*occupancy)(int*, int*);
 };
-#define NB_CFG(TPC, EPT) \
-  { TPC, EPT, TPC * EPT, nb_launch_chain_##TPC##_##EPT, nb_occupancy_chain_##TPC##_##EPT }
-const EngineConfig kConfigs[] = {NB_CFG(32, 1),  NB_CFG(32, 2),  NB_CFG(32, 4),   NB_CFG(64, 4),    NB_CFG(128, 4),  NB_CFG(128, 8),
-                                 NB_CFG(256, 8), NB_CFG(512, 8), NB_CFG(1024, 8), NB_CFG(1024, 10), NB_CFG(1024, 16)};
+#define NB_CFG(TPC, EPT, MINB) \
+  { TPC, EPT, MINB, TPC * EPT, nb_launch_chain_##TPC##_##EPT##_##MINB, nb_occupancy_chain_##TPC##_##EPT##_##MINB }
+// default choice: the first entry whose capacity (tpc*ept) covers dim.  Warp-per-chain up to dim 1024 (no barrier in
+// the whole kernel, all 1024 chains of config 2 resident at once); CTA-per-chain above.
+const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(128, 8, 4),
+                                 NB_CFG(256, 8, 2), NB_CFG(512, 8, 1), NB_CFG(1024, 8, 1), NB_CFG(1024, 10, 1), NB_CFG(1024, 16, 1)};
+// alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
+const EngineConfig kExtraConfigs[] = {NB_CFG(32, 32, 8), NB_CFG(64, 16, 4), NB_CFG(64, 16, 6), NB_CFG(64, 16, 7), NB_CFG(128, 8, 5), NB_CFG(128, 8, 7)};
 
 }  // namespace
 
@@ -642,11 +653,22 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
     return fail(NUTS_ERR_UNSUPPORTED, "maxdepth + extra_doublings must be <= %d", MAX_DOUBLING_DEPTH);
   if (st->adapt_options.mass_matrix_window_growth < 1.0) return fail(NUTS_ERR_INVALID, "mass_matrix_window_growth must be >= 1");
   const EngineConfig* cfg = nullptr;
-  for (const EngineConfig& c : kConfigs)
-    if ((uint64_t)c.max_d >= ctx->d) {
-      cfg = &c;
-      break;
+  if (const char* env = std::getenv("NUTS_B200_ENGINE")) {
+    int tpc = 0, ept = 0, minb = 0;
+    if (std::sscanf(env, "%d,%d,%d", &tpc, &ept, &minb) == 3) {
+      for (const EngineConfig& c : kConfigs)
+        if (c.tpc == tpc && c.ept == ept && c.minb == minb && (uint64_t)c.max_d >= ctx->d) cfg = &c;
+      for (const EngineConfig& c : kExtraConfigs)
+        if (c.tpc == tpc && c.ept == ept && c.minb == minb && (uint64_t)c.max_d >= ctx->d) cfg = &c;
+      if (!cfg) return fail(NUTS_ERR_INVALID, "NUTS_B200_ENGINE=%s is not a built configuration that covers dim %llu", env, (unsigned long long)ctx->d);
     }
+  }
+  if (!cfg)
+    for (const EngineConfig& c : kConfigs)
+      if ((uint64_t)c.max_d >= ctx->d) {
+        cfg = &c;
+        break;
+      }
   if (!cfg) return fail(NUTS_ERR_UNSUPPORTED, "dim %llu exceeds the largest register-resident configuration (16384)", (unsigned long long)ctx->d);
 
   nuts_sampler* s = new nuts_sampler();
@@ -716,6 +738,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   A((void**)&P.queue, sizeof(unsigned int));
   A((void**)&s->d_init, ctx->N * ctx->d * sizeof(double));
   A((void**)&s->d_status, ctx->N * sizeof(int));
+  A((void**)&P.phase_clocks, 8 * sizeof(unsigned long long));
   if (r != NUTS_OK) {
     nuts_sampler_destroy(s);
     return r;
@@ -945,6 +968,15 @@ int nuts_sampler_get_state(nuts_sampler_t* s, double* position, double* step_siz
       if (rng_counter) rng_counter[c] = cs[c].rng_counter;
     }
   }
+  return NUTS_OK;
+}
+
+// debug: per-phase clock totals of NB_PHASE_TIMING builds (zeros otherwise); resets the counters
+extern "C" int nuts_debug_phase_clocks(nuts_sampler_t* s, unsigned long long* out8) {
+  CUDA_TRY(cudaSetDevice(s->ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+  CUDA_TRY(cudaMemcpy(out8, s->P.phase_clocks, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(s->P.phase_clocks, 0, 8 * sizeof(unsigned long long)));
   return NUTS_OK;
 }
 

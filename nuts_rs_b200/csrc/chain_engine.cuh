@@ -104,11 +104,52 @@ struct EngineParams {
   double* draws_out;                // [n_draws][N][d] device (may be null)
   StatsDev stats;
   uint64_t stats_offset;            // unused draws before this call inside the stats arrays (always 0 for now)
+  unsigned long long* phase_clocks; // [8] debug phase timing (NB_PHASE_TIMING builds), else unused
 };
 
 enum { EXT_OK = 0, EXT_TURNING = 1, EXT_DIVERGING = 2 };
 
-template <int TPC, int EPT>
+// Optional phase timing (build with -DNB_PHASE_TIMING): per-phase clock64() totals of thread 0 of every team, added to
+// EngineParams::phase_clocks[8] at the end of a chain.  0 init_trajectory, 1 leapfrog, 2 leaf bookkeeping + checkpoint store,
+// 3 merges (turn checks), 4 doubling prologue/epilogue, 5 materialise, 6 adapt, 7 whole draw.
+#ifdef NB_PHASE_TIMING
+#define NB_T0(var) long long var = clock64()
+#define NB_ACC(k, var) do { long long _n = clock64(); phase[k] += _n - var; var = _n; } while (0)
+#else
+#define NB_T0(var)
+#define NB_ACC(k, var)
+#endif
+
+// The per-draw adaptation and Chain::set_position are COLD: they run in non-inlined functions on their own Engine
+// instance and exchange the chain scalars by value, so that the hot tree builder (run_draw -> extend -> leapfrog, all
+// force-inlined with one call site each) never has its address taken and its vectors really live in registers.
+struct ColdIO {
+  ChainState cs;
+  int parity;
+  int status;
+};
+template <int TPC, int EPT, bool MMS>
+__device__ __noinline__ ColdIO cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, ChainState cs,
+                                          int parity, double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error);
+template <int TPC, int EPT, bool MMS>
+__device__ __noinline__ ColdIO cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, ChainState cs);
+
+// Tree bookkeeping tables of one chain.  Warp teams keep them in shared memory (all lanes execute the same store with the
+// same value, then __syncwarp), CTA teams keep a private copy per thread in local memory (no extra barriers).
+struct TreeTables {
+  // pending sub-trees of the half under construction, one per level
+  double A_ls[MAX_DOUBLING_DEPTH], A_draw_energy[MAX_DOUBLING_DEPTH];
+  int A_draw_idx[MAX_DOUBLING_DEPTH];
+  signed char A_first[MAX_DOUBLING_DEPTH], A_last[MAX_DOUBLING_DEPTH], A_draw[MAX_DOUBLING_DEPTH];
+};
+
+// bytes of dynamic shared memory one team needs: [sigma | mean] (when MMS) followed by the TreeTables (warp teams)
+template <int TPC, int EPT, bool MMS>
+__host__ __device__ constexpr size_t team_smem_bytes() {
+  return (MMS ? 2 * (size_t)TPC * EPT * sizeof(double) : 0) + (TPC == 32 ? sizeof(TreeTables) : 0);
+}
+
+template <int TPC, int EPT, bool MMS>
 struct Engine {
   const EngineParams& P;
   const int chain;
@@ -119,7 +160,10 @@ struct Engine {
 
   // ---- register-resident vectors ----
   double z[EPT], v[EPT], g[EPT];  // current phase-space point (whitened position, velocity, whitened gradient)
-  double sig[EPT], mu[EPT];       // this chain's DiagMassMatrix: stds, mean
+  // this chain's DiagMassMatrix (stds, mean): registers, or shared memory when MMS (large EPT: registers go to z, v, g)
+  double sig[MMS ? 1 : EPT], mu[MMS ? 1 : EPT];
+  double *sm_sig, *sm_mu;
+  TreeTables& T;
 
   ChainState cs;
   uint64_t stream;
@@ -137,16 +181,38 @@ struct Engine {
   double draw_energy;
   int draw_idx;
 
-  // ---- pending sub-trees of the half under construction, one per level ----
-  double A_ls[MAX_DOUBLING_DEPTH], A_draw_energy[MAX_DOUBLING_DEPTH];
-  int A_draw_idx[MAX_DOUBLING_DEPTH];
-  signed char A_first[MAX_DOUBLING_DEPTH], A_last[MAX_DOUBLING_DEPTH], A_draw[MAX_DOUBLING_DEPTH];
-  unsigned char rc[MAX_SLOTS];
-  uint64_t free_mask;
+  // checkpoint pool: free-slot mask and 2-bit reference counts (first / last / draw roles => at most 3), all in registers
+  uint64_t free_mask, rc_lo, rc_hi;
+#ifdef NB_PHASE_TIMING
+  long long phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
-  __device__ Engine(const EngineParams& p, int chain_, int tid_, double* scratch)
-      : P(p), chain(chain_), tid(tid_), red(scratch), d(p.d), row((size_t)chain_ * p.ld) {
+  // team_smem: this team's slice of dynamic shared memory (team_smem_bytes()); tables: where the TreeTables live
+  __device__ __forceinline__ Engine(const EngineParams& p, int chain_, int tid_, double* scratch, double* team_smem, TreeTables& tables)
+      : P(p), chain(chain_), tid(tid_), red(scratch), d(p.d), row((size_t)chain_ * p.ld), sm_sig(team_smem),
+        sm_mu(team_smem + (MMS ? TPC * EPT : 0)), T(tables) {
     stream = p.chain_offset + (uint64_t)chain_ + 1;  // reference src/sampler.rs:1106 set_stream(chain_id + 1)
+  }
+  __device__ __forceinline__ double sg(int j) const { return MMS ? sm_sig[tid + j * TPC] : sig[MMS ? 0 : j]; }
+  __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[tid + j * TPC] : mu[MMS ? 0 : j]; }
+  // make table stores visible to the other lanes of a warp team (CTA teams use private tables)
+  __device__ __forceinline__ void tsync() const {
+    if (TPC == 32) __syncwarp();
+  }
+  // checkpoint traffic bypasses L1 (ld.cg / st.cg): it is streamed once, L1 is kept for the model parameters and tables
+  __device__ __forceinline__ void load_cg(const double* __restrict__ src, double (&a)[EPT]) const {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      a[j] = i < d ? __ldcg(src + i) : 0.0;
+    }
+  }
+  __device__ __forceinline__ void store_cg(double* __restrict__ dst, const double (&a)[EPT]) const {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      if (i < d) __stcg(dst + i, a[j]);
+    }
   }
 
   // ------------------------------------------------------------------ vector helpers
@@ -199,7 +265,7 @@ struct Engine {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = tid + j * TPC;
-        if (i < d) s[0] += x[j] - m.mu[i];
+        if (i < d) s[0] += x[j] - __ldg(m.mu + i);
       }
       red.allreduce(s);
       a0 = m.rank1_coeff * s[0];  // rank1_term
@@ -229,7 +295,7 @@ struct Engine {
         int i = tid + j * TPC;
         gx[j] = 0.0;
         if (i < d) {
-          double diff = x[j] - m.mu[i];
+          double diff = x[j] - __ldg(m.mu + i);
           lp -= diff * diff / 2.;
           gx[j] = -diff;
         }
@@ -240,8 +306,8 @@ struct Engine {
         int i = tid + j * TPC;
         gx[j] = 0.0;
         if (i < d) {
-          double diff = x[j] - m.mu[i];
-          double pd = diff * m.prec[i];
+          double diff = x[j] - __ldg(m.mu + i);
+          double pd = diff * __ldg(m.prec + i);
           lp -= diff * pd / 2.;
           gx[j] = -pd;
         }
@@ -252,7 +318,7 @@ struct Engine {
         int i = tid + j * TPC;
         gx[j] = 0.0;
         if (i < d) {
-          double diff = x[j] - m.mu[i];
+          double diff = x[j] - __ldg(m.mu + i);
           double ptd = diff - a0;
           gx[j] = -ptd;
           lp -= 0.5 * diff * ptd;
@@ -295,8 +361,8 @@ struct Engine {
     for (int j = 0; j < EPT; ++j) {
       v[j] = fma(eps_half, g[j], v[j]);  // first_velocity_halfstep :178-184  axpy_out(grad, v, eps/2)
       z[j] = fma(eps, v[j], z[j]);       // position_step :220-225            axpy_out(v', z, eps)
-      double t = z[j] * sig[j];          // compute_untransformed_position    diagonal.rs:253-255  multiply, then axpy(mean, x, 1)
-      x[j] = fma(1.0, mu[j], t);
+      double t = z[j] * sg(j);          // compute_untransformed_position    diagonal.rs:253-255  multiply, then axpy(mean, x, 1)
+      x[j] = fma(1.0, mn(j), t);
     }
     double a0, a1, ev;
     model_phase_a(x, a0, a1);
@@ -305,7 +371,7 @@ struct Engine {
     part[1] = 0.0;
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      g[j] = gx[j] * sig[j];             // compute_transformed_gradient      diagonal.rs:258-265
+      g[j] = gx[j] * sg(j);             // compute_transformed_gradient      diagonal.rs:258-265
       v[j] = fma(eps_half, g[j], v[j]);  // second_velocity_halfstep :245-247 axpy(grad', v, eps/2)
       part[1] = fma(v[j], v[j], part[1]);  // update_kinetic_energy :260-262
     }
@@ -326,8 +392,22 @@ struct Engine {
   }
 
   __device__ __forceinline__ void load_mass_matrix() {
-    load(P.stds + row, sig);
-    load(P.mean + row, mu);
+    if (MMS) {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        sm_sig[i] = i < d ? P.stds[row + i] : 0.0;
+        sm_mu[i] = i < d ? P.mean[row + i] : 0.0;
+      }
+      // each thread only ever reads back the entries it wrote itself: no barrier needed
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        sig[MMS ? 0 : j] = i < d ? P.stds[row + i] : 0.0;
+        mu[MMS ? 0 : j] = i < d ? P.mean[row + i] : 0.0;
+      }
+    }
   }
 
   // compute_transformed_position / _gradient (diagonal.rs:233-246, 258-265) of the chain point from the x, gx planes
@@ -341,9 +421,9 @@ struct Engine {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
       int i = tid + j * TPC;
-      double t = fma(-1.0, mu[j], x[j]);  // axpy_out(mean, x, -1)
+      double t = fma(-1.0, mn(j), x[j]);  // axpy_out(mean, x, -1)
       z[j] = is[j] * t;                   // multiply_inplace(z, inv_stds): out = x*out
-      g[j] = gx[j] * sig[j];
+      g[j] = gx[j] * sg(j);
       if (i < d) {
         bool ok = isfinite(z[j]) && isfinite(g[j]) && (g[j] != 0.0) && isfinite(gx[j]) && isfinite(x[j]);
         if (!ok) bad[0] = 1.0;
@@ -359,16 +439,20 @@ struct Engine {
   }
 
   // ------------------------------------------------------------------ slot pool
+  __device__ __forceinline__ int rc_get(int s) const { return (int)(((s < 32 ? rc_lo : rc_hi) >> (2 * (s & 31))) & 3ull); }
+  __device__ __forceinline__ void rc_add(int s, int delta) {
+    const uint64_t inc = (uint64_t)(long long)delta << (2 * (s & 31));  // two's complement add on the 2-bit field
+    if (s < 32) rc_lo += inc;
+    else rc_hi += inc;
+  }
   __device__ __forceinline__ int alloc_slot() {
     int s = __ffsll((long long)free_mask) - 1;
     free_mask &= ~(1ull << s);
-    rc[s] = 0;
-    return s;
+    return s;  // its count is 0
   }
-  __device__ __forceinline__ void ref(int s) { rc[s] += 1; }
   __device__ __forceinline__ void unref(int s) {
-    rc[s] -= 1;
-    if (rc[s] == 0) free_mask |= (1ull << s);
+    rc_add(s, -1);
+    if (rc_get(s) == 0) free_mask |= (1ull << s);
   }
 
   // ------------------------------------------------------------------ U-turn products (is_turning :617-638 -> scalar_prods3)
@@ -387,8 +471,8 @@ struct Engine {
       for (int j = 0; j < EPT; ++j) {
         int i = tid + j * TPC;
         if (i < d) {
-          double delta = (z[j] + 0.0) - Afz[i];
-          s[0] = fma(delta, Afv[i], s[0]);
+          double delta = (z[j] + 0.0) - __ldcg(Afz + i);
+          s[0] = fma(delta, __ldcg(Afv + i), s[0]);
           s[1] = fma(delta, v[j], s[1]);
         }
       }
@@ -400,7 +484,8 @@ struct Engine {
     for (int j = 0; j < EPT; ++j) {
       int i = tid + j * TPC;
       if (i < d) {
-        double afz = Afz[i], afv = Afv[i], alz = Alz[i], alv = Alv[i], bfz = Bfz[i], bfv = Bfv[i];
+        double afz = __ldcg(Afz + i), afv = __ldcg(Afv + i), alz = __ldcg(Alz + i), alv = __ldcg(Alv + i), bfz = __ldcg(Bfz + i),
+               bfv = __ldcg(Bfv + i);
         double d1 = (z[j] + 0.0) - afz;
         s[0] = fma(d1, afv, s[0]);
         s[1] = fma(d1, v[j], s[1]);
@@ -436,15 +521,17 @@ struct Engine {
   // of (A = earlier built, B = later built) checks the span (A.first, B.last) and, when A.depth > 0, (A.last, B.last)
   // and (A.first, B.first) (nuts.rs:143-161), and ALWAYS runs merge_into before the verdict (nuts.rs:163-169), which
   // is also the reference's RNG order.  An inner Turning / Diverging discards the whole half (nuts.rs:131-136).
-  __device__ int extend(int dir, bool check) {
+  __device__ __forceinline__ int extend(int dir, bool check) {
+    NB_T0(tq);
     const int D = depth;
     const uint32_t nleaf = 1u << D;
     const double eps = dir ? cs.step_size : -cs.step_size;
     const int sign = dir ? 1 : -1;
     free_mask = P.P >= 64 ? ~0ull : ((1ull << P.P) - 1ull);
+    rc_lo = rc_hi = 0;
     if (draw_slot >= 0) {
       free_mask &= ~(1ull << draw_slot);
-      rc[draw_slot] = 1;
+      rc_add(draw_slot, 1);
     }
     // start state = the end of the main tree in direction dir
     const double* nearZ = end_is_init[dir] ? P.z + row : end_ptr(dir, 0);
@@ -452,9 +539,9 @@ struct Engine {
     const double* farZ = end_is_init[1 - dir] ? P.z + row : end_ptr(1 - dir, 0);
     const double* farV = end_is_init[1 - dir] ? P.v0 + row : end_ptr(1 - dir, 1);
     if (!reg_holds[dir]) {
-      load(nearZ, z);
-      load(nearV, v);
-      load(end_is_init[dir] ? P.gz + row : end_ptr(dir, 2), g);
+      load_cg(nearZ, z);
+      load_cg(nearV, v);
+      load_cg(end_is_init[dir] ? P.gz + row : end_ptr(dir, 2), g);
     }
     reg_holds[0] = reg_holds[1] = false;
     int idx_cur = idx_end[dir];
@@ -465,7 +552,9 @@ struct Engine {
     for (uint32_t i = 0; i < nleaf; ++i) {
       // single_step (nuts.rs:209-245): one leapfrog from the previous leaf; baseline = initial energy
       double logp_new, ke_new;
+      NB_ACC(4, tq);
       leapfrog(eps, logp_new, ke_new);
+      NB_ACC(1, tq);
       cs.tree_leapfrogs += 1;
       double energy = ke_new - (logp_new + cs.pt_logdet);
       double energy_error = energy - E0;
@@ -474,9 +563,9 @@ struct Engine {
       if (divergent) return EXT_DIVERGING;
       idx_cur += sign;
       int s = alloc_slot();
-      store(slot_ptr(s, 0), z);
-      store(slot_ptr(s, 1), v);
-      rc[s] = 3;  // roles: first-of-B, draw-of-B, last-of-B (the newest leaf)
+      store_cg(slot_ptr(s, 0), z);
+      store_cg(slot_ptr(s, 1), v);
+      rc_add(s, 3);  // roles: first-of-B, draw-of-B, last-of-B (the newest leaf)
       B_first = s;
       B_draw = s;
       B_ls = -energy_error;
@@ -484,23 +573,24 @@ struct Engine {
       B_draw_idx = idx_cur;
       int t = __ffs(~i) - 1;  // trailing ones of i
       if (t > D) t = D;
+      NB_ACC(2, tq);
       for (int l = 0; l < t; ++l) {
-        const int Af = A_first[l], Al = A_last[l];
+        const int Af = T.A_first[l], Al = T.A_last[l];
         bool turning = false;
         if (check) {
           turning = merge_turning(slot_ptr(Af, 0), slot_ptr(Af, 1), slot_ptr(Al, 0), slot_ptr(Al, 1), slot_ptr(B_first, 0),
                                   slot_ptr(B_first, 1), l > 0, dir);
         }
         // merge_into, non-main (nuts.rs:172-207): self_log_size = log_size of the merged tree
-        double total = logaddexp(A_ls[l], B_ls);
+        double total = logaddexp(T.A_ls[l], B_ls);
         bool take_B = (B_ls >= total) || (rng_f64() < exp(B_ls - total));
         if (take_B) {
-          unref(A_draw[l]);
+          unref(T.A_draw[l]);
         } else {
           unref(B_draw);
-          B_draw = A_draw[l];
-          B_draw_energy = A_draw_energy[l];
-          B_draw_idx = A_draw_idx[l];
+          B_draw = T.A_draw[l];
+          B_draw_energy = T.A_draw_energy[l];
+          B_draw_idx = T.A_draw_idx[l];
         }
         unref(B_first);
         B_first = Af;
@@ -508,13 +598,15 @@ struct Engine {
         B_ls = total;
         if (turning) return EXT_TURNING;  // inner turn: the old tree is returned unchanged (nuts.rs:131-133)
       }
+      NB_ACC(3, tq);
       if (i + 1 < nleaf) {
-        A_first[t] = (signed char)B_first;
-        A_last[t] = (signed char)s;  // the last-of-B reference moves to the pending sub-tree
-        A_ls[t] = B_ls;
-        A_draw[t] = (signed char)B_draw;
-        A_draw_energy[t] = B_draw_energy;
-        A_draw_idx[t] = B_draw_idx;
+        T.A_first[t] = (signed char)B_first;
+        T.A_last[t] = (signed char)s;  // the last-of-B reference moves to the pending sub-tree
+        T.A_ls[t] = B_ls;
+        T.A_draw[t] = (signed char)B_draw;
+        T.A_draw_energy[t] = B_draw_energy;
+        T.A_draw_idx[t] = B_draw_idx;
+        tsync();
       }
     }
     // top-level merge of the main tree (A) with the finished half (B)
@@ -531,12 +623,13 @@ struct Engine {
     }
     ls_main = total;
     depth += 1;
-    store(end_ptr(dir, 0), z);
-    store(end_ptr(dir, 1), v);
-    store(end_ptr(dir, 2), g);
+    store_cg(end_ptr(dir, 0), z);
+    store_cg(end_ptr(dir, 1), v);
+    store_cg(end_ptr(dir, 2), g);
     idx_end[dir] = idx_cur;
     end_is_init[dir] = false;
     reg_holds[dir] = true;
+    NB_ACC(4, tq);
     return turning ? EXT_TURNING : EXT_OK;
   }
 
@@ -574,7 +667,7 @@ struct Engine {
   // ------------------------------------------------------------------ Strategy::init (stepsize/adapt.rs:91-199)
   // Doubling / halving search from the chain's current position (x, gx planes, cs.logp).  Returns false when
   // init_state fails check_all (NutsError::BadInitGrad).  Uses the ends[0] buffers as scratch for the start state.
-  __device__ bool stepsize_search() {
+  __device__ __forceinline__ bool stepsize_search() {
     if (P.s.method != 0) {
       cs.step_size = P.s.fixed_step;
       return true;
@@ -667,7 +760,7 @@ struct Engine {
   }
 
   // Strategy::adapt (transform/adapt/diagonal.rs:161-196) -> DiagMassMatrix::update_diag_draw_grad / update_diag_draw
-  __device__ bool mass_matrix_adapt() {
+  __device__ __forceinline__ bool mass_matrix_adapt() {
     if (cs.fg_count < 3) return false;
     const int set = cs.fg_set;
     const double* dm = est_ptr(set, 0);
@@ -710,7 +803,7 @@ struct Engine {
   }
 
   // ------------------------------------------------------------------ GlobalStrategy::adapt (adapt_strategy.rs:121-222)
-  __device__ bool adapt(uint64_t draw) {
+  __device__ __forceinline__ bool adapt(uint64_t draw) {
     // Strategy::update (stepsize/adapt.rs:201-209)
     cs.last_mean_tree_accept = acc_sum / (double)acc_count;
     cs.last_sym_mean_tree_accept = acc_sym_sum / (double)acc_count;
@@ -766,9 +859,11 @@ struct Engine {
   }
 
   // ------------------------------------------------------------------ Chain::draw (chain.rs:151-188) + nuts::draw (nuts.rs:281-388)
-  __device__ void run_draw(uint64_t t) {
+  __device__ __forceinline__ void run_draw(uint64_t t) {
     const SettingsDev& S = P.s;
     const size_t N = (size_t)P.N;
+    NB_T0(td);
+    NB_T0(tw);
     // ---- initialize_trajectory (transformed_hamiltonian.rs:687-736)
     load_mass_matrix();
     if (cs.mm_id != cs.pt_transform_id) {
@@ -791,6 +886,7 @@ struct Engine {
     acc_sym_sum = 0.;
     acc_count = 0;
     max_energy_error = 0.;
+    NB_ACC(0, td);
     // NutsTree::new (nuts.rs:94-105)
     ls_main = 0.;
     depth = 0;
@@ -806,25 +902,36 @@ struct Engine {
       mindepth = max((uint64_t)floor(log2((double)max_steps)), S.mindepth);
       maxdepth = min(max((uint64_t)ceil(log2((double)max_steps)), mindepth), S.maxdepth);
     }
-    bool diverging = false, reached_maxdepth = true;
-    while ((uint64_t)depth < maxdepth) {
-      const int dir = rng_bool() ? 1 : 0;  // hamiltonian.rs:111-119: true => Forward
-      const bool check = S.check_turning && !((uint64_t)depth < mindepth);
-      int r = extend(dir, check);
-      if (r == EXT_OK) continue;
-      reached_maxdepth = false;
-      if (r == EXT_TURNING) {
-        for (uint64_t k = 0; k < S.extra_doublings; ++k) {  // nuts.rs:349-374
-          if (extend(dir, false) == EXT_DIVERGING) {
-            diverging = true;
-            break;
-          }
+    // nuts.rs:333-385 with ONE extend() call site (the whole tree builder is inlined here): the regular doubling loop, then
+    // the optional extra doublings in the same direction without turn checks (nuts.rs:349-374).
+    bool diverging = false, reached_maxdepth = false, extra_mode = false;
+    uint64_t extra_left = 0;
+    int dir = 0;
+    for (;;) {
+      bool check;
+      if (!extra_mode) {
+        if (!((uint64_t)depth < maxdepth)) {
+          reached_maxdepth = true;
+          break;
         }
+        dir = rng_bool() ? 1 : 0;  // hamiltonian.rs:111-119: true => Forward
+        check = S.check_turning && !((uint64_t)depth < mindepth);
       } else {
-        diverging = true;
+        if (extra_left == 0) break;
+        extra_left -= 1;
+        check = false;
       }
-      break;
+      const int r = extend(dir, check);
+      if (r == EXT_DIVERGING) {
+        diverging = true;
+        break;
+      }
+      if (!extra_mode && r == EXT_TURNING) {
+        extra_mode = true;
+        extra_left = S.extra_doublings;
+      }
     }
+    NB_T0(tm);
     // ---- register_draw (transform/adapt/diagonal.rs:74-83)
     cs.is_good = diverging ? (abs(draw_idx) > 4) : (draw_idx != 0);
     // ---- materialise the selected draw: the chain point becomes (x, gx, z, gz, logp) of that leaf.
@@ -833,15 +940,15 @@ struct Engine {
     double fisher[1] = {0.0};
     if (draw_slot >= 0) {
       double x[EPT], gx[EPT];
-      load(slot_ptr(draw_slot, 0), z);
+      load_cg(slot_ptr(draw_slot, 0), z);
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        double tt = z[j] * sig[j];
-        x[j] = fma(1.0, mu[j], tt);
+        double tt = z[j] * sg(j);
+        x[j] = fma(1.0, mn(j), tt);
       }
       cs.logp = eval_at_position(x, gx);
 #pragma unroll
-      for (int j = 0; j < EPT; ++j) g[j] = gx[j] * sig[j];
+      for (int j = 0; j < EPT; ++j) g[j] = gx[j] * sg(j);
       store(P.x + row, x);
       store(P.gx + row, gx);
       store(P.z + row, z);
@@ -859,13 +966,20 @@ struct Engine {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) fisher[0] += (z[j] + g[j]) * (z[j] + g[j]);  // sq_norm_sum (cpu_math.rs:235-243)
     red.allreduce(fisher);
+    NB_ACC(5, tm);
     const double pt_energy = draw_energy;
     const double pt_energy_error = draw_energy - E0;
     // ---- adaptation
-    const uint64_t draw = cs.draw_count;
-    bool ok = adapt(draw);
+    {
+      ColdIO io = cold_adapt<TPC, EPT, MMS>(P, chain, tid, red.scratch, sm_sig, cs, red.parity, acc_sum, acc_sym_sum, acc_count,
+                                            max_energy_error);
+      cs = io.cs;
+      red.parity = io.parity;
+      if (!io.status) cs.alive = 0;
+    }
     cs.draw_count += 1;
-    if (!ok) cs.alive = 0;
+    NB_ACC(6, tm);
+    NB_ACC(7, tw);
     if (tid == 0) {
       const StatsDev& st = P.stats;
       const size_t k = (size_t)t * N + chain;
@@ -888,7 +1002,7 @@ struct Engine {
   }
 
   // ------------------------------------------------------------------ Chain::set_position (chain.rs:137-149)
-  __device__ int run_set_position() {
+  __device__ __forceinline__ int run_set_position() {
     double x[EPT], gx[EPT];
     load(P.init_position + (size_t)chain * d, x);
     // GlobalStrategy::init -> init_state_untransformed (transformed_hamiltonian.rs:663-685)
@@ -948,14 +1062,51 @@ struct Engine {
   }
 };
 
+template <int TPC, int EPT, bool MMS>
+__device__ __noinline__ ColdIO cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, ChainState cs,
+                                          int parity, double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error) {
+  TreeTables unused;  // the adaptation never touches the tree tables
+  Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, unused);
+  E.red.parity = parity;
+  E.cs = cs;
+  E.acc_sum = acc_sum;
+  E.acc_sym_sum = acc_sym_sum;
+  E.acc_count = acc_count;
+  E.max_energy_error = max_energy_error;
+  const bool ok = E.adapt(cs.draw_count);
+  ColdIO io;
+  io.cs = E.cs;
+  io.parity = E.red.parity;
+  io.status = ok ? 1 : 0;
+  return io;
+}
+
+template <int TPC, int EPT, bool MMS>
+__device__ __noinline__ ColdIO cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, ChainState cs) {
+  TreeTables unused;
+  Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, unused);
+  E.cs = cs;
+  ColdIO io;
+  io.status = E.run_set_position();
+  io.cs = E.cs;
+  io.parity = E.red.parity;
+  return io;
+}
+
 // One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).
-template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS>
+// Dynamic shared memory: TEAMS x team_smem_bytes<TPC, EPT, MMS>().
+template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, bool MMS>
 __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(const __grid_constant__ EngineParams P) {
   constexpr int TEAMS = CTA_THREADS / TPC;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ double scratch[TPC > 32 ? 2 * 32 * REDUCE_MAXK : 1];
   __shared__ int next_chain[TEAMS];
   const int team = threadIdx.x / TPC;
   const int tid = threadIdx.x % TPC;
+  unsigned char* my_smem = dyn_smem + (size_t)team * team_smem_bytes<TPC, EPT, MMS>();
+  double* team_smem = reinterpret_cast<double*>(my_smem);
+  TreeTables local_tables;  // CTA teams: private per thread; warp teams: shared, after the mass-matrix arrays
+  TreeTables& tables = (TPC == 32) ? *reinterpret_cast<TreeTables*>(my_smem + (MMS ? 2 * (size_t)TPC * EPT * sizeof(double) : 0)) : local_tables;
   for (;;) {
     if (tid == 0) next_chain[team] = (int)atomicAdd(P.queue, 1u);
     if (TPC > 32) __syncthreads();
@@ -964,12 +1115,14 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(con
     if (TPC > 32) __syncthreads();
     else __syncwarp();
     if (chain >= P.N) break;
-    Engine<TPC, EPT> E(P, chain, tid, scratch);
+    Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, tables);
     E.cs = P.cs[chain];
     if (P.mode == 0) {
-      int st = E.run_set_position();
-      E.cs.alive = st == 0 ? 1 : 0;
-      if (tid == 0 && P.status_out) P.status_out[chain] = st;
+      ColdIO io = cold_set_position<TPC, EPT, MMS>(P, chain, tid, scratch, team_smem, E.cs);
+      E.cs = io.cs;
+      E.red.parity = io.parity;
+      E.cs.alive = io.status == 0 ? 1 : 0;
+      if (tid == 0 && P.status_out) P.status_out[chain] = io.status;
     } else if (E.cs.alive) {
       for (uint64_t t = 0; t < P.n_draws; ++t) {
         E.run_draw(t);
@@ -979,6 +1132,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(con
     if (TPC > 32) __syncthreads();
     else __syncwarp();
     if (tid == 0) P.cs[chain] = E.cs;
+#ifdef NB_PHASE_TIMING
+    if (tid == 0 && P.phase_clocks)
+      for (int k = 0; k < 8; ++k) atomicAdd(P.phase_clocks + k, (unsigned long long)E.phase[k]);
+#endif
   }
 }
 

