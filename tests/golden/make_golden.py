@@ -1,0 +1,54 @@
+"""Generates tests/golden/*.npz with the CPU oracle.  The reference itself (Rust) cannot be run in this image and ships no
+golden trajectories, so these fixtures pin the ORACLE's output: test_golden.py re-checks the oracle against them on every
+run (guards against accidental changes of the restatement or of the RNG specification) and the GPU tests compare the CUDA
+path against the same files.  Run from the repo root:  python tests/golden/make_golden.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from nuts_rs_b200 import _abi  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (kind, model kwargs, N, d, settings overrides, n_draws, x0)
+    "c1_iso_mu3_maxdepth3": (_abi.NUTS_LOGP_GAUSS_ISO, dict(mu=3.0), 4, 10, dict(num_tune=1000, maxdepth=3), 40, "const3.5"),
+    "iso_mu05_noadapt": (_abi.NUTS_LOGP_GAUSS_ISO, dict(mu=0.5), 4, 10, dict(num_tune=0, maxdepth=6), 60, "normal"),
+    "diag_d100_noadapt": (_abi.NUTS_LOGP_GAUSS_DIAG, dict(mu=0.5, sigma="logspace"), 3, 100, dict(num_tune=0, maxdepth=6), 30, "normal"),
+    "rank1_d20_noadapt": (_abi.NUTS_LOGP_GAUSS_RANK1, dict(mu=0.0, rank1_scale=0.5), 3, 20, dict(num_tune=0, maxdepth=6), 30, "normal"),
+    "funnel_d10": (_abi.NUTS_LOGP_FUNNEL, dict(funnel_scale=3.0), 4, 10, dict(num_tune=20, maxdepth=8), 12, "normal"),
+}
+
+
+def build(name):
+    kind, mk, N, d, so, n_draws, x0kind = CASES[name]
+    mk = dict(mk)
+    if mk.get("sigma") == "logspace":
+        mk["sigma"] = np.exp(np.linspace(-1, 1, d))
+    s = _abi.default_settings()
+    for k, v in so.items():
+        setattr(s, k, v)
+    x0 = np.full((N, d), 3.5) if x0kind == "const3.5" else np.random.default_rng(123).normal(size=(N, d))
+    samp = O.Sampler(O.Model(kind, d, **mk), s, seed=2024, nchains=N)
+    status = samp.set_position(x0)
+    st0 = samp.state()
+    draws, stats = samp.draw(n_draws)
+    stats.pop("_total_leapfrogs")
+    return dict(x0=x0, status=status, step_size0=st0["step_size"], stds0=st0["stds"], mean0=st0["mean"], draws=draws,
+                **{"stat_" + k: v for k, v in stats.items()})
+
+
+if __name__ == "__main__":
+    for name in CASES:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **build(name))
+        print("wrote", name)
+    # RNG specification vectors
+    normals, ctr = O.fill_normal(42, 1, 0, 64)
+    unif = np.array([O.lib().orc_next_f64(42, 3, c) for c in range(16)])
+    bools = np.array([O.lib().orc_next_bool(42, 3, c) for c in range(64)], dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "rng_spec.npz"), normals=normals, uniforms=unif, bools=bools)
+    print("wrote rng_spec")
