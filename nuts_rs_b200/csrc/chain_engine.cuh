@@ -123,19 +123,18 @@ enum { EXT_OK = 0, EXT_TURNING = 1, EXT_DIVERGING = 2 };
 // The per-draw adaptation and Chain::set_position are COLD: they run in non-inlined functions on their own Engine
 // instance and exchange the chain scalars by value, so that the hot tree builder (run_draw -> extend -> leapfrog, all
 // force-inlined with one call site each) never has its address taken and its vectors really live in registers.
-struct ColdIO {
-  ChainState cs;
-  int parity;
-  int status;
-};
 template <int TPC, int EPT, bool MMS>
-__device__ __noinline__ ColdIO cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, ChainState cs,
-                                          int parity, double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error);
+__device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, int parity, uint64_t t,
+                                       double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
+                                       int depth, bool reached_maxdepth, bool diverging, int draw_idx, double pt_energy,
+                                       double pt_energy_error, double fisher);
 template <int TPC, int EPT, bool MMS>
-__device__ __noinline__ ColdIO cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, ChainState cs);
+__device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem);
 
-// Tree bookkeeping tables of one chain.  Warp teams keep them in shared memory (all lanes execute the same store with the
-// same value, then __syncwarp), CTA teams keep a private copy per thread in local memory (no extra barriers).
+// Tree bookkeeping tables of one chain, in shared memory (local-memory tables cost an L1 miss per access once the stacks of
+// all resident threads exceed L1).  Every thread computes the same values; thread 0 of the team stores them.  An entry
+// written after leaf i is first read during leaf i+1's merges, i.e. after the barrier / __syncwarp of that leaf's leapfrog
+// reduction, and entries of different levels never alias, so no extra synchronisation is needed for CTA teams.
 struct TreeTables {
   // pending sub-trees of the half under construction, one per level
   double A_ls[MAX_DOUBLING_DEPTH], A_draw_energy[MAX_DOUBLING_DEPTH];
@@ -143,10 +142,10 @@ struct TreeTables {
   signed char A_first[MAX_DOUBLING_DEPTH], A_last[MAX_DOUBLING_DEPTH], A_draw[MAX_DOUBLING_DEPTH];
 };
 
-// bytes of dynamic shared memory one team needs: [sigma | mean] (when MMS) followed by the TreeTables (warp teams)
+// bytes of dynamic shared memory one team needs: [sigma | mean | model mu | model prec] (when MMS) followed by the TreeTables
 template <int TPC, int EPT, bool MMS>
 __host__ __device__ constexpr size_t team_smem_bytes() {
-  return (MMS ? 2 * (size_t)TPC * EPT * sizeof(double) : 0) + (TPC == 32 ? sizeof(TreeTables) : 0);
+  return (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0) + sizeof(TreeTables);
 }
 
 template <int TPC, int EPT, bool MMS>
@@ -162,10 +161,17 @@ struct Engine {
   double z[EPT], v[EPT], g[EPT];  // current phase-space point (whitened position, velocity, whitened gradient)
   // this chain's DiagMassMatrix (stds, mean): registers, or shared memory when MMS (large EPT: registers go to z, v, g)
   double sig[MMS ? 1 : EPT], mu[MMS ? 1 : EPT];
-  double *sm_sig, *sm_mu;
+  double *sm_sig, *sm_mu, *sm_mmu, *sm_mprec;  // MMS: mass matrix and model parameters of this team's elements
   TreeTables& T;
 
-  ChainState cs;
+  // Chain scalars used on the hot path are plain members (registers).  `cs` is only touched by the cold functions, which
+  // exchange it with global memory themselves: an aggregate copy of a struct that also holds hot fields would pin the
+  // whole engine object in local memory (measured: 2 local accesses per counter update per leapfrog).
+  double hs_step, hs_logp, hs_pt_logdet, hs_mm_logdet;
+  long long hs_pt_tid, hs_mm_id;
+  uint64_t hs_rng, hs_total_lf, hs_tree_lf;
+  int hs_alive;
+  ChainState cs;  // cold path only
   uint64_t stream;
 
   // ---- per-draw collector (AcceptanceRateCollector, dual_avg.rs:112-166) ----
@@ -175,8 +181,9 @@ struct Engine {
   // ---- main tree ----
   double ls_main;
   int depth;
-  int idx_end[2];
-  bool end_is_init[2], reg_holds[2];
+  int idx_left, idx_right;                 // index_in_trajectory of the two ends
+  bool init_left, init_right;              // the end still is the initial point
+  bool holds_left, holds_right;            // the registers currently hold that end
   int draw_slot;  // -1: the draw is the initial point
   double draw_energy;
   int draw_idx;
@@ -190,11 +197,25 @@ struct Engine {
   // team_smem: this team's slice of dynamic shared memory (team_smem_bytes()); tables: where the TreeTables live
   __device__ __forceinline__ Engine(const EngineParams& p, int chain_, int tid_, double* scratch, double* team_smem, TreeTables& tables)
       : P(p), chain(chain_), tid(tid_), red(scratch), d(p.d), row((size_t)chain_ * p.ld), sm_sig(team_smem),
-        sm_mu(team_smem + (MMS ? TPC * EPT : 0)), T(tables) {
+        sm_mu(team_smem + (MMS ? TPC * EPT : 0)), sm_mmu(team_smem + (MMS ? 2 * TPC * EPT : 0)),
+        sm_mprec(team_smem + (MMS ? 3 * TPC * EPT : 0)), T(tables) {
     stream = p.chain_offset + (uint64_t)chain_ + 1;  // reference src/sampler.rs:1106 set_stream(chain_id + 1)
   }
   __device__ __forceinline__ double sg(int j) const { return MMS ? sm_sig[tid + j * TPC] : sig[MMS ? 0 : j]; }
   __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[tid + j * TPC] : mu[MMS ? 0 : j]; }
+  // model parameters of element i = tid + j*TPC
+  __device__ __forceinline__ double model_mu(int j, int i) const { return MMS ? sm_mmu[tid + j * TPC] : __ldg(P.model.mu + i); }
+  __device__ __forceinline__ double model_prec(int j, int i) const { return MMS ? sm_mprec[tid + j * TPC] : __ldg(P.model.prec + i); }
+  __device__ __forceinline__ void load_model_params() {
+    if (MMS) {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        sm_mmu[i] = i < d ? P.model.mu[i] : 0.0;
+        sm_mprec[i] = i < d ? P.model.prec[i] : 0.0;
+      }
+    }
+  }
   // make table stores visible to the other lanes of a warp team (CTA teams use private tables)
   __device__ __forceinline__ void tsync() const {
     if (TPC == 32) __syncwarp();
@@ -240,17 +261,67 @@ struct Engine {
     return P.est + (((size_t)chain * 2 + set) * 4 + which) * P.ld;
   }
 
+  // ------------------------------------------------------------------ chain scalars <-> global memory
+  __device__ __forceinline__ void load_hot() {
+    const ChainState* g = P.cs + chain;
+    hs_step = __ldcg(&g->step_size);
+    hs_logp = __ldcg(&g->logp);
+    hs_pt_logdet = __ldcg(&g->pt_logdet);
+    hs_mm_logdet = __ldcg(&g->mm_logdet);
+    hs_pt_tid = __ldcg(&g->pt_transform_id);
+    hs_mm_id = __ldcg(&g->mm_id);
+    hs_rng = __ldcg((const unsigned long long*)&g->rng_counter);
+    hs_total_lf = __ldcg((const unsigned long long*)&g->total_leapfrogs);
+    hs_tree_lf = __ldcg((const unsigned long long*)&g->tree_leapfrogs);
+    hs_alive = __ldcg(&g->alive);
+  }
+  __device__ __forceinline__ void team_sync() const {
+    if (TPC > 32) __syncthreads();
+    else __syncwarp();
+  }
+  // publish the hot scalars (all threads hold identical values; thread 0 writes) and make them visible to the team
+  __device__ __forceinline__ void store_hot() {
+    if (tid == 0) {
+      ChainState* g = P.cs + chain;
+      g->step_size = hs_step;
+      g->logp = hs_logp;
+      g->pt_logdet = hs_pt_logdet;
+      g->mm_logdet = hs_mm_logdet;
+      g->pt_transform_id = hs_pt_tid;
+      g->mm_id = hs_mm_id;
+      g->rng_counter = hs_rng;
+      g->total_leapfrogs = hs_total_lf;
+      g->tree_leapfrogs = hs_tree_lf;
+    }
+    team_sync();
+  }
+  // cold functions: whole ChainState from / to global
+  __device__ __forceinline__ void cold_load() {
+    cs = P.cs[chain];
+    hs_step = cs.step_size; hs_logp = cs.logp; hs_pt_logdet = cs.pt_logdet; hs_mm_logdet = cs.mm_logdet;
+    hs_pt_tid = cs.pt_transform_id; hs_mm_id = cs.mm_id; hs_rng = cs.rng_counter; hs_total_lf = cs.total_leapfrogs;
+    hs_tree_lf = cs.tree_leapfrogs; hs_alive = cs.alive;
+  }
+  __device__ __forceinline__ void cold_store() {
+    cs.step_size = hs_step; cs.logp = hs_logp; cs.pt_logdet = hs_pt_logdet; cs.mm_logdet = hs_mm_logdet;
+    cs.pt_transform_id = hs_pt_tid; cs.mm_id = hs_mm_id; cs.rng_counter = hs_rng; cs.total_leapfrogs = hs_total_lf;
+    cs.tree_leapfrogs = hs_tree_lf; cs.alive = hs_alive;
+    team_sync();  // every thread has finished reading the old record
+    if (tid == 0) P.cs[chain] = cs;
+    team_sync();
+  }
+
   // ------------------------------------------------------------------ random stream
-  __device__ __forceinline__ bool rng_bool() { return stream_bool(P.seed, stream, cs.rng_counter++); }
-  __device__ __forceinline__ double rng_f64() { return stream_f64(P.seed, stream, cs.rng_counter++); }
+  __device__ __forceinline__ bool rng_bool() { return stream_bool(P.seed, stream, hs_rng++); }
+  __device__ __forceinline__ double rng_f64() { return stream_f64(P.seed, stream, hs_rng++); }
   // array_gaussian(rng, v, ones): v[i] = 1.0 * normal   (cpu_math.rs:561-577)
   __device__ __forceinline__ void sample_velocity() {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
       int i = tid + j * TPC;
-      v[j] = i < d ? 1.0 * stream_normal(P.seed, stream, cs.rng_counter, (uint32_t)i) : 0.0;
+      v[j] = i < d ? 1.0 * stream_normal(P.seed, stream, hs_rng, (uint32_t)i) : 0.0;
     }
-    cs.rng_counter += (uint64_t)((d + 1) / 2);
+    hs_rng += (uint64_t)((d + 1) / 2);
   }
 
   // ------------------------------------------------------------------ log density
@@ -265,7 +336,7 @@ struct Engine {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = tid + j * TPC;
-        if (i < d) s[0] += x[j] - __ldg(m.mu + i);
+        if (i < d) s[0] += x[j] - model_mu(j, i);
       }
       red.allreduce(s);
       a0 = m.rank1_coeff * s[0];  // rank1_term
@@ -295,7 +366,7 @@ struct Engine {
         int i = tid + j * TPC;
         gx[j] = 0.0;
         if (i < d) {
-          double diff = x[j] - __ldg(m.mu + i);
+          double diff = x[j] - model_mu(j, i);
           lp -= diff * diff / 2.;
           gx[j] = -diff;
         }
@@ -306,8 +377,8 @@ struct Engine {
         int i = tid + j * TPC;
         gx[j] = 0.0;
         if (i < d) {
-          double diff = x[j] - __ldg(m.mu + i);
-          double pd = diff * __ldg(m.prec + i);
+          double diff = x[j] - model_mu(j, i);
+          double pd = diff * model_prec(j, i);
           lp -= diff * pd / 2.;
           gx[j] = -pd;
         }
@@ -318,7 +389,7 @@ struct Engine {
         int i = tid + j * TPC;
         gx[j] = 0.0;
         if (i < d) {
-          double diff = x[j] - __ldg(m.mu + i);
+          double diff = x[j] - model_mu(j, i);
           double ptd = diff - a0;
           gx[j] = -ptd;
           lp -= 0.5 * diff * ptd;
@@ -378,7 +449,7 @@ struct Engine {
     red.allreduce(part);
     logp_out = model_finish(part[0], a0, a1, ev);
     ke_out = 0.5 * part[1];
-    cs.total_leapfrogs += 1;
+    hs_total_lf += 1;
   }
 
   // logp + gradient at the x plane -> gx plane; returns logp (Math::logp_array)
@@ -525,7 +596,7 @@ struct Engine {
     NB_T0(tq);
     const int D = depth;
     const uint32_t nleaf = 1u << D;
-    const double eps = dir ? cs.step_size : -cs.step_size;
+    const double eps = dir ? hs_step : -hs_step;
     const int sign = dir ? 1 : -1;
     free_mask = P.P >= 64 ? ~0ull : ((1ull << P.P) - 1ull);
     rc_lo = rc_hi = 0;
@@ -534,17 +605,18 @@ struct Engine {
       rc_add(draw_slot, 1);
     }
     // start state = the end of the main tree in direction dir
-    const double* nearZ = end_is_init[dir] ? P.z + row : end_ptr(dir, 0);
-    const double* nearV = end_is_init[dir] ? P.v0 + row : end_ptr(dir, 1);
-    const double* farZ = end_is_init[1 - dir] ? P.z + row : end_ptr(1 - dir, 0);
-    const double* farV = end_is_init[1 - dir] ? P.v0 + row : end_ptr(1 - dir, 1);
-    if (!reg_holds[dir]) {
+    const bool near_init = dir ? init_right : init_left, far_init = dir ? init_left : init_right;
+    const double* nearZ = near_init ? P.z + row : end_ptr(dir, 0);
+    const double* nearV = near_init ? P.v0 + row : end_ptr(dir, 1);
+    const double* farZ = far_init ? P.z + row : end_ptr(1 - dir, 0);
+    const double* farV = far_init ? P.v0 + row : end_ptr(1 - dir, 1);
+    if (!(dir ? holds_right : holds_left)) {
       load_cg(nearZ, z);
       load_cg(nearV, v);
-      load_cg(end_is_init[dir] ? P.gz + row : end_ptr(dir, 2), g);
+      load_cg(near_init ? P.gz + row : end_ptr(dir, 2), g);
     }
-    reg_holds[0] = reg_holds[1] = false;
-    int idx_cur = idx_end[dir];
+    holds_left = holds_right = false;
+    int idx_cur = dir ? idx_right : idx_left;
     // the sub-tree B that the newest leaf belongs to
     int B_first = -1, B_draw = -1, B_draw_idx = 0;
     double B_ls = 0., B_draw_energy = 0.;
@@ -555,8 +627,8 @@ struct Engine {
       NB_ACC(4, tq);
       leapfrog(eps, logp_new, ke_new);
       NB_ACC(1, tq);
-      cs.tree_leapfrogs += 1;
-      double energy = ke_new - (logp_new + cs.pt_logdet);
+      hs_tree_lf += 1;
+      double energy = ke_new - (logp_new + hs_pt_logdet);
       double energy_error = energy - E0;
       bool divergent = (energy_error > P.s.max_energy_error) | !isfinite(energy_error);
       register_leapfrog(energy, divergent);
@@ -600,12 +672,14 @@ struct Engine {
       }
       NB_ACC(3, tq);
       if (i + 1 < nleaf) {
-        T.A_first[t] = (signed char)B_first;
-        T.A_last[t] = (signed char)s;  // the last-of-B reference moves to the pending sub-tree
-        T.A_ls[t] = B_ls;
-        T.A_draw[t] = (signed char)B_draw;
-        T.A_draw_energy[t] = B_draw_energy;
-        T.A_draw_idx[t] = B_draw_idx;
+        if (tid == 0) {
+          T.A_first[t] = (signed char)B_first;
+          T.A_last[t] = (signed char)s;  // the last-of-B reference moves to the pending sub-tree
+          T.A_ls[t] = B_ls;
+          T.A_draw[t] = (signed char)B_draw;
+          T.A_draw_energy[t] = B_draw_energy;
+          T.A_draw_idx[t] = B_draw_idx;
+        }
         tsync();
       }
     }
@@ -626,9 +700,15 @@ struct Engine {
     store_cg(end_ptr(dir, 0), z);
     store_cg(end_ptr(dir, 1), v);
     store_cg(end_ptr(dir, 2), g);
-    idx_end[dir] = idx_cur;
-    end_is_init[dir] = false;
-    reg_holds[dir] = true;
+    if (dir) {
+      idx_right = idx_cur;
+      init_right = false;
+      holds_right = true;
+    } else {
+      idx_left = idx_cur;
+      init_left = false;
+      holds_left = true;
+    }
     NB_ACC(4, tq);
     return turning ? EXT_TURNING : EXT_OK;
   }
@@ -658,38 +738,38 @@ struct Engine {
     if (P.s.has_jitter) {
       double lo = 1.0 - P.s.jitter, hi = 1.0 + P.s.jitter;
       double j = fma(hi - lo, rng_f64(), lo);
-      cs.step_size = step * j;
+      hs_step = step * j;
     } else {
-      cs.step_size = step;
+      hs_step = step;
     }
   }
 
   // ------------------------------------------------------------------ Strategy::init (stepsize/adapt.rs:91-199)
-  // Doubling / halving search from the chain's current position (x, gx planes, cs.logp).  Returns false when
+  // Doubling / halving search from the chain's current position (x, gx planes, hs_logp).  Returns false when
   // init_state fails check_all (NutsError::BadInitGrad).  Uses the ends[0] buffers as scratch for the start state.
   __device__ __forceinline__ bool stepsize_search() {
     if (P.s.method != 0) {
-      cs.step_size = P.s.fixed_step;
+      hs_step = P.s.fixed_step;
       return true;
     }
     load_mass_matrix();
     if (!whiten_from_planes()) return false;  // init_state: same x => same logp / gradient, new whitening
-    const double logdet = cs.mm_logdet;
+    const double logdet = hs_mm_logdet;
     sample_velocity();  // initialize_trajectory(resample = true)
     double ke[1] = {0.0};
 #pragma unroll
     for (int j = 0; j < EPT; ++j) ke[0] = fma(v[j], v[j], ke[0]);
     red.allreduce(ke);
-    const double e0 = 0.5 * ke[0] - (cs.logp + logdet);
+    const double e0 = 0.5 * ke[0] - (hs_logp + logdet);
     double* sz = end_ptr(0, 0);
     double* sv = end_ptr(0, 1);
     double* sg = end_ptr(0, 2);
     store(sz, z);
     store(sv, v);
     store(sg, g);
-    cs.step_size = P.s.initial_step;
+    hs_step = P.s.initial_step;
     double lp, k;
-    leapfrog(cs.step_size, lp, k);
+    leapfrog(hs_step, lp, k);
     double ee = (k - (lp + logdet)) - e0;
     if ((ee > 1000.0) | !isfinite(ee)) return true;
     double accept = exp(fmin(e0 - (k - (lp + logdet)), 0.)) / 1.0;
@@ -698,29 +778,29 @@ struct Engine {
       load(sz, z);
       load(sv, v);
       load(sg, g);
-      leapfrog(forward ? cs.step_size : -cs.step_size, lp, k);
+      leapfrog(forward ? hs_step : -hs_step, lp, k);
       double en = k - (lp + logdet);
       ee = en - e0;
       if ((ee > 1000.0) | !isfinite(ee)) {
-        cs.step_size = P.s.initial_step;
+        hs_step = P.s.initial_step;
         return true;
       }
       accept = exp(fmin(e0 - en, 0.));
       if (forward) {
-        if ((accept <= P.s.target_accept) | (cs.step_size > 1e5)) {
-          da_new(cs.step_size);
+        if ((accept <= P.s.target_accept) | (hs_step > 1e5)) {
+          da_new(hs_step);
           return true;
         }
-        cs.step_size *= 2.;
+        hs_step *= 2.;
       } else {
-        if ((accept >= P.s.target_accept) | (cs.step_size < 1e-10)) {
-          da_new(cs.step_size);
+        if ((accept >= P.s.target_accept) | (hs_step < 1e-10)) {
+          da_new(hs_step);
           return true;
         }
-        cs.step_size /= 2.;
+        hs_step /= 2.;
       }
     }
-    cs.step_size = P.s.initial_step;
+    hs_step = P.s.initial_step;
     return true;
   }
 
@@ -797,8 +877,8 @@ struct Engine {
       }
     }
     red.allreduce(ld);
-    cs.mm_logdet = ld[0];
-    cs.mm_id += 1;
+    hs_mm_logdet = ld[0];
+    hs_mm_id += 1;
     return true;
   }
 
@@ -866,10 +946,10 @@ struct Engine {
     NB_T0(tw);
     // ---- initialize_trajectory (transformed_hamiltonian.rs:687-736)
     load_mass_matrix();
-    if (cs.mm_id != cs.pt_transform_id) {
+    if (hs_mm_id != hs_pt_tid) {
       whiten_from_planes();  // inv_transform_normalize: no logp evaluation
-      cs.pt_logdet = cs.mm_logdet;
-      cs.pt_transform_id = cs.mm_id;
+      hs_pt_logdet = hs_mm_logdet;
+      hs_pt_tid = hs_mm_id;
     } else {
       load(P.z + row, z);
       load(P.gz + row, g);
@@ -880,7 +960,7 @@ struct Engine {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) ke[0] = fma(v[j], v[j], ke[0]);
     red.allreduce(ke);
-    E0 = 0.5 * ke[0] - (cs.logp + cs.pt_logdet);
+    E0 = 0.5 * ke[0] - (hs_logp + hs_pt_logdet);
     // collector.register_init (dual_avg.rs:160-165)
     acc_sum = 0.;
     acc_sym_sum = 0.;
@@ -890,15 +970,15 @@ struct Engine {
     // NutsTree::new (nuts.rs:94-105)
     ls_main = 0.;
     depth = 0;
-    idx_end[0] = idx_end[1] = 0;
-    end_is_init[0] = end_is_init[1] = true;
-    reg_holds[0] = reg_holds[1] = true;
+    idx_left = idx_right = 0;
+    init_left = init_right = true;
+    holds_left = holds_right = true;
     draw_slot = -1;
     draw_energy = E0;
     draw_idx = 0;
     uint64_t mindepth = S.mindepth, maxdepth = S.maxdepth;
     if (S.has_target_time) {  // nuts.rs:300-320
-      uint64_t max_steps = (uint64_t)ceil(S.target_time / cs.step_size);
+      uint64_t max_steps = (uint64_t)ceil(S.target_time / hs_step);
       mindepth = max((uint64_t)floor(log2((double)max_steps)), S.mindepth);
       maxdepth = min(max((uint64_t)ceil(log2((double)max_steps)), mindepth), S.maxdepth);
     }
@@ -932,8 +1012,6 @@ struct Engine {
       }
     }
     NB_T0(tm);
-    // ---- register_draw (transform/adapt/diagonal.rs:74-83)
-    cs.is_good = diverging ? (abs(draw_idx) > 4) : (draw_idx != 0);
     // ---- materialise the selected draw: the chain point becomes (x, gx, z, gz, logp) of that leaf.
     // z is read back from its checkpoint; x / logp / gradient are recomputed by the same instruction sequence the
     // leaf used, hence bit-identical to what the leapfrog produced.
@@ -946,7 +1024,7 @@ struct Engine {
         double tt = z[j] * sg(j);
         x[j] = fma(1.0, mn(j), tt);
       }
-      cs.logp = eval_at_position(x, gx);
+      hs_logp = eval_at_position(x, gx);
 #pragma unroll
       for (int j = 0; j < EPT; ++j) g[j] = gx[j] * sg(j);
       store(P.x + row, x);
@@ -967,38 +1045,15 @@ struct Engine {
     for (int j = 0; j < EPT; ++j) fisher[0] += (z[j] + g[j]) * (z[j] + g[j]);  // sq_norm_sum (cpu_math.rs:235-243)
     red.allreduce(fisher);
     NB_ACC(5, tm);
-    const double pt_energy = draw_energy;
-    const double pt_energy_error = draw_energy - E0;
-    // ---- adaptation
-    {
-      ColdIO io = cold_adapt<TPC, EPT, MMS>(P, chain, tid, red.scratch, sm_sig, cs, red.parity, acc_sum, acc_sym_sum, acc_count,
-                                            max_energy_error);
-      cs = io.cs;
-      red.parity = io.parity;
-      if (!io.status) cs.alive = 0;
-    }
-    cs.draw_count += 1;
+    // ---- adaptation + statistics: cold, through global memory
+    store_hot();
+    const int ret = cold_adapt<TPC, EPT, MMS>(P, chain, tid, red.scratch, sm_sig, red.parity, t, acc_sum, acc_sym_sum, acc_count,
+                                              max_energy_error, diverging ? (abs(draw_idx) > 4) : (draw_idx != 0), depth, reached_maxdepth,
+                                              diverging, draw_idx, draw_energy, draw_energy - E0, fisher[0]);
+    red.parity = ret & 1;
+    load_hot();
     NB_ACC(6, tm);
     NB_ACC(7, tw);
-    if (tid == 0) {
-      const StatsDev& st = P.stats;
-      const size_t k = (size_t)t * N + chain;
-      if (st.depth) st.depth[k] = (uint64_t)depth;
-      if (st.maxdepth_reached) st.maxdepth_reached[k] = reached_maxdepth ? 1 : 0;
-      if (st.index_in_trajectory) st.index_in_trajectory[k] = draw_idx;
-      if (st.logp) st.logp[k] = cs.logp;
-      if (st.energy) st.energy[k] = pt_energy;
-      if (st.energy_error) st.energy_error[k] = pt_energy_error;
-      if (st.diverging) st.diverging[k] = diverging ? 1 : 0;
-      if (st.step_size) st.step_size[k] = cs.step_size;
-      if (st.step_size_bar) st.step_size_bar[k] = P.s.method != 0 ? P.s.fixed_step : exp(cs.da_log_step_adapted);
-      if (st.mean_tree_accept) st.mean_tree_accept[k] = cs.last_mean_tree_accept;
-      if (st.mean_tree_accept_sym) st.mean_tree_accept_sym[k] = cs.last_sym_mean_tree_accept;
-      if (st.n_steps) st.n_steps[k] = cs.last_n_steps;
-      if (st.max_energy_error) st.max_energy_error[k] = cs.last_max_energy_error;
-      if (st.tuning) st.tuning[k] = cs.tuning ? 1 : 0;
-      if (st.fisher_distance) st.fisher_distance[k] = fisher[0];
-    }
   }
 
   // ------------------------------------------------------------------ Chain::set_position (chain.rs:137-149)
@@ -1006,7 +1061,7 @@ struct Engine {
     double x[EPT], gx[EPT];
     load(P.init_position + (size_t)chain * d, x);
     // GlobalStrategy::init -> init_state_untransformed (transformed_hamiltonian.rs:663-685)
-    cs.logp = eval_at_position(x, gx);
+    hs_logp = eval_at_position(x, gx);
     double bad[1] = {0.0};
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
@@ -1045,52 +1100,74 @@ struct Engine {
       }
     }
     red.allreduce(ld);
-    cs.mm_logdet = ld[0];
-    cs.mm_id += 1;
+    hs_mm_logdet = ld[0];
+    hs_mm_id += 1;
     // step_size.init
     if (P.s.method == 0) {
       if (!stepsize_search()) return 3;
     } else {
-      cs.step_size = P.s.fixed_step;
+      hs_step = P.s.fixed_step;
     }
     // self.state = hamiltonian.init_state(position) (transformed_hamiltonian.rs:640-661)
     load_mass_matrix();
     if (!whiten_from_planes()) return 3;
-    cs.pt_logdet = cs.mm_logdet;
-    cs.pt_transform_id = cs.mm_id;
+    hs_pt_logdet = hs_mm_logdet;
+    hs_pt_tid = hs_mm_id;
     return 0;
   }
 };
 
+// GlobalStrategy::adapt + the statistics of Chain::expanded_draw for one chain; returns the reduction parity (bit 0).
 template <int TPC, int EPT, bool MMS>
-__device__ __noinline__ ColdIO cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, ChainState cs,
-                                          int parity, double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error) {
-  TreeTables unused;  // the adaptation never touches the tree tables
-  Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, unused);
+__device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, int parity, uint64_t t,
+                                       double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
+                                       int depth, bool reached_maxdepth, bool diverging, int draw_idx, double pt_energy,
+                                       double pt_energy_error, double fisher) {
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0));
+  Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, tables);
   E.red.parity = parity;
-  E.cs = cs;
+  E.cold_load();
   E.acc_sum = acc_sum;
   E.acc_sym_sum = acc_sym_sum;
   E.acc_count = acc_count;
   E.max_energy_error = max_energy_error;
-  const bool ok = E.adapt(cs.draw_count);
-  ColdIO io;
-  io.cs = E.cs;
-  io.parity = E.red.parity;
-  io.status = ok ? 1 : 0;
-  return io;
+  E.cs.is_good = is_good ? 1 : 0;  // register_draw (transform/adapt/diagonal.rs:74-83)
+  const bool ok = E.adapt(E.cs.draw_count);
+  E.cs.draw_count += 1;
+  if (!ok) E.hs_alive = 0;
+  if (tid == 0) {
+    const StatsDev& st = P.stats;
+    const size_t k = (size_t)t * (size_t)P.N + chain;
+    if (st.depth) st.depth[k] = (uint64_t)depth;
+    if (st.maxdepth_reached) st.maxdepth_reached[k] = reached_maxdepth ? 1 : 0;
+    if (st.index_in_trajectory) st.index_in_trajectory[k] = draw_idx;
+    if (st.logp) st.logp[k] = E.hs_logp;
+    if (st.energy) st.energy[k] = pt_energy;
+    if (st.energy_error) st.energy_error[k] = pt_energy_error;
+    if (st.diverging) st.diverging[k] = diverging ? 1 : 0;
+    if (st.step_size) st.step_size[k] = E.hs_step;
+    if (st.step_size_bar) st.step_size_bar[k] = P.s.method != 0 ? P.s.fixed_step : exp(E.cs.da_log_step_adapted);
+    if (st.mean_tree_accept) st.mean_tree_accept[k] = E.cs.last_mean_tree_accept;
+    if (st.mean_tree_accept_sym) st.mean_tree_accept_sym[k] = E.cs.last_sym_mean_tree_accept;
+    if (st.n_steps) st.n_steps[k] = E.cs.last_n_steps;
+    if (st.max_energy_error) st.max_energy_error[k] = E.cs.last_max_energy_error;
+    if (st.tuning) st.tuning[k] = E.cs.tuning ? 1 : 0;
+    if (st.fisher_distance) st.fisher_distance[k] = fisher;
+  }
+  E.cold_store();
+  return E.red.parity & 1;
 }
 
+// Chain::set_position for one chain; returns the per-chain status (0 ok, 3 bad initial point).
 template <int TPC, int EPT, bool MMS>
-__device__ __noinline__ ColdIO cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, ChainState cs) {
-  TreeTables unused;
-  Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, unused);
-  E.cs = cs;
-  ColdIO io;
-  io.status = E.run_set_position();
-  io.cs = E.cs;
-  io.parity = E.red.parity;
-  return io;
+__device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem) {
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0));
+  Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, tables);
+  E.cold_load();
+  const int status = E.run_set_position();
+  E.hs_alive = status == 0 ? 1 : 0;
+  E.cold_store();
+  return status;
 }
 
 // One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).
@@ -1105,8 +1182,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(con
   const int tid = threadIdx.x % TPC;
   unsigned char* my_smem = dyn_smem + (size_t)team * team_smem_bytes<TPC, EPT, MMS>();
   double* team_smem = reinterpret_cast<double*>(my_smem);
-  TreeTables local_tables;  // CTA teams: private per thread; warp teams: shared, after the mass-matrix arrays
-  TreeTables& tables = (TPC == 32) ? *reinterpret_cast<TreeTables*>(my_smem + (MMS ? 2 * (size_t)TPC * EPT * sizeof(double) : 0)) : local_tables;
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(my_smem + (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0));
   for (;;) {
     if (tid == 0) next_chain[team] = (int)atomicAdd(P.queue, 1u);
     if (TPC > 32) __syncthreads();
@@ -1116,22 +1192,21 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(con
     else __syncwarp();
     if (chain >= P.N) break;
     Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, tables);
-    E.cs = P.cs[chain];
+    E.load_model_params();
     if (P.mode == 0) {
-      ColdIO io = cold_set_position<TPC, EPT, MMS>(P, chain, tid, scratch, team_smem, E.cs);
-      E.cs = io.cs;
-      E.red.parity = io.parity;
-      E.cs.alive = io.status == 0 ? 1 : 0;
-      if (tid == 0 && P.status_out) P.status_out[chain] = io.status;
-    } else if (E.cs.alive) {
-      for (uint64_t t = 0; t < P.n_draws; ++t) {
-        E.run_draw(t);
-        if (!E.cs.alive) break;
+      const int status = cold_set_position<TPC, EPT, MMS>(P, chain, tid, scratch, team_smem);
+      if (tid == 0 && P.status_out) P.status_out[chain] = status;
+    } else {
+      E.load_hot();
+      if (E.hs_alive) {
+        for (uint64_t t = 0; t < P.n_draws; ++t) {
+          E.run_draw(t);
+          if (!E.hs_alive) break;
+        }
       }
     }
     if (TPC > 32) __syncthreads();
     else __syncwarp();
-    if (tid == 0) P.cs[chain] = E.cs;
 #ifdef NB_PHASE_TIMING
     if (tid == 0 && P.phase_clocks)
       for (int k = 0; k < 8; ++k) atomicAdd(P.phase_clocks + k, (unsigned long long)E.phase[k]);

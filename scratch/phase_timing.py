@@ -2,7 +2,7 @@ import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, bench
 from nuts_rs_b200 import _abi, lib
-N = bench.CHAINS_PER_GPU; d = bench.DIM
+N = int(os.environ.get('PROF_N', bench.CHAINS_PER_GPU)); d = bench.DIM
 math = lib.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_DIAG, mu=0.5, sigma=bench.model_sigma())
 s = lib.Sampler(math, bench.settings(), seed=bench.SEED)
 s.set_position(bench.initial_positions(N, 0)); s.draw_device(bench.NUM_TUNE)
