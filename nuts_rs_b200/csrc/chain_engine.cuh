@@ -154,8 +154,10 @@ struct Engine {
   const int chain;
   const int tid;  // thread index inside the team
   TeamReduce<TPC> red;
-  const int d;
+  const int d, ld;
   const size_t row;  // chain * ld
+  double* const slots_base;  // this chain's checkpoint pool / endpoint buffers (thread-offset included)
+  double* const ends_base;
 
   // ---- register-resident vectors ----
   double z[EPT], v[EPT], g[EPT];  // current phase-space point (whitened position, velocity, whitened gradient)
@@ -196,7 +198,8 @@ struct Engine {
 
   // team_smem: this team's slice of dynamic shared memory (team_smem_bytes()); tables: where the TreeTables live
   __device__ __forceinline__ Engine(const EngineParams& p, int chain_, int tid_, double* scratch, double* team_smem, TreeTables& tables)
-      : P(p), chain(chain_), tid(tid_), red(scratch), d(p.d), row((size_t)chain_ * p.ld), sm_sig(team_smem),
+      : P(p), chain(chain_), tid(tid_), red(scratch), d(p.d), ld(p.ld), row((size_t)chain_ * p.ld),
+        slots_base(p.slots + (size_t)chain_ * p.P * 2 * p.ld), ends_base(p.ends + (size_t)chain_ * 6 * p.ld), sm_sig(team_smem),
         sm_mu(team_smem + (MMS ? TPC * EPT : 0)), sm_mmu(team_smem + (MMS ? 2 * TPC * EPT : 0)),
         sm_mprec(team_smem + (MMS ? 3 * TPC * EPT : 0)), T(tables) {
     stream = p.chain_offset + (uint64_t)chain_ + 1;  // reference src/sampler.rs:1106 set_stream(chain_id + 1)
@@ -251,12 +254,8 @@ struct Engine {
       if (i < d) dst[i] = a[j];
     }
   }
-  __device__ __forceinline__ double* slot_ptr(int s, int which) const {
-    return P.slots + (((size_t)chain * P.P + s) * 2 + which) * P.ld;
-  }
-  __device__ __forceinline__ double* end_ptr(int dir, int which) const {
-    return P.ends + (((size_t)chain * 2 + dir) * 3 + which) * P.ld;
-  }
+  __device__ __forceinline__ double* slot_ptr(int s, int which) const { return slots_base + (size_t)((s * 2 + which) * ld); }
+  __device__ __forceinline__ double* end_ptr(int dir, int which) const { return ends_base + (size_t)((dir * 3 + which) * ld); }
   __device__ __forceinline__ double* est_ptr(int set, int which) const {
     return P.est + (((size_t)chain * 2 + set) * 4 + which) * P.ld;
   }
@@ -316,10 +315,35 @@ struct Engine {
   __device__ __forceinline__ double rng_f64() { return stream_f64(P.seed, stream, hs_rng++); }
   // array_gaussian(rng, v, ones): v[i] = 1.0 * normal   (cpu_math.rs:561-577)
   __device__ __forceinline__ void sample_velocity() {
+    // Elements 2p and 2p+1 (one Box-Muller pair) belong to threads t (even) and t+1 at the same j.  Even threads evaluate the
+    // pairs of even j, odd threads those of odd j, and the partner's normal travels through one shuffle: EPT/2 Box-Mullers
+    // per thread instead of EPT.  Values are exactly those of stream_normal().
+    if (EPT % 2 == 0) {
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
-      v[j] = i < d ? 1.0 * stream_normal(P.seed, stream, hs_rng, (uint32_t)i) : 0.0;
+      for (int j = 0; j < EPT; j += 2) {
+        const int jj = j + (tid & 1);            // the j this thread evaluates
+        const int i_even = (tid & ~1) + jj * TPC;  // even element of that pair
+        double n0 = 0.0, n1 = 0.0;
+        if (i_even < d) stream_normal_pair(P.seed, stream, hs_rng, (uint32_t)i_even, n0, n1);
+        // mine: component (tid & 1) of my pair goes to v[jj]; the other component belongs to the neighbour's element at jj
+        const double keep = (tid & 1) ? n1 : n0;
+        const double give = (tid & 1) ? n0 : n1;
+        const double got = __shfl_xor_sync(0xffffffffu, give, 1);  // neighbour's pair was for its own jj = j + ((tid^1)&1)
+        // I evaluated jj = j + (tid&1); the neighbour evaluated j + 1 - (tid&1): that is the j I still need
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int jq = j + q;
+          const int i = tid + jq * TPC;
+          const double val = (q == (tid & 1)) ? keep : got;
+          v[jq] = i < d ? 1.0 * val : 0.0;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        v[j] = i < d ? 1.0 * stream_normal(P.seed, stream, hs_rng, (uint32_t)i) : 0.0;
+      }
     }
     hs_rng += (uint64_t)((d + 1) / 2);
   }
@@ -578,9 +602,10 @@ struct Engine {
       max_energy_error = -INFINITY;
     } else {
       double diff = E0 - energy;
-      double e = exp(fmin(diff, 0.));
+      const double ed = exp(diff);
+      const double e = diff < 0. ? ed : 1.0;  // == exp(min(diff, 0)) bit for bit (diff is finite here), one exp instead of two
       acc_sum += e;
-      acc_sym_sum += 2. * e / (1. + exp(diff));
+      acc_sym_sum += 2. * e / (1. + ed);
       if (fabs(diff) > fabs(max_energy_error)) max_energy_error = diff;
     }
     acc_count += 1;
