@@ -15,21 +15,18 @@
 using namespace nb;
 
 // ---- per-configuration launchers (engine_inst.cu) ----
-#define NB_DECL(TPC, EPT, MINB)                                                                                     \
-  extern "C" cudaError_t nb_launch_chain_##TPC##_##EPT##_##MINB(const EngineParams* p, int grid, cudaStream_t s);   \
-  extern "C" cudaError_t nb_occupancy_chain_##TPC##_##EPT##_##MINB(int* blocks_per_sm, int* cta_threads);
+// Weak declarations: a development build may contain only a subset of the (tiling, model) matrix (make CONFIGS=.. MODELS=..).
+#define NB_DECL1(TPC, EPT, MINB, MODEL)                                                                                                      \
+  extern "C" __attribute__((weak)) cudaError_t nb_launch_chain_##TPC##_##EPT##_##MINB##_##MODEL(const EngineParams* p, int grid, cudaStream_t s); \
+  extern "C" __attribute__((weak)) cudaError_t nb_occupancy_chain_##TPC##_##EPT##_##MINB##_##MODEL(int* blocks_per_sm, int* cta_threads);
+#define NB_DECL(TPC, EPT, MINB) NB_DECL1(TPC, EPT, MINB, 1) NB_DECL1(TPC, EPT, MINB, 2) NB_DECL1(TPC, EPT, MINB, 3)
 NB_DECL(32, 1, 16)
 NB_DECL(32, 2, 16)
 NB_DECL(32, 4, 16)
 NB_DECL(32, 8, 12)
 NB_DECL(32, 16, 8)
-NB_DECL(32, 32, 8)
 NB_DECL(64, 16, 4)
-NB_DECL(64, 16, 6)
-NB_DECL(64, 16, 7)
 NB_DECL(128, 8, 4)
-NB_DECL(128, 8, 5)
-NB_DECL(128, 8, 7)
 NB_DECL(256, 8, 2)
 NB_DECL(512, 8, 1)
 NB_DECL(1024, 8, 1)
@@ -58,17 +55,24 @@ int fail(int code, const char* fmt, ...) {
 
 struct EngineConfig {
   int tpc, ept, minb, max_d;
-  cudaError_t (*launch)(const EngineParams*, int, cudaStream_t);
-  cudaError_t (*occupancy)(int*, int*);
+  // indexed by model variant - 1 (1 diagonal/isotropic Gaussian, 2 rank-1 Gaussian, 3 funnel)
+  cudaError_t (*launch[3])(const EngineParams*, int, cudaStream_t);
+  cudaError_t (*occupancy[3])(int*, int*);
 };
-#define NB_CFG(TPC, EPT, MINB) \
-  { TPC, EPT, MINB, TPC * EPT, nb_launch_chain_##TPC##_##EPT##_##MINB, nb_occupancy_chain_##TPC##_##EPT##_##MINB }
+#define NB_CFG(TPC, EPT, MINB)                                                                                                             \
+  {                                                                                                                                        \
+    TPC, EPT, MINB, TPC* EPT,                                                                                                              \
+        {nb_launch_chain_##TPC##_##EPT##_##MINB##_1, nb_launch_chain_##TPC##_##EPT##_##MINB##_2, nb_launch_chain_##TPC##_##EPT##_##MINB##_3}, \
+    {                                                                                                                                      \
+      nb_occupancy_chain_##TPC##_##EPT##_##MINB##_1, nb_occupancy_chain_##TPC##_##EPT##_##MINB##_2, nb_occupancy_chain_##TPC##_##EPT##_##MINB##_3 \
+    }                                                                                                                                      \
+  }
 // default choice: the first entry whose capacity (tpc*ept) covers dim.  Warp-per-chain up to dim 1024 (no barrier in
 // the whole kernel, all 1024 chains of config 2 resident at once); CTA-per-chain above.
-const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(128, 8, 4),
+const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(64, 16, 4),
                                  NB_CFG(256, 8, 2), NB_CFG(512, 8, 1), NB_CFG(1024, 8, 1), NB_CFG(1024, 10, 1), NB_CFG(1024, 16, 1)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(32, 32, 8), NB_CFG(64, 16, 4), NB_CFG(64, 16, 6), NB_CFG(64, 16, 7), NB_CFG(128, 8, 5), NB_CFG(128, 8, 7)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(128, 8, 4)};
 
 }  // namespace
 
@@ -106,6 +110,7 @@ struct nuts_sampler {
   nuts_settings_t settings{};
   EngineParams P{};
   const EngineConfig* cfg = nullptr;
+  int model_variant = 0;  // index into cfg->launch
   int grid = 0;
   std::vector<void*> allocations;
   double* d_init = nullptr;
@@ -251,6 +256,7 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
   ctx->model.dim = (int)dim;
   switch (model->kind) {
     case NUTS_LOGP_GAUSS_ISO:
+      for (uint64_t i = 0; i < dim; ++i) prec[i] = 1.0;  // diff * 1.0 is exact: the DIAG kernels serve this target bit-identically
       break;
     case NUTS_LOGP_GAUSS_DIAG:
       if (!model->sigma) {
@@ -765,7 +771,12 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   CUDA_TRY(cudaMemcpy(P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice));
   // persistent grid: one wave of resident CTAs
   int blocks_per_sm = 0, cta_threads = 0;
-  CUDA_TRY(cfg->occupancy(&blocks_per_sm, &cta_threads));
+  s->model_variant = ctx->model.kind == NUTS_LOGP_GAUSS_RANK1 ? 1 : ctx->model.kind == NUTS_LOGP_FUNNEL ? 2 : 0;
+  if (!cfg->launch[s->model_variant] || !cfg->occupancy[s->model_variant]) {
+    nuts_sampler_destroy(s);
+    return fail(NUTS_ERR_UNSUPPORTED, "engine %dx%d for model kind %d is not part of this build", cfg->tpc, cfg->ept, ctx->model.kind);
+  }
+  CUDA_TRY(cfg->occupancy[s->model_variant](&blocks_per_sm, &cta_threads));
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   const int teams_per_cta = cta_threads / cfg->tpc;
   const uint64_t ctas_needed = (ctx->N + teams_per_cta - 1) / teams_per_cta;
@@ -811,7 +822,7 @@ static int launch_engine(nuts_sampler* s) {
   nuts_ctx* ctx = s->ctx;
   CUDA_TRY(cudaMemsetAsync(s->P.queue, 0, sizeof(unsigned int), ctx->stream));
   CUDA_TRY(cudaEventRecord(s->ev0, ctx->stream));
-  CUDA_TRY(s->cfg->launch(&s->P, s->grid, ctx->stream));
+  CUDA_TRY(s->cfg->launch[s->model_variant](&s->P, s->grid, ctx->stream));
   CUDA_TRY(cudaEventRecord(s->ev1, ctx->stream));
   s->last_launches += 1;
   return NUTS_OK;

@@ -123,12 +123,12 @@ enum { EXT_OK = 0, EXT_TURNING = 1, EXT_DIVERGING = 2 };
 // The per-draw adaptation and Chain::set_position are COLD: they run in non-inlined functions on their own Engine
 // instance and exchange the chain scalars by value, so that the hot tree builder (run_draw -> extend -> leapfrog, all
 // force-inlined with one call site each) never has its address taken and its vectors really live in registers.
-template <int TPC, int EPT, bool MMS>
+template <int TPC, int EPT, bool MMS, int MODEL>
 __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, int parity, uint64_t t,
                                        double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
                                        int depth, bool reached_maxdepth, bool diverging, int draw_idx, double pt_energy,
                                        double pt_energy_error, double fisher);
-template <int TPC, int EPT, bool MMS>
+template <int TPC, int EPT, bool MMS, int MODEL>
 __device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem);
 
 // Tree bookkeeping tables of one chain, in shared memory (local-memory tables cost an L1 miss per access once the stacks of
@@ -148,7 +148,7 @@ __host__ __device__ constexpr size_t team_smem_bytes() {
   return (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0) + sizeof(TreeTables);
 }
 
-template <int TPC, int EPT, bool MMS>
+template <int TPC, int EPT, bool MMS, int MODEL>
 struct Engine {
   const EngineParams& P;
   const int chain;
@@ -355,7 +355,7 @@ struct Engine {
     const ModelDev& m = P.model;
     a0 = 0.0;
     a1 = 0.0;
-    if (m.kind == LOGP_GAUSS_RANK1) {
+    if (MODEL == LOGP_GAUSS_RANK1) {
       double s[1] = {0.0};
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
@@ -364,7 +364,7 @@ struct Engine {
       }
       red.allreduce(s);
       a0 = m.rank1_coeff * s[0];  // rank1_term
-    } else if (m.kind == LOGP_FUNNEL) {
+    } else if (MODEL == LOGP_FUNNEL) {
       double s[2] = {0.0, 0.0};
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
@@ -384,7 +384,7 @@ struct Engine {
     const ModelDev& m = P.model;
     double lp = 0.0;
     ev_out = 0.0;
-    if (m.kind == LOGP_GAUSS_ISO) {
+    if (false /* ISO is served by the DIAG code path with prec = 1 */) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = tid + j * TPC;
@@ -395,7 +395,7 @@ struct Engine {
           gx[j] = -diff;
         }
       }
-    } else if (m.kind == LOGP_GAUSS_DIAG) {
+    } else if (MODEL == LOGP_GAUSS_DIAG) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = tid + j * TPC;
@@ -407,7 +407,7 @@ struct Engine {
           gx[j] = -pd;
         }
       }
-    } else if (m.kind == LOGP_GAUSS_RANK1) {
+    } else if (MODEL == LOGP_GAUSS_RANK1) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = tid + j * TPC;
@@ -439,7 +439,7 @@ struct Engine {
   }
   __device__ __forceinline__ double model_finish(double lp_sum, double a0, double a1, double ev) const {
     const ModelDev& m = P.model;
-    if (m.kind == LOGP_FUNNEL) {
+    if (MODEL == LOGP_FUNNEL) {
       double nm1 = (double)(d - 1);
       double half_ev_S = 0.5 * ev * a1;
       return -0.5 * a0 * a0 * m.funnel_inv_var - 0.5 * nm1 * a0 - half_ev_S;
@@ -449,14 +449,63 @@ struct Engine {
 
   // ------------------------------------------------------------------ leapfrog (transformed_hamiltonian.rs:524-615, Euclidean)
   // (z, v, g) <- one velocity-Verlet step of size eps in the whitened space; returns logp' and kinetic energy'.
-  __device__ __forceinline__ void leapfrog(double eps, double& logp_out, double& ke_out) {
+  // When `with_prev` is set it also returns the U-turn products of the pair (previous leaf, new leaf):
+  //   sP = (z' - z) . v ,  sQ = (z' - z) . v'   (same operation order as merge_turning; the previous leaf IS the register
+  // state before the step, so the most frequent merge - two single leaves - needs no checkpoint load and no extra reduction).
+  __device__ __forceinline__ void leapfrog(double eps, double& logp_out, double& ke_out, bool with_prev, double& sP, double& sQ) {
     const double eps_half = eps / 2.;
+    hs_total_lf += 1;
+    if (MODEL == LOGP_GAUSS_DIAG) {
+      // elementwise target: the whole step is ONE pass, nothing but accumulators outlives an element
+      double part[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int i = tid + j * TPC;
+        const double zp = z[j], vp = v[j];
+        const double vh = fma(eps_half, g[j], vp);   // first_velocity_halfstep :178-184  axpy_out(grad, v, eps/2)
+        const double zn = fma(eps, vh, zp);          // position_step :220-225            axpy_out(v', z, eps)
+        const double sgm = sg(j);
+        const double t = zn * sgm;                   // compute_untransformed_position    diagonal.rs:253-255
+        const double xn = fma(1.0, mn(j), t);
+        double gxn = 0.0;
+        if (i < d) {
+          const double diff = xn - model_mu(j, i);
+          const double pd = diff * model_prec(j, i);
+          part[0] -= diff * pd / 2.;
+          gxn = -pd;
+        }
+        const double gn = gxn * sgm;                 // compute_transformed_gradient      diagonal.rs:258-265
+        const double vn = fma(eps_half, gn, vh);     // second_velocity_halfstep :245-247 axpy(grad', v, eps/2)
+        part[1] = fma(vn, vn, part[1]);              // update_kinetic_energy :260-262
+        if (i < d) {
+          const double delta = (zn + 0.0) - zp;
+          part[2] = fma(delta, vp, part[2]);
+          part[3] = fma(delta, vn, part[3]);
+        }
+        z[j] = zn;
+        v[j] = vn;
+        g[j] = gn;
+      }
+      if (with_prev) {
+        red.allreduce(part);
+      } else {
+        double p2[2] = {part[0], part[1]};
+        red.allreduce(p2);
+        part[0] = p2[0];
+        part[1] = p2[1];
+      }
+      logp_out = part[0];
+      ke_out = 0.5 * part[1];
+      sP = part[2];
+      sQ = part[3];
+      return;
+    }
     double x[EPT], gx[EPT];
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      v[j] = fma(eps_half, g[j], v[j]);  // first_velocity_halfstep :178-184  axpy_out(grad, v, eps/2)
-      z[j] = fma(eps, v[j], z[j]);       // position_step :220-225            axpy_out(v', z, eps)
-      double t = z[j] * sg(j);          // compute_untransformed_position    diagonal.rs:253-255  multiply, then axpy(mean, x, 1)
+      v[j] = fma(eps_half, g[j], v[j]);
+      z[j] = fma(eps, v[j], z[j]);
+      double t = z[j] * sg(j);
       x[j] = fma(1.0, mn(j), t);
     }
     double a0, a1, ev;
@@ -466,15 +515,18 @@ struct Engine {
     part[1] = 0.0;
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      g[j] = gx[j] * sg(j);             // compute_transformed_gradient      diagonal.rs:258-265
-      v[j] = fma(eps_half, g[j], v[j]);  // second_velocity_halfstep :245-247 axpy(grad', v, eps/2)
-      part[1] = fma(v[j], v[j], part[1]);  // update_kinetic_energy :260-262
+      g[j] = gx[j] * sg(j);
+      v[j] = fma(eps_half, g[j], v[j]);
+      part[1] = fma(v[j], v[j], part[1]);
     }
     red.allreduce(part);
     logp_out = model_finish(part[0], a0, a1, ev);
     ke_out = 0.5 * part[1];
-    hs_total_lf += 1;
+    sP = 0.0;
+    sQ = 0.0;
   }
+  // whether leapfrog() delivers the products of (previous leaf, new leaf)
+  static constexpr bool kFusedPrevCheck = (MODEL == LOGP_GAUSS_DIAG);
 
   // logp + gradient at the x plane -> gx plane; returns logp (Math::logp_array)
   __device__ __forceinline__ double eval_at_position(double (&x)[EPT], double (&gx)[EPT]) {
@@ -648,9 +700,11 @@ struct Engine {
 
     for (uint32_t i = 0; i < nleaf; ++i) {
       // single_step (nuts.rs:209-245): one leapfrog from the previous leaf; baseline = initial energy
-      double logp_new, ke_new;
+      double logp_new, ke_new, sP0, sQ0;
       NB_ACC(4, tq);
-      leapfrog(eps, logp_new, ke_new);
+      // odd leaves merge with their predecessor first (level 0): its U-turn products come out of the leapfrog itself
+      const bool fuse0 = kFusedPrevCheck && check && (i & 1u);
+      leapfrog(eps, logp_new, ke_new, fuse0, sP0, sQ0);
       NB_ACC(1, tq);
       hs_tree_lf += 1;
       double energy = ke_new - (logp_new + hs_pt_logdet);
@@ -675,8 +729,10 @@ struct Engine {
         const int Af = T.A_first[l], Al = T.A_last[l];
         bool turning = false;
         if (check) {
-          turning = merge_turning(slot_ptr(Af, 0), slot_ptr(Af, 1), slot_ptr(Al, 0), slot_ptr(Al, 1), slot_ptr(B_first, 0),
-                                  slot_ptr(B_first, 1), l > 0, dir);
+          if (l == 0 && fuse0) turning = turn_eval(sP0, sQ0, dir);
+          else
+            turning = merge_turning(slot_ptr(Af, 0), slot_ptr(Af, 1), slot_ptr(Al, 0), slot_ptr(Al, 1), slot_ptr(B_first, 0),
+                                    slot_ptr(B_first, 1), l > 0, dir);
         }
         // merge_into, non-main (nuts.rs:172-207): self_log_size = log_size of the merged tree
         double total = logaddexp(T.A_ls[l], B_ls);
@@ -794,7 +850,8 @@ struct Engine {
     store(sg, g);
     hs_step = P.s.initial_step;
     double lp, k;
-    leapfrog(hs_step, lp, k);
+    double u0, u1;
+    leapfrog(hs_step, lp, k, false, u0, u1);
     double ee = (k - (lp + logdet)) - e0;
     if ((ee > 1000.0) | !isfinite(ee)) return true;
     double accept = exp(fmin(e0 - (k - (lp + logdet)), 0.)) / 1.0;
@@ -803,7 +860,7 @@ struct Engine {
       load(sz, z);
       load(sv, v);
       load(sg, g);
-      leapfrog(forward ? hs_step : -hs_step, lp, k);
+      leapfrog(forward ? hs_step : -hs_step, lp, k, false, u0, u1);
       double en = k - (lp + logdet);
       ee = en - e0;
       if ((ee > 1000.0) | !isfinite(ee)) {
@@ -1072,7 +1129,7 @@ struct Engine {
     NB_ACC(5, tm);
     // ---- adaptation + statistics: cold, through global memory
     store_hot();
-    const int ret = cold_adapt<TPC, EPT, MMS>(P, chain, tid, red.scratch, sm_sig, red.parity, t, acc_sum, acc_sym_sum, acc_count,
+    const int ret = cold_adapt<TPC, EPT, MMS, MODEL>(P, chain, tid, red.scratch, sm_sig, red.parity, t, acc_sum, acc_sym_sum, acc_count,
                                               max_energy_error, diverging ? (abs(draw_idx) > 4) : (draw_idx != 0), depth, reached_maxdepth,
                                               diverging, draw_idx, draw_energy, draw_energy - E0, fisher[0]);
     red.parity = ret & 1;
@@ -1143,13 +1200,13 @@ struct Engine {
 };
 
 // GlobalStrategy::adapt + the statistics of Chain::expanded_draw for one chain; returns the reduction parity (bit 0).
-template <int TPC, int EPT, bool MMS>
+template <int TPC, int EPT, bool MMS, int MODEL>
 __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, int parity, uint64_t t,
                                        double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
                                        int depth, bool reached_maxdepth, bool diverging, int draw_idx, double pt_energy,
                                        double pt_energy_error, double fisher) {
   TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0));
-  Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, tables);
+  Engine<TPC, EPT, MMS, MODEL> E(P, chain, tid, scratch, team_smem, tables);
   E.red.parity = parity;
   E.cold_load();
   E.acc_sum = acc_sum;
@@ -1184,10 +1241,10 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
 }
 
 // Chain::set_position for one chain; returns the per-chain status (0 ok, 3 bad initial point).
-template <int TPC, int EPT, bool MMS>
+template <int TPC, int EPT, bool MMS, int MODEL>
 __device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem) {
   TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0));
-  Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, tables);
+  Engine<TPC, EPT, MMS, MODEL> E(P, chain, tid, scratch, team_smem, tables);
   E.cold_load();
   const int status = E.run_set_position();
   E.hs_alive = status == 0 ? 1 : 0;
@@ -1197,7 +1254,7 @@ __device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, 
 
 // One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).
 // Dynamic shared memory: TEAMS x team_smem_bytes<TPC, EPT, MMS>().
-template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, bool MMS>
+template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, bool MMS, int MODEL>
 __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(const __grid_constant__ EngineParams P) {
   constexpr int TEAMS = CTA_THREADS / TPC;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -1216,10 +1273,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(con
     if (TPC > 32) __syncthreads();
     else __syncwarp();
     if (chain >= P.N) break;
-    Engine<TPC, EPT, MMS> E(P, chain, tid, scratch, team_smem, tables);
+    Engine<TPC, EPT, MMS, MODEL> E(P, chain, tid, scratch, team_smem, tables);
     E.load_model_params();
     if (P.mode == 0) {
-      const int status = cold_set_position<TPC, EPT, MMS>(P, chain, tid, scratch, team_smem);
+      const int status = cold_set_position<TPC, EPT, MMS, MODEL>(P, chain, tid, scratch, team_smem);
       if (tid == 0 && P.status_out) P.status_out[chain] = status;
     } else {
       E.load_hot();

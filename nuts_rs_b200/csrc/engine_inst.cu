@@ -1,15 +1,15 @@
 // engine_inst.cu — one instantiation of the chain kernel per (threads-per-chain, elements-per-thread) pair.
-// Compiled once per configuration with -DCFG_TPC=.. -DCFG_EPT=.. -DCFG_CTA=.. -DCFG_MINB=.. -DCFG_MMS=.. (see Makefile) so
+// Compiled once per configuration with -DCFG_TPC=.. -DCFG_EPT=.. -DCFG_CTA=.. -DCFG_MINB=.. -DCFG_MMS=.. -DCFG_MODEL=.. (see Makefile) so
 // the configurations build in parallel.
 #include "chain_engine.cuh"
 
-#define NB_CAT2(a, b, c, d) a##_##b##_##c##_##d
-#define NB_CAT(a, b, c, d) NB_CAT2(a, b, c, d)
-#define NB_KERNEL nb::nuts_chain_kernel<CFG_TPC, CFG_EPT, CFG_CTA, CFG_MINB, (CFG_MMS != 0)>
+#define NB_CAT2(a, b, c, d, e) a##_##b##_##c##_##d##_##e
+#define NB_CAT(a, b, c, d, e) NB_CAT2(a, b, c, d, e)
+#define NB_KERNEL nb::nuts_chain_kernel<CFG_TPC, CFG_EPT, CFG_CTA, CFG_MINB, (CFG_MMS != 0), CFG_MODEL>
 
 static constexpr size_t kSmem = (CFG_CTA / CFG_TPC) * nb::team_smem_bytes<CFG_TPC, CFG_EPT, (CFG_MMS != 0)>();
 
-extern "C" cudaError_t NB_CAT(nb_launch_chain, CFG_TPC, CFG_EPT, CFG_MINB)(const nb::EngineParams* p, int grid, cudaStream_t stream) {
+extern "C" cudaError_t NB_CAT(nb_launch_chain, CFG_TPC, CFG_EPT, CFG_MINB, CFG_MODEL)(const nb::EngineParams* p, int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured && kSmem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(NB_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
@@ -21,7 +21,7 @@ extern "C" cudaError_t NB_CAT(nb_launch_chain, CFG_TPC, CFG_EPT, CFG_MINB)(const
 }
 
 // resident CTAs per SM for this configuration (grid sizing of the persistent kernel)
-extern "C" cudaError_t NB_CAT(nb_occupancy_chain, CFG_TPC, CFG_EPT, CFG_MINB)(int* blocks_per_sm, int* cta_threads) {
+extern "C" cudaError_t NB_CAT(nb_occupancy_chain, CFG_TPC, CFG_EPT, CFG_MINB, CFG_MODEL)(int* blocks_per_sm, int* cta_threads) {
   *cta_threads = CFG_CTA;
   if (kSmem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(NB_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
