@@ -26,6 +26,9 @@ NB_DECL(32, 4, 16)
 NB_DECL(32, 8, 12)
 NB_DECL(32, 16, 8)
 NB_DECL(64, 16, 4)
+NB_DECL(64, 16, 7)
+NB_DECL(64, 16, 8)
+NB_DECL(128, 8, 5)
 NB_DECL(128, 8, 4)
 NB_DECL(256, 8, 2)
 NB_DECL(512, 8, 1)
@@ -72,7 +75,7 @@ struct EngineConfig {
 const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(64, 16, 4),
                                  NB_CFG(256, 8, 2), NB_CFG(512, 8, 1), NB_CFG(1024, 8, 1), NB_CFG(1024, 10, 1), NB_CFG(1024, 16, 1)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(128, 8, 4)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 

@@ -123,12 +123,12 @@ enum { EXT_OK = 0, EXT_TURNING = 1, EXT_DIVERGING = 2 };
 // The per-draw adaptation and Chain::set_position are COLD: they run in non-inlined functions on their own Engine
 // instance and exchange the chain scalars by value, so that the hot tree builder (run_draw -> extend -> leapfrog, all
 // force-inlined with one call site each) never has its address taken and its vectors really live in registers.
-template <int TPC, int EPT, bool MMS, int MODEL>
+template <int TPC, int EPT, int SMF, int MODEL>
 __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, int parity, uint64_t t,
                                        double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
                                        int depth, bool reached_maxdepth, bool diverging, int draw_idx, double pt_energy,
                                        double pt_energy_error, double fisher);
-template <int TPC, int EPT, bool MMS, int MODEL>
+template <int TPC, int EPT, int SMF, int MODEL>
 __device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem);
 
 // Tree bookkeeping tables of one chain, in shared memory (local-memory tables cost an L1 miss per access once the stacks of
@@ -142,13 +142,19 @@ struct TreeTables {
   signed char A_first[MAX_DOUBLING_DEPTH], A_last[MAX_DOUBLING_DEPTH], A_draw[MAX_DOUBLING_DEPTH];
 };
 
-// bytes of dynamic shared memory one team needs: [sigma | mean | model mu | model prec] (when MMS) followed by the TreeTables
-template <int TPC, int EPT, bool MMS>
+// What lives in the team's dynamic shared memory (SMF bit flags); everything else is registers (or L1-cached global for the
+// model parameters).  Layout: [sigma | mean] (SM_MASS) [model mu | model prec] (SM_MODEL) [grad_z] (SM_GRAD) TreeTables.
+enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4 };
+template <int SMF>
+__host__ __device__ constexpr int smem_vectors() {
+  return ((SMF & SM_MASS) ? 2 : 0) + ((SMF & SM_MODEL) ? 2 : 0) + ((SMF & SM_GRAD) ? 1 : 0);
+}
+template <int TPC, int EPT, int SMF>
 __host__ __device__ constexpr size_t team_smem_bytes() {
-  return (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0) + sizeof(TreeTables);
+  return smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double) + sizeof(TreeTables);
 }
 
-template <int TPC, int EPT, bool MMS, int MODEL>
+template <int TPC, int EPT, int SMF, int MODEL>
 struct Engine {
   const EngineParams& P;
   const int chain;
@@ -160,10 +166,12 @@ struct Engine {
   double* const ends_base;
 
   // ---- register-resident vectors ----
-  double z[EPT], v[EPT], g[EPT];  // current phase-space point (whitened position, velocity, whitened gradient)
-  // this chain's DiagMassMatrix (stds, mean): registers, or shared memory when MMS (large EPT: registers go to z, v, g)
+  static constexpr bool MMS = (SMF & SM_MASS) != 0, MODS = (SMF & SM_MODEL) != 0, GS = (SMF & SM_GRAD) != 0;
+  double z[EPT], v[EPT];  // current phase-space point: whitened position, velocity
+  double g_reg[GS ? 1 : EPT];  // whitened gradient: registers, or shared memory (GS) to fit more chains per SM
+  // this chain's DiagMassMatrix (stds, mean): registers, or shared memory when MMS
   double sig[MMS ? 1 : EPT], mu[MMS ? 1 : EPT];
-  double *sm_sig, *sm_mu, *sm_mmu, *sm_mprec;  // MMS: mass matrix and model parameters of this team's elements
+  double *sm_sig, *sm_mu, *sm_mmu, *sm_mprec, *sm_g;
   TreeTables& T;
 
   // Chain scalars used on the hot path are plain members (registers).  `cs` is only touched by the cold functions, which
@@ -200,17 +208,20 @@ struct Engine {
   __device__ __forceinline__ Engine(const EngineParams& p, int chain_, int tid_, double* scratch, double* team_smem, TreeTables& tables)
       : P(p), chain(chain_), tid(tid_), red(scratch), d(p.d), ld(p.ld), row((size_t)chain_ * p.ld),
         slots_base(p.slots + (size_t)chain_ * p.P * 2 * p.ld), ends_base(p.ends + (size_t)chain_ * 6 * p.ld), sm_sig(team_smem),
-        sm_mu(team_smem + (MMS ? TPC * EPT : 0)), sm_mmu(team_smem + (MMS ? 2 * TPC * EPT : 0)),
-        sm_mprec(team_smem + (MMS ? 3 * TPC * EPT : 0)), T(tables) {
+        sm_mu(team_smem + (MMS ? TPC * EPT : 0)), sm_mmu(team_smem + (MMS ? 2 : 0) * TPC * EPT),
+        sm_mprec(team_smem + ((MMS ? 2 : 0) + (MODS ? 1 : 0)) * TPC * EPT),
+        sm_g(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0)) * TPC * EPT), T(tables) {
     stream = p.chain_offset + (uint64_t)chain_ + 1;  // reference src/sampler.rs:1106 set_stream(chain_id + 1)
   }
   __device__ __forceinline__ double sg(int j) const { return MMS ? sm_sig[tid + j * TPC] : sig[MMS ? 0 : j]; }
   __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[tid + j * TPC] : mu[MMS ? 0 : j]; }
   // model parameters of element i = tid + j*TPC
-  __device__ __forceinline__ double model_mu(int j, int i) const { return MMS ? sm_mmu[tid + j * TPC] : __ldg(P.model.mu + i); }
-  __device__ __forceinline__ double model_prec(int j, int i) const { return MMS ? sm_mprec[tid + j * TPC] : __ldg(P.model.prec + i); }
+  __device__ __forceinline__ double model_mu(int j, int i) const { return MODS ? sm_mmu[tid + j * TPC] : __ldg(P.model.mu + i); }
+  __device__ __forceinline__ double model_prec(int j, int i) const { return MODS ? sm_mprec[tid + j * TPC] : __ldg(P.model.prec + i); }
+  // element j of the whitened gradient (each thread only touches its own entries: no synchronisation)
+  __device__ __forceinline__ double& G(int j) { return GS ? sm_g[tid + j * TPC] : g_reg[GS ? 0 : j]; }
   __device__ __forceinline__ void load_model_params() {
-    if (MMS) {
+    if (MODS) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = tid + j * TPC;
@@ -252,6 +263,23 @@ struct Engine {
     for (int j = 0; j < EPT; ++j) {
       int i = tid + j * TPC;
       if (i < d) dst[i] = a[j];
+    }
+  }
+  __device__ __forceinline__ void load_g(const double* __restrict__ src, bool cg) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      G(j) = i < d ? (cg ? __ldcg(src + i) : src[i]) : 0.0;
+    }
+  }
+  __device__ __forceinline__ void store_g(double* __restrict__ dst, bool cg) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      if (i < d) {
+        if (cg) __stcg(dst + i, G(j));
+        else dst[i] = G(j);
+      }
     }
   }
   __device__ __forceinline__ double* slot_ptr(int s, int which) const { return slots_base + (size_t)((s * 2 + which) * ld); }
@@ -462,7 +490,7 @@ struct Engine {
       for (int j = 0; j < EPT; ++j) {
         const int i = tid + j * TPC;
         const double zp = z[j], vp = v[j];
-        const double vh = fma(eps_half, g[j], vp);   // first_velocity_halfstep :178-184  axpy_out(grad, v, eps/2)
+        const double vh = fma(eps_half, G(j), vp);   // first_velocity_halfstep :178-184  axpy_out(grad, v, eps/2)
         const double zn = fma(eps, vh, zp);          // position_step :220-225            axpy_out(v', z, eps)
         const double sgm = sg(j);
         const double t = zn * sgm;                   // compute_untransformed_position    diagonal.rs:253-255
@@ -484,7 +512,7 @@ struct Engine {
         }
         z[j] = zn;
         v[j] = vn;
-        g[j] = gn;
+        G(j) = gn;
       }
       if (with_prev) {
         red.allreduce(part);
@@ -503,7 +531,7 @@ struct Engine {
     double x[EPT], gx[EPT];
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      v[j] = fma(eps_half, g[j], v[j]);
+      v[j] = fma(eps_half, G(j), v[j]);
       z[j] = fma(eps, v[j], z[j]);
       double t = z[j] * sg(j);
       x[j] = fma(1.0, mn(j), t);
@@ -515,8 +543,8 @@ struct Engine {
     part[1] = 0.0;
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      g[j] = gx[j] * sg(j);
-      v[j] = fma(eps_half, g[j], v[j]);
+      G(j) = gx[j] * sg(j);
+      v[j] = fma(eps_half, G(j), v[j]);
       part[1] = fma(v[j], v[j], part[1]);
     }
     red.allreduce(part);
@@ -570,17 +598,17 @@ struct Engine {
       int i = tid + j * TPC;
       double t = fma(-1.0, mn(j), x[j]);  // axpy_out(mean, x, -1)
       z[j] = is[j] * t;                   // multiply_inplace(z, inv_stds): out = x*out
-      g[j] = gx[j] * sg(j);
+      G(j) = gx[j] * sg(j);
       if (i < d) {
-        bool ok = isfinite(z[j]) && isfinite(g[j]) && (g[j] != 0.0) && isfinite(gx[j]) && isfinite(x[j]);
+        bool ok = isfinite(z[j]) && isfinite(G(j)) && (G(j) != 0.0) && isfinite(gx[j]) && isfinite(x[j]);
         if (!ok) bad[0] = 1.0;
       } else {
         z[j] = 0.0;
-        g[j] = 0.0;
+        G(j) = 0.0;
       }
     }
     store(P.z + row, z);
-    store(P.gz + row, g);
+    store_g(P.gz + row, false);
     red.allreduce(bad);
     return bad[0] == 0.0;
   }
@@ -690,7 +718,7 @@ struct Engine {
     if (!(dir ? holds_right : holds_left)) {
       load_cg(nearZ, z);
       load_cg(nearV, v);
-      load_cg(near_init ? P.gz + row : end_ptr(dir, 2), g);
+      load_g(near_init ? P.gz + row : end_ptr(dir, 2), true);
     }
     holds_left = holds_right = false;
     int idx_cur = dir ? idx_right : idx_left;
@@ -780,7 +808,7 @@ struct Engine {
     depth += 1;
     store_cg(end_ptr(dir, 0), z);
     store_cg(end_ptr(dir, 1), v);
-    store_cg(end_ptr(dir, 2), g);
+    store_g(end_ptr(dir, 2), true);
     if (dir) {
       idx_right = idx_cur;
       init_right = false;
@@ -847,7 +875,7 @@ struct Engine {
     double* sg = end_ptr(0, 2);
     store(sz, z);
     store(sv, v);
-    store(sg, g);
+    store_g(sg, false);
     hs_step = P.s.initial_step;
     double lp, k;
     double u0, u1;
@@ -859,7 +887,7 @@ struct Engine {
     for (int it = 0; it < 100; ++it) {
       load(sz, z);
       load(sv, v);
-      load(sg, g);
+      load_g(sg, false);
       leapfrog(forward ? hs_step : -hs_step, lp, k, false, u0, u1);
       double en = k - (lp + logdet);
       ee = en - e0;
@@ -1034,7 +1062,7 @@ struct Engine {
       hs_pt_tid = hs_mm_id;
     } else {
       load(P.z + row, z);
-      load(P.gz + row, g);
+      load_g(P.gz + row, false);
     }
     sample_velocity();
     store(P.v0 + row, v);
@@ -1108,15 +1136,15 @@ struct Engine {
       }
       hs_logp = eval_at_position(x, gx);
 #pragma unroll
-      for (int j = 0; j < EPT; ++j) g[j] = gx[j] * sg(j);
+      for (int j = 0; j < EPT; ++j) G(j) = gx[j] * sg(j);
       store(P.x + row, x);
       store(P.gx + row, gx);
       store(P.z + row, z);
-      store(P.gz + row, g);
+      store_g(P.gz + row, false);
       if (P.draws_out) store(P.draws_out + (t * N + chain) * (size_t)d, x);
     } else {
       load(P.z + row, z);
-      load(P.gz + row, g);
+      load_g(P.gz + row, false);
       if (P.draws_out) {
         double x[EPT];
         load(P.x + row, x);
@@ -1124,12 +1152,12 @@ struct Engine {
       }
     }
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) fisher[0] += (z[j] + g[j]) * (z[j] + g[j]);  // sq_norm_sum (cpu_math.rs:235-243)
+    for (int j = 0; j < EPT; ++j) fisher[0] += (z[j] + G(j)) * (z[j] + G(j));  // sq_norm_sum (cpu_math.rs:235-243)
     red.allreduce(fisher);
     NB_ACC(5, tm);
     // ---- adaptation + statistics: cold, through global memory
     store_hot();
-    const int ret = cold_adapt<TPC, EPT, MMS, MODEL>(P, chain, tid, red.scratch, sm_sig, red.parity, t, acc_sum, acc_sym_sum, acc_count,
+    const int ret = cold_adapt<TPC, EPT, SMF, MODEL>(P, chain, tid, red.scratch, sm_sig, red.parity, t, acc_sum, acc_sym_sum, acc_count,
                                               max_energy_error, diverging ? (abs(draw_idx) > 4) : (draw_idx != 0), depth, reached_maxdepth,
                                               diverging, draw_idx, draw_energy, draw_energy - E0, fisher[0]);
     red.parity = ret & 1;
@@ -1200,13 +1228,13 @@ struct Engine {
 };
 
 // GlobalStrategy::adapt + the statistics of Chain::expanded_draw for one chain; returns the reduction parity (bit 0).
-template <int TPC, int EPT, bool MMS, int MODEL>
+template <int TPC, int EPT, int SMF, int MODEL>
 __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, int parity, uint64_t t,
                                        double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
                                        int depth, bool reached_maxdepth, bool diverging, int draw_idx, double pt_energy,
                                        double pt_energy_error, double fisher) {
-  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0));
-  Engine<TPC, EPT, MMS, MODEL> E(P, chain, tid, scratch, team_smem, tables);
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
+  Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
   E.red.parity = parity;
   E.cold_load();
   E.acc_sum = acc_sum;
@@ -1241,10 +1269,10 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
 }
 
 // Chain::set_position for one chain; returns the per-chain status (0 ok, 3 bad initial point).
-template <int TPC, int EPT, bool MMS, int MODEL>
+template <int TPC, int EPT, int SMF, int MODEL>
 __device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem) {
-  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0));
-  Engine<TPC, EPT, MMS, MODEL> E(P, chain, tid, scratch, team_smem, tables);
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
+  Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
   E.cold_load();
   const int status = E.run_set_position();
   E.hs_alive = status == 0 ? 1 : 0;
@@ -1253,8 +1281,8 @@ __device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, 
 }
 
 // One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).
-// Dynamic shared memory: TEAMS x team_smem_bytes<TPC, EPT, MMS>().
-template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, bool MMS, int MODEL>
+// Dynamic shared memory: TEAMS x team_smem_bytes<TPC, EPT, SMF>().
+template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, int SMF, int MODEL>
 __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(const __grid_constant__ EngineParams P) {
   constexpr int TEAMS = CTA_THREADS / TPC;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -1262,9 +1290,9 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(con
   __shared__ int next_chain[TEAMS];
   const int team = threadIdx.x / TPC;
   const int tid = threadIdx.x % TPC;
-  unsigned char* my_smem = dyn_smem + (size_t)team * team_smem_bytes<TPC, EPT, MMS>();
+  unsigned char* my_smem = dyn_smem + (size_t)team * team_smem_bytes<TPC, EPT, SMF>();
   double* team_smem = reinterpret_cast<double*>(my_smem);
-  TreeTables& tables = *reinterpret_cast<TreeTables*>(my_smem + (MMS ? 4 * (size_t)TPC * EPT * sizeof(double) : 0));
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(my_smem + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
   for (;;) {
     if (tid == 0) next_chain[team] = (int)atomicAdd(P.queue, 1u);
     if (TPC > 32) __syncthreads();
@@ -1273,10 +1301,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(con
     if (TPC > 32) __syncthreads();
     else __syncwarp();
     if (chain >= P.N) break;
-    Engine<TPC, EPT, MMS, MODEL> E(P, chain, tid, scratch, team_smem, tables);
+    Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
     E.load_model_params();
     if (P.mode == 0) {
-      const int status = cold_set_position<TPC, EPT, MMS, MODEL>(P, chain, tid, scratch, team_smem);
+      const int status = cold_set_position<TPC, EPT, SMF, MODEL>(P, chain, tid, scratch, team_smem);
       if (tid == 0 && P.status_out) P.status_out[chain] = status;
     } else {
       E.load_hot();

@@ -5,9 +5,9 @@
 
 #define NB_CAT2(a, b, c, d, e) a##_##b##_##c##_##d##_##e
 #define NB_CAT(a, b, c, d, e) NB_CAT2(a, b, c, d, e)
-#define NB_KERNEL nb::nuts_chain_kernel<CFG_TPC, CFG_EPT, CFG_CTA, CFG_MINB, (CFG_MMS != 0), CFG_MODEL>
+#define NB_KERNEL nb::nuts_chain_kernel<CFG_TPC, CFG_EPT, CFG_CTA, CFG_MINB, CFG_MMS, CFG_MODEL>
 
-static constexpr size_t kSmem = (CFG_CTA / CFG_TPC) * nb::team_smem_bytes<CFG_TPC, CFG_EPT, (CFG_MMS != 0)>();
+static constexpr size_t kSmem = (CFG_CTA / CFG_TPC) * nb::team_smem_bytes<CFG_TPC, CFG_EPT, CFG_MMS>();
 
 extern "C" cudaError_t NB_CAT(nb_launch_chain, CFG_TPC, CFG_EPT, CFG_MINB, CFG_MODEL)(const nb::EngineParams* p, int grid, cudaStream_t stream) {
   static bool configured = false;

@@ -14,7 +14,8 @@ from . import _abi
 from ._abi import c_double_p as dp
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnuts_b200.so")
+# NUTS_B200_LIB selects an instrumented build of the same library (e.g. the -DNB_PHASE_TIMING one) for experiments
+LIB_PATH = os.environ.get("NUTS_B200_LIB") or os.path.join(_HERE, "libnuts_b200.so")
 _LIB = None
 
 EXPORTED_SYMBOLS = [
