@@ -57,23 +57,59 @@ def settings():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML through pynvml (one
+    sample per ~2 ms, the timed region is tens of ms); falls back to polling nvidia-smi when pynvml is unavailable."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device_index):
-        self.rows = []
+        self.rows = []  # (sm_mhz, sm_max_mhz, power_w, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap)
         self.stop = False
         self.idx = device_index
+        self.nvml = None
+        self.source = "nvidia-smi"
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = device_index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if device_index < len(ids) and ids[device_index].isdigit():
+                    phys = int(ids[device_index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self.run, daemon=True)
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        return (float(sm), float(mx), pw, bool(r & n.nvmlClocksThrottleReasonHwSlowdown), bool(r & n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                bool(r & n.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & n.nvmlClocksThrottleReasonSwPowerCap))
 
     def run(self):
         while not self.stop:
             try:
+                if self.nvml is not None:
+                    self.rows.append(self.sample_nvml())
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.check_output(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                               timeout=5).decode().strip()
-                self.rows.append([c.strip() for c in out.split(",")])
+                c = [x.strip() for x in out.split(",")]
+                self.rows.append((float(c[0]), float(c[1]), float(c[2])) + tuple(x.lower().startswith("active") for x in c[3:7]))
             except Exception:
                 pass
             time.sleep(0.2)
@@ -88,14 +124,12 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        reasons = []
-        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(r[col].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows),
-                "power_w_max": max(float(r[2]) for r in self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [name for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6))
+                   if any(r[col] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows),
+                "power_w_max": max(r[2] for r in self.rows), "source": self.source}
 
 
 def cpu_oracle_throughput(max_seconds, nthreads):
@@ -210,7 +244,8 @@ def main():
     tune_leapfrogs, _ = samp.counters()
 
     dev_draws = torch.empty((dps, N, DIM), dtype=torch.float64, device="cuda")
-    host_draws = torch.empty((dps, N, DIM), dtype=torch.float64).pin_memory().numpy()
+    host_buf = lib.HostBuffer((dps, N, DIM))  # page-locked + device-mapped: nuts_draw lets the kernel write it directly
+    host_draws = host_buf.array
     stats_struct, stats_arrays = lib.alloc_stats(dps, N)
 
     def barrier():
@@ -255,6 +290,7 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - e0
     d2h = host_draws.nbytes + sum(a.nbytes for a in stats_arrays.values())
+    e2e_direct = samp.last_draw_direct()
 
     # ---------------- reduce over ranks: max time, summed work
     t = torch.tensor([kernel_ms, wall_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -289,6 +325,15 @@ def main():
         per_gpu_steps_per_launch = steps_dev / max(1, launches)
         avg_launch_ms = kernel_ms / max(1, launches)
         achieved = per_gpu_steps_per_launch * alg_bytes_per_step / (avg_launch_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the same kernel on the same workload (10 draws x 1024 chains),
+        # from the committed `ncu --set full` capture (profiles/); scaled to this run's draws per launch
+        traffic, traffic_src = None, None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "draw_kernel_ncu_latest.json")))
+            traffic = float(prof["dram_traffic_bytes_per_launch"]) * dps / float(prof.get("draws_per_launch", 10))
+            traffic_src = f"profiles/draw_kernel_ncu_latest.json ({prof.get('Kernel Name', '?')})"
+        except Exception:
+            pass
         cpu = None
         if not args.no_cpu_baseline:
             cpu, _, _ = cpu_oracle_throughput(args.cpu_seconds, os.cpu_count() or 1)
@@ -304,13 +349,15 @@ def main():
                        "tuning_phase": {"draws": NUM_TUNE, "kernel_ms": tune_ms, "wall_s": tune_wall, "leapfrogs": tune_leapfrogs,
                                         "leapfrogs_per_s": tune_leapfrogs / max(tune_ms * 1e-3, 1e-9)}},
             "e2e": {"value": steps_e2e_all / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
-                    "note": "nuts_draw with pinned host buffers: every draw [draws x chains x dim] f64 and all 15 statistics copied D2H inside "
-                            "the timed region; chain state stays resident between calls like the reference's Chain (initial positions: one "
-                            f"{x0.nbytes}-byte H2D in nuts_set_position, outside the steps)"},
+                    "draws_path": "kernel writes the page-locked host buffer directly (posted PCIe writes overlapping the sampling)"
+                                  if e2e_direct else "device staging buffer + cudaMemcpyAsync D2H after the kernel",
+                    "note": "nuts_draw with page-locked host buffers: every draw [draws x chains x dim] f64 and all 15 statistics reach host "
+                            "memory inside the timed region; chain state stays resident between calls like the reference's Chain (initial "
+                            f"positions: one {x0.nbytes}-byte H2D in nuts_set_position, outside the steps)"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_kind,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src, "peak_source": peak_kind,
                          "note": "achieved = leapfrogs per launch x 48*dim algorithmic bytes / launch duration; the engine keeps z, v, grad in "
                                  "registers across leapfrogs, so algorithmic bytes are NOT DRAM bytes (frac > 1 is possible); see DESIGN.md"},
             "cpu_baseline": cpu,
@@ -320,6 +367,7 @@ def main():
         print(json.dumps(line), flush=True)
     samp.close()
     math.close()
+    host_buf.close()
     if world > 1:
         dist.destroy_process_group()
 

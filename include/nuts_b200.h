@@ -238,6 +238,13 @@ int nuts_set_position(nuts_sampler_t*, const double* position, int32_t* status);
 /* n_draws x Chain::draw for every chain.  draws_out: HOST [n_draws x N x d] (may be NULL); stats: HOST SoA (may be NULL).
  * Returns after the stream is synchronised. */
 int nuts_draw(nuts_sampler_t*, uint64_t n_draws, double* draws_out, const nuts_stats_t* stats);
+/* draws_out placement decides how the draws leave the GPU: a page-locked host buffer (nuts_host_alloc, cudaHostAlloc,
+ * cudaHostRegister, torch pin_memory) or a device buffer is written DIRECTLY by the draw kernel (posted PCIe writes that
+ * overlap the sampling; no staging copy); pageable host memory is staged through a device buffer and copied afterwards. */
+int nuts_host_alloc(void** ptr, uint64_t bytes);   /* page-locked, device-mapped host memory (cudaHostAlloc) */
+int nuts_host_free(void* ptr);
+/* 1 when the last nuts_draw wrote the draws straight into the caller's buffer, 0 when it staged them. */
+int nuts_sampler_last_draw_direct(nuts_sampler_t*, int32_t* direct);
 /* Same, but draws stay on the device: draws_dev is a DEVICE pointer [n_draws x N x d] (may be NULL). Asynchronous on the ctx stream. */
 int nuts_draw_device(nuts_sampler_t*, uint64_t n_draws, double* draws_dev);
 /* total leapfrog steps (sum over chains, incl. init searches and divergent steps) and draws done so far. */

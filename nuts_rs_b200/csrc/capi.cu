@@ -25,7 +25,11 @@ NB_DECL(32, 2, 16)
 NB_DECL(32, 4, 16)
 NB_DECL(32, 8, 12)
 NB_DECL(32, 16, 8)
+NB_DECL(32, 32, 8)
+NB_DECL(32, 32, 7)
 NB_DECL(64, 16, 4)
+NB_DECL(64, 16, 5)
+NB_DECL(64, 16, 6)
 NB_DECL(64, 16, 7)
 NB_DECL(64, 16, 8)
 NB_DECL(128, 8, 5)
@@ -75,7 +79,7 @@ struct EngineConfig {
 const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(64, 16, 4),
                                  NB_CFG(256, 8, 2), NB_CFG(512, 8, 1), NB_CFG(1024, 8, 1), NB_CFG(1024, 10, 1), NB_CFG(1024, 16, 1)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 
@@ -130,6 +134,7 @@ struct nuts_sampler {
   uint64_t last_launches = 0;
   uint64_t draws_done = 0;
   bool positioned = false;
+  bool last_direct = false;  // the last nuts_draw wrote its draws straight into the caller's buffer
 };
 
 namespace {
@@ -904,13 +909,27 @@ int nuts_draw(nuts_sampler_t* s, uint64_t n_draws, double* draws_out, const nuts
   if (n_draws == 0) return NUTS_OK;
   s->last_launches = 0;
   const size_t per_draw = ctx->N * ctx->d;
-  if (draws_out && n_draws > s->draws_capacity) {
+  // Where the kernel writes the draws.  A pinned (page-locked, device-mapped) host buffer or a device buffer is written
+  // DIRECTLY by the kernel: 8*d bytes per draw and chain leave as coalesced posted writes over PCIe / into HBM while the
+  // chains keep stepping, so there is no device staging buffer and no serial D2H copy after the kernel.  Pageable host
+  // memory goes through a device buffer and one cudaMemcpyAsync.  NUTS_B200_STAGED_D2H=1 forces the staged path (A/B timing).
+  double* direct = nullptr;
+  if (draws_out && !std::getenv("NUTS_B200_STAGED_D2H")) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, draws_out) == cudaSuccess) {
+      if ((attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged) && attr.devicePointer) direct = (double*)attr.devicePointer;
+      else if (attr.type == cudaMemoryTypeDevice && attr.device == ctx->device) direct = draws_out;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  if (draws_out && !direct && n_draws > s->draws_capacity) {
     TRY(grow(&s->d_draws, n_draws * per_draw));
     s->draws_capacity = n_draws;
   }
-  if (draws_out) CUDA_TRY(cudaMemsetAsync(s->d_draws, 0xff, n_draws * per_draw * sizeof(double), ctx->stream));  // NaN for dead chains
-  TRY(run_draws(s, n_draws, draws_out ? s->d_draws : nullptr, stats != nullptr));
-  if (draws_out)
+  TRY(run_draws(s, n_draws, draws_out ? (direct ? direct : s->d_draws) : nullptr, stats != nullptr));
+  s->last_direct = direct != nullptr;
+  if (draws_out && !direct)
     CUDA_TRY(cudaMemcpyAsync(draws_out, s->d_draws, n_draws * per_draw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (stats) {
     const size_t n = n_draws * ctx->N;
@@ -938,6 +957,23 @@ int nuts_draw(nuts_sampler_t* s, uint64_t n_draws, double* draws_out, const nuts
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
   s->last_kernel_ms = ms;
+  return NUTS_OK;
+}
+
+int nuts_host_alloc(void** ptr, uint64_t bytes) {
+  if (!ptr) return fail(NUTS_ERR_INVALID, "nuts_host_alloc: ptr is NULL");
+  TRY(check_device());
+  CUDA_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+  return NUTS_OK;
+}
+
+int nuts_host_free(void* ptr) {
+  if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+  return NUTS_OK;
+}
+
+int nuts_sampler_last_draw_direct(nuts_sampler_t* s, int32_t* direct) {
+  if (direct) *direct = s->last_direct ? 1 : 0;
   return NUTS_OK;
 }
 

@@ -130,6 +130,7 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
                                        double pt_energy_error, double fisher);
 template <int TPC, int EPT, int SMF, int MODEL>
 __device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem);
+static __device__ __noinline__ void cold_fill_dead(const EngineParams& P, int chain, int tid, int tpc, uint64_t t0);
 
 // Tree bookkeeping tables of one chain, in shared memory (local-memory tables cost an L1 miss per access once the stacks of
 // all resident threads exceed L1).  Every thread computes the same values; thread 0 of the team stores them.  An entry
@@ -1244,7 +1245,10 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
   E.cs.is_good = is_good ? 1 : 0;  // register_draw (transform/adapt/diagonal.rs:74-83)
   const bool ok = E.adapt(E.cs.draw_count);
   E.cs.draw_count += 1;
-  if (!ok) E.hs_alive = 0;
+  if (!ok) {
+    E.hs_alive = 0;
+    if (P.draws_out) cold_fill_dead(P, chain, tid, TPC, t + 1);
+  }
   if (tid == 0) {
     const StatsDev& st = P.stats;
     const size_t k = (size_t)t * (size_t)P.N + chain;
@@ -1280,6 +1284,14 @@ __device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, 
   return status;
 }
 
+static __device__ __noinline__ void cold_fill_dead(const EngineParams& P, int chain, int tid, int tpc, uint64_t t0) {
+  const double nan = __longlong_as_double(-1ll);
+  for (uint64_t t = t0; t < P.n_draws; ++t) {
+    double* dst = P.draws_out + (t * (size_t)P.N + chain) * (size_t)P.d;
+    for (int i = tid; i < P.d; i += tpc) dst[i] = nan;
+  }
+}
+
 // One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).
 // Dynamic shared memory: TEAMS x team_smem_bytes<TPC, EPT, SMF>().
 template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, int SMF, int MODEL>
@@ -1311,8 +1323,11 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(con
       if (E.hs_alive) {
         for (uint64_t t = 0; t < P.n_draws; ++t) {
           E.run_draw(t);
-          if (!E.hs_alive) break;
+          if (!E.hs_alive) break;  // cold_adapt has NaN-filled the draws this chain will never produce
         }
+      } else if (P.draws_out) {
+        // draws a dead chain never produced read NaN (the output buffer may be host memory the kernel writes directly)
+        cold_fill_dead(P, chain, tid, TPC, 0);
       }
     }
     if (TPC > 32) __syncthreads();

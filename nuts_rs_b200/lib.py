@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "nuts_set_transform", "nuts_get_transform", "nuts_init_state", "nuts_initialize_trajectory", "nuts_leapfrog", "nuts_is_turning",
     "nuts_sampler_create", "nuts_sampler_destroy", "nuts_set_position", "nuts_draw", "nuts_draw_device",
     "nuts_sampler_counters", "nuts_sampler_last_timing", "nuts_sampler_get_state", "nuts_sampler_set_step_size",
+    "nuts_host_alloc", "nuts_host_free", "nuts_sampler_last_draw_direct",
 ]
 
 
@@ -106,6 +107,9 @@ def load():
     L.nuts_sampler_last_timing.argtypes = [vp, dp, _abi.c_u64_p]
     L.nuts_sampler_get_state.argtypes = [vp, dp, dp, dp, dp, _abi.c_u64_p]
     L.nuts_sampler_set_step_size.argtypes = [vp, dp]
+    L.nuts_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
+    L.nuts_host_free.argtypes = [vp]
+    L.nuts_sampler_last_draw_direct.argtypes = [vp, _abi.c_i32_p]
     _LIB = L
     return L
 
@@ -386,6 +390,24 @@ class CudaMath:
         pass  # explicit close(); planes / points may outlive python GC order
 
 
+class HostBuffer:
+    """Page-locked, device-mapped host memory (nuts_host_alloc) viewed as a numpy f64 array.  Passed as `out=` to
+    Sampler.draw it is written directly by the draw kernel (no staging copy).  Keep the object alive while `array` is used."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.ptr = C.c_void_p()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        _check(load().nuts_host_alloc(C.byref(self.ptr), max(n, 1)))
+        buf = (C.c_char * max(n, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            load().nuts_host_free(self.ptr)
+            self.ptr = None
+
+
 def alloc_stats(n_draws, nchains, names=None):
     st = _abi.Stats()
     arrays = {}
@@ -431,6 +453,11 @@ class Sampler:
         a, b = C.c_uint64(), C.c_uint64()
         _check(load().nuts_sampler_counters(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def last_draw_direct(self):
+        v = C.c_int32()
+        _check(load().nuts_sampler_last_draw_direct(self.h, C.byref(v)))
+        return bool(v.value)
 
     def last_timing(self):
         ms, n = C.c_double(), C.c_uint64()

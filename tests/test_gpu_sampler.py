@@ -275,3 +275,32 @@ def test_chain_offset_invariance_and_split_draw_calls(L, orc):
         x.close()
     for x in (m_all, m_sh):
         x.close()
+
+
+def test_draws_written_directly_into_pinned_host_memory(L):
+    """nuts_draw picks the output path from where draws_out lives (include/nuts_b200.h): page-locked host memory is written
+    by the draw kernel itself, pageable memory is staged.  Both must deliver bit-identical draws (≙ Chain::draw's position,
+    src/chain.rs:169-171) and a dead chain's missing draws must read NaN on both."""
+    N, d, n = 24, 100, 12
+    x0 = np.random.default_rng(3).normal(size=(N, d))
+    x0[5, 7] = np.inf  # BadInitGrad for chain 5 (transformed_hamiltonian.rs:678-681): it never produces a draw
+    outs = []
+    for pinned in (False, True):
+        m = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_DIAG, **_model_kwargs(_abi.NUTS_LOGP_GAUSS_DIAG, d))
+        s = L.Sampler(m, _settings(L, num_tune=6, maxdepth=6), seed=11)
+        st = s.set_position(x0)
+        assert st[5] == 3 and (np.delete(st, 5) == 0).all()
+        buf = L.HostBuffer((n, N, d)) if pinned else None
+        draws, stats = s.draw(n, out=buf.array if pinned else None)
+        assert s.last_draw_direct() == pinned
+        outs.append((draws.copy(), stats))
+        s.close()
+        m.close()
+        if buf is not None:
+            buf.close()
+    (a, sa), (b, sb) = outs
+    assert np.isnan(a[:, 5]).all() and np.isnan(b[:, 5]).all()
+    live = np.delete(np.arange(N), 5)
+    assert np.array_equal(a[:, live], b[:, live])
+    for k in sa:
+        assert np.array_equal(sa[k][:, live], sb[k][:, live]), k
