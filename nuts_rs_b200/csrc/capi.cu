@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../include/nuts_b200.h"
-#include "chain_engine.cuh"
+#include "chain_engine_v2.cuh"
 #include "plane_kernels.cuh"
 
 using namespace nb;
@@ -18,7 +18,7 @@ using namespace nb;
 // Weak declarations: a development build may contain only a subset of the (tiling, model) matrix (make CONFIGS=.. MODELS=..).
 #define NB_DECL1(TPC, EPT, MINB, MODEL)                                                                                                      \
   extern "C" __attribute__((weak)) cudaError_t nb_launch_chain_##TPC##_##EPT##_##MINB##_##MODEL(const EngineParams* p, int grid, cudaStream_t s); \
-  extern "C" __attribute__((weak)) cudaError_t nb_occupancy_chain_##TPC##_##EPT##_##MINB##_##MODEL(int* blocks_per_sm, int* cta_threads);
+  extern "C" __attribute__((weak)) cudaError_t nb_occupancy_chain_##TPC##_##EPT##_##MINB##_##MODEL(int* blocks_per_sm, int* cta_threads, int* smf);
 #define NB_DECL(TPC, EPT, MINB) NB_DECL1(TPC, EPT, MINB, 1) NB_DECL1(TPC, EPT, MINB, 2) NB_DECL1(TPC, EPT, MINB, 3)
 NB_DECL(32, 1, 16)
 NB_DECL(32, 2, 16)
@@ -28,6 +28,7 @@ NB_DECL(32, 16, 8)
 NB_DECL(32, 32, 8)
 NB_DECL(32, 32, 7)
 NB_DECL(64, 16, 4)
+NB_DECL(64, 16, 54)  // SM_EXACT variant of 64x16x4 (rows padded to 1024)
 NB_DECL(64, 16, 5)
 NB_DECL(64, 16, 6)
 NB_DECL(64, 16, 7)
@@ -39,6 +40,8 @@ NB_DECL(512, 8, 1)
 NB_DECL(1024, 8, 1)
 NB_DECL(1024, 10, 1)
 NB_DECL(1024, 16, 1)
+// decoupled engine (engine_v2_inst.cu): third number = 100 + teams per CTA; diagonal / isotropic Gaussian only
+NB_DECL1(64, 16, 107, 1)
 
 namespace {
 
@@ -64,7 +67,7 @@ struct EngineConfig {
   int tpc, ept, minb, max_d;
   // indexed by model variant - 1 (1 diagonal/isotropic Gaussian, 2 rank-1 Gaussian, 3 funnel)
   cudaError_t (*launch[3])(const EngineParams*, int, cudaStream_t);
-  cudaError_t (*occupancy[3])(int*, int*);
+  cudaError_t (*occupancy[3])(int*, int*, int*);
 };
 #define NB_CFG(TPC, EPT, MINB)                                                                                                             \
   {                                                                                                                                        \
@@ -74,12 +77,14 @@ struct EngineConfig {
       nb_occupancy_chain_##TPC##_##EPT##_##MINB##_1, nb_occupancy_chain_##TPC##_##EPT##_##MINB##_2, nb_occupancy_chain_##TPC##_##EPT##_##MINB##_3 \
     }                                                                                                                                      \
   }
+#define NB_CFG1(TPC, EPT, MINB) \
+  { TPC, EPT, MINB, TPC* EPT, {nb_launch_chain_##TPC##_##EPT##_##MINB##_1, nullptr, nullptr}, {nb_occupancy_chain_##TPC##_##EPT##_##MINB##_1, nullptr, nullptr} }
 // default choice: the first entry whose capacity (tpc*ept) covers dim.  Warp-per-chain up to dim 1024 (no barrier in
 // the whole kernel, all 1024 chains of config 2 resident at once); CTA-per-chain above.
 const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(64, 16, 4),
                                  NB_CFG(256, 8, 2), NB_CFG(512, 8, 1), NB_CFG(1024, 8, 1), NB_CFG(1024, 10, 1), NB_CFG(1024, 16, 1)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 
@@ -358,8 +363,10 @@ static int plane_from_host(nuts_ctx* ctx, double* plane, const double* src) {
   CHECK_LAUNCH();
   return sync(ctx);
 }
-static int plane_to_host(nuts_ctx* ctx, const double* plane, double* dst) {
-  k_unpack<<<(unsigned)ctx->N, PK_THREADS, 0, ctx->stream>>>(ctx->row_args(), plane, ctx->d_dense);
+static int plane_to_host(nuts_ctx* ctx, const double* plane, double* dst, int ld = 0) {
+  RowArgs ra = ctx->row_args();
+  if (ld > 0) ra.ld = ld;
+  k_unpack<<<(unsigned)ctx->N, PK_THREADS, 0, ctx->stream>>>(ra, plane, ctx->d_dense);
   CHECK_LAUNCH();
   CUDA_TRY(cudaMemcpyAsync(dst, ctx->d_dense, ctx->N * ctx->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   return sync(ctx);
@@ -692,8 +699,23 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   EngineParams& P = s->P;
   P.N = (int)ctx->N;
   P.d = (int)ctx->d;
-  P.ld = (int)ctx->ld;
-  P.P = (int)std::min<uint64_t>(MAX_SLOTS, 3 * (st->maxdepth + st->extra_doublings) + 4);
+  int blocks_per_sm = 0, cta_threads = 0, smf = 0;
+  s->model_variant = ctx->model.kind == NUTS_LOGP_GAUSS_RANK1 ? 1 : ctx->model.kind == NUTS_LOGP_FUNNEL ? 2 : 0;
+  if (!cfg->launch[s->model_variant] || !cfg->occupancy[s->model_variant]) {
+    delete s;
+    return fail(NUTS_ERR_UNSUPPORTED, "engine %dx%d for model kind %d is not part of this build", cfg->tpc, cfg->ept, ctx->model.kind);
+  }
+  CUDA_TRY(cfg->occupancy[s->model_variant](&blocks_per_sm, &cta_threads, &smf));
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  // SM_EXACT engines run their hot loops without bounds checks: every sampler row is zero-padded to tpc*ept elements
+  P.ld = (smf & SM_EXACT) ? (int)std::max<uint64_t>(ctx->ld, (uint64_t)cfg->tpc * cfg->ept) : (int)ctx->ld;
+  const bool decoupled = cfg->minb >= 100;  // chain_engine_v2.cuh
+  if (decoupled && st->maxdepth + st->extra_doublings > (uint64_t)V2_MAXD + 1) {
+    delete s;
+    return fail(NUTS_ERR_UNSUPPORTED, "the decoupled engine needs maxdepth + extra_doublings <= %d", V2_MAXD + 1);
+  }
+  // checkpoint pool: 3 roles per pending level + the main tree's draw; the decoupled engine hands slots out V2_K leaves ahead
+  P.P = (int)std::min<uint64_t>(MAX_SLOTS, 3 * (st->maxdepth + st->extra_doublings) + 4 + (decoupled ? V2_K : 0));
   P.model = ctx->model;
   P.seed = seed;
   P.chain_offset = chain_id_offset;
@@ -732,7 +754,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   S.mm_update_freq = a.mass_matrix_update_freq;
   S.mm_window_growth = a.mass_matrix_window_growth;
 
-  const size_t plane = ctx->N * ctx->ld * sizeof(double);
+  const size_t plane = ctx->N * (size_t)P.ld * sizeof(double);
   int r = NUTS_OK;
   auto A = [&](void** p, size_t bytes) {
     if (r == NUTS_OK) r = sampler_alloc(s, p, bytes);
@@ -747,7 +769,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   A((void**)&P.mean, plane);
   A((void**)&P.est, plane * 8);
   A((void**)&P.slots, plane * 2 * (size_t)P.P);
-  A((void**)&P.ends, plane * 6);
+  A((void**)&P.ends, plane * 3 * NB_END_BUFFERS);
   A((void**)&P.cs, ctx->N * sizeof(ChainState));
   A((void**)&P.queue, sizeof(unsigned int));
   A((void**)&s->d_init, ctx->N * ctx->d * sizeof(double));
@@ -778,14 +800,6 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   }
   CUDA_TRY(cudaMemcpy(P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice));
   // persistent grid: one wave of resident CTAs
-  int blocks_per_sm = 0, cta_threads = 0;
-  s->model_variant = ctx->model.kind == NUTS_LOGP_GAUSS_RANK1 ? 1 : ctx->model.kind == NUTS_LOGP_FUNNEL ? 2 : 0;
-  if (!cfg->launch[s->model_variant] || !cfg->occupancy[s->model_variant]) {
-    nuts_sampler_destroy(s);
-    return fail(NUTS_ERR_UNSUPPORTED, "engine %dx%d for model kind %d is not part of this build", cfg->tpc, cfg->ept, ctx->model.kind);
-  }
-  CUDA_TRY(cfg->occupancy[s->model_variant](&blocks_per_sm, &cta_threads));
-  if (blocks_per_sm < 1) blocks_per_sm = 1;
   const int teams_per_cta = cta_threads / cfg->tpc;
   const uint64_t ctas_needed = (ctx->N + teams_per_cta - 1) / teams_per_cta;
   s->grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)blocks_per_sm * ctx->num_sms);
@@ -1006,9 +1020,9 @@ int nuts_sampler_last_timing(nuts_sampler_t* s, double* kernel_ms, uint64_t* lau
 int nuts_sampler_get_state(nuts_sampler_t* s, double* position, double* step_size, double* stds, double* mean, uint64_t* rng_counter) {
   nuts_ctx* ctx = s->ctx;
   CUDA_TRY(cudaSetDevice(ctx->device));
-  if (position) TRY(plane_to_host(ctx, s->P.x, position));
-  if (stds) TRY(plane_to_host(ctx, s->P.stds, stds));
-  if (mean) TRY(plane_to_host(ctx, s->P.mean, mean));
+  if (position) TRY(plane_to_host(ctx, s->P.x, position, s->P.ld));
+  if (stds) TRY(plane_to_host(ctx, s->P.stds, stds, s->P.ld));
+  if (mean) TRY(plane_to_host(ctx, s->P.mean, mean, s->P.ld));
   if (step_size || rng_counter) {
     std::vector<ChainState> cs(ctx->N);
     CUDA_TRY(cudaMemcpyAsync(cs.data(), s->P.cs, cs.size() * sizeof(ChainState), cudaMemcpyDeviceToHost, ctx->stream));

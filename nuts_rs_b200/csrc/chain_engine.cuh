@@ -30,6 +30,7 @@ namespace nb {
 
 constexpr int MAX_DOUBLING_DEPTH = 20;  // deepest new half has 2^20 leaves
 constexpr int MAX_SLOTS = 64;
+constexpr int NB_END_BUFFERS = 3;  // main-tree endpoint buffers per chain: left, right + one pending (decoupled engine)
 
 struct SettingsDev {
   uint64_t num_tune, maxdepth, mindepth, extra_doublings;
@@ -93,7 +94,7 @@ struct EngineParams {
   double *stds, *inv_stds, *mean;   // DiagMassMatrix planes [N][ld]
   double* est;                      // [N][2 sets][4: draw_mean, draw_var, grad_mean, grad_var][ld]
   double* slots;                    // [N][P][2: z, v][ld]   leaf checkpoints of the half under construction
-  double* ends;                     // [N][2: left,right][3: z, v, grad_z][ld]   main-tree endpoints
+  double* ends;                     // [N][NB_END_BUFFERS][3: z, v, grad_z][ld]   main-tree endpoints (v1: 0 left, 1 right)
   ChainState* cs;
   unsigned int* queue;              // persistent chain queue
   // mode 0: set_position ; mode 1: draw
@@ -123,14 +124,69 @@ enum { EXT_OK = 0, EXT_TURNING = 1, EXT_DIVERGING = 2 };
 // The per-draw adaptation and Chain::set_position are COLD: they run in non-inlined functions on their own Engine
 // instance and exchange the chain scalars by value, so that the hot tree builder (run_draw -> extend -> leapfrog, all
 // force-inlined with one call site each) never has its address taken and its vectors really live in registers.
-template <int TPC, int EPT, int SMF, int MODEL>
-__device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, int parity, uint64_t t,
-                                       double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
+struct MultiCtx;  // decoupled engine only (several teams per CTA), see below
+template <int TPC, int EPT, int SMF, int MODEL, bool MULTI>
+__device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc, int parity,
+                                       uint64_t t, double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
                                        int depth, bool reached_maxdepth, bool diverging, int draw_idx, double pt_energy,
                                        double pt_energy_error, double fisher);
-template <int TPC, int EPT, int SMF, int MODEL>
-__device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem);
+template <int TPC, int EPT, int SMF, int MODEL, bool MULTI>
+__device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc);
 static __device__ __noinline__ void cold_fill_dead(const EngineParams& P, int chain, int tid, int tpc, uint64_t t0);
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Decoupled engine (chain_engine_v2.cuh): protocol between the VECTOR warps of a team (leapfrogs, checkpoints, U-turn
+// products; they never wait for a scalar result inside a doubling) and the LEADER warp of the CTA (lane c runs the scalar
+// tree logic of team c: energies, divergence, multinomial draws, reference counts, U-turn verdicts, RNG).
+// All of it lives in shared memory; flags are volatile words published after __threadfence_block().
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int V2_K = 4;                  // leaf entries a team may be ahead of its leader lane
+constexpr int V2_MAXD = 10;              // deepest doubling (2^10 leaves): maxdepth + extra_doublings <= V2_MAXD + 1
+constexpr int V2_NV = 4 + 6 * V2_MAXD;   // values per leaf entry and warp: leapfrog sums + 6 per bundled merge (<= V2_MAXD merges)
+constexpr int V2_NT = V2_MAXD + 2;       // per-level table size
+constexpr int V2_MAXW = 4;               // warps per team
+enum { V2_CMD_DOUBLING = 1, V2_CMD_TREE_DONE = 2 };
+
+struct V2Ctl {
+  // leader -> team
+  volatile unsigned cmd_seq;    // bumped for every command; the value also is the epoch of the doubling it starts
+  volatile unsigned cons;       // (epoch << 12) | leaves of the current doubling the leader has consumed
+  int cmd_kind, cmd_dir, cmd_check, cmd_depth, cmd_prev_accepted;
+  volatile signed char slot_ring[8];  // checkpoint slot of leaf i at [i & 7], published V2_K leaves ahead
+  // team -> leader
+  volatile unsigned prod[V2_MAXW];  // per warp: (epoch << 12) | leaves of the current doubling produced
+  volatile unsigned start_seq;      // bumped when the start record below is valid (one per draw)
+  volatile unsigned exit_flag;      // the team has left the kernel
+  // start record (team -> leader): initialize_trajectory is done
+  double E0, pt_logdet, step;
+  unsigned long long rng;
+  // the team's chain scalars that are not needed while the tree is built (parked here to keep them out of the registers)
+  double pk_logp, pk_mm_logdet;
+  long long pk_pt_tid, pk_mm_id;
+  unsigned long long pk_total_lf, pk_tree_lf;
+  // result record (leader -> team), valid with V2_CMD_TREE_DONE
+  double acc_sum, acc_sym_sum, max_energy_error, draw_energy;
+  unsigned long long acc_count, rng_out;
+  int depth, draw_slot, draw_idx, reached_maxdepth, diverging;
+  // leader lane's pending sub-trees, one per level (the leader is the only reader and writer)
+  double A_ls[V2_NT], A_draw_energy[V2_NT];
+  int A_draw_idx[V2_NT];
+  signed char A_first[V2_NT], A_last[V2_NT], A_draw[V2_NT];
+  // vector side: first / last checkpoint slot of the pending sub-trees, one private copy per warp
+  signed char VA_first[V2_MAXW][V2_NT], VA_last[V2_MAXW][V2_NT];
+};
+
+// leaf entry ring of one team: double ring[V2_K][W][V2_NV], per-warp partial sums of one leaf:
+// [0..3] logp, v.v, sP, sQ of the leapfrog; then 6 products per bundled merge (inner levels 1.., then the top-level merge)
+
+struct MultiCtx {
+  double* model_smem;  // [2][TPC*EPT] model mu | prec, one copy per CTA
+  int bar_id, warp;    // the team's named barrier, this warp's index inside the team
+  V2Ctl* ctl;
+  double* ring;        // [V2_K][W][V2_NV]
+};
+
+__device__ __forceinline__ unsigned v2_ld(const volatile unsigned* p) { return *p; }
 
 // Tree bookkeeping tables of one chain, in shared memory (local-memory tables cost an L1 miss per access once the stacks of
 // all resident threads exceed L1).  Every thread computes the same values; thread 0 of the team stores them.  An entry
@@ -145,7 +201,9 @@ struct TreeTables {
 
 // What lives in the team's dynamic shared memory (SMF bit flags); everything else is registers (or L1-cached global for the
 // model parameters).  Layout: [sigma | mean] (SM_MASS) [model mu | model prec] (SM_MODEL) [grad_z] (SM_GRAD) TreeTables.
-enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4 };
+// SM_EXACT: every sampler row is padded with zeros to TPC*EPT elements (EngineParams::ld >= TPC*EPT), so the hot loops run
+// without bounds checks: the padding lanes compute on zeros and stay zero.
+enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8 };
 template <int SMF>
 __host__ __device__ constexpr int smem_vectors() {
   return ((SMF & SM_MASS) ? 2 : 0) + ((SMF & SM_MODEL) ? 2 : 0) + ((SMF & SM_GRAD) ? 1 : 0);
@@ -155,19 +213,22 @@ __host__ __device__ constexpr size_t team_smem_bytes() {
   return smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double) + sizeof(TreeTables);
 }
 
-template <int TPC, int EPT, int SMF, int MODEL>
+template <int TPC, int EPT, int SMF, int MODEL, bool MULTI = false>
 struct Engine {
   const EngineParams& P;
   const int chain;
   const int tid;  // thread index inside the team
-  TeamReduce<TPC> red;
+  TeamReduce<TPC, MULTI> red;
+  const MultiCtx* const mc;  // MULTI only
   const int d, ld;
   const size_t row;  // chain * ld
   double* const slots_base;  // this chain's checkpoint pool / endpoint buffers (thread-offset included)
   double* const ends_base;
 
   // ---- register-resident vectors ----
-  static constexpr bool MMS = (SMF & SM_MASS) != 0, MODS = (SMF & SM_MODEL) != 0, GS = (SMF & SM_GRAD) != 0;
+  static constexpr bool MMS = (SMF & SM_MASS) != 0, MODS = (SMF & SM_MODEL) != 0, GS = (SMF & SM_GRAD) != 0, EXACT = (SMF & SM_EXACT) != 0;
+  static_assert(!EXACT || ((MODS || MULTI) && MMS), "SM_EXACT needs zero-padded on-chip copies of the model parameters and the mass matrix");
+  __device__ __forceinline__ bool inb(int i) const { return EXACT || i < d; }  // element i exists (or is zero padding that may be touched)
   double z[EPT], v[EPT];  // current phase-space point: whitened position, velocity
   double g_reg[GS ? 1 : EPT];  // whitened gradient: registers, or shared memory (GS) to fit more chains per SM
   // this chain's DiagMassMatrix (stds, mean): registers, or shared memory when MMS
@@ -206,23 +267,31 @@ struct Engine {
 #endif
 
   // team_smem: this team's slice of dynamic shared memory (team_smem_bytes()); tables: where the TreeTables live
-  __device__ __forceinline__ Engine(const EngineParams& p, int chain_, int tid_, double* scratch, double* team_smem, TreeTables& tables)
-      : P(p), chain(chain_), tid(tid_), red(scratch), d(p.d), ld(p.ld), row((size_t)chain_ * p.ld),
-        slots_base(p.slots + (size_t)chain_ * p.P * 2 * p.ld), ends_base(p.ends + (size_t)chain_ * 6 * p.ld), sm_sig(team_smem),
+  __device__ __forceinline__ Engine(const EngineParams& p, int chain_, int tid_, double* scratch, double* team_smem, TreeTables& tables,
+                                    const MultiCtx* mc_ = nullptr)
+      : P(p), chain(chain_), tid(tid_), red(scratch), mc(mc_), d(p.d), ld(p.ld), row((size_t)chain_ * p.ld),
+        slots_base(p.slots + (size_t)chain_ * p.P * 2 * p.ld), ends_base(p.ends + (size_t)chain_ * NB_END_BUFFERS * 3 * p.ld), sm_sig(team_smem),
         sm_mu(team_smem + (MMS ? TPC * EPT : 0)), sm_mmu(team_smem + (MMS ? 2 : 0) * TPC * EPT),
         sm_mprec(team_smem + ((MMS ? 2 : 0) + (MODS ? 1 : 0)) * TPC * EPT),
         sm_g(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0)) * TPC * EPT), T(tables) {
     stream = p.chain_offset + (uint64_t)chain_ + 1;  // reference src/sampler.rs:1106 set_stream(chain_id + 1)
+    if (MULTI) {  // several teams per CTA: named barrier, per-team reduction scratch, CTA-wide copy of the model parameters
+      red.bar_id = mc->bar_id;
+      red.warp = mc->warp;
+      sm_mmu = mc->model_smem;
+      sm_mprec = mc->model_smem + TPC * EPT;
+    }
   }
   __device__ __forceinline__ double sg(int j) const { return MMS ? sm_sig[tid + j * TPC] : sig[MMS ? 0 : j]; }
   __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[tid + j * TPC] : mu[MMS ? 0 : j]; }
   // model parameters of element i = tid + j*TPC
-  __device__ __forceinline__ double model_mu(int j, int i) const { return MODS ? sm_mmu[tid + j * TPC] : __ldg(P.model.mu + i); }
-  __device__ __forceinline__ double model_prec(int j, int i) const { return MODS ? sm_mprec[tid + j * TPC] : __ldg(P.model.prec + i); }
+  // (MULTI: one copy per CTA shared by all its teams, filled by the kernel prologue)
+  __device__ __forceinline__ double model_mu(int j, int i) const { return (MODS || MULTI) ? sm_mmu[tid + j * TPC] : __ldg(P.model.mu + i); }
+  __device__ __forceinline__ double model_prec(int j, int i) const { return (MODS || MULTI) ? sm_mprec[tid + j * TPC] : __ldg(P.model.prec + i); }
   // element j of the whitened gradient (each thread only touches its own entries: no synchronisation)
   __device__ __forceinline__ double& G(int j) { return GS ? sm_g[tid + j * TPC] : g_reg[GS ? 0 : j]; }
   __device__ __forceinline__ void load_model_params() {
-    if (MODS) {
+    if (MODS && !MULTI) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = tid + j * TPC;
@@ -240,14 +309,14 @@ struct Engine {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
       int i = tid + j * TPC;
-      a[j] = i < d ? __ldcg(src + i) : 0.0;
+      a[j] = inb(i) ? __ldcg(src + i) : 0.0;
     }
   }
   __device__ __forceinline__ void store_cg(double* __restrict__ dst, const double (&a)[EPT]) const {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
       int i = tid + j * TPC;
-      if (i < d) __stcg(dst + i, a[j]);
+      if (inb(i)) __stcg(dst + i, a[j]);
     }
   }
 
@@ -304,7 +373,7 @@ struct Engine {
     hs_alive = __ldcg(&g->alive);
   }
   __device__ __forceinline__ void team_sync() const {
-    if (TPC > 32) __syncthreads();
+    if (TPC > 32) red.barrier();
     else __syncwarp();
   }
   // publish the hot scalars (all threads hold identical values; thread 0 writes) and make them visible to the team
@@ -347,33 +416,36 @@ struct Engine {
     // Elements 2p and 2p+1 (one Box-Muller pair) belong to threads t (even) and t+1 at the same j.  Even threads evaluate the
     // pairs of even j, odd threads those of odd j, and the partner's normal travels through one shuffle: EPT/2 Box-Mullers
     // per thread instead of EPT.  Values are exactly those of stream_normal().
+    // The loop is ROLLED (the Box-Muller body is ~250 instructions; unrolled it would sweep 30 KB of code through the 32 KB
+    // instruction cache once per draw): the normals go to the chain's v0 plane - where initialize_trajectory stores the fresh
+    // velocity anyway - and every thread reads back the elements it wrote itself.
+    double* v0 = P.v0 + row;
     if (EPT % 2 == 0) {
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < EPT; j += 2) {
-        const int jj = j + (tid & 1);            // the j this thread evaluates
+        const int jj = j + (tid & 1);              // the j this thread evaluates
         const int i_even = (tid & ~1) + jj * TPC;  // even element of that pair
         double n0 = 0.0, n1 = 0.0;
         if (i_even < d) stream_normal_pair(P.seed, stream, hs_rng, (uint32_t)i_even, n0, n1);
-        // mine: component (tid & 1) of my pair goes to v[jj]; the other component belongs to the neighbour's element at jj
+        // mine: component (tid & 1) of my pair goes to element jj; the other component belongs to the neighbour's element at jj
         const double keep = (tid & 1) ? n1 : n0;
         const double give = (tid & 1) ? n0 : n1;
-        const double got = __shfl_xor_sync(0xffffffffu, give, 1);  // neighbour's pair was for its own jj = j + ((tid^1)&1)
-        // I evaluated jj = j + (tid&1); the neighbour evaluated j + 1 - (tid&1): that is the j I still need
+        const double got = __shfl_xor_sync(0xffffffffu, give, 1);  // the neighbour evaluated j + 1 - (tid&1): the j I still need
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const int jq = j + q;
-          const int i = tid + jq * TPC;
+          const int i = tid + (j + q) * TPC;
           const double val = (q == (tid & 1)) ? keep : got;
-          v[jq] = i < d ? 1.0 * val : 0.0;
+          if (i < d) v0[i] = 1.0 * val;
         }
       }
     } else {
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < EPT; ++j) {
         int i = tid + j * TPC;
-        v[j] = i < d ? 1.0 * stream_normal(P.seed, stream, hs_rng, (uint32_t)i) : 0.0;
+        if (i < d) v0[i] = 1.0 * stream_normal(P.seed, stream, hs_rng, (uint32_t)i);
       }
     }
+    load(v0, v);
     hs_rng += (uint64_t)((d + 1) / 2);
   }
 
@@ -476,6 +548,42 @@ struct Engine {
     return lp_sum;
   }
 
+  // One velocity-Verlet step of the diagonal Gaussian WITHOUT the team reduction: (z, v, g) advance in place, part = this thread's
+  // partial sums of (logp', v'.v', sP, sQ).  Elementwise target: the whole step is ONE pass, nothing but accumulators outlives
+  // an element.
+  __device__ __forceinline__ void leapfrog_partials(double eps, double (&part)[4]) {
+    const double eps_half = eps / 2.;
+    part[0] = part[1] = part[2] = part[3] = 0.0;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const int i = tid + j * TPC;
+      const double zp = z[j], vp = v[j];
+      const double vh = fma(eps_half, G(j), vp);   // first_velocity_halfstep :178-184  axpy_out(grad, v, eps/2)
+      const double zn = fma(eps, vh, zp);          // position_step :220-225            axpy_out(v', z, eps)
+      const double sgm = sg(j);
+      const double t = zn * sgm;                   // compute_untransformed_position    diagonal.rs:253-255
+      const double xn = fma(1.0, mn(j), t);
+      double gxn = 0.0;
+      if (inb(i)) {
+        const double diff = xn - model_mu(j, i);
+        const double pd = diff * model_prec(j, i);
+        part[0] -= diff * pd / 2.;
+        gxn = -pd;
+      }
+      const double gn = gxn * sgm;                 // compute_transformed_gradient      diagonal.rs:258-265
+      const double vn = fma(eps_half, gn, vh);     // second_velocity_halfstep :245-247 axpy(grad', v, eps/2)
+      part[1] = fma(vn, vn, part[1]);              // update_kinetic_energy :260-262
+      if (inb(i)) {
+        const double delta = (zn + 0.0) - zp;
+        part[2] = fma(delta, vp, part[2]);
+        part[3] = fma(delta, vn, part[3]);
+      }
+      z[j] = zn;
+      v[j] = vn;
+      G(j) = gn;
+    }
+  }
+
   // ------------------------------------------------------------------ leapfrog (transformed_hamiltonian.rs:524-615, Euclidean)
   // (z, v, g) <- one velocity-Verlet step of size eps in the whitened space; returns logp' and kinetic energy'.
   // When `with_prev` is set it also returns the U-turn products of the pair (previous leaf, new leaf):
@@ -485,36 +593,8 @@ struct Engine {
     const double eps_half = eps / 2.;
     hs_total_lf += 1;
     if (MODEL == LOGP_GAUSS_DIAG) {
-      // elementwise target: the whole step is ONE pass, nothing but accumulators outlives an element
-      double part[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-      for (int j = 0; j < EPT; ++j) {
-        const int i = tid + j * TPC;
-        const double zp = z[j], vp = v[j];
-        const double vh = fma(eps_half, G(j), vp);   // first_velocity_halfstep :178-184  axpy_out(grad, v, eps/2)
-        const double zn = fma(eps, vh, zp);          // position_step :220-225            axpy_out(v', z, eps)
-        const double sgm = sg(j);
-        const double t = zn * sgm;                   // compute_untransformed_position    diagonal.rs:253-255
-        const double xn = fma(1.0, mn(j), t);
-        double gxn = 0.0;
-        if (i < d) {
-          const double diff = xn - model_mu(j, i);
-          const double pd = diff * model_prec(j, i);
-          part[0] -= diff * pd / 2.;
-          gxn = -pd;
-        }
-        const double gn = gxn * sgm;                 // compute_transformed_gradient      diagonal.rs:258-265
-        const double vn = fma(eps_half, gn, vh);     // second_velocity_halfstep :245-247 axpy(grad', v, eps/2)
-        part[1] = fma(vn, vn, part[1]);              // update_kinetic_energy :260-262
-        if (i < d) {
-          const double delta = (zn + 0.0) - zp;
-          part[2] = fma(delta, vp, part[2]);
-          part[3] = fma(delta, vn, part[3]);
-        }
-        z[j] = zn;
-        v[j] = vn;
-        G(j) = gn;
-      }
+      double part[4];
+      leapfrog_partials(eps, part);
       if (with_prev) {
         red.allreduce(part);
       } else {
@@ -646,7 +726,7 @@ struct Engine {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = tid + j * TPC;
-        if (i < d) {
+        if (inb(i)) {
           double delta = (z[j] + 0.0) - __ldcg(Afz + i);
           s[0] = fma(delta, __ldcg(Afv + i), s[0]);
           s[1] = fma(delta, v[j], s[1]);
@@ -659,7 +739,7 @@ struct Engine {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
       int i = tid + j * TPC;
-      if (i < d) {
+      if (inb(i)) {
         double afz = __ldcg(Afz + i), afv = __ldcg(Afv + i), alz = __ldcg(Alz + i), alv = __ldcg(Alv + i), bfz = __ldcg(Bfz + i),
                bfv = __ldcg(Bfv + i);
         double d1 = (z[j] + 0.0) - afz;
@@ -1050,12 +1130,8 @@ struct Engine {
   }
 
   // ------------------------------------------------------------------ Chain::draw (chain.rs:151-188) + nuts::draw (nuts.rs:281-388)
-  __device__ __forceinline__ void run_draw(uint64_t t) {
-    const SettingsDev& S = P.s;
-    const size_t N = (size_t)P.N;
-    NB_T0(td);
-    NB_T0(tw);
-    // ---- initialize_trajectory (transformed_hamiltonian.rs:687-736)
+  // initialize_trajectory (transformed_hamiltonian.rs:687-736) + collector.register_init (dual_avg.rs:160-165)
+  __device__ __forceinline__ void draw_begin() {
     load_mass_matrix();
     if (hs_mm_id != hs_pt_tid) {
       whiten_from_planes();  // inv_transform_normalize: no logp evaluation
@@ -1065,18 +1141,69 @@ struct Engine {
       load(P.z + row, z);
       load_g(P.gz + row, false);
     }
-    sample_velocity();
-    store(P.v0 + row, v);
+    sample_velocity();  // also stores the v0 plane
     double ke[1] = {0.0};
 #pragma unroll
     for (int j = 0; j < EPT; ++j) ke[0] = fma(v[j], v[j], ke[0]);
     red.allreduce(ke);
     E0 = 0.5 * ke[0] - (hs_logp + hs_pt_logdet);
-    // collector.register_init (dual_avg.rs:160-165)
     acc_sum = 0.;
     acc_sym_sum = 0.;
     acc_count = 0;
     max_energy_error = 0.;
+  }
+
+  // Materialise the selected draw - the chain point becomes (x, gx, z, gz, logp) of that leaf - then run the per-draw
+  // adaptation + statistics (cold, through global memory).  z is read back from its checkpoint; x / logp / gradient are
+  // recomputed by the same instruction sequence the leaf used, hence bit-identical to what the leapfrog produced.
+  __device__ __forceinline__ void draw_finish(uint64_t t, bool diverging, bool reached_maxdepth) {
+    const size_t N = (size_t)P.N;
+    NB_T0(tm);
+    double fisher[1] = {0.0};
+    if (draw_slot >= 0) {
+      double x[EPT], gx[EPT];
+      load_cg(slot_ptr(draw_slot, 0), z);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        double tt = z[j] * sg(j);
+        x[j] = fma(1.0, mn(j), tt);
+      }
+      hs_logp = eval_at_position(x, gx);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) G(j) = gx[j] * sg(j);
+      store(P.x + row, x);
+      store(P.gx + row, gx);
+      store(P.z + row, z);
+      store_g(P.gz + row, false);
+      if (P.draws_out) store(P.draws_out + (t * N + chain) * (size_t)d, x);
+    } else {
+      load(P.z + row, z);
+      load_g(P.gz + row, false);
+      if (P.draws_out) {
+        double x[EPT];
+        load(P.x + row, x);
+        store(P.draws_out + (t * N + chain) * (size_t)d, x);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) fisher[0] += (z[j] + G(j)) * (z[j] + G(j));  // sq_norm_sum (cpu_math.rs:235-243)
+    red.allreduce(fisher);
+    NB_ACC(5, tm);
+    // ---- adaptation + statistics: cold, through global memory
+    store_hot();
+    const int ret = cold_adapt<TPC, EPT, SMF, MODEL, MULTI>(P, chain, tid, red.scratch, sm_sig, mc, red.parity, t, acc_sum, acc_sym_sum, acc_count,
+                                              max_energy_error, diverging ? (abs(draw_idx) > 4) : (draw_idx != 0), depth, reached_maxdepth,
+                                              diverging, draw_idx, draw_energy, draw_energy - E0, fisher[0]);
+    red.parity = ret & 1;
+    load_hot();
+    NB_ACC(6, tm);
+  }
+
+  __device__ __forceinline__ void run_draw(uint64_t t) {
+    const SettingsDev& S = P.s;
+    NB_T0(td);
+    NB_T0(tw);
+    draw_begin();
     NB_ACC(0, td);
     // NutsTree::new (nuts.rs:94-105)
     ls_main = 0.;
@@ -1122,49 +1249,318 @@ struct Engine {
         extra_left = S.extra_doublings;
       }
     }
-    NB_T0(tm);
-    // ---- materialise the selected draw: the chain point becomes (x, gx, z, gz, logp) of that leaf.
-    // z is read back from its checkpoint; x / logp / gradient are recomputed by the same instruction sequence the
-    // leaf used, hence bit-identical to what the leapfrog produced.
-    double fisher[1] = {0.0};
-    if (draw_slot >= 0) {
-      double x[EPT], gx[EPT];
-      load_cg(slot_ptr(draw_slot, 0), z);
+    draw_finish(t, diverging, reached_maxdepth);
+    NB_ACC(7, tw);
+  }
+
+  // ================================================================== decoupled engine, vector side (MULTI only) =============
+  // The team's warps run the vector work of one doubling without ever waiting for a scalar verdict: leapfrog, checkpoint
+  // store, the U-turn products of every merge this leaf completes (their operands are structural: a binary counter), all
+  // bundled into ONE ring entry per leaf that the leader lane consumes up to V2_K leaves later.  When the leader ends the
+  // doubling early (inner U-turn, divergence) the leaves computed ahead are simply dropped.
+  __device__ __forceinline__ double* endbuf_ptr(int buf, int which) const { return ends_base + (size_t)((buf * 3 + which) * ld); }
+
+  // U-turn products of one merge, per-thread partials (no reduction): (Af, cur) always; when `full` also (Al, cur), (Af, Bf).
+  __device__ __forceinline__ void merge_products(const double* Afz, const double* Afv, const double* Alz, const double* Alv,
+                                                 const double* Bfz, const double* Bfv, bool full, double (&s)[6]) {
+    s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.0;
+    if (!full) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        double tt = z[j] * sg(j);
-        x[j] = fma(1.0, mn(j), tt);
+        int i = tid + j * TPC;
+        if (inb(i)) {
+          double delta = (z[j] + 0.0) - __ldcg(Afz + i);
+          s[0] = fma(delta, __ldcg(Afv + i), s[0]);
+          s[1] = fma(delta, v[j], s[1]);
+        }
       }
-      hs_logp = eval_at_position(x, gx);
-#pragma unroll
-      for (int j = 0; j < EPT; ++j) G(j) = gx[j] * sg(j);
-      store(P.x + row, x);
-      store(P.gx + row, gx);
-      store(P.z + row, z);
-      store_g(P.gz + row, false);
-      if (P.draws_out) store(P.draws_out + (t * N + chain) * (size_t)d, x);
-    } else {
-      load(P.z + row, z);
-      load_g(P.gz + row, false);
-      if (P.draws_out) {
-        double x[EPT];
-        load(P.x + row, x);
-        store(P.draws_out + (t * N + chain) * (size_t)d, x);
-      }
+      return;
     }
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) fisher[0] += (z[j] + G(j)) * (z[j] + G(j));  // sq_norm_sum (cpu_math.rs:235-243)
-    red.allreduce(fisher);
-    NB_ACC(5, tm);
-    // ---- adaptation + statistics: cold, through global memory
-    store_hot();
-    const int ret = cold_adapt<TPC, EPT, SMF, MODEL>(P, chain, tid, red.scratch, sm_sig, red.parity, t, acc_sum, acc_sym_sum, acc_count,
-                                              max_energy_error, diverging ? (abs(draw_idx) > 4) : (draw_idx != 0), depth, reached_maxdepth,
-                                              diverging, draw_idx, draw_energy, draw_energy - E0, fisher[0]);
-    red.parity = ret & 1;
-    load_hot();
-    NB_ACC(6, tm);
+    for (int j = 0; j < EPT; ++j) {
+      int i = tid + j * TPC;
+      if (inb(i)) {
+        double afz = __ldcg(Afz + i), afv = __ldcg(Afv + i), alz = __ldcg(Alz + i), alv = __ldcg(Alv + i), bfz = __ldcg(Bfz + i),
+               bfv = __ldcg(Bfv + i);
+        double d1 = (z[j] + 0.0) - afz;
+        s[0] = fma(d1, afv, s[0]);
+        s[1] = fma(d1, v[j], s[1]);
+        double d2 = (z[j] + 0.0) - alz;
+        s[2] = fma(d2, alv, s[2]);
+        s[3] = fma(d2, v[j], s[3]);
+        double d3 = (bfz + 0.0) - afz;
+        s[4] = fma(d3, afv, s[4]);
+        s[5] = fma(d3, bfv, s[5]);
+      }
+    }
+  }
+
+  // gradient of the diagonal Gaussian in the whitened space at whitened position zz, element j: the very instruction sequence
+  // the leapfrog uses for the new point, so recomputing it is bit-identical to having stored it
+  __device__ __forceinline__ double grad_z_at(double zz, int j, int i) const {
+    const double sgm = sg(j);
+    const double t = zz * sgm;
+    const double xn = fma(1.0, mn(j), t);
+    double gxn = 0.0;
+    if (inb(i)) {
+      const double diff = xn - model_mu(j, i);
+      const double pd = diff * model_prec(j, i);
+      gxn = -pd;
+    }
+    return gxn * sgm;
+  }
+  // leapfrog_partials without a stored gradient vector: grad_z of the current point is recomputed from z (5 more flops per
+  // element instead of a shared-memory load + store; shared-memory bandwidth is what bounds 7 resident chains per SM).
+  // `half_done`: v already holds the first half-step (done with the LOADED gradient when the state came from memory: after a
+  // mass-matrix change the stored gradient is not a function of the stored z, see whiten_from_planes).
+  __device__ __forceinline__ void leapfrog_partials_nog(double eps, bool half_done, double (&part)[4]) {
+    const double eps_half = eps / 2.;
+    part[0] = part[1] = part[2] = part[3] = 0.0;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const int i = tid + j * TPC;
+      const double zp = z[j], vp = v[j];
+      const double sgm = sg(j), mnj = mn(j);
+      double mmu = 0.0, mprec = 0.0;
+      if (inb(i)) {
+        mmu = model_mu(j, i);
+        mprec = model_prec(j, i);
+      }
+      double g0;
+      {
+        const double t = zp * sgm;
+        const double x0 = fma(1.0, mnj, t);
+        double gx0 = 0.0;
+        if (inb(i)) {
+          const double diff = x0 - mmu;
+          const double pd = diff * mprec;
+          gx0 = -pd;
+        }
+        g0 = gx0 * sgm;
+      }
+      const double vh1 = fma(eps_half, g0, vp);    // first_velocity_halfstep :178-184  axpy_out(grad, v, eps/2)
+      const double vh = half_done ? vp : vh1;
+      const double zn = fma(eps, vh, zp);          // position_step :220-225            axpy_out(v', z, eps)
+      const double t = zn * sgm;                   // compute_untransformed_position    diagonal.rs:253-255
+      const double xn = fma(1.0, mnj, t);
+      double gxn = 0.0;
+      if (inb(i)) {
+        const double diff = xn - mmu;
+        const double pd = diff * mprec;
+        part[0] -= diff * pd / 2.;
+        gxn = -pd;
+      }
+      const double gn = gxn * sgm;                 // compute_transformed_gradient      diagonal.rs:258-265
+      const double vn = fma(eps_half, gn, vh);     // second_velocity_halfstep :245-247 axpy(grad', v, eps/2)
+      part[1] = fma(vn, vn, part[1]);              // update_kinetic_energy :260-262
+      if (inb(i)) {
+        const double delta = (zn + 0.0) - zp;
+        part[2] = fma(delta, vp, part[2]);
+        part[3] = fma(delta, vn, part[3]);
+      }
+      z[j] = zn;
+      v[j] = vn;
+    }
+  }
+
+  struct VecTree {  // what the vector side knows about the main tree: all of it follows from the command sequence
+    bool init_left, init_right;    // the end still is the initial point (P.z, P.v0, P.gz planes)
+    bool holds_left, holds_right;  // the registers currently hold that end
+    int eb_left, eb_right, eb_pend;  // endpoint buffer of each end; eb_pend receives the end of the doubling under construction
+  };
+
+  // entry i may be written once the leader has consumed leaf i - V2_K; false when a new command arrived instead (abort)
+  __device__ __forceinline__ bool v2_wait_credit(const V2Ctl& c, unsigned epoch, unsigned i) const {
+    for (;;) {
+      if (v2_ld(&c.cmd_seq) != epoch) return false;
+      if (i < (unsigned)V2_K) return true;
+      const unsigned cv = v2_ld(&c.cons);
+      if ((cv >> 12) == (epoch & 0xFFFFFu) && (cv & 0xFFFu) + (unsigned)V2_K > i) return true;
+      __nanosleep(32);
+    }
+  }
+
+  // one doubling (2^D leaves from the `dir` end of the main tree); returns true when the leader aborted it
+  __device__ __forceinline__ bool extend_vec(V2Ctl& c, unsigned epoch, int dir, bool check, int D, VecTree& vt) {
+    static_assert(!MULTI || MODEL == LOGP_GAUSS_DIAG, "the decoupled engine covers the elementwise (diagonal Gaussian) target");
+    static_assert(!MULTI || !GS, "the decoupled engine recomputes grad_z instead of keeping it");
+    constexpr int W = TPC / 32;
+    const int w = mc->warp, lane = threadIdx.x & 31;
+    const uint32_t nleaf = 1u << D;
+    const double eps = dir ? hs_step : -hs_step;
+    bool half_done = false;
+    if (!(dir ? vt.holds_right : vt.holds_left)) {
+      const bool near_init = dir ? vt.init_right : vt.init_left;
+      const int eb_near = dir ? vt.eb_right : vt.eb_left;
+      load_cg(near_init ? P.z + row : endbuf_ptr(eb_near, 0), z);
+      load_cg(near_init ? P.v0 + row : endbuf_ptr(eb_near, 1), v);
+      const double* gp = near_init ? P.gz + row : endbuf_ptr(eb_near, 2);
+      const double eps_half = eps / 2.;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int i = tid + j * TPC;
+        const double gl = inb(i) ? __ldcg(gp + i) : 0.0;
+        v[j] = fma(eps_half, gl, v[j]);  // first_velocity_halfstep of leaf 0 with the stored gradient
+      }
+      half_done = true;
+    } else if (dir ? vt.init_right : vt.init_left) {
+      // the registers hold the initial point of the draw: its gradient is the one draw_begin() loaded (after a mass-matrix
+      // change it is not a function of z, see above)
+      const double eps_half = eps / 2.;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) v[j] = fma(eps_half, G(j), v[j]);
+      half_done = true;
+    }
+    vt.holds_left = vt.holds_right = false;
+    NB_T0(tq);
+    for (uint32_t i = 0; i < nleaf; ++i) {
+      NB_ACC(4, tq);
+      if (!v2_wait_credit(c, epoch, i)) return true;
+      NB_ACC(0, tq);
+      __threadfence_block();
+      const int s = c.slot_ring[i & 7];
+      double part[4];
+      leapfrog_partials_nog(eps, half_done, part);
+      half_done = false;
+      NB_ACC(1, tq);
+      store_cg(slot_ptr(s, 0), z);
+      store_cg(slot_ptr(s, 1), v);
+      double* e = mc->ring + ((size_t)(i % V2_K) * W + w) * V2_NV;
+      {
+        const double mine = warp_reduce_scatter8<4>(part);
+        if (lane < 4) e[lane] = mine;
+      }
+      int t = __ffs(~i) - 1;  // trailing ones of i: the merges this leaf completes (levels 0 .. t-1)
+      if (t > D) t = D;
+      int B_first = s, g = 0;
+      NB_ACC(2, tq);
+      for (int l = 0; l < t; ++l) {
+        const int Af = c.VA_first[w][l], Al = c.VA_last[w][l];
+        if (check && l > 0) {  // level 0 = (previous leaf, this leaf): its products came out of the leapfrog itself
+          double sp[6];
+          merge_products(slot_ptr(Af, 0), slot_ptr(Af, 1), slot_ptr(Al, 0), slot_ptr(Al, 1), slot_ptr(B_first, 0), slot_ptr(B_first, 1), true, sp);
+          const double mine = warp_reduce_scatter8<6>(sp);
+          if (lane < 6) e[4 + 6 * g + lane] = mine;
+          ++g;
+        }
+        B_first = Af;
+      }
+      if (i + 1 < nleaf) {
+        __syncwarp();
+        if (lane == 0) {
+          c.VA_first[w][t] = (signed char)B_first;
+          c.VA_last[w][t] = (signed char)s;
+        }
+      } else if (check) {  // top-level merge of the main tree with the finished half
+        const bool near_init = dir ? vt.init_right : vt.init_left, far_init = dir ? vt.init_left : vt.init_right;
+        const int eb_near = dir ? vt.eb_right : vt.eb_left, eb_far = dir ? vt.eb_left : vt.eb_right;
+        const double* nearZ = near_init ? P.z + row : endbuf_ptr(eb_near, 0);
+        const double* nearV = near_init ? P.v0 + row : endbuf_ptr(eb_near, 1);
+        const double* farZ = far_init ? P.z + row : endbuf_ptr(eb_far, 0);
+        const double* farV = far_init ? P.v0 + row : endbuf_ptr(eb_far, 1);
+        double sp[6];
+        merge_products(farZ, farV, nearZ, nearV, slot_ptr(B_first, 0), slot_ptr(B_first, 1), D > 0, sp);
+        const double mine = warp_reduce_scatter8<6>(sp);
+        if (lane < 6) e[4 + 6 * g + lane] = mine;
+      }
+      __syncwarp();  // entry values and table stores of every lane are ordered before the flag
+      if (lane == 0) {
+        __threadfence_block();
+        c.prod[w] = ((epoch & 0xFFFFFu) << 12) | (i + 1);
+      }
+      NB_ACC(3, tq);
+    }
+    // the new end of the main tree - if the leader merges this half: the next command tells
+    store_cg(endbuf_ptr(vt.eb_pend, 0), z);
+    store_cg(endbuf_ptr(vt.eb_pend, 1), v);
+    {
+      double* gp = endbuf_ptr(vt.eb_pend, 2);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int i = tid + j * TPC;
+        if (inb(i)) __stcg(gp + i, grad_z_at(z[j], j, i));
+      }
+    }
+    return false;
+  }
+
+  __device__ __forceinline__ void run_draw_v2(uint64_t t, unsigned& cmd_seen) {
+    V2Ctl& c = *mc->ctl;
+    draw_begin();
+    if (tid == 0) {  // start record: the leader lane takes over the scalar side of the tree
+      c.E0 = E0;
+      c.pt_logdet = hs_pt_logdet;
+      c.step = hs_step;
+      c.rng = hs_rng;
+      c.pk_logp = hs_logp;
+      c.pk_mm_logdet = hs_mm_logdet;
+      c.pk_pt_tid = hs_pt_tid;
+      c.pk_mm_id = hs_mm_id;
+      c.pk_total_lf = hs_total_lf;
+      c.pk_tree_lf = hs_tree_lf;
+      __threadfence_block();
+      c.start_seq = v2_ld(&c.start_seq) + 1;
+    }
+    VecTree vt;
+    vt.init_left = vt.init_right = true;
+    vt.holds_left = vt.holds_right = true;
+    vt.eb_left = 0;
+    vt.eb_right = 1;
+    vt.eb_pend = 2;
+    bool pending = false;
+    int prev_dir = 0;
+    NB_T0(tw);
+    NB_T0(tc);
+    for (;;) {
+      unsigned cs;
+      NB_ACC(4, tc);
+      while ((cs = v2_ld(&c.cmd_seq)) == cmd_seen) __nanosleep(64);
+      NB_ACC(5, tc);
+      cmd_seen = cs;
+      __threadfence_block();
+      const int kind = c.cmd_kind, dir = c.cmd_dir, check = c.cmd_check, D = c.cmd_depth, accepted = c.cmd_prev_accepted;
+      if (pending && accepted) {  // the finished half became part of the main tree: its end is the new `prev_dir` end
+        if (prev_dir) {
+          const int o = vt.eb_right;
+          vt.eb_right = vt.eb_pend;
+          vt.eb_pend = o;
+          vt.init_right = false;
+          vt.holds_right = true;
+        } else {
+          const int o = vt.eb_left;
+          vt.eb_left = vt.eb_pend;
+          vt.eb_pend = o;
+          vt.init_left = false;
+          vt.holds_left = true;
+        }
+      }
+      pending = false;
+      if (kind == V2_CMD_TREE_DONE) break;
+      pending = !extend_vec(c, cs, dir, check != 0, D, vt);
+      prev_dir = dir;
+    }
+    team_sync();  // every warp of the team has left the tree
+    // result record + the parked chain scalars
+    acc_sum = c.acc_sum;
+    acc_sym_sum = c.acc_sym_sum;
+    max_energy_error = c.max_energy_error;
+    acc_count = c.acc_count;
+    hs_rng = c.rng_out;
+    E0 = c.E0;
+    hs_pt_logdet = c.pt_logdet;
+    hs_logp = c.pk_logp;
+    hs_mm_logdet = c.pk_mm_logdet;
+    hs_pt_tid = c.pk_pt_tid;
+    hs_mm_id = c.pk_mm_id;
+    hs_tree_lf = c.pk_tree_lf + acc_count;
+    hs_total_lf = c.pk_total_lf + acc_count;
+    depth = c.depth;
+    draw_slot = c.draw_slot;
+    draw_idx = c.draw_idx;
+    draw_energy = c.draw_energy;
+    const bool diverging = c.diverging != 0, reached_maxdepth = c.reached_maxdepth != 0;
     NB_ACC(7, tw);
+    draw_finish(t, diverging, reached_maxdepth);
   }
 
   // ------------------------------------------------------------------ Chain::set_position (chain.rs:137-149)
@@ -1229,13 +1625,13 @@ struct Engine {
 };
 
 // GlobalStrategy::adapt + the statistics of Chain::expanded_draw for one chain; returns the reduction parity (bit 0).
-template <int TPC, int EPT, int SMF, int MODEL>
-__device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, int parity, uint64_t t,
-                                       double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
+template <int TPC, int EPT, int SMF, int MODEL, bool MULTI>
+__device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc, int parity,
+                                       uint64_t t, double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
                                        int depth, bool reached_maxdepth, bool diverging, int draw_idx, double pt_energy,
                                        double pt_energy_error, double fisher) {
   TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
-  Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
+  Engine<TPC, EPT, SMF, MODEL, MULTI> E(P, chain, tid, scratch, team_smem, tables, mc);
   E.red.parity = parity;
   E.cold_load();
   E.acc_sum = acc_sum;
@@ -1273,10 +1669,10 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
 }
 
 // Chain::set_position for one chain; returns the per-chain status (0 ok, 3 bad initial point).
-template <int TPC, int EPT, int SMF, int MODEL>
-__device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem) {
+template <int TPC, int EPT, int SMF, int MODEL, bool MULTI>
+__device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc) {
   TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
-  Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
+  Engine<TPC, EPT, SMF, MODEL, MULTI> E(P, chain, tid, scratch, team_smem, tables, mc);
   E.cold_load();
   const int status = E.run_set_position();
   E.hs_alive = status == 0 ? 1 : 0;
@@ -1316,7 +1712,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(con
     Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
     E.load_model_params();
     if (P.mode == 0) {
-      const int status = cold_set_position<TPC, EPT, SMF, MODEL>(P, chain, tid, scratch, team_smem);
+      const int status = cold_set_position<TPC, EPT, SMF, MODEL, false>(P, chain, tid, scratch, team_smem, nullptr);
       if (tid == 0 && P.status_out) P.status_out[chain] = status;
     } else {
       E.load_hot();

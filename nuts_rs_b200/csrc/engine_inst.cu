@@ -1,5 +1,6 @@
 // engine_inst.cu — one instantiation of the chain kernel per (threads-per-chain, elements-per-thread) pair.
-// Compiled once per configuration with -DCFG_TPC=.. -DCFG_EPT=.. -DCFG_CTA=.. -DCFG_MINB=.. -DCFG_MMS=.. -DCFG_MODEL=.. (see Makefile) so
+// Compiled once per configuration with -DCFG_TPC=.. -DCFG_EPT=.. -DCFG_CTA=.. -DCFG_MINB=.. -DCFG_MMS=.. -DCFG_MODEL=.. -DCFG_TAG=.. (see Makefile;
+// the tag names the symbols: it equals MINB except for variants of one tiling that differ in their flags) so
 // the configurations build in parallel.
 #include "chain_engine.cuh"
 
@@ -7,9 +8,10 @@
 #define NB_CAT(a, b, c, d, e) NB_CAT2(a, b, c, d, e)
 #define NB_KERNEL nb::nuts_chain_kernel<CFG_TPC, CFG_EPT, CFG_CTA, CFG_MINB, CFG_MMS, CFG_MODEL>
 
+static constexpr int kSmf = CFG_MMS;  // shared-memory / padding flags (chain_engine.cuh SM_*)
 static constexpr size_t kSmem = (CFG_CTA / CFG_TPC) * nb::team_smem_bytes<CFG_TPC, CFG_EPT, CFG_MMS>();
 
-extern "C" cudaError_t NB_CAT(nb_launch_chain, CFG_TPC, CFG_EPT, CFG_MINB, CFG_MODEL)(const nb::EngineParams* p, int grid, cudaStream_t stream) {
+extern "C" cudaError_t NB_CAT(nb_launch_chain, CFG_TPC, CFG_EPT, CFG_TAG, CFG_MODEL)(const nb::EngineParams* p, int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured && kSmem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(NB_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
@@ -21,7 +23,8 @@ extern "C" cudaError_t NB_CAT(nb_launch_chain, CFG_TPC, CFG_EPT, CFG_MINB, CFG_M
 }
 
 // resident CTAs per SM for this configuration (grid sizing of the persistent kernel)
-extern "C" cudaError_t NB_CAT(nb_occupancy_chain, CFG_TPC, CFG_EPT, CFG_MINB, CFG_MODEL)(int* blocks_per_sm, int* cta_threads) {
+extern "C" cudaError_t NB_CAT(nb_occupancy_chain, CFG_TPC, CFG_EPT, CFG_TAG, CFG_MODEL)(int* blocks_per_sm, int* cta_threads, int* smf) {
+  *smf = kSmf;
   *cta_threads = CFG_CTA;
   if (kSmem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(NB_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
