@@ -42,6 +42,8 @@ NB_DECL(1024, 10, 1)
 NB_DECL(1024, 16, 1)
 // decoupled engine (engine_v2_inst.cu): third number = 100 + teams per CTA; diagonal / isotropic Gaussian only
 NB_DECL1(64, 16, 107, 1)
+NB_DECL1(64, 16, 117, 1)
+NB_DECL1(64, 16, 127, 1)
 
 namespace {
 
@@ -84,7 +86,7 @@ struct EngineConfig {
 const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(64, 16, 4),
                                  NB_CFG(256, 8, 2), NB_CFG(512, 8, 1), NB_CFG(1024, 8, 1), NB_CFG(1024, 10, 1), NB_CFG(1024, 16, 1)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 
@@ -715,7 +717,8 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
     return fail(NUTS_ERR_UNSUPPORTED, "the decoupled engine needs maxdepth + extra_doublings <= %d", V2_MAXD + 1);
   }
   // checkpoint pool: 3 roles per pending level + the main tree's draw; the decoupled engine hands slots out V2_K leaves ahead
-  P.P = (int)std::min<uint64_t>(MAX_SLOTS, 3 * (st->maxdepth + st->extra_doublings) + 4 + (decoupled ? V2_K : 0));
+  // and keeps the two ends of the main tree in slots
+  P.P = (int)std::min<uint64_t>(MAX_SLOTS, 3 * (st->maxdepth + st->extra_doublings) + 4 + (decoupled ? V2_K + 2 : 0));
   P.model = ctx->model;
   P.seed = seed;
   P.chain_offset = chain_id_offset;
@@ -800,7 +803,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   }
   CUDA_TRY(cudaMemcpy(P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice));
   // persistent grid: one wave of resident CTAs
-  const int teams_per_cta = cta_threads / cfg->tpc;
+  const int teams_per_cta = decoupled ? cfg->minb % 10 : cta_threads / cfg->tpc;  // decoupled tags end in the number of teams
   const uint64_t ctas_needed = (ctx->N + teams_per_cta - 1) / teams_per_cta;
   s->grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)blocks_per_sm * ctx->num_sms);
   CUDA_TRY(cudaEventCreate(&s->ev0));

@@ -140,6 +140,12 @@ static __device__ __noinline__ void cold_fill_dead(const EngineParams& P, int ch
 // tree logic of team c: energies, divergence, multinomial draws, reference counts, U-turn verdicts, RNG).
 // All of it lives in shared memory; flags are volatile words published after __threadfence_block().
 // ------------------------------------------------------------------------------------------------------------------------
+#ifndef NB_V2_SLEEP
+#define NB_V2_SLEEP 64         // ns between two polls of a flag word (command wait, idle leader)
+#endif
+#ifndef NB_V2_SLEEP_CREDIT
+#define NB_V2_SLEEP_CREDIT 32  // ns between two polls of the ring credit
+#endif
 constexpr int V2_K = 4;                  // leaf entries a team may be ahead of its leader lane
 constexpr int V2_MAXD = 10;              // deepest doubling (2^10 leaves): maxdepth + extra_doublings <= V2_MAXD + 1
 constexpr int V2_NV = 4 + 6 * V2_MAXD;   // values per leaf entry and warp: leapfrog sums + 6 per bundled merge (<= V2_MAXD merges)
@@ -179,14 +185,22 @@ struct V2Ctl {
 // leaf entry ring of one team: double ring[V2_K][W][V2_NV], per-warp partial sums of one leaf:
 // [0..3] logp, v.v, sP, sQ of the leapfrog; then 6 products per bundled merge (inner levels 1.., then the top-level merge)
 
+// Byte OFFSETS into the CTA's dynamic shared memory, not pointers: the struct travels through local memory (the cold functions
+// take its address), and a pointer loaded from memory is a generic pointer to the compiler (generic LD / ST); rebuilding the
+// pointers from the `extern __shared__` base keeps every access an LDS / STS.
 struct MultiCtx {
-  double* model_smem;  // [2][TPC*EPT] model mu | prec, one copy per CTA
+  unsigned off_model;  // [2][TPC*EPT] model mu | prec, one copy per CTA
+  unsigned off_ctl;    // V2Ctl of the team
+  unsigned off_ring;   // double [V2_K][W][V2_NV]
   int bar_id, warp;    // the team's named barrier, this warp's index inside the team
-  V2Ctl* ctl;
-  double* ring;        // [V2_K][W][V2_NV]
 };
 
-__device__ __forceinline__ unsigned v2_ld(const volatile unsigned* p) { return *p; }
+// volatile load of a flag word in SHARED memory (a plain volatile access through a generic pointer would be a generic LD)
+__device__ __forceinline__ unsigned v2_ld(const volatile unsigned* p) {
+  unsigned v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(const_cast<const unsigned*>(p))) : "memory");
+  return v;
+}
 
 // Tree bookkeeping tables of one chain, in shared memory (local-memory tables cost an L1 miss per access once the stacks of
 // all resident threads exceed L1).  Every thread computes the same values; thread 0 of the team stores them.  An entry
@@ -278,10 +292,18 @@ struct Engine {
     if (MULTI) {  // several teams per CTA: named barrier, per-team reduction scratch, CTA-wide copy of the model parameters
       red.bar_id = mc->bar_id;
       red.warp = mc->warp;
-      sm_mmu = mc->model_smem;
-      sm_mprec = mc->model_smem + TPC * EPT;
+      extern __shared__ __align__(16) unsigned char nb_dyn_smem[];
+      sm_mmu = reinterpret_cast<double*>(nb_dyn_smem + mc->off_model);
+      sm_mprec = sm_mmu + TPC * EPT;
+      // keep what the hot loops use in registers (*mc lives in local memory)
+      v2_ctl = reinterpret_cast<V2Ctl*>(nb_dyn_smem + mc->off_ctl);
+      v2_ring = reinterpret_cast<double*>(nb_dyn_smem + mc->off_ring);
+      v2_warp = mc->warp;
     }
   }
+  V2Ctl* v2_ctl;    // MULTI only
+  double* v2_ring;
+  int v2_warp;
   __device__ __forceinline__ double sg(int j) const { return MMS ? sm_sig[tid + j * TPC] : sig[MMS ? 0 : j]; }
   __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[tid + j * TPC] : mu[MMS ? 0 : j]; }
   // model parameters of element i = tid + j*TPC
@@ -1364,9 +1386,9 @@ struct Engine {
   }
 
   struct VecTree {  // what the vector side knows about the main tree: all of it follows from the command sequence
-    bool init_left, init_right;    // the end still is the initial point (P.z, P.v0, P.gz planes)
     bool holds_left, holds_right;  // the registers currently hold that end
-    int eb_left, eb_right, eb_pend;  // endpoint buffer of each end; eb_pend receives the end of the doubling under construction
+    int es_left, es_right;         // checkpoint slot holding (z, v) of that end; -1: the end still is the initial point
+    int last_slot;                 // slot of the last leaf of the doubling that was just built
   };
 
   // entry i may be written once the leader has consumed leaf i - V2_K; false when a new command arrived instead (abort)
@@ -1376,40 +1398,44 @@ struct Engine {
       if (i < (unsigned)V2_K) return true;
       const unsigned cv = v2_ld(&c.cons);
       if ((cv >> 12) == (epoch & 0xFFFFFu) && (cv & 0xFFFu) + (unsigned)V2_K > i) return true;
-      __nanosleep(32);
+      __nanosleep(NB_V2_SLEEP_CREDIT);
     }
   }
 
-  // one doubling (2^D leaves from the `dir` end of the main tree); returns true when the leader aborted it
+  // one doubling (2^D leaves from the `dir` end of the main tree); returns true when the leader aborted it.
+  // The ends of the main tree are not copied anywhere: (z, v) of an end IS the checkpoint of the leaf that became that end (the
+  // leader keeps the two end slots out of the pool, like the slot of the main tree's draw), and its gradient is recomputed from z.
   __device__ __forceinline__ bool extend_vec(V2Ctl& c, unsigned epoch, int dir, bool check, int D, VecTree& vt) {
     static_assert(!MULTI || MODEL == LOGP_GAUSS_DIAG, "the decoupled engine covers the elementwise (diagonal Gaussian) target");
     static_assert(!MULTI || !GS, "the decoupled engine recomputes grad_z instead of keeping it");
     constexpr int W = TPC / 32;
-    const int w = mc->warp, lane = threadIdx.x & 31;
+    const int w = v2_warp, lane = threadIdx.x & 31;
     const uint32_t nleaf = 1u << D;
     const double eps = dir ? hs_step : -hs_step;
+    const int es_near = dir ? vt.es_right : vt.es_left, es_far = dir ? vt.es_left : vt.es_right;
     bool half_done = false;
-    if (!(dir ? vt.holds_right : vt.holds_left)) {
-      const bool near_init = dir ? vt.init_right : vt.init_left;
-      const int eb_near = dir ? vt.eb_right : vt.eb_left;
-      load_cg(near_init ? P.z + row : endbuf_ptr(eb_near, 0), z);
-      load_cg(near_init ? P.v0 + row : endbuf_ptr(eb_near, 1), v);
-      const double* gp = near_init ? P.gz + row : endbuf_ptr(eb_near, 2);
+    if (es_near < 0) {
+      // start from the initial point of the draw: first half-step with the gradient draw_begin() loaded (after a mass-matrix
+      // change it is not a function of z, see whiten_from_planes)
       const double eps_half = eps / 2.;
+      if (!(dir ? vt.holds_right : vt.holds_left)) {
+        load_cg(P.z + row, z);
+        load_cg(P.v0 + row, v);
+        const double* gp = P.gz + row;
 #pragma unroll
-      for (int j = 0; j < EPT; ++j) {
-        const int i = tid + j * TPC;
-        const double gl = inb(i) ? __ldcg(gp + i) : 0.0;
-        v[j] = fma(eps_half, gl, v[j]);  // first_velocity_halfstep of leaf 0 with the stored gradient
+        for (int j = 0; j < EPT; ++j) {
+          const int i = tid + j * TPC;
+          const double gl = inb(i) ? __ldcg(gp + i) : 0.0;
+          v[j] = fma(eps_half, gl, v[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) v[j] = fma(eps_half, G(j), v[j]);
       }
       half_done = true;
-    } else if (dir ? vt.init_right : vt.init_left) {
-      // the registers hold the initial point of the draw: its gradient is the one draw_begin() loaded (after a mass-matrix
-      // change it is not a function of z, see above)
-      const double eps_half = eps / 2.;
-#pragma unroll
-      for (int j = 0; j < EPT; ++j) v[j] = fma(eps_half, G(j), v[j]);
-      half_done = true;
+    } else if (!(dir ? vt.holds_right : vt.holds_left)) {
+      load_cg(slot_ptr(es_near, 0), z);
+      load_cg(slot_ptr(es_near, 1), v);
     }
     vt.holds_left = vt.holds_right = false;
     NB_T0(tq);
@@ -1425,43 +1451,49 @@ struct Engine {
       NB_ACC(1, tq);
       store_cg(slot_ptr(s, 0), z);
       store_cg(slot_ptr(s, 1), v);
-      double* e = mc->ring + ((size_t)(i % V2_K) * W + w) * V2_NV;
+      double* e = v2_ring + ((size_t)(i % V2_K) * W + w) * V2_NV;
       {
         const double mine = warp_reduce_scatter8<4>(part);
         if (lane < 4) e[lane] = mine;
       }
       int t = __ffs(~i) - 1;  // trailing ones of i: the merges this leaf completes (levels 0 .. t-1)
       if (t > D) t = D;
-      int B_first = s, g = 0;
       NB_ACC(2, tq);
-      for (int l = 0; l < t; ++l) {
-        const int Af = c.VA_first[w][l], Al = c.VA_last[w][l];
-        if (check && l > 0) {  // level 0 = (previous leaf, this leaf): its products came out of the leapfrog itself
-          double sp[6];
-          merge_products(slot_ptr(Af, 0), slot_ptr(Af, 1), slot_ptr(Al, 0), slot_ptr(Al, 1), slot_ptr(B_first, 0), slot_ptr(B_first, 1), true, sp);
-          const double mine = warp_reduce_scatter8<6>(sp);
-          if (lane < 6) e[4 + 6 * g + lane] = mine;
-          ++g;
+      const bool last = i + 1 == nleaf;
+      // merges whose products are loaded from checkpoints: inner levels 1 .. t-1 (level 0 = (previous leaf, this leaf) came out of
+      // the leapfrog itself), then - after the last leaf - the top-level merge of the main tree with the finished half.
+      // B's first leaf at level l is A_first[l-1] (the merged tree of the levels below), the new leaf itself at level 0.
+      const int nm = check ? ((t > 1 ? t - 1 : 0) + (last ? 1 : 0)) : 0;
+      for (int m = 0; m < nm; ++m) {
+        const int l = m + 1;
+        const bool top = l >= t;  // only the last iteration of the last leaf
+        const int Bf = t > 0 ? c.VA_first[w][(top ? t : l) - 1] : s;
+        const double *az, *av, *lz, *lv;
+        if (!top) {
+          const int Af = c.VA_first[w][l], Al = c.VA_last[w][l];
+          az = slot_ptr(Af, 0);
+          av = slot_ptr(Af, 1);
+          lz = slot_ptr(Al, 0);
+          lv = slot_ptr(Al, 1);
+        } else {  // A = the main tree: first = far end, last = near end (for D == 0 both are the initial point; extras unused)
+          az = es_far < 0 ? P.z + row : slot_ptr(es_far, 0);
+          av = es_far < 0 ? P.v0 + row : slot_ptr(es_far, 1);
+          lz = es_near < 0 ? P.z + row : slot_ptr(es_near, 0);
+          lv = es_near < 0 ? P.v0 + row : slot_ptr(es_near, 1);
         }
-        B_first = Af;
+        double sp[6];
+        merge_products(az, av, lz, lv, slot_ptr(Bf, 0), slot_ptr(Bf, 1), true, sp);
+        const double mine = warp_reduce_scatter8<6>(sp);
+        if (lane < 6) e[4 + 6 * m + lane] = mine;
       }
-      if (i + 1 < nleaf) {
+      if (!last) {
         __syncwarp();
         if (lane == 0) {
-          c.VA_first[w][t] = (signed char)B_first;
+          c.VA_first[w][t] = (signed char)(t > 0 ? c.VA_first[w][t - 1] : s);
           c.VA_last[w][t] = (signed char)s;
         }
-      } else if (check) {  // top-level merge of the main tree with the finished half
-        const bool near_init = dir ? vt.init_right : vt.init_left, far_init = dir ? vt.init_left : vt.init_right;
-        const int eb_near = dir ? vt.eb_right : vt.eb_left, eb_far = dir ? vt.eb_left : vt.eb_right;
-        const double* nearZ = near_init ? P.z + row : endbuf_ptr(eb_near, 0);
-        const double* nearV = near_init ? P.v0 + row : endbuf_ptr(eb_near, 1);
-        const double* farZ = far_init ? P.z + row : endbuf_ptr(eb_far, 0);
-        const double* farV = far_init ? P.v0 + row : endbuf_ptr(eb_far, 1);
-        double sp[6];
-        merge_products(farZ, farV, nearZ, nearV, slot_ptr(B_first, 0), slot_ptr(B_first, 1), D > 0, sp);
-        const double mine = warp_reduce_scatter8<6>(sp);
-        if (lane < 6) e[4 + 6 * g + lane] = mine;
+      } else {
+        vt.last_slot = s;
       }
       __syncwarp();  // entry values and table stores of every lane are ordered before the flag
       if (lane == 0) {
@@ -1470,22 +1502,11 @@ struct Engine {
       }
       NB_ACC(3, tq);
     }
-    // the new end of the main tree - if the leader merges this half: the next command tells
-    store_cg(endbuf_ptr(vt.eb_pend, 0), z);
-    store_cg(endbuf_ptr(vt.eb_pend, 1), v);
-    {
-      double* gp = endbuf_ptr(vt.eb_pend, 2);
-#pragma unroll
-      for (int j = 0; j < EPT; ++j) {
-        const int i = tid + j * TPC;
-        if (inb(i)) __stcg(gp + i, grad_z_at(z[j], j, i));
-      }
-    }
     return false;
   }
 
   __device__ __forceinline__ void run_draw_v2(uint64_t t, unsigned& cmd_seen) {
-    V2Ctl& c = *mc->ctl;
+    V2Ctl& c = *v2_ctl;
     draw_begin();
     if (tid == 0) {  // start record: the leader lane takes over the scalar side of the tree
       c.E0 = E0;
@@ -1502,11 +1523,9 @@ struct Engine {
       c.start_seq = v2_ld(&c.start_seq) + 1;
     }
     VecTree vt;
-    vt.init_left = vt.init_right = true;
     vt.holds_left = vt.holds_right = true;
-    vt.eb_left = 0;
-    vt.eb_right = 1;
-    vt.eb_pend = 2;
+    vt.es_left = vt.es_right = -1;
+    vt.last_slot = -1;
     bool pending = false;
     int prev_dir = 0;
     NB_T0(tw);
@@ -1514,23 +1533,17 @@ struct Engine {
     for (;;) {
       unsigned cs;
       NB_ACC(4, tc);
-      while ((cs = v2_ld(&c.cmd_seq)) == cmd_seen) __nanosleep(64);
+      while ((cs = v2_ld(&c.cmd_seq)) == cmd_seen) __nanosleep(NB_V2_SLEEP);
       NB_ACC(5, tc);
       cmd_seen = cs;
       __threadfence_block();
       const int kind = c.cmd_kind, dir = c.cmd_dir, check = c.cmd_check, D = c.cmd_depth, accepted = c.cmd_prev_accepted;
-      if (pending && accepted) {  // the finished half became part of the main tree: its end is the new `prev_dir` end
+      if (pending && accepted) {  // the finished half became part of the main tree: its last leaf is the new `prev_dir` end
         if (prev_dir) {
-          const int o = vt.eb_right;
-          vt.eb_right = vt.eb_pend;
-          vt.eb_pend = o;
-          vt.init_right = false;
+          vt.es_right = vt.last_slot;
           vt.holds_right = true;
         } else {
-          const int o = vt.eb_left;
-          vt.eb_left = vt.eb_pend;
-          vt.eb_pend = o;
-          vt.init_left = false;
+          vt.es_left = vt.last_slot;
           vt.holds_left = true;
         }
       }

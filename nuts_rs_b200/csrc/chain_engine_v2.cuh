@@ -23,6 +23,37 @@ __device__ __forceinline__ bool v2_turn_eval(double sP, double sQ, int dir) {
   return dir ? ((sP < 0.) | (sQ < 0.)) : ((sP > 0.) | (sQ > 0.));
 }
 
+// The leader's transcendental / RNG work goes through ONE copy of each routine (the kernel's hot code has to stay inside the
+// 32 KB instruction cache next to the unrolled vector loops).
+static __device__ __noinline__ uint2 v2_philox01(uint64_t seed, uint64_t stream, uint64_t counter) {  // words 0, 1 of the block
+  const PhiloxBlock b = philox4x32_10(seed, stream, counter);
+  return make_uint2(b.r0, b.r1);
+}
+__device__ __forceinline__ double v2_stream_f64(uint64_t seed, uint64_t stream, uint64_t counter) {  // == stream_f64
+  const uint2 b = v2_philox01(seed, stream, counter);
+  return u53((uint64_t)b.x | ((uint64_t)b.y << 32));
+}
+// NutsTree::merge_into weights (nuts.rs:189-203): log_size of the merged tree and whether the other tree's draw is taken.
+// is_main: self_log_size is the OLD log_size of self, else that of the merged tree.  Everything by value: a reference to a
+// member of the leader's state would pin that state in local memory.
+struct V2Merge {
+  double total;
+  int take_other, consumed;  // consumed: random numbers drawn (0 or 1)
+};
+static __device__ __noinline__ V2Merge v2_merge_into(double self_ls, double other_ls, bool is_main, uint64_t seed, uint64_t stream, uint64_t rng) {
+  V2Merge r;
+  r.total = logaddexp(self_ls, other_ls);
+  const double ref = is_main ? self_ls : r.total;
+  r.consumed = 0;
+  bool take = other_ls >= ref;
+  if (!take) {
+    take = v2_stream_f64(seed, stream, rng) < exp(other_ls - ref);
+    r.consumed = 1;
+  }
+  r.take_other = take ? 1 : 0;
+  return r;
+}
+
 // Scalar side of one chain's trees; lives in the registers of ONE lane of the leader warp.
 template <int W>
 struct LeaderLane {
@@ -40,6 +71,7 @@ struct LeaderLane {
   // main tree
   double ls_main, draw_energy;
   int depth, idx_left, idx_right, draw_slot, draw_idx;
+  int end_slot_left, end_slot_right;  // checkpoint slots that hold the two ends of the main tree (-1: the initial point)
   uint64_t free_mask, rc_lo, rc_hi;
   // doubling under construction
   int D, dir, check, idx_cur;
@@ -65,8 +97,7 @@ struct LeaderLane {
     rc_add(s, -1);
     if (rc_get(s) == 0) free_mask |= (1ull << s);
   }
-  __device__ __forceinline__ double rng_f64() { return stream_f64(P.seed, stream, rng++); }
-  __device__ __forceinline__ bool rng_bool() { return stream_bool(P.seed, stream, rng++); }
+  __device__ __forceinline__ bool rng_bool() { return (v2_philox01(P.seed, stream, rng++).x & 1u) != 0; }  // == stream_bool
   __device__ __forceinline__ double val(const double* e, int k) const {  // sum of the per-warp partials, warp 0 first
     double t = e[k];
 #pragma unroll
@@ -147,6 +178,8 @@ struct LeaderLane {
       free_mask &= ~(1ull << draw_slot);
       rc_add(draw_slot, 1);
     }
+    if (end_slot_left >= 0) free_mask &= ~(1ull << end_slot_left);  // never referenced by the half under construction
+    if (end_slot_right >= 0) free_mask &= ~(1ull << end_slot_right);
     idx_cur = dir ? idx_right : idx_left;
     const unsigned npub = nleaf < (unsigned)V2_K ? nleaf : (unsigned)V2_K;
     for (unsigned j = 0; j < npub; ++j) c.slot_ring[j & 7] = (signed char)alloc_slot();
@@ -170,6 +203,7 @@ struct LeaderLane {
     depth = 0;
     idx_left = idx_right = 0;
     draw_slot = -1;
+    end_slot_left = end_slot_right = -1;
     draw_energy = E0;
     draw_idx = 0;
     mindepth = S.mindepth;
@@ -237,8 +271,10 @@ struct LeaderLane {
         }
       }
       // merge_into, non-main (nuts.rs:172-207): self_log_size = log_size of the merged tree
-      const double total = logaddexp(c.A_ls[l], B_ls);
-      const bool take_B = (B_ls >= total) || (rng_f64() < exp(B_ls - total));
+      const V2Merge mg = v2_merge_into(c.A_ls[l], B_ls, false, P.seed, stream, rng);
+      rng += (uint64_t)mg.consumed;
+      const bool take_B = mg.take_other != 0;
+      const double total = mg.total;
       if (take_B) {
         unref(c.A_draw[l]);
       } else {
@@ -277,8 +313,10 @@ struct LeaderLane {
       turning = v2_turn_eval(val(e, o), val(e, o + 1), dir);
       if (D > 0) turning = turning | v2_turn_eval(val(e, o + 2), val(e, o + 3), dir) | v2_turn_eval(val(e, o + 4), val(e, o + 5), dir);
     }
-    const double total = logaddexp(ls_main, B_ls);
-    const bool take = (B_ls >= ls_main) || (rng_f64() < exp(B_ls - ls_main));  // is_main: self_log_size = old log_size
+    const V2Merge mg = v2_merge_into(ls_main, B_ls, true, P.seed, stream, rng);  // is_main: self_log_size = old log_size
+    rng += (uint64_t)mg.consumed;
+    const bool take = mg.take_other != 0;
+    const double total = mg.total;
     if (take) {
       draw_slot = B_draw;
       draw_energy = B_draw_energy;
@@ -286,8 +324,13 @@ struct LeaderLane {
     }
     ls_main = total;
     depth += 1;
-    if (dir) idx_right = idx_cur;
-    else idx_left = idx_cur;
+    if (dir) {
+      idx_right = idx_cur;
+      end_slot_right = s;
+    } else {
+      idx_left = idx_cur;
+      end_slot_left = s;
+    }
     doubling_done(turning ? EXT_TURNING : EXT_OK, 1);
   }
 
@@ -338,9 +381,11 @@ struct V2Layout {
   static constexpr size_t total = off_chain + (size_t)C * 2 * sizeof(int);
 };
 
-// One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).  Warp 0 = leader, then C teams of TPC threads.
-template <int TPC, int EPT, int C, int MODEL>
-__global__ void __launch_bounds__(32 + C * TPC, 1) nuts_chain_kernel_v2(const __grid_constant__ EngineParams P) {
+// One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).  Warps 0 .. NL-1 = leaders, then C teams of TPC threads.
+// NL leader warps share the teams (leader warp lw, lane j -> team lw + j * NL): a lane only advances when ITS team has an entry
+// ready, so the lanes of one leader warp mostly run one at a time and a single leader warp saturates.
+template <int TPC, int EPT, int C, int MODEL, int NL>
+__global__ void __launch_bounds__(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(const __grid_constant__ EngineParams P) {
   using L = V2Layout<TPC, EPT, C>;
   constexpr int W = TPC / 32;
   constexpr int SMF = L::SMF;
@@ -355,26 +400,52 @@ __global__ void __launch_bounds__(32 + C * TPC, 1) nuts_chain_kernel_v2(const __
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
-  if (warp == 0) {
+  if (warp < NL) {
     // ---------------------------------------------------------------- leader: lane c = scalar side of team c
-    const int lane = threadIdx.x;
-    const int cidx = lane < C ? lane : 0;
+    const int lane = threadIdx.x & 31;
+    const int my_team = warp + lane * NL;
+    const int cidx = my_team < C ? my_team : 0;
     V2Ctl& ctl = *reinterpret_cast<V2Ctl*>(dyn_smem + L::off_ctl + (size_t)cidx * L::ctl_bytes);
     const volatile int* chain_of_team = reinterpret_cast<const volatile int*>(dyn_smem + L::off_chain) + 2 * cidx;
-    LeaderLane<W> lead(P, ctl, reinterpret_cast<const double*>(dyn_smem + L::off_ring + (size_t)cidx * L::ring_bytes));
-    if (lane >= C) lead.st = LeaderLane<W>::ST_EXITED;
+    const double* my_ring = reinterpret_cast<const double*>(dyn_smem + L::off_ring + (size_t)cidx * L::ring_bytes);
+    LeaderLane<W> lead(P, ctl, my_ring);
+    if (my_team >= C) lead.st = LeaderLane<W>::ST_EXITED;
+#ifdef NB_PHASE_TIMING
+    long long t_busy = 0, t_all0 = clock64(), n_polls = 0, n_prog = 0, n_multi = 0;
+#endif
     for (;;) {
       bool progress = false;
+#ifdef NB_PHASE_TIMING
+      const long long t0 = clock64();
+#endif
       if (lead.st != LeaderLane<W>::ST_EXITED) progress = lead.poll(*chain_of_team);
       const unsigned alive = __ballot_sync(0xffffffffu, lead.st != LeaderLane<W>::ST_EXITED);
+#ifdef NB_PHASE_TIMING
+      const unsigned pm = __ballot_sync(0xffffffffu, progress);
+      n_polls += 1;
+      if (pm) {
+        t_busy += clock64() - t0;
+        n_prog += 1;
+        n_multi += __popc(pm);
+      }
+#endif
       if (alive == 0u) break;
-      if (!__any_sync(0xffffffffu, progress)) __nanosleep(64);
+      if (!__any_sync(0xffffffffu, progress)) __nanosleep(NB_V2_SLEEP);
     }
+#ifdef NB_PHASE_TIMING
+    if (lane == 0 && P.phase_clocks) {  // leader statistics of this CTA: busy cycles, total cycles, polls, polls with progress, lane-events
+      atomicAdd(P.phase_clocks + 0, (unsigned long long)t_busy);
+      atomicAdd(P.phase_clocks + 1, (unsigned long long)(clock64() - t_all0));
+      atomicAdd(P.phase_clocks + 2, (unsigned long long)n_polls);
+      atomicAdd(P.phase_clocks + 3, (unsigned long long)n_prog);
+      atomicAdd(P.phase_clocks + 4, (unsigned long long)n_multi);
+    }
+#endif
     return;
   }
   // ------------------------------------------------------------------ teams: vector side
-  const int team = (warp - 1) / W;
-  const int tid = threadIdx.x - 32 - team * TPC;
+  const int team = (warp - NL) / W;
+  const int tid = threadIdx.x - 32 * NL - team * TPC;
   unsigned char* my_smem = dyn_smem + (size_t)team * L::team_bytes;
   double* team_smem = reinterpret_cast<double*>(my_smem);
   TreeTables& tables = *reinterpret_cast<TreeTables*>(my_smem + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
@@ -382,11 +453,11 @@ __global__ void __launch_bounds__(32 + C * TPC, 1) nuts_chain_kernel_v2(const __
   volatile int* next_chain = reinterpret_cast<volatile int*>(dyn_smem + L::off_chain) + 2 * team;
   double* scratch = reinterpret_cast<double*>(dyn_smem + L::off_scratch + (size_t)team * L::scratch_bytes);
   MultiCtx mc;
-  mc.model_smem = model_smem;
+  mc.off_model = (unsigned)L::off_model;
+  mc.off_ctl = (unsigned)(L::off_ctl + (size_t)team * L::ctl_bytes);
+  mc.off_ring = (unsigned)(L::off_ring + (size_t)team * L::ring_bytes);
   mc.bar_id = 1 + team;
-  mc.warp = (warp - 1) % W;
-  mc.ctl = &ctl;
-  mc.ring = reinterpret_cast<double*>(dyn_smem + L::off_ring + (size_t)team * L::ring_bytes);
+  mc.warp = (warp - NL) % W;
   unsigned cmd_seen = 0;
   for (;;) {
     if (tid == 0) next_chain[0] = (int)atomicAdd(P.queue, 1u);
@@ -410,7 +481,7 @@ __global__ void __launch_bounds__(32 + C * TPC, 1) nuts_chain_kernel_v2(const __
       }
     }
     bar_sync(mc.bar_id, TPC);
-#ifdef NB_PHASE_TIMING
+#ifdef NB_PHASE_TIMING_TEAM
     if (tid == 0 && P.phase_clocks)
       for (int k = 0; k < 8; ++k) atomicAdd(P.phase_clocks + k, (unsigned long long)E.phase[k]);
 #endif

@@ -1,18 +1,19 @@
 // engine_v2_inst.cu — one instantiation of the decoupled chain kernel (chain_engine_v2.cuh) per (threads-per-team,
-// elements-per-thread, teams-per-CTA) triple: -DCFG_TPC=.. -DCFG_EPT=.. -DCFG_C=.. -DCFG_MODEL=..  The launcher symbols follow the
-// naming of engine_inst.cu with "min blocks" = 100 + teams per CTA, so capi.cu's configuration table treats both kinds alike.
+// elements-per-thread, teams-per-CTA, leader warps) tuple: -DCFG_TPC=.. -DCFG_EPT=.. -DCFG_C=.. -DCFG_NL=.. -DCFG_TAG=.. -DCFG_MODEL=..  The
+// launcher symbols follow the naming of engine_inst.cu with the tag (>= 100, last digit = teams per CTA) in place of "min blocks",
+// so capi.cu's configuration table treats both kinds alike.
 #include "chain_engine_v2.cuh"
 
 #define NB_CAT2(a, b, c, d, e) a##_##b##_##c##_##d##_##e
 #define NB_CAT(a, b, c, d, e) NB_CAT2(a, b, c, d, e)
-#define NB_KERNEL nb::nuts_chain_kernel_v2<CFG_TPC, CFG_EPT, CFG_C, CFG_MODEL>
-#define CFG_TAG NB_V2TAG(CFG_C)
-#define NB_V2TAG(c) NB_V2TAG2(c)
-#define NB_V2TAG2(c) 10##c
+#ifndef CFG_NL
+#define CFG_NL 2
+#endif
+#define NB_KERNEL nb::nuts_chain_kernel_v2<CFG_TPC, CFG_EPT, CFG_C, CFG_MODEL, CFG_NL>
 
 static constexpr int kSmf = nb::V2Layout<CFG_TPC, CFG_EPT, CFG_C>::SMF;
 static constexpr size_t kSmem = nb::V2Layout<CFG_TPC, CFG_EPT, CFG_C>::total;
-static constexpr int kThreads = 32 + CFG_C * CFG_TPC;
+static constexpr int kThreads = 32 * CFG_NL + CFG_C * CFG_TPC;
 
 extern "C" cudaError_t NB_CAT(nb_launch_chain, CFG_TPC, CFG_EPT, CFG_TAG, CFG_MODEL)(const nb::EngineParams* p, int grid, cudaStream_t stream) {
   static bool configured = false;
