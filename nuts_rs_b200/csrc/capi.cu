@@ -85,6 +85,8 @@ struct EngineConfig {
 // the whole kernel, all 1024 chains of config 2 resident at once); CTA-per-chain above.
 const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(64, 16, 4),
                                  NB_CFG(256, 8, 2), NB_CFG(512, 8, 1), NB_CFG(1024, 8, 1), NB_CFG(1024, 10, 1), NB_CFG(1024, 16, 1)};
+// SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
+const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
 const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
@@ -693,6 +695,11 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
         break;
       }
   if (!cfg) return fail(NUTS_ERR_UNSUPPORTED, "dim %llu exceeds the largest register-resident configuration (16384)", (unsigned long long)ctx->d);
+  if (!std::getenv("NUTS_B200_ENGINE")) {
+    // same tiling without bounds checks (SM_EXACT: rows zero-padded to tpc*ept) when the padding costs at most 7 % more traffic
+    for (const EngineConfig& c : kExactConfigs)
+      if (c.tpc == cfg->tpc && c.ept == cfg->ept && c.launch[0] && (uint64_t)c.max_d - ctx->d <= ctx->d * 7 / 100) cfg = &c;
+  }
 
   nuts_sampler* s = new nuts_sampler();
   s->ctx = ctx;
@@ -775,6 +782,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   A((void**)&P.ends, plane * 3 * NB_END_BUFFERS);
   A((void**)&P.cs, ctx->N * sizeof(ChainState));
   A((void**)&P.queue, sizeof(unsigned int));
+  A((void**)&P.done, ctx->N * sizeof(unsigned int));
   A((void**)&s->d_init, ctx->N * ctx->d * sizeof(double));
   A((void**)&s->d_status, ctx->N * sizeof(int));
   A((void**)&P.phase_clocks, 8 * sizeof(unsigned long long));
@@ -846,6 +854,7 @@ int nuts_sampler_destroy(nuts_sampler_t* s) {
 static int launch_engine(nuts_sampler* s) {
   nuts_ctx* ctx = s->ctx;
   CUDA_TRY(cudaMemsetAsync(s->P.queue, 0, sizeof(unsigned int), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(s->P.done, 0, ctx->N * sizeof(unsigned int), ctx->stream));
   CUDA_TRY(cudaEventRecord(s->ev0, ctx->stream));
   CUDA_TRY(s->cfg->launch[s->model_variant](&s->P, s->grid, ctx->stream));
   CUDA_TRY(cudaEventRecord(s->ev1, ctx->stream));
@@ -901,6 +910,7 @@ static int ensure_stats(nuts_sampler* s, uint64_t n_draws) {
 static int run_draws(nuts_sampler* s, uint64_t n_draws, double* draws_dev, bool want_stats) {
   nuts_ctx* ctx = s->ctx;
   if (!s->positioned) return fail(NUTS_ERR_INVALID, "nuts_draw: call nuts_set_position first");
+  if (n_draws * ctx->N >= (1ull << 31)) return fail(NUTS_ERR_INVALID, "nuts_draw: n_draws x chains must stay below 2^31 per call; draw in batches");
   if (want_stats) TRY(ensure_stats(s, n_draws));
   s->P.mode = 1;
   s->P.init_position = nullptr;

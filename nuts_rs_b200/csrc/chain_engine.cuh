@@ -96,7 +96,8 @@ struct EngineParams {
   double* slots;                    // [N][P][2: z, v][ld]   leaf checkpoints of the half under construction
   double* ends;                     // [N][NB_END_BUFFERS][3: z, v, grad_z][ld]   main-tree endpoints (v1: 0 left, 1 right)
   ChainState* cs;
-  unsigned int* queue;              // persistent chain queue
+  unsigned int* queue;              // persistent work-unit queue
+  unsigned int* done;               // [N] draws of this launch each chain has completed
   // mode 0: set_position ; mode 1: draw
   int mode, _pad;
   const double* init_position;      // [N][d] device
@@ -1714,29 +1715,55 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(con
   unsigned char* my_smem = dyn_smem + (size_t)team * team_smem_bytes<TPC, EPT, SMF>();
   double* team_smem = reinterpret_cast<double*>(my_smem);
   TreeTables& tables = *reinterpret_cast<TreeTables*>(my_smem + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
+  {  // model parameters: the same for every chain, loaded once per team
+    Engine<TPC, EPT, SMF, MODEL> E0(P, 0, tid, scratch, team_smem, tables);
+    E0.load_model_params();
+  }
+  // Work units.  set_position: one chain.  Draws: ONE DRAW of one chain, in draw-major order (unit u = draw u / N of chain u % N):
+  // a chain's state lives in global memory between draws anyway, so any team can run its next draw, and with more chains than
+  // resident teams (config 2: 1024 chains, 592 teams) the launch ends after total_work / teams instead of ceil(N / teams) whole
+  // chains.  Draw t of a chain waits for its draw t-1 (P.done, release / acquire at gpu scope; the engine's global loads bypass
+  // L1: -dlcm=cg, so data written by another SM is read from L2).
+  const unsigned total_units = P.mode == 0 ? (unsigned)P.N : (unsigned)P.N * (unsigned)P.n_draws;
   for (;;) {
     if (tid == 0) next_chain[team] = (int)atomicAdd(P.queue, 1u);
     if (TPC > 32) __syncthreads();
     else __syncwarp();
-    const int chain = next_chain[team];
+    const unsigned unit = (unsigned)next_chain[team];
     if (TPC > 32) __syncthreads();
     else __syncwarp();
-    if (chain >= P.N) break;
+    if (unit >= total_units) break;
+    const int chain = (int)(unit % (unsigned)P.N);
+    const uint64_t t = unit / (unsigned)P.N;
     Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
-    E.load_model_params();
     if (P.mode == 0) {
       const int status = cold_set_position<TPC, EPT, SMF, MODEL, false>(P, chain, tid, scratch, team_smem, nullptr);
       if (tid == 0 && P.status_out) P.status_out[chain] = status;
     } else {
+      if (t > 0) {
+        if (tid == 0) {
+          unsigned dn;
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(P.done + chain) : "memory");
+            if (dn >= (unsigned)t) break;
+            __nanosleep(200);
+          }
+        }
+        E.team_sync();
+        __threadfence();
+      }
       E.load_hot();
       if (E.hs_alive) {
-        for (uint64_t t = 0; t < P.n_draws; ++t) {
-          E.run_draw(t);
-          if (!E.hs_alive) break;  // cold_adapt has NaN-filled the draws this chain will never produce
-        }
-      } else if (P.draws_out) {
+        E.run_draw(t);  // a chain that dies here has its remaining draws NaN-filled by cold_adapt
+      } else if (t == 0 && P.draws_out) {
         // draws a dead chain never produced read NaN (the output buffer may be host memory the kernel writes directly)
         cold_fill_dead(P, chain, tid, TPC, 0);
+      }
+      __threadfence();
+      E.team_sync();
+      if (tid == 0) {
+        const unsigned dn = (unsigned)t + 1u;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.done + chain), "r"(dn) : "memory");
       }
     }
     if (TPC > 32) __syncthreads();

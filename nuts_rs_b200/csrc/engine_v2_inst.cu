@@ -7,7 +7,7 @@
 #define NB_CAT2(a, b, c, d, e) a##_##b##_##c##_##d##_##e
 #define NB_CAT(a, b, c, d, e) NB_CAT2(a, b, c, d, e)
 #ifndef CFG_NL
-#define CFG_NL 2
+#define CFG_NL 1
 #endif
 #define NB_KERNEL nb::nuts_chain_kernel_v2<CFG_TPC, CFG_EPT, CFG_C, CFG_MODEL, CFG_NL>
 
