@@ -29,7 +29,7 @@ CHAINS_PER_GPU = 1024
 MAXDEPTH = 10
 NUM_TUNE = 400
 SEED = 42
-DRAWS_PER_STEP = 10
+DRAWS_PER_STEP = 50
 METRIC = "leapfrog-steps/sec (all chains)"
 UNIT = "leapfrog-steps/s"
 WORKLOAD = "configs[1]: 1000-dim diagonal Gaussian, 1024 chains per GPU, maxdepth=10, num_tune=400 (untimed), post-warmup draws"

@@ -723,9 +723,9 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
     delete s;
     return fail(NUTS_ERR_UNSUPPORTED, "the decoupled engine needs maxdepth + extra_doublings <= %d", V2_MAXD + 1);
   }
-  // checkpoint pool: 3 roles per pending level + the main tree's draw; the decoupled engine hands slots out V2_K leaves ahead
-  // and keeps the two ends of the main tree in slots
-  P.P = (int)std::min<uint64_t>(MAX_SLOTS, 3 * (st->maxdepth + st->extra_doublings) + 4 + (decoupled ? V2_K + 2 : 0));
+  // checkpoint pool: 3 roles per pending level + the main tree's draw and its two ends; the decoupled engine hands slots out V2_K
+  // leaves ahead
+  P.P = (int)std::min<uint64_t>(MAX_SLOTS, 3 * (st->maxdepth + st->extra_doublings) + 6 + (decoupled ? V2_K : 0));
   P.model = ctx->model;
   P.seed = seed;
   P.chain_offset = chain_id_offset;

@@ -28,7 +28,7 @@
 
 namespace nb {
 
-constexpr int MAX_DOUBLING_DEPTH = 20;  // deepest new half has 2^20 leaves
+constexpr int MAX_DOUBLING_DEPTH = 19;  // deepest new half has 2^19 leaves (checkpoint pool: 3 per level + 6 <= MAX_SLOTS)
 constexpr int MAX_SLOTS = 64;
 constexpr int NB_END_BUFFERS = 3;  // main-tree endpoint buffers per chain: left, right + one pending (decoupled engine)
 
@@ -270,6 +270,7 @@ struct Engine {
   int depth;
   int idx_left, idx_right;                 // index_in_trajectory of the two ends
   bool init_left, init_right;              // the end still is the initial point
+  int es_left, es_right;                   // checkpoint slot that holds (z, v) of that end (the last leaf of the half that was merged in)
   bool holds_left, holds_right;            // the registers currently hold that end
   int draw_slot;  // -1: the draw is the initial point
   double draw_energy;
@@ -432,8 +433,34 @@ struct Engine {
   }
 
   // ------------------------------------------------------------------ random stream
-  __device__ __forceinline__ bool rng_bool() { return stream_bool(P.seed, stream, hs_rng++); }
-  __device__ __forceinline__ double rng_f64() { return stream_f64(P.seed, stream, hs_rng++); }
+  // Every thread of the team consumes the same scalar random numbers, so a warp evaluates 32 consecutive Philox blocks at once
+  // (lane k: event counter pc_base + k) and serves them by shuffle: one block evaluation per ~32 events instead of one per event.
+  // A block is a pure function of (seed, stream, counter): values equal stream_bool / stream_f64 of rng_spec bit for bit.
+  uint64_t pc_base = 1ull << 63;  // no counter ever gets near: the first use refills
+  uint32_t pc_r0 = 0, pc_r1 = 0;
+  __device__ __forceinline__ void rng_words(uint32_t& r0, uint32_t& r1) {
+    uint64_t off = hs_rng - pc_base;
+    if (off >= 32ull) {  // warp-uniform
+      pc_base = hs_rng;
+      const PhiloxBlock b = philox4x32_10(P.seed, stream, hs_rng + (uint64_t)(threadIdx.x & 31));
+      pc_r0 = b.r0;
+      pc_r1 = b.r1;
+      off = 0;
+    }
+    r0 = __shfl_sync(0xffffffffu, pc_r0, (int)off);
+    r1 = __shfl_sync(0xffffffffu, pc_r1, (int)off);
+    hs_rng += 1;
+  }
+  __device__ __forceinline__ bool rng_bool() {
+    uint32_t r0, r1;
+    rng_words(r0, r1);
+    return (r0 & 1u) != 0;
+  }
+  __device__ __forceinline__ double rng_f64() {
+    uint32_t r0, r1;
+    rng_words(r0, r1);
+    return u53((uint64_t)r0 | ((uint64_t)r1 << 32));
+  }
   // array_gaussian(rng, v, ones): v[i] = 1.0 * normal   (cpu_math.rs:561-577)
   __device__ __forceinline__ void sample_velocity() {
     // Elements 2p and 2p+1 (one Box-Muller pair) belong to threads t (even) and t+1 at the same j.  Even threads evaluate the
@@ -813,18 +840,32 @@ struct Engine {
       free_mask &= ~(1ull << draw_slot);
       rc_add(draw_slot, 1);
     }
+    // The ends of the main tree are not copied: (z, v) of an end IS the checkpoint of the leaf that became that end; its slot
+    // stays out of the pool like the slot of the main tree's draw.
+    if (!init_left) free_mask &= ~(1ull << es_left);
+    if (!init_right) free_mask &= ~(1ull << es_right);
     // start state = the end of the main tree in direction dir
     const bool near_init = dir ? init_right : init_left, far_init = dir ? init_left : init_right;
-    const double* nearZ = near_init ? P.z + row : end_ptr(dir, 0);
-    const double* nearV = near_init ? P.v0 + row : end_ptr(dir, 1);
-    const double* farZ = far_init ? P.z + row : end_ptr(1 - dir, 0);
-    const double* farV = far_init ? P.v0 + row : end_ptr(1 - dir, 1);
+    const int es_near = dir ? es_right : es_left, es_far = dir ? es_left : es_right;
+    const double* nearZ = near_init ? P.z + row : slot_ptr(es_near, 0);
+    const double* nearV = near_init ? P.v0 + row : slot_ptr(es_near, 1);
+    const double* farZ = far_init ? P.z + row : slot_ptr(es_far, 0);
+    const double* farV = far_init ? P.v0 + row : slot_ptr(es_far, 1);
     if (!(dir ? holds_right : holds_left)) {
       load_cg(nearZ, z);
       load_cg(nearV, v);
-      load_g(near_init ? P.gz + row : end_ptr(dir, 2), true);
+      if (near_init) {
+        load_g(P.gz + row, true);
+      } else if (MODEL == LOGP_GAUSS_DIAG) {
+        // elementwise target: the gradient of a leaf is a function of its z (the leapfrog's own instruction sequence)
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) G(j) = grad_z_at(z[j], j, tid + j * TPC);
+      } else {
+        load_g(end_ptr(dir, 2), true);
+      }
     }
     holds_left = holds_right = false;
+    int s_last = -1;
     int idx_cur = dir ? idx_right : idx_left;
     // the sub-tree B that the newest leaf belongs to
     int B_first = -1, B_draw = -1, B_draw_idx = 0;
@@ -846,6 +887,7 @@ struct Engine {
       if (divergent) return EXT_DIVERGING;
       idx_cur += sign;
       int s = alloc_slot();
+      s_last = s;
       store_cg(slot_ptr(s, 0), z);
       store_cg(slot_ptr(s, 1), v);
       rc_add(s, 3);  // roles: first-of-B, draw-of-B, last-of-B (the newest leaf)
@@ -910,15 +952,15 @@ struct Engine {
     }
     ls_main = total;
     depth += 1;
-    store_cg(end_ptr(dir, 0), z);
-    store_cg(end_ptr(dir, 1), v);
-    store_g(end_ptr(dir, 2), true);
+    if (MODEL != LOGP_GAUSS_DIAG) store_g(end_ptr(dir, 2), true);  // gradient of the new end (not a cheap function of z here)
     if (dir) {
       idx_right = idx_cur;
+      es_right = s_last;
       init_right = false;
       holds_right = true;
     } else {
       idx_left = idx_cur;
+      es_left = s_last;
       init_left = false;
       holds_left = true;
     }
@@ -1233,6 +1275,7 @@ struct Engine {
     depth = 0;
     idx_left = idx_right = 0;
     init_left = init_right = true;
+    es_left = es_right = -1;
     holds_left = holds_right = true;
     draw_slot = -1;
     draw_energy = E0;
