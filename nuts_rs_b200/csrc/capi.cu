@@ -29,6 +29,8 @@ NB_DECL(32, 32, 8)
 NB_DECL(32, 32, 7)
 NB_DECL(64, 16, 4)
 NB_DECL(64, 16, 54)  // SM_EXACT variant of 64x16x4 (rows padded to 1024)
+NB_DECL(64, 16, 55)  // + SM_NOGRAD, 5 resident CTAs per SM
+NB_DECL(64, 16, 56)  // + SM_NOGRAD, 6 resident CTAs per SM
 NB_DECL(64, 16, 5)
 NB_DECL(64, 16, 6)
 NB_DECL(64, 16, 7)
@@ -88,7 +90,7 @@ const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 

@@ -218,7 +218,9 @@ struct TreeTables {
 // model parameters).  Layout: [sigma | mean] (SM_MASS) [model mu | model prec] (SM_MODEL) [grad_z] (SM_GRAD) TreeTables.
 // SM_EXACT: every sampler row is padded with zeros to TPC*EPT elements (EngineParams::ld >= TPC*EPT), so the hot loops run
 // without bounds checks: the padding lanes compute on zeros and stay zero.
-enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8 };
+// SM_NOGRAD (elementwise target only): the tree builder keeps no gradient vector at all; a leapfrog recomputes grad_z of its start
+// point from z (5 flops per element) - 2*EPT registers less per thread, i.e. more resident teams per SM.
+enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16 };
 template <int SMF>
 __host__ __device__ constexpr int smem_vectors() {
   return ((SMF & SM_MASS) ? 2 : 0) + ((SMF & SM_MODEL) ? 2 : 0) + ((SMF & SM_GRAD) ? 1 : 0);
@@ -241,7 +243,8 @@ struct Engine {
   double* const ends_base;
 
   // ---- register-resident vectors ----
-  static constexpr bool MMS = (SMF & SM_MASS) != 0, MODS = (SMF & SM_MODEL) != 0, GS = (SMF & SM_GRAD) != 0, EXACT = (SMF & SM_EXACT) != 0;
+  static constexpr bool MMS = (SMF & SM_MASS) != 0, MODS = (SMF & SM_MODEL) != 0, GS = (SMF & SM_GRAD) != 0, EXACT = (SMF & SM_EXACT) != 0,
+                        NOG = (SMF & SM_NOGRAD) != 0 && MODEL == LOGP_GAUSS_DIAG;
   static_assert(!EXACT || ((MODS || MULTI) && MMS), "SM_EXACT needs zero-padded on-chip copies of the model parameters and the mass matrix");
   __device__ __forceinline__ bool inb(int i) const { return EXACT || i < d; }  // element i exists (or is zero padding that may be touched)
   double z[EPT], v[EPT];  // current phase-space point: whitened position, velocity
@@ -851,7 +854,30 @@ struct Engine {
     const double* nearV = near_init ? P.v0 + row : slot_ptr(es_near, 1);
     const double* farZ = far_init ? P.z + row : slot_ptr(es_far, 0);
     const double* farV = far_init ? P.v0 + row : slot_ptr(es_far, 1);
-    if (!(dir ? holds_right : holds_left)) {
+    bool half_done = false;  // NOG: v already holds the first half-step of leaf 0 (done with the stored gradient of the initial point)
+    if (NOG) {
+      if (near_init) {
+        const double eps_half = eps / 2.;
+        if (!(dir ? holds_right : holds_left)) {
+          load_cg(nearZ, z);
+          load_cg(nearV, v);
+          const double* gp = P.gz + row;
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) {
+            const int i = tid + j * TPC;
+            const double gl = inb(i) ? __ldcg(gp + i) : 0.0;
+            v[j] = fma(eps_half, gl, v[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) v[j] = fma(eps_half, G(j), v[j]);  // gradient loaded by draw_begin()
+        }
+        half_done = true;
+      } else if (!(dir ? holds_right : holds_left)) {
+        load_cg(nearZ, z);
+        load_cg(nearV, v);
+      }
+    } else if (!(dir ? holds_right : holds_left)) {
       load_cg(nearZ, z);
       load_cg(nearV, v);
       if (near_init) {
@@ -877,7 +903,26 @@ struct Engine {
       NB_ACC(4, tq);
       // odd leaves merge with their predecessor first (level 0): its U-turn products come out of the leapfrog itself
       const bool fuse0 = kFusedPrevCheck && check && (i & 1u);
-      leapfrog(eps, logp_new, ke_new, fuse0, sP0, sQ0);
+      if (NOG) {
+        double part[4];
+        leapfrog_partials_nog(eps, half_done, part);
+        half_done = false;
+        hs_total_lf += 1;
+        if (fuse0) {
+          red.allreduce(part);
+        } else {
+          double p2[2] = {part[0], part[1]};
+          red.allreduce(p2);
+          part[0] = p2[0];
+          part[1] = p2[1];
+        }
+        logp_new = part[0];
+        ke_new = 0.5 * part[1];
+        sP0 = part[2];
+        sQ0 = part[3];
+      } else {
+        leapfrog(eps, logp_new, ke_new, fuse0, sP0, sQ0);
+      }
       NB_ACC(1, tq);
       hs_tree_lf += 1;
       double energy = ke_new - (logp_new + hs_pt_logdet);
@@ -1747,8 +1792,14 @@ static __device__ __noinline__ void cold_fill_dead(const EngineParams& P, int ch
 
 // One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).
 // Dynamic shared memory: TEAMS x team_smem_bytes<TPC, EPT, SMF>().
+// NB_MAXNREG (optional, per translation unit): exact register budget instead of the one ptxas derives from MIN_BLOCKS
+#ifdef NB_MAXNREG
+#define NB_KERNEL_BOUNDS(T, B) __maxnreg__(NB_MAXNREG)
+#else
+#define NB_KERNEL_BOUNDS(T, B) __launch_bounds__(T, B)
+#endif
 template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, int SMF, int MODEL>
-__global__ void __launch_bounds__(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(const __grid_constant__ EngineParams P) {
+__global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(const __grid_constant__ EngineParams P) {
   constexpr int TEAMS = CTA_THREADS / TPC;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ double scratch[TPC > 32 ? 2 * 32 * REDUCE_MAXK : 1];

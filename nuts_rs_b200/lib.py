@@ -428,6 +428,7 @@ class Sampler:
         self.math = math
         self.nchains, self.dim = math.nchains, math.dim
         self.settings = settings
+        self.chain_id_offset = chain_id_offset
         h = C.c_void_p()
         _check(load().nuts_sampler_create(math.h, C.byref(h), C.byref(settings), seed, chain_id_offset))
         self.h = h
@@ -445,6 +446,14 @@ class Sampler:
         st, arrays = (alloc_stats(n_draws, self.nchains) if stats else (None, {}))
         _check(load().nuts_draw(self.h, n_draws, _p(draws), C.byref(st) if stats else None))
         return draws, arrays
+
+    def draw_trace(self, n_draws, out=None):
+        """`draw`, returned in the reference's trace schema ([chain, draw, ...], reference statistic names): see trace.py."""
+        from . import trace
+
+        done = self.counters()[1]
+        draws, stats = self.draw(n_draws, out=out)
+        return trace.to_trace(draws, stats, chain_offset=self.chain_id_offset, draw_offset=done)
 
     def draw_device(self, n_draws, draws_dev_ptr=None):
         _check(load().nuts_draw_device(self.h, n_draws, draws_dev_ptr))

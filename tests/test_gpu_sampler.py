@@ -304,3 +304,21 @@ def test_draws_written_directly_into_pinned_host_memory(L):
     assert np.array_equal(a[:, live], b[:, live])
     for k in sa:
         assert np.array_equal(sa[k][:, live], sb[k][:, live]), k
+
+
+def test_draw_trace_schema_on_device(L):
+    """Sampler.draw_trace: the engine's output in the reference's trace layout ([chain, draw], src/storage/core.rs:12-77),
+    `draw` continuing across calls and `chain` carrying the global chain id of a shard (src/sampler.rs:165-174)."""
+    N, d = 6, 20
+    m = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_ISO, mu=3.0)
+    s = L.Sampler(m, _settings(L, num_tune=5, maxdepth=5), seed=3, chain_id_offset=100)
+    assert (s.set_position(np.full((N, d), 3.5)) == 0).all()
+    a = s.draw_trace(7)
+    b = s.draw_trace(4)
+    s.close()
+    m.close()
+    assert a["posterior"]["unconstrained_draw"].shape == (N, 7, d)
+    assert (a["sample_stats"]["chain"][:, 0] == np.arange(100, 100 + N)).all()
+    assert (a["sample_stats"]["draw"][0] == np.arange(7)).all() and (b["sample_stats"]["draw"][0] == np.arange(7, 11)).all()
+    assert a["sample_stats"]["tuning"][:, :5].all() and not a["sample_stats"]["tuning"][:, 5:].any() and not b["sample_stats"]["tuning"].any()
+    assert (a["sample_stats"]["n_steps"] >= 1).all() and np.isfinite(a["sample_stats"]["logp"]).all()
