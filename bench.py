@@ -132,6 +132,34 @@ class ClockSampler:
                 "power_w_max": max(r[2] for r in self.rows), "source": self.source}
 
 
+def microbench_fixed_depth(lib, _abi, device, chain_offset, depth=6, draws=8):
+    """SURVEY §8(d) microbench: fixed step size, unit mass matrix, no adaptation, mindepth = maxdepth (no U-turn checks):
+    every draw is exactly 2^depth - 1 leapfrogs + checkpoints, nothing data-dependent - the pure leapfrog throughput of the engine."""
+    s = settings()
+    s.num_tune = 0
+    s.maxdepth = depth
+    s.mindepth = depth
+    ss = s.adapt_options.step_size_settings
+    ss.adapt_options.method = _abi.NUTS_STEPSIZE_FIXED
+    ss.adapt_options.fixed_step = 0.05
+    ss.has_jitter = 0
+    math = lib.CudaMath(CHAINS_PER_GPU, DIM, _abi.NUTS_LOGP_GAUSS_DIAG, mu=0.5, sigma=model_sigma(), device=device)
+    samp = lib.Sampler(math, s, seed=SEED, chain_id_offset=chain_offset)
+    samp.set_position(initial_positions(CHAINS_PER_GPU, chain_offset))
+    samp.draw_device(2)
+    lf0, _ = samp.counters()
+    ms = 0.0
+    for _ in range(3):
+        samp.draw_device(draws)
+        ms += samp.last_timing()[0]
+    lf1, _ = samp.counters()
+    samp.close()
+    math.close()
+    rate = (lf1 - lf0) / (ms * 1e-3)
+    return {"leapfrogs_per_s": rate, "depth": depth, "leapfrogs_per_draw": 2 ** depth - 1, "draws_per_launch": draws,
+            "algorithmic_GBps": rate * 48 * DIM / 1e9}
+
+
 def cpu_oracle_throughput(max_seconds, nthreads):
     """The oracle (C++ restatement of nuts-rs's CPU path, one chain per thread like the reference's rayon pool,
     src/sampler.rs:1287-1326) on a bounded sample of the same workload: `4 x cores` chains, 400 tuning draws (untimed),
@@ -293,6 +321,8 @@ def main():
     d2h = host_draws.nbytes + sum(a.nbytes for a in stats_arrays.values())
     e2e_direct = samp.last_draw_direct()
 
+    micro = microbench_fixed_depth(lib, _abi, local_rank, chain_offset) if rank == 0 else None
+
     # ---------------- reduce over ranks: max time, summed work
     t = torch.tensor([kernel_ms, wall_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     w = torch.tensor([float(steps_dev), float(steps_e2e)], dtype=torch.float64, device="cuda")
@@ -363,6 +393,7 @@ def main():
                                  "registers across leapfrogs, so algorithmic bytes are NOT DRAM bytes (frac > 1 is possible); see DESIGN.md"},
             "cpu_baseline": cpu,
         }
+        line["config"]["microbench_fixed_step_no_turn_checks_rank0"] = micro
         if gather_ms is not None:
             line["config"]["nccl_all_gather_last_step_ms"] = gather_ms
         print(json.dumps(line), flush=True)

@@ -30,6 +30,7 @@ namespace nb {
 
 constexpr int MAX_DOUBLING_DEPTH = 19;  // deepest new half has 2^19 leaves (checkpoint pool: 3 per level + 6 <= MAX_SLOTS)
 constexpr int MAX_SLOTS = 64;
+constexpr int ACC_RING = 32;  // leaves whose acceptance statistics are evaluated together (one exp per lane)
 constexpr int NB_END_BUFFERS = 3;  // main-tree endpoint buffers per chain: left, right + one pending (decoupled engine)
 
 struct SettingsDev {
@@ -212,7 +213,34 @@ struct TreeTables {
   double A_ls[MAX_DOUBLING_DEPTH], A_draw_energy[MAX_DOUBLING_DEPTH];
   int A_draw_idx[MAX_DOUBLING_DEPTH];
   signed char A_first[MAX_DOUBLING_DEPTH], A_last[MAX_DOUBLING_DEPTH], A_draw[MAX_DOUBLING_DEPTH];
+  // deferred AcceptanceRateCollector: energy differences of the leaves not yet accumulated, and the batch of their statistics
+  double acc_diff[ACC_RING], acc_e[ACC_RING], acc_s[ACC_RING];
 };
+
+// Evaluate the acceptance statistics of the n pending leaves (TreeTables::acc_diff) and add them in leaf order.
+struct AccSums {
+  double sum, sym, max_err;
+};
+static __device__ __noinline__ AccSums accept_batch(TreeTables* T, int n, double acc_sum, double acc_sym_sum, double max_energy_error) {
+  const int lane = threadIdx.x & 31;
+  if (lane < n) {  // every warp of the team evaluates the whole batch (identical values; no cross-warp traffic)
+    const double diff = T->acc_diff[lane];
+    const double ed = exp(diff);
+    const double e = diff < 0. ? ed : 1.0;  // == exp(min(diff, 0)) bit for bit (diff is finite here), one exp instead of two
+    T->acc_e[lane] = e;
+    T->acc_s[lane] = 2. * e / (1. + ed);
+  }
+  __syncwarp();
+  AccSums r{acc_sum, acc_sym_sum, max_energy_error};
+  for (int k = 0; k < n; ++k) {
+    r.sum += T->acc_e[k];
+    r.sym += T->acc_s[k];
+    const double diff = T->acc_diff[k];
+    if (fabs(diff) > fabs(r.max_err)) r.max_err = diff;
+  }
+  __syncwarp();  // the batch is consumed before any lane records the next leaf
+  return r;
+}
 
 // What lives in the team's dynamic shared memory (SMF bit flags); everything else is registers (or L1-cached global for the
 // model parameters).  Layout: [sigma | mean] (SM_MASS) [model mu | model prec] (SM_MODEL) [grad_z] (SM_GRAD) TreeTables.
@@ -811,18 +839,31 @@ struct Engine {
   }
 
   // ------------------------------------------------------------------ AcceptanceRateCollector::register_leapfrog (dual_avg.rs:131-158)
+  // The statistics (exp(min(diff, 0)), its symmetric variant, the signed maximum) only matter at the end of the draw, and their
+  // exp + division are ~150 dependent instructions on the critical path of every leaf.  Each leaf just records its energy
+  // difference; ACC_RING of them are evaluated together - one exp per lane - and then added in leaf order, so the sums are
+  // bit-identical to the reference's sequential accumulation.
+  int acc_pending = 0;
   __device__ __forceinline__ void register_leapfrog(double energy, bool divergent) {
     if (divergent) {
+      flush_accept();
       max_energy_error = -INFINITY;
     } else {
-      double diff = E0 - energy;
-      const double ed = exp(diff);
-      const double e = diff < 0. ? ed : 1.0;  // == exp(min(diff, 0)) bit for bit (diff is finite here), one exp instead of two
-      acc_sum += e;
-      acc_sym_sum += 2. * e / (1. + ed);
-      if (fabs(diff) > fabs(max_energy_error)) max_energy_error = diff;
+      // every thread of the team stores the same value: a thread reads back what it (also) wrote, no barrier needed here
+      T.acc_diff[acc_pending] = E0 - energy;
+      acc_pending += 1;
+      if (acc_pending == ACC_RING) flush_accept();
     }
     acc_count += 1;
+  }
+  __device__ __forceinline__ void flush_accept() {
+    if (acc_pending == 0) return;
+    // by value: a member function that is not inlined would take `this` and pin the whole engine in local memory
+    const AccSums r = accept_batch(&T, acc_pending, acc_sum, acc_sym_sum, max_energy_error);
+    acc_sum = r.sum;
+    acc_sym_sum = r.sym;
+    max_energy_error = r.max_err;
+    acc_pending = 0;
   }
 
   // ------------------------------------------------------------------ NutsTree::extend for the MAIN tree (nuts.rs:108-170)
@@ -1260,6 +1301,7 @@ struct Engine {
     acc_sum = 0.;
     acc_sym_sum = 0.;
     acc_count = 0;
+    acc_pending = 0;
     max_energy_error = 0.;
   }
 
@@ -1360,6 +1402,7 @@ struct Engine {
         extra_left = S.extra_doublings;
       }
     }
+    flush_accept();
     draw_finish(t, diverging, reached_maxdepth);
     NB_ACC(7, tw);
   }
