@@ -9,3 +9,4 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 3 -c 1 -f -o gpurun_out/prof_$TAG python scratch/prof_run.py > gpurun_out/prof_$TAG.log 2>&1; echo "ncu full rc=$?"
 timeout 600 python scratch/configs_run.py > gpurun_out/configs_$TAG.log 2>&1; echo "configs rc=$?"; cat gpurun_out/configs_$TAG.log
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_leapfrog --csv --log-file gpurun_out/plane_leapfrog_$TAG.csv python scratch/plane_leapfrog_run.py > gpurun_out/plane_leapfrog_$TAG.log 2>&1; echo "plane ncu rc=$?"; tail -1 gpurun_out/plane_leapfrog_$TAG.log
