@@ -46,6 +46,8 @@ NB_DECL(1024, 16, 1)
 NB_DECL1(64, 16, 107, 1)
 NB_DECL1(64, 16, 117, 1)
 NB_DECL1(64, 16, 144, 1)
+NB_DECL1(512, 20, 161, 1)
+NB_DECL1(480, 21, 171, 1)
 NB_DECL1(64, 16, 155, 1)
 NB_DECL1(64, 16, 127, 1)
 
@@ -74,6 +76,7 @@ struct EngineConfig {
   // indexed by model variant - 1 (1 diagonal/isotropic Gaussian, 2 rank-1 Gaussian, 3 funnel)
   cudaError_t (*launch[3])(const EngineParams*, int, cudaStream_t);
   cudaError_t (*occupancy[3])(int*, int*, int*);
+  int min_d = 0;  // kDecoupledLarge only: chosen for min_d < dim <= max_d
 };
 #define NB_CFG(TPC, EPT, MINB)                                                                                                             \
   {                                                                                                                                        \
@@ -89,10 +92,12 @@ struct EngineConfig {
 // the whole kernel, all 1024 chains of config 2 resident at once); CTA-per-chain above.
 const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(64, 16, 4),
                                  NB_CFG(256, 8, 2), NB_CFG(512, 8, 1), NB_CFG(1024, 8, 1), NB_CFG(1024, 10, 1), NB_CFG(1024, 16, 1)};
+// decoupled engine for large dims (chosen for min_d < dim <= max_d, elementwise targets)
+const EngineConfig kDecoupledLarge[] = {{480, 21, 171, 480 * 21, {nb_launch_chain_480_21_171_1, nullptr, nullptr}, {nb_occupancy_chain_480_21_171_1, nullptr, nullptr}, 8192}};
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 
@@ -271,7 +276,8 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
   ctx->num_sms = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   // model parameters
-  std::vector<double> mu(ctx->ld, 0.0), prec(ctx->ld, 0.0);
+  const size_t model_ld = (ctx->ld + 1023) / 1024 * 1024;  // zero padding: SM_EXACT engines read whole tiles
+  std::vector<double> mu(model_ld, 0.0), prec(model_ld, 0.0);
   for (uint64_t i = 0; i < dim; ++i) mu[i] = model->mu ? model->mu[i] : model->mu_scalar;
   ctx->model.kind = model->kind;
   ctx->model.dim = (int)dim;
@@ -296,10 +302,10 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
       delete ctx;
       return fail(NUTS_ERR_INVALID, "unknown logp kind %d", model->kind);
   }
-  TRY(dev_alloc(&ctx->d_model_mu, ctx->ld));
-  TRY(dev_alloc(&ctx->d_model_prec, ctx->ld));
-  CUDA_TRY(cudaMemcpy(ctx->d_model_mu, mu.data(), ctx->ld * sizeof(double), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(ctx->d_model_prec, prec.data(), ctx->ld * sizeof(double), cudaMemcpyHostToDevice));
+  TRY(dev_alloc(&ctx->d_model_mu, model_ld));
+  TRY(dev_alloc(&ctx->d_model_prec, model_ld));
+  CUDA_TRY(cudaMemcpy(ctx->d_model_mu, mu.data(), model_ld * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(ctx->d_model_prec, prec.data(), model_ld * sizeof(double), cudaMemcpyHostToDevice));
   ctx->model.mu = ctx->d_model_mu;
   ctx->model.prec = ctx->d_model_prec;
   // transformation planes: DiagMassMatrix::new (diagonal.rs:73-83): zero vectors, logdet 0, id -1
@@ -700,6 +706,14 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
       }
   if (!cfg) return fail(NUTS_ERR_UNSUPPORTED, "dim %llu exceeds the largest register-resident configuration (16384)", (unsigned long long)ctx->d);
   if (!std::getenv("NUTS_B200_ENGINE")) {
+    // dim ~ 10^4: a chain's (z, v, sigma, mu) plus the redundant scalar state of the register-resident engine no longer fit one SM
+    // (1024x10 runs at 64 registers per thread and spills 2.5 KB); the decoupled engine keeps the scalar state in ONE leader warp
+    for (const EngineConfig& c : kDecoupledLarge)
+      if (ctx->model.kind != NUTS_LOGP_GAUSS_RANK1 && ctx->model.kind != NUTS_LOGP_FUNNEL && c.launch[0] && ctx->d > (uint64_t)c.min_d &&
+          ctx->d <= (uint64_t)c.max_d && st->maxdepth + st->extra_doublings <= (uint64_t)V2_MAXD + 1) {
+        cfg = &c;
+        break;
+      }
     // same tiling without bounds checks (SM_EXACT: rows zero-padded to tpc*ept) when the padding costs at most 7 % more traffic
     for (const EngineConfig& c : kExactConfigs)
       if (c.tpc == cfg->tpc && c.ept == cfg->ept && c.launch[0] && (uint64_t)c.max_d - ctx->d <= ctx->d * 7 / 100) cfg = &c;

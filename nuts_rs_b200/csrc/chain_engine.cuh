@@ -152,7 +152,7 @@ constexpr int V2_K = 4;                  // leaf entries a team may be ahead of 
 constexpr int V2_MAXD = 10;              // deepest doubling (2^10 leaves): maxdepth + extra_doublings <= V2_MAXD + 1
 constexpr int V2_NV = 4 + 6 * V2_MAXD;   // values per leaf entry and warp: leapfrog sums + 6 per bundled merge (<= V2_MAXD merges)
 constexpr int V2_NT = V2_MAXD + 2;       // per-level table size
-constexpr int V2_MAXW = 4;               // warps per team
+constexpr int V2_MAXW = 16;              // warps per team
 enum { V2_CMD_DOUBLING = 1, V2_CMD_TREE_DONE = 2 };
 
 struct V2Ctl {
@@ -248,7 +248,9 @@ static __device__ __noinline__ AccSums accept_batch(TreeTables* T, int n, double
 // without bounds checks: the padding lanes compute on zeros and stay zero.
 // SM_NOGRAD (elementwise target only): the tree builder keeps no gradient vector at all; a leapfrog recomputes grad_z of its start
 // point from z (5 flops per element) - 2*EPT registers less per thread, i.e. more resident teams per SM.
-enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16 };
+// SM_MODEL_GLOBAL (decoupled engine): no CTA-wide shared-memory copy of the model parameters (they do not fit for dim ~ 10^4);
+// they are read through the read-only path from global memory, where capi.cu pads them with zeros to a multiple of 1024.
+enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32 };
 template <int SMF>
 __host__ __device__ constexpr int smem_vectors() {
   return ((SMF & SM_MASS) ? 2 : 0) + ((SMF & SM_MODEL) ? 2 : 0) + ((SMF & SM_GRAD) ? 1 : 0);
@@ -272,8 +274,9 @@ struct Engine {
 
   // ---- register-resident vectors ----
   static constexpr bool MMS = (SMF & SM_MASS) != 0, MODS = (SMF & SM_MODEL) != 0, GS = (SMF & SM_GRAD) != 0, EXACT = (SMF & SM_EXACT) != 0,
-                        NOG = (SMF & SM_NOGRAD) != 0 && MODEL == LOGP_GAUSS_DIAG;
-  static_assert(!EXACT || ((MODS || MULTI) && MMS), "SM_EXACT needs zero-padded on-chip copies of the model parameters and the mass matrix");
+                        NOG = (SMF & SM_NOGRAD) != 0 && MODEL == LOGP_GAUSS_DIAG,
+                        MSH = MODS || (MULTI && (SMF & SM_MODEL_GLOBAL) == 0);  // model parameters are read from shared memory
+  static_assert(!EXACT || ((MODS || MULTI) && MMS), "SM_EXACT needs zero-padded copies of the model parameters and the mass matrix");
   __device__ __forceinline__ bool inb(int i) const { return EXACT || i < d; }  // element i exists (or is zero padding that may be touched)
   double z[EPT], v[EPT];  // current phase-space point: whitened position, velocity
   double g_reg[GS ? 1 : EPT];  // whitened gradient: registers, or shared memory (GS) to fit more chains per SM
@@ -341,8 +344,8 @@ struct Engine {
   __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[tid + j * TPC] : mu[MMS ? 0 : j]; }
   // model parameters of element i = tid + j*TPC
   // (MULTI: one copy per CTA shared by all its teams, filled by the kernel prologue)
-  __device__ __forceinline__ double model_mu(int j, int i) const { return (MODS || MULTI) ? sm_mmu[tid + j * TPC] : __ldg(P.model.mu + i); }
-  __device__ __forceinline__ double model_prec(int j, int i) const { return (MODS || MULTI) ? sm_mprec[tid + j * TPC] : __ldg(P.model.prec + i); }
+  __device__ __forceinline__ double model_mu(int j, int i) const { return MSH ? sm_mmu[tid + j * TPC] : __ldg(P.model.mu + i); }
+  __device__ __forceinline__ double model_prec(int j, int i) const { return MSH ? sm_mprec[tid + j * TPC] : __ldg(P.model.prec + i); }
   // element j of the whitened gradient (each thread only touches its own entries: no synchronisation)
   __device__ __forceinline__ double& G(int j) { return GS ? sm_g[tid + j * TPC] : g_reg[GS ? 0 : j]; }
   __device__ __forceinline__ void load_model_params() {

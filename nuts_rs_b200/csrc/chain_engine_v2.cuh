@@ -368,10 +368,13 @@ struct LeaderLane {
 template <int TPC, int EPT, int C>
 struct V2Layout {
   static constexpr int W = TPC / 32;
-  static constexpr int SMF = SM_MASS | SM_EXACT;  // rows padded to TPC*EPT; sigma | mean in shared memory; grad_z is recomputed, never stored on chip
+  // the CTA-wide copy of the model parameters only when it leaves room for the teams (dim ~ 10^4: 160 KB of sigma | mean alone)
+  static constexpr bool MODEL_SHARED = (size_t)(2 * C + 2) * TPC * EPT * sizeof(double) <= 200 * 1024;
+  // rows padded to TPC*EPT; sigma | mean in shared memory; grad_z is recomputed, never stored on chip
+  static constexpr int SMF = SM_MASS | SM_EXACT | (MODEL_SHARED ? 0 : SM_MODEL_GLOBAL);
   static constexpr size_t team_bytes = team_smem_bytes<TPC, EPT, SMF>();
   static constexpr size_t off_model = (size_t)C * team_bytes;
-  static constexpr size_t off_ring = off_model + 2 * (size_t)TPC * EPT * sizeof(double);
+  static constexpr size_t off_ring = off_model + (MODEL_SHARED ? 2 * (size_t)TPC * EPT * sizeof(double) : 0);
   static constexpr size_t ring_bytes = (size_t)V2_K * W * V2_NV * sizeof(double);
   static constexpr size_t off_ctl = off_ring + (size_t)C * ring_bytes;
   static constexpr size_t ctl_bytes = (sizeof(V2Ctl) + 15) / 16 * 16;
@@ -394,10 +397,11 @@ __global__ void __launch_bounds__(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(con
   double* model_smem = reinterpret_cast<double*>(dyn_smem + L::off_model);
   // prologue: control blocks and the CTA-wide copy of the model parameters
   for (int k = threadIdx.x; k < (int)(C * L::ctl_bytes / 4); k += blockDim.x) reinterpret_cast<unsigned*>(dyn_smem + L::off_ctl)[k] = 0u;
-  for (int k = threadIdx.x; k < TPC * EPT; k += blockDim.x) {
-    model_smem[k] = k < P.d ? P.model.mu[k] : 0.0;
-    model_smem[TPC * EPT + k] = k < P.d ? P.model.prec[k] : 0.0;
-  }
+  if (L::MODEL_SHARED)
+    for (int k = threadIdx.x; k < TPC * EPT; k += blockDim.x) {
+      model_smem[k] = k < P.d ? P.model.mu[k] : 0.0;
+      model_smem[TPC * EPT + k] = k < P.d ? P.model.prec[k] : 0.0;
+    }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
   if (warp < NL) {
@@ -459,25 +463,48 @@ __global__ void __launch_bounds__(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(con
   mc.bar_id = 1 + team;
   mc.warp = (warp - NL) % W;
   unsigned cmd_seen = 0;
+  // work units as in nuts_chain_kernel: one chain for set_position, ONE DRAW of one chain (draw-major) for draws
+  const unsigned total_units = P.mode == 0 ? (unsigned)P.N : (unsigned)P.N * (unsigned)P.n_draws;
   for (;;) {
-    if (tid == 0) next_chain[0] = (int)atomicAdd(P.queue, 1u);
+    if (tid == 0) {
+      const unsigned u = atomicAdd(P.queue, 1u);
+      next_chain[1] = (int)u;
+      next_chain[0] = u < total_units ? (int)(u % (unsigned)P.N) : -1;  // the leader lane reads the chain id from here
+    }
     bar_sync(mc.bar_id, TPC);
-    const int chain = next_chain[0];
+    const unsigned unit = (unsigned)next_chain[1];
     bar_sync(mc.bar_id, TPC);
-    if (chain >= P.N) break;
+    if (unit >= total_units) break;
+    const int chain = (int)(unit % (unsigned)P.N);
+    const uint64_t t = unit / (unsigned)P.N;
     Engine<TPC, EPT, SMF, MODEL, true> E(P, chain, tid, scratch, team_smem, tables, &mc);
     if (P.mode == 0) {
       const int status = cold_set_position<TPC, EPT, SMF, MODEL, true>(P, chain, tid, scratch, team_smem, &mc);
       if (tid == 0 && P.status_out) P.status_out[chain] = status;
     } else {
+      if (t > 0) {
+        if (tid == 0) {
+          unsigned dn;
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(P.done + chain) : "memory");
+            if (dn >= (unsigned)t) break;
+            __nanosleep(200);
+          }
+        }
+        bar_sync(mc.bar_id, TPC);
+        __threadfence();
+      }
       E.load_hot();
       if (E.hs_alive) {
-        for (uint64_t t = 0; t < P.n_draws; ++t) {
-          E.run_draw_v2(t, cmd_seen);
-          if (!E.hs_alive) break;
-        }
-      } else if (P.draws_out) {
+        E.run_draw_v2(t, cmd_seen);
+      } else if (t == 0 && P.draws_out) {
         cold_fill_dead(P, chain, tid, TPC, 0);
+      }
+      __threadfence();
+      bar_sync(mc.bar_id, TPC);
+      if (tid == 0) {
+        const unsigned dn = (unsigned)t + 1u;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.done + chain), "r"(dn) : "memory");
       }
     }
     bar_sync(mc.bar_id, TPC);
