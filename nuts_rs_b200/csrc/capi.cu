@@ -1,5 +1,6 @@
 // capi.cu — host side of libnuts_b200.so: the C ABI declared in include/nuts_b200.h.
 // No torch, no CPU fallback: every entry point needs an sm_100 device and fails loudly otherwise.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -48,6 +49,7 @@ NB_DECL1(64, 16, 117, 1)
 NB_DECL1(64, 16, 144, 1)
 NB_DECL1(512, 20, 161, 1)
 NB_DECL1(480, 21, 171, 1)
+NB_DECL1(480, 18, 181, 1)
 NB_DECL1(64, 16, 155, 1)
 NB_DECL1(64, 16, 127, 1)
 
@@ -93,11 +95,13 @@ struct EngineConfig {
 const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(64, 16, 4),
                                  NB_CFG(256, 8, 2), NB_CFG(512, 8, 1), NB_CFG(1024, 8, 1), NB_CFG(1024, 10, 1), NB_CFG(1024, 16, 1)};
 // decoupled engine for large dims (chosen for min_d < dim <= max_d, elementwise targets)
-const EngineConfig kDecoupledLarge[] = {{480, 21, 171, 480 * 21, {nb_launch_chain_480_21_171_1, nullptr, nullptr}, {nb_occupancy_chain_480_21_171_1, nullptr, nullptr}, 8192}};
+const EngineConfig kDecoupledLarge[] = {
+    {480, 18, 181, 480 * 18, {nb_launch_chain_480_18_181_1, nullptr, nullptr}, {nb_occupancy_chain_480_18_181_1, nullptr, nullptr}, 4096},
+    {480, 21, 171, 480 * 21, {nb_launch_chain_480_21_171_1, nullptr, nullptr}, {nb_occupancy_chain_480_21_171_1, nullptr, nullptr}, 480 * 18}};
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 
@@ -276,7 +280,7 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
   ctx->num_sms = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   // model parameters
-  const size_t model_ld = (ctx->ld + 1023) / 1024 * 1024;  // zero padding: SM_EXACT engines read whole tiles
+  const size_t model_ld = std::max<size_t>(ctx->ld, 16384);  // zero padding up to the largest tile: SM_EXACT engines read whole tiles
   std::vector<double> mu(model_ld, 0.0), prec(model_ld, 0.0);
   for (uint64_t i = 0; i < dim; ++i) mu[i] = model->mu ? model->mu[i] : model->mu_scalar;
   ctx->model.kind = model->kind;

@@ -146,7 +146,7 @@ def test_c1_default_depth_with_adaptation(L, orc):
 
 
 ENGINE_DIMS = [(1, 4, 60), (2, 4, 60), (33, 5, 60), (64, 3, 60), (100, 6, 80), (129, 3, 60), (256, 3, 60), (400, 3, 50), (1000, 4, 50),
-               (1025, 2, 40), (2048, 2, 30), (3000, 2, 30), (5000, 2, 24), (9000, 3, 16), (10000, 2, 20), (12000, 2, 16)]
+               (1025, 2, 40), (2048, 2, 30), (3000, 2, 30), (5000, 2, 24), (7000, 3, 16), (9000, 3, 16), (10000, 2, 20), (12000, 2, 16)]
 
 
 @pytest.mark.parametrize("d,N,draws", ENGINE_DIMS)
