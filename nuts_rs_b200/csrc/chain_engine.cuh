@@ -115,6 +115,13 @@ enum { EXT_OK = 0, EXT_TURNING = 1, EXT_DIVERGING = 2 };
 // Optional phase timing (build with -DNB_PHASE_TIMING): per-phase clock64() totals of thread 0 of every team, added to
 // EngineParams::phase_clocks[8] at the end of a chain.  0 init_trajectory, 1 leapfrog, 2 leaf bookkeeping + checkpoint store,
 // 3 merges (turn checks), 4 doubling prologue/epilogue, 5 materialise, 6 adapt, 7 whole draw.
+#ifdef NB_PHASE_TIMING_COLD
+#define NB_COLD_T(k) cold_t[k] = clock64()
+#define NB_COLD_T0 const long long cold_t0 = clock64()
+#else
+#define NB_COLD_T(k)
+#define NB_COLD_T0
+#endif
 #ifdef NB_PHASE_TIMING
 #define NB_T0(var) long long var = clock64()
 #define NB_ACC(k, var) do { long long _n = clock64(); phase[k] += _n - var; var = _n; } while (0)
@@ -470,6 +477,9 @@ struct Engine {
   // Every thread of the team consumes the same scalar random numbers, so a warp evaluates 32 consecutive Philox blocks at once
   // (lane k: event counter pc_base + k) and serves them by shuffle: one block evaluation per ~32 events instead of one per event.
   // A block is a pure function of (seed, stream, counter): values equal stream_bool / stream_f64 of rng_spec bit for bit.
+#ifdef NB_PHASE_TIMING_COLD
+  long long cold_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   uint64_t pc_base = 1ull << 63;  // no counter ever gets near: the first use refills
   uint32_t pc_r0 = 0, pc_r1 = 0;
   __device__ __forceinline__ void rng_words(uint32_t& r0, uint32_t& r1) {
@@ -1150,6 +1160,8 @@ struct Engine {
   }
 
   // ------------------------------------------------------------------ RunningVariance::add_sample x4 (transform/adapt/diagonal.rs:32-44,134-141)
+  // Operands are loaded in batches (all loads of a vector pass issued before the first store): the compiler may not move a load of
+  // one estimator plane above a store to another one, and a read-modify-write per element would serialise 64 global round trips.
   __device__ __forceinline__ void add_sample_set(int set, uint64_t new_count, const double (&x)[EPT], const double (&gx)[EPT]) {
     double* dm = est_ptr(set, 0);
     double* dv = est_ptr(set, 1);
@@ -1168,19 +1180,25 @@ struct Engine {
       }
     } else {
       const double scale = 1.0 / (double)new_count;
+      double m0[EPT], q0[EPT], m1[EPT], q1[EPT];
+      load(dm, m0);
+      load(dv, q0);
+      load(gm, m1);
+      load(gv, q1);
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
-        if (i < d) {
-          // array_update_variance (cpu_math.rs:605-631): both terms use the OLD mean
-          double m0 = dm[i], diff = x[j] - m0;
-          dm[i] = m0 + diff * scale;
-          dv[i] = dv[i] + diff * diff;
-          double m1 = gm[i], diff1 = gx[j] - m1;
-          gm[i] = m1 + diff1 * scale;
-          gv[i] = gv[i] + diff1 * diff1;
-        }
+        // array_update_variance (cpu_math.rs:605-631): both terms use the OLD mean
+        const double diff = x[j] - m0[j];
+        m0[j] = m0[j] + diff * scale;
+        q0[j] = q0[j] + diff * diff;
+        const double diff1 = gx[j] - m1[j];
+        m1[j] = m1[j] + diff1 * scale;
+        q1[j] = q1[j] + diff1 * diff1;
       }
+      store(dm, m0);
+      store(dv, q0);
+      store(gm, m1);
+      store(gv, q1);
     }
   }
 
@@ -1188,38 +1206,47 @@ struct Engine {
   __device__ __forceinline__ bool mass_matrix_adapt() {
     if (cs.fg_count < 3) return false;
     const int set = cs.fg_set;
-    const double* dm = est_ptr(set, 0);
-    const double* dv = est_ptr(set, 1);
-    const double* gm = est_ptr(set, 2);
-    const double* gv = est_ptr(set, 3);
     double* sd = P.stds + row;
     double* isd = P.inv_stds + row;
     double* mn = P.mean + row;
     double ld[1] = {0.0};
     const double scale = 1.0 / (double)cs.fg_count;
+    double s_new[EPT];
+    {
+      double dv[EPT], gv[EPT], is_new[EPT];
+      load(est_ptr(set, 1), dv);
+      load(est_ptr(set, 3), gv);
+      load(sd, s_new);
+      load(isd, is_new);
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
-      if (i < d) {
-        double s_old = sd[i], is_old = isd[i];
-        double s_new = s_old, is_new = is_old;
-        double val = P.s.use_grad_based ? sqrt(dv[i] / gv[i]) : dv[i] * scale;  // cpu_math.rs:695 / :658
-        if (!((!isfinite(val)) | (val == 0.0))) {                               // fill_invalid = None: leave untouched
-          val = clampd(val, 1e-20, 1e20);
-          s_new = sqrt(val);
-          is_new = sqrt(1.0 / val);
+      for (int j = 0; j < EPT; ++j) {
+        int i = tid + j * TPC;
+        if (i < d) {
+          double val = P.s.use_grad_based ? sqrt(dv[j] / gv[j]) : dv[j] * scale;  // cpu_math.rs:695 / :658
+          if (!((!isfinite(val)) | (val == 0.0))) {                               // fill_invalid = None: leave untouched
+            val = clampd(val, 1e-20, 1e20);
+            s_new[j] = sqrt(val);
+            is_new[j] = sqrt(1.0 / val);
+          }
+          ld[0] += log(is_new[j]);            // array_sum_ln(inv_stds)
         }
-        sd[i] = s_new;
-        isd[i] = is_new;
-        if (P.s.use_grad_based) {
-          double var = s_new * s_new;       // array_mult(stds, stds, var)
-          double m = var * gm[i];           // array_mult(var, grad_mean, mean)
-          mn[i] = fma(1.0, dm[i], m);       // axpy(draw_mean, mean, 1.0)
-        } else {
-          mn[i] = dm[i];
-        }
-        ld[0] += log(is_new);               // array_sum_ln(inv_stds)
       }
+      store(sd, s_new);
+      store(isd, is_new);
+    }
+    {
+      double dm[EPT], gm[EPT];
+      load(est_ptr(set, 0), dm);
+      if (P.s.use_grad_based) {
+        load(est_ptr(set, 2), gm);
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+          const double var = s_new[j] * s_new[j];  // array_mult(stds, stds, var)
+          const double m = var * gm[j];             // array_mult(var, grad_mean, mean)
+          dm[j] = fma(1.0, dm[j], m);               // axpy(draw_mean, mean, 1.0)
+        }
+      }
+      store(mn, dm);
     }
     red.allreduce(ld);
     hs_mm_logdet = ld[0];
@@ -1244,6 +1271,7 @@ struct Engine {
       const bool is_early = draw < S.early_end;
       if (!is_early && draw == S.early_end) cs.current_window_size = max(cs.current_window_size, cs.bg_count);
       const uint64_t switch_freq = is_early ? S.early_mm_switch_freq : cs.current_window_size;
+      NB_COLD_T(1);
       if (cs.is_good) {  // update_estimators
         double x[EPT], gx[EPT];
         load(P.x + row, x);
@@ -1251,8 +1279,10 @@ struct Engine {
         cs.fg_count += 1;
         cs.bg_count += 1;
         add_sample_set(cs.fg_set, cs.fg_count, x, gx);
+        NB_COLD_T(2);
         add_sample_set(1 - cs.fg_set, cs.bg_count, x, gx);
       }
+      NB_COLD_T(3);
       const bool could_switch = cs.bg_count >= switch_freq;
       const uint64_t next_window_size =
           is_early ? S.early_mm_switch_freq
@@ -1268,6 +1298,7 @@ struct Engine {
       }
       bool did_change = false;
       if (force_update | (draw - cs.last_update >= S.mm_update_freq)) did_change = mass_matrix_adapt();
+      NB_COLD_T(4);
       if (did_change) cs.last_update = draw;
       if (is_late) da_advance(cs.last_sym_mean_tree_accept);
       else da_advance(cs.last_mean_tree_accept);
@@ -1781,6 +1812,7 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
   TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
   Engine<TPC, EPT, SMF, MODEL, MULTI> E(P, chain, tid, scratch, team_smem, tables, mc);
   E.red.parity = parity;
+  NB_COLD_T0;
   E.cold_load();
   E.acc_sum = acc_sum;
   E.acc_sym_sum = acc_sym_sum;
@@ -1813,6 +1845,20 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
     if (st.fisher_distance) st.fisher_distance[k] = fisher;
   }
   E.cold_store();
+#ifdef NB_PHASE_TIMING_COLD
+  if (tid == 0 && P.phase_clocks) {  // 0 cold_load..estimators, 1 first set, 2 second set, 3 mass matrix, 4 rest, 7 total
+    const long long t_end = clock64();
+    const long long* c = E.cold_t;
+    if (c[1]) {
+      atomicAdd(P.phase_clocks + 0, (unsigned long long)(c[1] - cold_t0));
+      atomicAdd(P.phase_clocks + 1, (unsigned long long)((c[2] ? c[2] : c[3]) - c[1]));
+      atomicAdd(P.phase_clocks + 2, (unsigned long long)(c[3] - (c[2] ? c[2] : c[3])));
+      atomicAdd(P.phase_clocks + 3, (unsigned long long)(c[4] - c[3]));
+      atomicAdd(P.phase_clocks + 4, (unsigned long long)(t_end - c[4]));
+    }
+    atomicAdd(P.phase_clocks + 7, (unsigned long long)(t_end - cold_t0));
+  }
+#endif
   return E.red.parity & 1;
 }
 
