@@ -1,0 +1,215 @@
+// nuts_b200.hpp — C++17 host side over the C ABI (include/nuts_b200.h), mirroring the public surface of the reference for the
+// accelerated path.  The reference is compiled code (Rust) and this image has no Rust toolchain, so the host mirror of
+// `DiagNutsSettings` / `Model + Math` / `Chain` is written in C++ (header-only, no CUDA or torch types); INTEGRATION.md shows the
+// Rust binding a nuts-rs maintainer would add over the same entry points.
+//
+//   reference                                              here
+//   DiagNutsSettings { num_tune, maxdepth, .. }             nuts_b200::DiagNutsSettings      (src/sampler.rs:199-239, 507-531)
+//   Model::math() -> CpuMath<impl CpuLogpFunc>              nuts_b200::CudaMath              (src/model.rs:18-33, src/math/cpu_math.rs:885-970)
+//   Settings::new_chain(chain, math, rng) -> impl Chain     nuts_b200::Chains                (src/sampler.rs:745-772; ALL chains of one GPU)
+//   Chain::set_position(&init) -> Result<()>                Chains::set_position             (src/chain.rs:137-149; per-chain status)
+//   Chain::draw() -> (position, stats)  x n                 Chains::draw(n) -> Draws         (src/chain.rs:151-188, 215-231)
+//   NutsError::BadInitGrad / LogpFailure                    status 3 per chain; nuts_b200::Error for fatal library errors
+//
+// Chains::draw hands back the draws draw-major ([draw][chain][dim], what one kernel launch produces); Draws::position(chain, draw)
+// and the statistics accessors give the reference's per-chain view.  With `pinned = true` the draws live in page-locked memory and
+// are written by the kernel directly.  There is no CPU fallback: without an sm_100 device every call throws Error(NUTS_ERR_NO_DEVICE).
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "nuts_b200.h"
+
+namespace nuts_b200 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+inline void check(int rc) {
+  if (rc != NUTS_OK) throw Error(rc, std::string("libnuts_b200: ") + nuts_last_error());
+}
+inline bool device_available() { return nuts_device_available() == NUTS_OK; }
+
+// DiagNutsSettings::default() with public fields, like the reference's struct-update syntax:
+//   DiagNutsSettings s; s.num_tune = 1000; s.maxdepth = 3;
+struct DiagNutsSettings : nuts_settings_t {
+  DiagNutsSettings() { nuts_settings_default(this); }
+};
+
+// Device-side log density of `nchains` independent chains (the stand-ins for CpuLogpFunc::logp of SURVEY §8 a4').
+class CudaMath {
+ public:
+  // logp = -sum (x - mu)^2 / 2                      (reference benches/sample.rs:49-62, src/math/test_logps.rs:49-58)
+  static CudaMath normal(uint64_t nchains, uint64_t dim, double mu, int device = 0) {
+    nuts_logp_desc_t m{};
+    m.kind = NUTS_LOGP_GAUSS_ISO;
+    m.mu_scalar = mu;
+    return CudaMath(nchains, dim, m, device);
+  }
+  // logp = -sum (x_i - mu)^2 / (2 sigma_i^2)
+  static CudaMath diag_normal(uint64_t nchains, uint64_t dim, double mu, const std::vector<double>& sigma, int device = 0) {
+    if (sigma.size() != dim) throw Error(NUTS_ERR_INVALID, "diag_normal: sigma must have dim entries");
+    nuts_logp_desc_t m{};
+    m.kind = NUTS_LOGP_GAUSS_DIAG;
+    m.mu_scalar = mu;
+    m.sigma = sigma.data();
+    return CudaMath(nchains, dim, m, device);
+  }
+  // Sigma = I + s 1 1^T                              (reference tests/sample_normal.rs:29-96)
+  static CudaMath correlated_normal(uint64_t nchains, uint64_t dim, double mu, double s, int device = 0) {
+    nuts_logp_desc_t m{};
+    m.kind = NUTS_LOGP_GAUSS_RANK1;
+    m.mu_scalar = mu;
+    m.rank1_scale = s;
+    return CudaMath(nchains, dim, m, device);
+  }
+  static CudaMath funnel(uint64_t nchains, uint64_t dim, double scale = 3.0, int device = 0) {
+    nuts_logp_desc_t m{};
+    m.kind = NUTS_LOGP_FUNNEL;
+    m.funnel_scale = scale;
+    return CudaMath(nchains, dim, m, device);
+  }
+  CudaMath(uint64_t nchains, uint64_t dim, const nuts_logp_desc_t& model, int device = 0) : nchains_(nchains), dim_(dim) {
+    check(nuts_ctx_create(&ctx_, device, nchains, dim, &model));
+  }
+  CudaMath(CudaMath&& o) noexcept : ctx_(o.ctx_), nchains_(o.nchains_), dim_(o.dim_) { o.ctx_ = nullptr; }
+  CudaMath(const CudaMath&) = delete;
+  CudaMath& operator=(const CudaMath&) = delete;
+  ~CudaMath() {
+    if (ctx_) nuts_ctx_destroy(ctx_);
+  }
+  uint64_t dim() const { return dim_; }  // Math::dim (src/math/math.rs:69)
+  uint64_t nchains() const { return nchains_; }
+  nuts_ctx_t* handle() const { return ctx_; }
+
+ private:
+  nuts_ctx_t* ctx_ = nullptr;
+  uint64_t nchains_, dim_;
+};
+
+// What n x Chain::draw returned for every chain: positions + the NutsStats columns (src/chain.rs:215-231 and the flattened
+// hamiltonian / adapt / point / divergence statistics).
+class Draws {
+ public:
+  Draws(uint64_t n_draws, uint64_t nchains, uint64_t dim, bool pinned) : n_(n_draws), N_(nchains), d_(dim) {
+    const uint64_t nd = n_ * N_ * d_;
+    if (pinned) {
+      void* p = nullptr;
+      check(nuts_host_alloc(&p, (nd > 0 ? nd : 1) * sizeof(double)));
+      pinned_ = static_cast<double*>(p);
+    } else {
+      pageable_.resize(nd);
+    }
+    const size_t m = n_ * N_;
+    depth.resize(m), n_steps.resize(m), index_in_trajectory.resize(m);
+    maxdepth_reached.resize(m), diverging.resize(m), tuning.resize(m);
+    logp.resize(m), energy.resize(m), energy_error.resize(m), step_size.resize(m), step_size_bar.resize(m);
+    mean_tree_accept.resize(m), mean_tree_accept_sym.resize(m), max_energy_error.resize(m), fisher_distance.resize(m);
+  }
+  Draws(Draws&& o) noexcept { *this = std::move(o); }
+  Draws& operator=(Draws&& o) noexcept {
+    if (this != &o) {
+      release();
+      n_ = o.n_, N_ = o.N_, d_ = o.d_, pinned_ = o.pinned_, o.pinned_ = nullptr;
+      pageable_ = std::move(o.pageable_);
+      depth = std::move(o.depth), n_steps = std::move(o.n_steps), index_in_trajectory = std::move(o.index_in_trajectory);
+      maxdepth_reached = std::move(o.maxdepth_reached), diverging = std::move(o.diverging), tuning = std::move(o.tuning);
+      logp = std::move(o.logp), energy = std::move(o.energy), energy_error = std::move(o.energy_error);
+      step_size = std::move(o.step_size), step_size_bar = std::move(o.step_size_bar), mean_tree_accept = std::move(o.mean_tree_accept);
+      mean_tree_accept_sym = std::move(o.mean_tree_accept_sym), max_energy_error = std::move(o.max_energy_error);
+      fisher_distance = std::move(o.fisher_distance);
+    }
+    return *this;
+  }
+  Draws(const Draws&) = delete;
+  Draws& operator=(const Draws&) = delete;
+  ~Draws() { release(); }
+
+  uint64_t n_draws() const { return n_; }
+  uint64_t nchains() const { return N_; }
+  uint64_t dim() const { return d_; }
+  double* data() { return pinned_ ? pinned_ : pageable_.data(); }  // [draw][chain][dim]
+  const double* data() const { return pinned_ ? pinned_ : pageable_.data(); }
+  // the `position` of Chain::draw number `draw` of chain `chain` (dim doubles)
+  const double* position(uint64_t chain, uint64_t draw) const { return data() + (draw * N_ + chain) * d_; }
+  size_t at(uint64_t chain, uint64_t draw) const { return draw * N_ + chain; }  // index into the statistics columns
+
+  std::vector<uint64_t> depth, n_steps;
+  std::vector<int64_t> index_in_trajectory;
+  std::vector<uint8_t> maxdepth_reached, diverging, tuning;
+  std::vector<double> logp, energy, energy_error, step_size, step_size_bar, mean_tree_accept, mean_tree_accept_sym, max_energy_error,
+      fisher_distance;
+
+  nuts_stats_t view() {
+    nuts_stats_t s{};
+    s.depth = depth.data(), s.maxdepth_reached = maxdepth_reached.data(), s.index_in_trajectory = index_in_trajectory.data();
+    s.logp = logp.data(), s.energy = energy.data(), s.energy_error = energy_error.data(), s.diverging = diverging.data();
+    s.step_size = step_size.data(), s.step_size_bar = step_size_bar.data(), s.mean_tree_accept = mean_tree_accept.data();
+    s.mean_tree_accept_sym = mean_tree_accept_sym.data(), s.n_steps = n_steps.data(), s.max_energy_error = max_energy_error.data();
+    s.tuning = tuning.data(), s.fisher_distance = fisher_distance.data();
+    return s;
+  }
+
+ private:
+  void release() {
+    if (pinned_) nuts_host_free(pinned_);
+    pinned_ = nullptr;
+  }
+  uint64_t n_ = 0, N_ = 0, d_ = 0;
+  double* pinned_ = nullptr;
+  std::vector<double> pageable_;
+};
+
+// All chains of one GPU: `settings.new_chain(chain_id, math, rng)` for chain ids chain_id_offset .. chain_id_offset + nchains - 1
+// (random streams are keyed by the global chain id, src/sampler.rs:1105-1106, so shards reproduce the unsharded run).
+class Chains {
+ public:
+  Chains(const CudaMath& math, const DiagNutsSettings& settings, uint64_t seed, uint64_t chain_id_offset = 0)
+      : nchains_(math.nchains()), dim_(math.dim()) {
+    check(nuts_sampler_create(math.handle(), &s_, &settings, seed, chain_id_offset));
+  }
+  Chains(const Chains&) = delete;
+  Chains& operator=(const Chains&) = delete;
+  ~Chains() {
+    if (s_) nuts_sampler_destroy(s_);
+  }
+  // Chain::set_position for every chain; positions [nchains][dim].  Per-chain status: 0 ok, 3 = NutsError::BadInitGrad.
+  std::vector<int32_t> set_position(const double* positions) {
+    std::vector<int32_t> status(nchains_);
+    check(nuts_set_position(s_, positions, status.data()));
+    return status;
+  }
+  std::vector<int32_t> set_position(const std::vector<double>& positions) {
+    if (positions.size() != nchains_ * dim_) throw Error(NUTS_ERR_INVALID, "set_position: need nchains x dim values");
+    return set_position(positions.data());
+  }
+  // n x Chain::draw for every chain
+  Draws draw(uint64_t n_draws, bool pinned = true) {
+    Draws out(n_draws, nchains_, dim_, pinned);
+    nuts_stats_t st = out.view();
+    check(nuts_draw(s_, n_draws, out.data(), &st));
+    return out;
+  }
+  // leapfrog steps so far (all chains; incl. step-size searches and divergent steps) and draws per chain
+  std::pair<uint64_t, uint64_t> counters() {
+    uint64_t lf = 0, draws = 0;
+    check(nuts_sampler_counters(s_, &lf, &draws));
+    return {lf, draws};
+  }
+  bool last_draw_direct() {
+    int32_t v = 0;
+    check(nuts_sampler_last_draw_direct(s_, &v));
+    return v != 0;
+  }
+  nuts_sampler_t* handle() const { return s_; }
+
+ private:
+  nuts_sampler_t* s_ = nullptr;
+  uint64_t nchains_, dim_;
+};
+
+}  // namespace nuts_b200
