@@ -1381,7 +1381,7 @@ struct Engine {
                                               max_energy_error, diverging ? (abs(draw_idx) > 4) : (draw_idx != 0), depth, reached_maxdepth,
                                               diverging, draw_idx, draw_energy, draw_energy - E0, fisher[0]);
     red.parity = ret & 1;
-    load_hot();
+    // the chain scalars now live in ChainState again; the next work unit (possibly on another team) reloads them
     NB_ACC(6, tm);
   }
 
