@@ -1894,7 +1894,7 @@ template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, int SMF, int MODEL>
 __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(const __grid_constant__ EngineParams P) {
   constexpr int TEAMS = CTA_THREADS / TPC;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ double scratch[TPC > 32 ? 2 * 32 * REDUCE_MAXK : 1];
+  __shared__ double scratch[TPC > 32 ? 2 * (TPC / 32) * REDUCE_MAXK : 1];
   __shared__ int next_chain[TEAMS];
   const int team = threadIdx.x / TPC;
   const int tid = threadIdx.x % TPC;

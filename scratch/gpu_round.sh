@@ -2,6 +2,7 @@
 # One GPU visit: parity tests, bench line, ncu launch list of the same command, one --set full capture of the draw kernel,
 # throughput of the other BASELINE configs.
 TAG=${1:-r1x}
+export PYTHONDONTWRITEBYTECODE=1
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" ; tail -3 gpurun_out/pytest_$TAG.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cut -c1-600 gpurun_out/bench_$TAG.json
