@@ -64,7 +64,8 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device_index):
-        self.rows = []  # (sm_mhz, sm_max_mhz, power_w, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap)
+        self.rows = []  # (sm_mhz, sm_max_mhz, power_w, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap, timestamp)
+        self.windows = []  # [t0, t1] of the timed regions
         self.stop = False
         self.idx = device_index
         self.nvml = None
@@ -103,13 +104,14 @@ class ClockSampler:
         while not self.stop:
             try:
                 if self.nvml is not None:
-                    self.rows.append(self.sample_nvml())
+                    self.rows.append(self.sample_nvml() + (time.perf_counter(),))
                     time.sleep(0.002)
                     continue
                 out = subprocess.check_output(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                               timeout=5).decode().strip()
                 c = [x.strip() for x in out.split(",")]
-                self.rows.append((float(c[0]), float(c[1]), float(c[2])) + tuple(x.lower().startswith("active") for x in c[3:7]))
+                self.rows.append((float(c[0]), float(c[1]), float(c[2])) + tuple(x.lower().startswith("active") for x in c[3:7])
+                                 + (time.perf_counter(),))
             except Exception:
                 pass
             time.sleep(0.2)
@@ -122,14 +124,19 @@ class ClockSampler:
         self.stop = True
         self.t.join(timeout=6)
 
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
-        sm = sorted(r[0] for r in self.rows)
+        # samples taken inside the timed regions (the sampler also runs through the warm-up steps right before them)
+        rows = [r for r in self.rows if any(a <= r[7] <= b for a, b in self.windows)] or self.rows
+        sm = sorted(r[0] for r in rows)
         reasons = [name for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6))
-                   if any(r[col] for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows),
-                "power_w_max": max(r[2] for r in self.rows), "source": self.source}
+                   if any(r[col] for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": rows[0][1], "reasons": reasons, "samples": len(rows),
+                "samples_incl_warmup": len(self.rows), "power_w_max": max(r[2] for r in rows), "source": self.source}
 
 
 def microbench_fixed_depth(lib, _abi, device, chain_offset, depth=6, draws=8):
@@ -284,21 +291,23 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm: `value`
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()  # samples through the warm-up and both timed regions; only samples inside the timed regions are reported
     for _ in range(args.warmup):
         samp.draw_device(dps, dev_draws.data_ptr())
     math.synchronize()
     lf0, _ = samp.counters()
     barrier()
     kernel_ms, launches = 0.0, 0
-    with ClockSampler(local_rank) as clocks:
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            samp.draw_device(dps, dev_draws.data_ptr())
-            ms, n = samp.last_timing()  # CUDA events around the kernel on the launching stream (waits for the kernel)
-            kernel_ms += ms
-            launches += n
-        barrier()
-        wall_ms = 1e3 * (time.perf_counter() - w0)
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        samp.draw_device(dps, dev_draws.data_ptr())
+        ms, n = samp.last_timing()  # CUDA events around the kernel on the launching stream (waits for the kernel)
+        kernel_ms += ms
+        launches += n
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - w0)
+    clocks.window(w0, time.perf_counter())
     lf1, _ = samp.counters()
     steps_dev = lf1 - lf0
 
@@ -318,6 +327,8 @@ def main():
         steps_e2e += e2e_step()
     barrier()
     e2e_s = time.perf_counter() - e0
+    clocks.window(e0, time.perf_counter())
+    clocks.__exit__(None, None, None)
     d2h = host_draws.nbytes + sum(a.nbytes for a in stats_arrays.values())
     e2e_direct = samp.last_draw_direct()
 
