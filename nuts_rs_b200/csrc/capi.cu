@@ -142,6 +142,7 @@ struct nuts_sampler {
   const EngineConfig* cfg = nullptr;
   int model_variant = 0;  // index into cfg->launch
   int grid = 0;
+  int teams_per_cta = 1;
   std::vector<void*> allocations;
   double* d_init = nullptr;
   int* d_status = nullptr;
@@ -837,6 +838,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   const int teams_per_cta = decoupled ? cfg->minb % 10 : cta_threads / cfg->tpc;  // decoupled tags end in the number of teams
   const uint64_t ctas_needed = (ctx->N + teams_per_cta - 1) / teams_per_cta;
   s->grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)blocks_per_sm * ctx->num_sms);
+  s->teams_per_cta = teams_per_cta;
   CUDA_TRY(cudaEventCreate(&s->ev0));
   CUDA_TRY(cudaEventCreate(&s->ev1));
   *out = s;
@@ -894,6 +896,7 @@ int nuts_set_position(nuts_sampler_t* s, const double* position, int32_t* status
   s->P.init_position = s->d_init;
   s->P.status_out = s->d_status;
   s->P.n_draws = 0;
+  s->P.draws_per_unit = 1;
   s->P.draws_out = nullptr;
   s->P.stats = StatsDev{};
   s->last_launches = 0;
@@ -939,6 +942,16 @@ static int run_draws(nuts_sampler* s, uint64_t n_draws, double* draws_dev, bool 
   s->P.init_position = nullptr;
   s->P.status_out = nullptr;
   s->P.n_draws = n_draws;
+  {
+    // draws per work unit: the whole call when every chain has its own team (no hand-over at all), else one draw - or a few
+    // for tiny dims; NUTS_B200_DRAWS_PER_UNIT overrides (experiments)
+    const uint64_t teams = (uint64_t)s->grid * (uint64_t)s->teams_per_cta;
+    // (measured: blocks of draws pay for tiny dims, where the hand-over is a large part of a draw: config 3 +4 % sampling, +10 %
+    // tuning; config 5 shard (dim 100) -5 %; config 2 +-0)
+    uint64_t b = ctx->N <= teams ? n_draws : (ctx->d <= 32 ? std::max<uint64_t>(1, std::min<uint64_t>(8, n_draws / 8)) : 1);
+    if (const char* env = std::getenv("NUTS_B200_DRAWS_PER_UNIT")) b = std::max<uint64_t>(1, std::strtoull(env, nullptr, 10));
+    s->P.draws_per_unit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(b, 1), std::max<uint64_t>(n_draws, 1));
+  }
   s->P.draws_out = draws_dev;
   s->P.stats = want_stats ? s->d_stats : StatsDev{};
   TRY(launch_engine(s));

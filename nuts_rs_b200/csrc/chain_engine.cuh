@@ -98,12 +98,14 @@ struct EngineParams {
   double* ends;                     // [N][NB_END_BUFFERS][3: z, v, grad_z][ld]   main-tree endpoints (v1: 0 left, 1 right)
   ChainState* cs;
   unsigned int* queue;              // persistent work-unit queue
-  unsigned int* done;               // [N] draws of this launch each chain has completed
+  unsigned int* done;               // [N] work units (blocks of draws) of this launch each chain has completed
   // mode 0: set_position ; mode 1: draw
   int mode, _pad;
   const double* init_position;      // [N][d] device
   int* status_out;                  // [N]
   uint64_t n_draws;
+  uint32_t draws_per_unit;          // work unit of a draw launch = this many consecutive draws of one chain (>= 1)
+  uint32_t _pad2;
   double* draws_out;                // [n_draws][N][d] device (may be null)
   StatsDev stats;
   uint64_t stats_offset;            // unused draws before this call inside the stats arrays (always 0 for now)
@@ -1910,7 +1912,9 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
   // resident teams (config 2: 1024 chains, 592 teams) the launch ends after total_work / teams instead of ceil(N / teams) whole
   // chains.  Draw t of a chain waits for its draw t-1 (P.done, release / acquire at gpu scope; the engine's global loads bypass
   // L1: -dlcm=cg, so data written by another SM is read from L2).
-  const unsigned total_units = P.mode == 0 ? (unsigned)P.N : (unsigned)P.N * (unsigned)P.n_draws;
+  const unsigned B = P.draws_per_unit;
+  const unsigned blocks = P.mode == 0 ? 1u : ((unsigned)P.n_draws + B - 1u) / B;
+  const unsigned total_units = (unsigned)P.N * blocks;
   for (;;) {
     if (tid == 0) next_chain[team] = (int)atomicAdd(P.queue, 1u);
     if (TPC > 32) __syncthreads();
@@ -1920,35 +1924,39 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
     else __syncwarp();
     if (unit >= total_units) break;
     const int chain = (int)(unit % (unsigned)P.N);
-    const uint64_t t = unit / (unsigned)P.N;
+    const unsigned blk = unit / (unsigned)P.N;  // block of B consecutive draws (a few draws per unit amortise the hand-over)
     Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
     if (P.mode == 0) {
       const int status = cold_set_position<TPC, EPT, SMF, MODEL, false>(P, chain, tid, scratch, team_smem, nullptr);
       if (tid == 0 && P.status_out) P.status_out[chain] = status;
     } else {
-      if (t > 0) {
+      if (blk > 0) {
         if (tid == 0) {
           unsigned dn;
           for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(P.done + chain) : "memory");
-            if (dn >= (unsigned)t) break;
+            if (dn >= blk) break;
             __nanosleep(200);
           }
         }
         E.team_sync();
         __threadfence();
       }
-      E.load_hot();
-      if (E.hs_alive) {
-        E.run_draw(t);  // a chain that dies here has its remaining draws NaN-filled by cold_adapt
-      } else if (t == 0 && P.draws_out) {
-        // draws a dead chain never produced read NaN (the output buffer may be host memory the kernel writes directly)
-        cold_fill_dead(P, chain, tid, TPC, 0);
+      const uint64_t t_end = min((uint64_t)(blk + 1u) * B, (uint64_t)P.n_draws);
+      for (uint64_t t = (uint64_t)blk * B; t < t_end; ++t) {
+        E.load_hot();
+        if (E.hs_alive) {
+          E.run_draw(t);  // a chain that dies here has its remaining draws NaN-filled by cold_adapt
+        } else {
+          // draws a dead chain never produced read NaN (the output buffer may be host memory the kernel writes directly)
+          if (t == 0 && P.draws_out) cold_fill_dead(P, chain, tid, TPC, 0);
+          break;
+        }
       }
       __threadfence();
       E.team_sync();
       if (tid == 0) {
-        const unsigned dn = (unsigned)t + 1u;
+        const unsigned dn = blk + 1u;
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.done + chain), "r"(dn) : "memory");
       }
     }

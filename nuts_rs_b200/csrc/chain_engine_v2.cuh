@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(con
   mc.warp = (warp - NL) % W;
   unsigned cmd_seen = 0;
   // work units as in nuts_chain_kernel: one chain for set_position, ONE DRAW of one chain (draw-major) for draws
-  const unsigned total_units = P.mode == 0 ? (unsigned)P.N : (unsigned)P.N * (unsigned)P.n_draws;
+  const unsigned B = P.draws_per_unit;
+  const unsigned blocks = P.mode == 0 ? 1u : ((unsigned)P.n_draws + B - 1u) / B;
+  const unsigned total_units = (unsigned)P.N * blocks;
   for (;;) {
     if (tid == 0) {
       const unsigned u = atomicAdd(P.queue, 1u);
@@ -476,34 +478,38 @@ __global__ void __launch_bounds__(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(con
     bar_sync(mc.bar_id, TPC);
     if (unit >= total_units) break;
     const int chain = (int)(unit % (unsigned)P.N);
-    const uint64_t t = unit / (unsigned)P.N;
+    const unsigned blk = unit / (unsigned)P.N;
     Engine<TPC, EPT, SMF, MODEL, true> E(P, chain, tid, scratch, team_smem, tables, &mc);
     if (P.mode == 0) {
       const int status = cold_set_position<TPC, EPT, SMF, MODEL, true>(P, chain, tid, scratch, team_smem, &mc);
       if (tid == 0 && P.status_out) P.status_out[chain] = status;
     } else {
-      if (t > 0) {
+      if (blk > 0) {
         if (tid == 0) {
           unsigned dn;
           for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(P.done + chain) : "memory");
-            if (dn >= (unsigned)t) break;
+            if (dn >= blk) break;
             __nanosleep(200);
           }
         }
         bar_sync(mc.bar_id, TPC);
         __threadfence();
       }
-      E.load_hot();
-      if (E.hs_alive) {
-        E.run_draw_v2(t, cmd_seen);
-      } else if (t == 0 && P.draws_out) {
-        cold_fill_dead(P, chain, tid, TPC, 0);
+      const uint64_t t_end = min((uint64_t)(blk + 1u) * B, (uint64_t)P.n_draws);
+      for (uint64_t t = (uint64_t)blk * B; t < t_end; ++t) {
+        E.load_hot();
+        if (E.hs_alive) {
+          E.run_draw_v2(t, cmd_seen);
+        } else {
+          if (t == 0 && P.draws_out) cold_fill_dead(P, chain, tid, TPC, 0);
+          break;
+        }
       }
       __threadfence();
       bar_sync(mc.bar_id, TPC);
       if (tid == 0) {
-        const unsigned dn = (unsigned)t + 1u;
+        const unsigned dn = blk + 1u;
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.done + chain), "r"(dn) : "memory");
       }
     }
