@@ -691,8 +691,8 @@ struct Engine {
     if (MODEL == LOGP_GAUSS_DIAG) {
       double part[4];
       leapfrog_partials(eps, part);
-      if (with_prev) {
-        red.allreduce(part);
+      if (TPC > 32 || with_prev) {
+        red.allreduce(part);  // CTA teams: always all four sums - ONE reduction routine on the leaf path (instruction cache)
       } else {
         double p2[2] = {part[0], part[1]};
         red.allreduce(p2);
@@ -817,7 +817,7 @@ struct Engine {
   // checks of one merge: (Af, cur) always; when `full` also (Al, cur) and (Af, Bf).   cur = registers.
   __device__ __forceinline__ bool merge_turning(const double* Afz, const double* Afv, const double* Alz, const double* Alv,
                                                 const double* Bfz, const double* Bfv, bool full, int dir) {
-    if (!full) {
+    if (!full && MODEL != LOGP_GAUSS_DIAG) {  // (the elementwise target takes the full path below and ignores the extra products)
       double s[2] = {0.0, 0.0};
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
@@ -850,6 +850,7 @@ struct Engine {
       }
     }
     red.allreduce(s);
+    if (!full) return turn_eval(s[0], s[1], dir);
     return turn_eval(s[0], s[1], dir) | turn_eval(s[2], s[3], dir) | turn_eval(s[4], s[5], dir);
   }
 
