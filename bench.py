@@ -35,6 +35,25 @@ UNIT = "leapfrog-steps/s"
 WORKLOAD = "configs[1]: 1000-dim diagonal Gaussian, 1024 chains per GPU, maxdepth=10, num_tune=400 (untimed), post-warmup draws"
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Only the JSON line may reach stdout: point fd 1 at stderr for the whole run (NCCL prints its version banner to stdout,
+    whatever NCCL_DEBUG_FILE says) and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def model_sigma():
     return np.exp(np.linspace(-1.0, 1.0, DIM))
 
@@ -230,7 +249,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -246,6 +265,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    claim_stdout()
 
     if args.impl == "reference":
         run_reference(args, rank)
@@ -407,7 +427,7 @@ def main():
         line["config"]["microbench_fixed_step_no_turn_checks_rank0"] = micro
         if gather_ms is not None:
             line["config"]["nccl_all_gather_last_step_ms"] = gather_ms
-        print(json.dumps(line), flush=True)
+        emit(line)
     samp.close()
     math.close()
     host_buf.close()
