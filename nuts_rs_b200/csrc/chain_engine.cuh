@@ -26,6 +26,12 @@
 #pragma once
 #include "device_common.cuh"
 
+// NB_MAXNREG (optional, per translation unit): exact register budget instead of the one ptxas derives from MIN_BLOCKS
+#ifdef NB_MAXNREG
+#define NB_KERNEL_BOUNDS(T, B) __maxnreg__(NB_MAXNREG)
+#else
+#define NB_KERNEL_BOUNDS(T, B) __launch_bounds__(T, B)
+#endif
 namespace nb {
 
 constexpr int MAX_DOUBLING_DEPTH = 19;  // deepest new half has 2^19 leaves (checkpoint pool: 3 per level + 6 <= MAX_SLOTS)
@@ -1887,12 +1893,6 @@ static __device__ __noinline__ void cold_fill_dead(const EngineParams& P, int ch
 
 // One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).
 // Dynamic shared memory: TEAMS x team_smem_bytes<TPC, EPT, SMF>().
-// NB_MAXNREG (optional, per translation unit): exact register budget instead of the one ptxas derives from MIN_BLOCKS
-#ifdef NB_MAXNREG
-#define NB_KERNEL_BOUNDS(T, B) __maxnreg__(NB_MAXNREG)
-#else
-#define NB_KERNEL_BOUNDS(T, B) __launch_bounds__(T, B)
-#endif
 template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, int SMF, int MODEL>
 __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(const __grid_constant__ EngineParams P) {
   constexpr int TEAMS = CTA_THREADS / TPC;

@@ -388,7 +388,7 @@ struct V2Layout {
 // NL leader warps share the teams (leader warp lw, lane j -> team lw + j * NL): a lane only advances when ITS team has an entry
 // ready, so the lanes of one leader warp mostly run one at a time and a single leader warp saturates.
 template <int TPC, int EPT, int C, int MODEL, int NL>
-__global__ void __launch_bounds__(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(const __grid_constant__ EngineParams P) {
+__global__ void NB_KERNEL_BOUNDS(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(const __grid_constant__ EngineParams P) {
   using L = V2Layout<TPC, EPT, C>;
   constexpr int W = TPC / 32;
   constexpr int SMF = L::SMF;
