@@ -1,14 +1,18 @@
 #!/usr/bin/env python
 """bench.py — leapfrog-steps/sec of the many-chain NUTS hot path on B200 (BASELINE.json metric).
 
-Workload (config.workload): BASELINE.json configs[1] — 1000-dim diagonal Gaussian (sigma_i = exp(lin(-1,1)), mu = 0.5),
+Headline workload (config.workload): BASELINE.json configs[1] — 1000-dim diagonal Gaussian (sigma_i = exp(lin(-1,1)), mu = 0.5),
 1024 chains per GPU, maxdepth = 10, DiagNutsSettings defaults (num_tune = 400), seed 42, x0 ~ N(0,1).
 Setup (untimed): nuts_set_position + the 400 tuning draws.  A "step" = one nuts_draw call of DRAWS_PER_STEP post-warmup
-draws for every chain.  `value` = leapfrogs / device time of the draw kernel with the draws written to an HBM buffer;
-`e2e` = the same steps through nuts_draw with pinned HOST buffers (D2H of every draw + all sampler statistics inside the
+draws for every chain.  `value` = leapfrogs / device time of the draw kernel with the draws AND the 15 statistics written to HBM
+buffers; `e2e` = the same steps through nuts_draw with pinned HOST buffers (D2H of every draw + all sampler statistics inside the
 timed region; the chain state is resident between calls exactly like the reference's Chain, so there is no per-step H2D).
 
-  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1, one rank per GPU, weak scaling)
+The same JSON line also carries (config.other_configs) device-timed sub-records of BASELINE configs 3, 4 and 5 - config 5 as the
+65536-chain job split over the N ranks (strong scaling) -, the tuning phase and a whole default run (400 tuning + 1000 sampling
+draws, wall clock through nuts_draw) of the headline workload.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1, one rank per GPU, weak scaling of configs[1])
   python bench.py --impl reference ...                     (the CPU oracle = C++ restatement of nuts-rs on all host cores)
 """
 import argparse
@@ -34,6 +38,22 @@ METRIC = "leapfrog-steps/sec (all chains)"
 UNIT = "leapfrog-steps/s"
 WORKLOAD = "configs[1]: 1000-dim diagonal Gaussian, 1024 chains per GPU, maxdepth=10, num_tune=400 (untimed), post-warmup draws"
 
+# BASELINE.json configs as concrete inputs (SURVEY.md §8d / BASELINE.md §3).  kind: NUTS_LOGP_* (1 diag Gaussian, 2 rank-1, 3 funnel)
+CONFIGS = {
+    "c2": dict(index=1, kind=1, dim=1000, chains=1024, num_tune=400, hbm_bound=True,
+               what="1000-dim diagonal Gaussian, sigma = exp(lin(-1,1)), mu = 0.5, 1024 chains",
+               model=lambda d: dict(mu=0.5, sigma=np.exp(np.linspace(-1.0, 1.0, d)))),
+    "c3": dict(index=2, kind=3, dim=10, chains=8192, num_tune=400, hbm_bound=False,
+               what="Neal's funnel (10-dim), 8192 chains - divergent tree-depth stress",
+               model=lambda d: dict(funnel_scale=3.0)),
+    "c4": dict(index=3, kind=1, dim=10000, chains=256, num_tune=1000, hbm_bound=True,
+               what="10000-dim ill-conditioned Gaussian (sigma = 10^lin(-3,3)), diag mass-matrix tuning, 256 chains",
+               model=lambda d: dict(mu=0.0, sigma=10.0 ** np.linspace(-3.0, 3.0, d))),
+    "c5": dict(index=4, kind=2, dim=100, chains=65536, num_tune=400, hbm_bound=False,
+               what="100-dim correlated Gaussian (Sigma = I + 0.5 11^T), 65536 chains sharded over the ranks",
+               model=lambda d: dict(mu=0.0, rank1_scale=0.5)),
+}
+
 
 _REAL_STDOUT = None
 
@@ -58,11 +78,19 @@ def model_sigma():
     return np.exp(np.linspace(-1.0, 1.0, DIM))
 
 
-def initial_positions(nchains, chain_offset):
-    # one stream of N(0,1) rows keyed by the global chain id, so shards of a multi-GPU run see the rows of the unsharded run
-    rng = np.random.default_rng(SEED)
-    x = rng.normal(size=(chain_offset + nchains, DIM))
-    return np.ascontiguousarray(x[chain_offset:])
+def initial_positions(nchains, chain_offset, dim=DIM):
+    # rows of N(0,1) keyed by the GLOBAL chain id (one generator per block of 1024 chains), so the shards of a multi-GPU run see
+    # the rows of the unsharded run without generating everybody else's
+    out = np.empty((nchains, dim))
+    blk = 1024
+    c = chain_offset
+    while c < chain_offset + nchains:
+        b = c // blk
+        rows = np.random.default_rng([SEED, dim, b]).normal(size=(blk, dim))
+        hi = min((b + 1) * blk, chain_offset + nchains)
+        out[c - chain_offset:hi - chain_offset] = rows[c - b * blk:hi - b * blk]
+        c = hi
+    return out
 
 
 def settings():
@@ -73,6 +101,41 @@ def settings():
     s.maxdepth = MAXDEPTH
     s.seed = SEED
     return s
+
+
+def config_settings(cfg, num_tune=None):
+    s = settings()
+    s.num_tune = cfg["num_tune"] if num_tune is None else num_tune
+    return s
+
+
+def run_config(lib, name, nchains, chain_offset, device, steps, warmup, dps):
+    """Device-timed sub-record of one BASELINE config on this rank: set_position + the config's tuning phase, then `steps` launches
+    of `dps` post-warmup draws (draws + statistics into HBM buffers).  Returns per-rank numbers; the caller reduces over ranks."""
+    import torch
+
+    cfg = CONFIGS[name]
+    d = cfg["dim"]
+    math = lib.CudaMath(nchains, d, cfg["kind"], device=device, **cfg["model"](d))
+    samp = lib.Sampler(math, config_settings(cfg), seed=SEED, chain_id_offset=chain_offset)
+    st = samp.set_position(initial_positions(nchains, chain_offset, d))
+    samp.draw_device(cfg["num_tune"])
+    tune_ms, _ = samp.last_timing()
+    lf_tune, _ = samp.counters()
+    buf = torch.empty((dps, nchains, d), dtype=torch.float64, device="cuda")
+    for _ in range(warmup):
+        samp.draw_device(dps, buf.data_ptr())
+    math.synchronize()
+    lf0, _ = samp.counters()
+    ms = 0.0
+    for _ in range(steps):
+        samp.draw_device(dps, buf.data_ptr())
+        ms += samp.last_timing()[0]
+    lf1, _ = samp.counters()
+    samp.close()
+    math.close()
+    del buf
+    return {"kernel_ms": ms, "leapfrogs": lf1 - lf0, "tune_ms": tune_ms, "tune_leapfrogs": lf_tune, "bad_init": int((st != 0).sum())}
 
 
 class ClockSampler:
@@ -145,6 +208,15 @@ class ClockSampler:
 
     def window(self, t0, t1):
         self.windows.append((t0, t1))
+
+    def summary_between(self, t0, t1):
+        rows = [r for r in self.rows if t0 <= r[7] <= t1]
+        if not rows:
+            return {"sm_mhz": None, "reasons": ["no sample in the window"]}
+        sm = sorted(r[0] for r in rows)
+        reasons = [name for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6))
+                   if any(r[col] for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": rows[0][1], "reasons": reasons, "samples": len(rows)}
 
     def summary(self):
         if not self.rows:
@@ -261,6 +333,7 @@ def main():
     ap.add_argument("--draws-per-step", type=int, default=DRAWS_PER_STEP)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the sub-records of configs 3-5 and the whole-run entry")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -348,31 +421,76 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - e0
     clocks.window(e0, time.perf_counter())
-    clocks.__exit__(None, None, None)
     d2h = host_draws.nbytes + sum(a.nbytes for a in stats_arrays.values())
     e2e_direct = samp.last_draw_direct()
+    samp.close()
+    math.close()
+
+    # ---------------- a whole default run of the headline workload, wall clock through the public call (per rank: 1024 chains,
+    # 400 tuning + 1000 sampling draws, every draw and statistic delivered to host memory in batches of `dps` draws)
+    whole = None
+    if not args.no_other_configs:
+        math = lib.CudaMath(N, DIM, _abi.NUTS_LOGP_GAUSS_DIAG, mu=0.5, sigma=model_sigma(), device=local_rank)
+        samp = lib.Sampler(math, settings(), seed=SEED, chain_id_offset=chain_offset)
+        barrier()
+        r0 = time.perf_counter()
+        samp.set_position(x0)
+        total_lf, tune_lf, done = 0, 0, 0
+        while done < NUM_TUNE + 1000:
+            lib._check(lib.load().nuts_draw(samp.h, dps, host_draws.ctypes.data_as(_abi.c_double_p), C.byref(stats_struct)))
+            n = int(stats_arrays["n_steps"].sum())
+            total_lf += n
+            if done < NUM_TUNE:
+                tune_lf += n
+                r_tune = time.perf_counter() - r0
+            done += dps
+        barrier()
+        whole_s = time.perf_counter() - r0
+        clocks.window(r0, time.perf_counter())
+        whole = {"wall_s": whole_s, "tune_wall_s": r_tune, "leapfrogs": total_lf, "tune_leapfrogs": tune_lf}
+        samp.close()
+        math.close()
+    host_buf.close()
+    del dev_draws
+
+    # ---------------- the other BASELINE configs on this rank (device-timed sub-records); config 5 = 65536 chains over the ranks
+    other = {}
+    if not args.no_other_configs:
+        from nuts_rs_b200 import sharding
+
+        for name, k_steps, k_dps in (("c3", 5, 50), ("c4", 3, 10), ("c5", 3, 20)):
+            cfg = CONFIGS[name]
+            if name == "c5":
+                off_c, n_c = sharding.shard_range(cfg["chains"], world, rank)
+            else:
+                n_c, off_c = cfg["chains"], rank * cfg["chains"]
+            barrier()
+            c0 = time.perf_counter()
+            other[name] = run_config(lib, name, n_c, off_c, local_rank, k_steps, 2, k_dps)
+            other[name].update(chains_this_rank=n_c, steps=k_steps, draws_per_step=k_dps)
+            barrier()
+            clocks.window(c0, time.perf_counter())
+            other[name]["clocks"] = clocks.summary_between(c0, time.perf_counter())
+    clocks.__exit__(None, None, None)
 
     micro = microbench_fixed_depth(lib, _abi, local_rank, chain_offset) if rank == 0 else None
 
     # ---------------- reduce over ranks: max time, summed work
-    t = torch.tensor([kernel_ms, wall_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    w = torch.tensor([float(steps_dev), float(steps_e2e)], dtype=torch.float64, device="cuda")
-    gather_ms = None
+    names = sorted(other)
+    tl = [kernel_ms, wall_ms, e2e_s * 1e3, tune_ms] + [other[n]["kernel_ms"] for n in names] + [other[n]["tune_ms"] for n in names]
+    wl = [float(steps_dev), float(steps_e2e), float(tune_leapfrogs)] + [float(other[n]["leapfrogs"]) for n in names] \
+        + [float(other[n]["tune_leapfrogs"]) for n in names]
+    if whole:
+        tl += [whole["wall_s"] * 1e3, whole["tune_wall_s"] * 1e3]
+        wl += [float(whole["leapfrogs"]), float(whole["tune_leapfrogs"])]
+    t = torch.tensor(tl, dtype=torch.float64, device="cuda")
+    w = torch.tensor(wl, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        # the only exchange of the path: gather the draws of the last step on every rank (NCCL over NVLink), timed on its own
-        out = [torch.empty_like(dev_draws) for _ in range(world)]
-        torch.cuda.synchronize()
-        g0 = torch.cuda.Event(enable_timing=True)
-        g1 = torch.cuda.Event(enable_timing=True)
-        g0.record()
-        dist.all_gather(out, dev_draws)
-        g1.record()
-        torch.cuda.synchronize()
-        gather_ms = g0.elapsed_time(g1)
-    kernel_ms_max, wall_ms_max, e2e_ms_max = (float(v) for v in t.tolist())
-    steps_dev_all, steps_e2e_all = (float(v) for v in w.tolist())
+    t, w = t.tolist(), w.tolist()
+    kernel_ms_max, wall_ms_max, e2e_ms_max, tune_ms_max = t[:4]
+    steps_dev_all, steps_e2e_all, tune_lf_all = w[:3]
 
     if rank == 0:
         peaks = {}
@@ -386,31 +504,72 @@ def main():
         alg_bytes_per_step = 48 * DIM  # read z, v, grad_z + write z', v', grad_z' per leapfrog per chain
         per_gpu_steps_per_launch = steps_dev / max(1, launches)
         avg_launch_ms = kernel_ms / max(1, launches)
-        achieved = per_gpu_steps_per_launch * alg_bytes_per_step / (avg_launch_ms * 1e-3) / 1e9
+        per_gpu_rate = per_gpu_steps_per_launch / (avg_launch_ms * 1e-3)
+        achieved = per_gpu_rate * alg_bytes_per_step / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the same kernel on the same workload (10 draws x 1024 chains),
         # from the committed `ncu --set full` capture (profiles/); scaled to this run's draws per launch
-        traffic, traffic_src = None, None
+        traffic, traffic_src, prof = None, None, {}
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "draw_kernel_ncu_latest.json")))
             traffic = float(prof["dram_traffic_bytes_per_launch"]) * dps / float(prof.get("draws_per_launch", 10))
             traffic_src = f"profiles/draw_kernel_ncu_latest.json ({prof.get('Kernel Name', '?')})"
         except Exception:
             pass
+        # the ceilings that actually bind this kernel (the 48*d state never reaches DRAM: it lives in registers)
+        ckpt_bytes = 16 * DIM  # one (z, v) checkpoint per leapfrog is what HAS to be written
+        fp64_pct = prof.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
+        ceilings = {
+            "checkpoint_hbm": {"bytes_per_leapfrog": ckpt_bytes, "ceiling_leapfrogs_per_s": peak * 1e9 / ckpt_bytes,
+                               "frac": per_gpu_rate * ckpt_bytes / 1e9 / peak,
+                               "note": "the (z, v) checkpoint of every leaf (16*d bytes) is the only traffic a leapfrog must send to HBM"},
+            "fp64_pipe": {"pct_of_peak_in_ncu_capture": None if fp64_pct is None else float(fp64_pct),
+                          "source": "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active of the committed ncu capture "
+                                    "(profiles/draw_kernel_ncu_latest.json); scales with value / the capture's own rate",
+                          "capture_leapfrogs_per_s": prof.get("leapfrogs_per_s")},
+            "algorithmic_48d": {"bytes_per_leapfrog": alg_bytes_per_step, "frac": achieved / peak,
+                                "note": "SURVEY 8(d) figure; saturates (> 1 possible) because these bytes stay on chip"},
+        }
         cpu = None
         if not args.no_cpu_baseline:
             cpu, _, _ = cpu_oracle_throughput(args.cpu_seconds, os.cpu_count() or 1)
+        other_out = {}
+        for i, n in enumerate(names):
+            cfg = CONFIGS[n]
+            k_ms, k_tune_ms = t[4 + i], t[4 + len(names) + i]
+            k_lf, k_tune_lf = w[3 + i], w[3 + len(names) + i]
+            rate = k_lf / (k_ms * 1e-3)
+            o = other[n]
+            rec = {"workload": f"configs[{cfg['index']}]: {cfg['what']}", "value": rate, "unit": UNIT,
+                   "scaling": "strong (65536 chains split over the ranks)" if n == "c5" else "weak (the config per GPU)",
+                   "chains_rank0": o["chains_this_rank"], "chains_all_ranks": cfg["chains"] if n == "c5" else cfg["chains"] * world,
+                   "dim": cfg["dim"], "num_tune": cfg["num_tune"], "steps": o["steps"], "draws_per_step": o["draws_per_step"],
+                   "ms_per_step": k_ms / o["steps"], "tuning_phase_leapfrogs_per_s": k_tune_lf / (k_tune_ms * 1e-3),
+                   "tuning_phase_ms": k_tune_ms, "bad_init_rank0": o["bad_init"], "clocks_rank0": o["clocks"],
+                   "algorithmic_GBps_48d": rate * 48 * cfg["dim"] / 1e9,
+                   "timing": "CUDA events around the draw kernel, summed over the steps, max over ranks"}
+            if cfg["hbm_bound"]:
+                rec["roofline"] = {"bound": "hbm", "achieved": rate / world * 48 * cfg["dim"] / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": rate / world * 48 * cfg["dim"] / 1e9 / peak,
+                                   "checkpoint_hbm_frac": rate / world * 16 * cfg["dim"] / 1e9 / peak}
+            else:
+                rec["roofline"] = "not meaningful: the chain state fits on chip (SURVEY 8d); latency / occupancy bound"
+            other_out[n] = rec
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "chains_per_gpu": N, "dim": DIM, "draws_per_step": dps,
                        "leapfrogs_per_step_all_gpus": steps_dev_all / args.steps,
-                       "cache": "inputs larger than L2: per-GPU checkpoint pool 1024 x 34 x 16 kB = 557 MB vs 126 MB L2; no flush between steps",
-                       "timing": "CUDA events around the draw kernel on the launching stream, summed over K steps, max over ranks",
+                       "cache": "inputs larger than L2: the checkpoint pools of the resident chains (one 16 kB slot per leaf) + 8 estimator / "
+                                "13 state planes of 8 MB cycle through far more than the 126 MB L2; no flush between steps",
+                       "timing": "CUDA events around the draw kernel on the launching stream, summed over K steps, max over ranks; the "
+                                 "kernel writes the draws and all 15 statistics of Chain::draw to HBM buffers",
                        "wall_ms_per_step_incl_launch": wall_ms_max / args.steps,
-                       "tuning_phase": {"draws": NUM_TUNE, "kernel_ms": tune_ms, "wall_s": tune_wall, "leapfrogs": tune_leapfrogs,
-                                        "leapfrogs_per_s": tune_leapfrogs / max(tune_ms * 1e-3, 1e-9)}},
+                       "tuning_phase": {"draws": NUM_TUNE, "kernel_ms": tune_ms_max, "wall_s": tune_wall, "leapfrogs": tune_lf_all,
+                                        "leapfrogs_per_s": tune_lf_all / max(tune_ms_max * 1e-3, 1e-9),
+                                        "ratio_to_sampling_rate": tune_lf_all / max(tune_ms_max * 1e-3, 1e-9) / value}},
             "e2e": {"value": steps_e2e_all / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
+                    "d2h_GBps_per_rank": d2h * args.steps / (e2e_ms_max * 1e-3) / 1e9,
                     "draws_path": "kernel writes the page-locked host buffer directly (posted PCIe writes overlapping the sampling)"
                                   if e2e_direct else "device staging buffer + cudaMemcpyAsync D2H after the kernel",
                     "note": "nuts_draw with page-locked host buffers: every draw [draws x chains x dim] f64 and all 15 statistics reach host "
@@ -419,18 +578,22 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "traffic_source": traffic_src, "peak_source": peak_kind,
+                         "traffic_source": traffic_src, "peak_source": peak_kind, "binding_ceilings": ceilings,
                          "note": "achieved = leapfrogs per launch x 48*dim algorithmic bytes / launch duration; the engine keeps z, v, grad in "
                                  "registers across leapfrogs, so algorithmic bytes are NOT DRAM bytes (frac > 1 is possible); see DESIGN.md"},
             "cpu_baseline": cpu,
         }
         line["config"]["microbench_fixed_step_no_turn_checks_rank0"] = micro
-        if gather_ms is not None:
-            line["config"]["nccl_all_gather_last_step_ms"] = gather_ms
+        line["config"]["other_configs"] = other_out
+        if whole:
+            k = 4 + 2 * len(names)
+            line["config"]["whole_run"] = {
+                "what": "nuts_set_position + 400 tuning + 1000 sampling draws of the headline workload per rank through nuts_draw, every "
+                        "draw and statistic delivered to page-locked host memory in batches; wall clock, max over ranks",
+                "wall_s": t[k] * 1e-3, "tuning_wall_s": t[k + 1] * 1e-3, "leapfrogs_all_gpus": w[3 + 2 * len(names)],
+                "leapfrogs_per_s": w[3 + 2 * len(names)] / (t[k] * 1e-3),
+                "tuning_share_of_wall": t[k + 1] / t[k]}
         emit(line)
-    samp.close()
-    math.close()
-    host_buf.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -257,6 +257,39 @@ int nuts_sampler_last_timing(nuts_sampler_t*, double* kernel_ms, uint64_t* launc
 int nuts_sampler_get_state(nuts_sampler_t*, double* position, double* step_size, double* stds, double* mean, uint64_t* rng_counter);
 int nuts_sampler_set_step_size(nuts_sampler_t*, const double* step_size /*[N]*/);
 
+/* ---- complete per-chain state between two draws: checkpoint / resume, and teacher-forced parity tests --------------
+ * Everything a NutsChain (reference src/chain.rs:44-61) carries from one Chain::draw to the next, SoA over chains, HOST
+ * arrays; vectors are dense [N*d], scalars [N].  In nuts_sampler_get_chain_state any member may be NULL (skipped); in
+ * nuts_sampler_set_chain_state every member must be set.  A sampler restored with set_chain_state continues bit-identically
+ * to the sampler the state was read from (same settings, seed, chain_id_offset and model).
+ *   point        = NutsChain.state: TransformedPoint x, grad_x, z, grad_z, logp, logdet, transform_id (transformed_hamiltonian.rs:56-77)
+ *   mass matrix  = DiagMassMatrix stds, inv_stds, mean, logdet, id (src/transform/diagonal.rs:9-17)
+ *   step size    = Hamiltonian.step_size + DualAverage log_step, log_step_adapted, hbar, mu, count (src/stepsize/dual_avg.rs:33-41)
+ *   estimators   = DiagAdaptStrategy's four RunningVariance: foreground / background x draw / grad, each mean + variance
+ *                  accumulator + count (src/transform/adapt/diagonal.rs:17-55,108-118)
+ *   schedule     = GlobalStrategy tuning, has_initial_mass_matrix, last_update, current_window_size (src/adapt_strategy.rs:27-39)
+ *   chain        = draw_count (chain.rs:56), position of the chain's random stream, alive (0 after BadInitGrad), leapfrog total */
+typedef struct {
+  double *position, *gradient, *transformed_position, *transformed_gradient; /* [N*d] */
+  double *logp, *point_logdet;                                               /* [N]   */
+  int64_t* point_transform_id;
+  double *stds, *inv_stds, *mean; /* [N*d] */
+  double* mass_matrix_logdet;     /* [N]   */
+  int64_t* mass_matrix_id;
+  double* step_size;
+  double *da_log_step, *da_log_step_adapted, *da_hbar, *da_mu;
+  uint64_t* da_count;
+  double *draw_mean, *draw_var, *grad_mean, *grad_var;             /* foreground estimators [N*d] */
+  double *draw_mean_bg, *draw_var_bg, *grad_mean_bg, *grad_var_bg; /* background estimators [N*d] */
+  uint64_t *foreground_count, *background_count;
+  uint8_t *tuning, *has_initial_mass_matrix;
+  uint64_t *last_update, *current_window_size;
+  uint64_t *draw_count, *rng_counter, *total_leapfrogs;
+  uint8_t* alive;
+} nuts_chain_state_t;
+int nuts_sampler_get_chain_state(nuts_sampler_t*, const nuts_chain_state_t* out);
+int nuts_sampler_set_chain_state(nuts_sampler_t*, const nuts_chain_state_t* in);
+
 #ifdef __cplusplus
 }
 #endif

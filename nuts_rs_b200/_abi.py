@@ -126,6 +126,41 @@ class Stats(C.Structure):
     ]
 
 
+# nuts_chain_state_t: (field, numpy dtype, is a [N*d] vector) in struct order
+CHAIN_STATE_FIELDS = (
+    [(n, "float64", True) for n in ("position", "gradient", "transformed_position", "transformed_gradient")]
+    + [("logp", "float64", False), ("point_logdet", "float64", False), ("point_transform_id", "int64", False)]
+    + [(n, "float64", True) for n in ("stds", "inv_stds", "mean")]
+    + [("mass_matrix_logdet", "float64", False), ("mass_matrix_id", "int64", False), ("step_size", "float64", False)]
+    + [(n, "float64", False) for n in ("da_log_step", "da_log_step_adapted", "da_hbar", "da_mu")]
+    + [("da_count", "uint64", False)]
+    + [(n, "float64", True) for n in ("draw_mean", "draw_var", "grad_mean", "grad_var", "draw_mean_bg", "draw_var_bg", "grad_mean_bg",
+                                      "grad_var_bg")]
+    + [("foreground_count", "uint64", False), ("background_count", "uint64", False), ("tuning", "uint8", False),
+       ("has_initial_mass_matrix", "uint8", False), ("last_update", "uint64", False), ("current_window_size", "uint64", False),
+       ("draw_count", "uint64", False), ("rng_counter", "uint64", False), ("total_leapfrogs", "uint64", False), ("alive", "uint8", False)]
+)
+_CT = {"float64": c_double_p, "int64": c_i64_p, "uint64": c_u64_p, "uint8": c_u8_p}
+
+
+class ChainState(C.Structure):
+    _fields_ = [(n, _CT[dt]) for n, dt, _ in CHAIN_STATE_FIELDS]
+
+
+def alloc_chain_state(nchains, dim, arrays=None):
+    """(ChainState struct, dict of numpy arrays).  `arrays`: an existing dict (e.g. read from another sampler) to wrap."""
+    import numpy as np
+
+    st = ChainState()
+    out = {}
+    for name, dt, vec in CHAIN_STATE_FIELDS:
+        shape = (nchains, dim) if vec else (nchains,)
+        a = np.zeros(shape, dtype=dt) if arrays is None else np.ascontiguousarray(arrays[name], dtype=dt).reshape(shape)
+        out[name] = a
+        setattr(st, name, a.ctypes.data_as(_CT[dt]))
+    return st, out
+
+
 # numpy dtype per stat, in struct order
 STAT_DTYPES = {
     "depth": "uint64",

@@ -108,6 +108,7 @@ const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB
 
 struct nuts_plane {
   double* ptr;
+  uint64_t ld;  // row stride in doubles (dim rounded up to 16: rows start on 128-byte lines)
 };
 
 struct nuts_ctx {
@@ -146,9 +147,14 @@ struct nuts_sampler {
   std::vector<void*> allocations;
   double* d_init = nullptr;
   int* d_status = nullptr;
-  // device stats buffers (grown on demand)
+  // device stats buffers (grown on demand): ONE allocation holding the 15 arrays + a page-locked host mirror, so the statistics
+  // of a nuts_draw call leave in a single D2H copy
   uint64_t stats_capacity = 0;  // in draws
   StatsDev d_stats{};
+  unsigned char* d_stats_blob = nullptr;
+  unsigned char* h_stats_blob = nullptr;
+  size_t stats_offset[15] = {};
+  size_t stats_blob_bytes = 0;
   double* d_draws = nullptr;
   uint64_t draws_capacity = 0;  // in draws
   double* h_pinned = nullptr;   // pinned staging for D2H of draws
@@ -210,6 +216,17 @@ int sync(nuts_ctx* ctx) {
     if (_r != NUTS_OK) return _r; \
   } while (0)
 #define CHECK_LAUNCH() CUDA_TRY(cudaGetLastError())
+
+// Destroys a half-built object when a constructor-like entry point returns early; dismiss() on success.
+template <class T, int (*Destroy)(T*)>
+struct Guard {
+  T* p;
+  explicit Guard(T* q) : p(q) {}
+  ~Guard() {
+    if (p) Destroy(p);
+  }
+  void dismiss() { p = nullptr; }
+};
 
 template <class T>
 int grow(T** p, size_t count) {
@@ -275,6 +292,7 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
   CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
   if (prop.major != 10) return fail(NUTS_ERR_NO_DEVICE, "device %d is sm_%d%d; libnuts_b200 is built for sm_100a only", device_id, prop.major, prop.minor);
   nuts_ctx* ctx = new nuts_ctx();
+  Guard<nuts_ctx, nuts_ctx_destroy> guard(ctx);  // every early return below releases what was allocated so far
   ctx->device = device_id;
   ctx->N = nchains;
   ctx->d = dim;
@@ -292,10 +310,7 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
       for (uint64_t i = 0; i < dim; ++i) prec[i] = 1.0;  // diff * 1.0 is exact: the DIAG kernels serve this target bit-identically
       break;
     case NUTS_LOGP_GAUSS_DIAG:
-      if (!model->sigma) {
-        delete ctx;
-        return fail(NUTS_ERR_INVALID, "GAUSS_DIAG needs sigma");
-      }
+      if (!model->sigma) return fail(NUTS_ERR_INVALID, "GAUSS_DIAG needs sigma");
       for (uint64_t i = 0; i < dim; ++i) prec[i] = 1.0 / (model->sigma[i] * model->sigma[i]);
       break;
     case NUTS_LOGP_GAUSS_RANK1:
@@ -305,7 +320,6 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
       ctx->model.funnel_inv_var = 1.0 / (model->funnel_scale * model->funnel_scale);
       break;
     default:
-      delete ctx;
       return fail(NUTS_ERR_INVALID, "unknown logp kind %d", model->kind);
   }
   TRY(dev_alloc(&ctx->d_model_mu, model_ld));
@@ -328,6 +342,7 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
   TRY(dev_alloc(&ctx->d_i8, nchains));
   TRY(dev_alloc(&ctx->d_i32, nchains));
   TRY(dev_alloc(&ctx->d_i64, nchains));
+  guard.dismiss();
   *out = ctx;
   return NUTS_OK;
 }
@@ -335,7 +350,7 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
 int nuts_ctx_destroy(nuts_ctx_t* ctx) {
   if (!ctx) return NUTS_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_model_mu);
   cudaFree(ctx->d_model_prec);
   cudaFree(ctx->T.stds);
@@ -349,7 +364,7 @@ int nuts_ctx_destroy(nuts_ctx_t* ctx) {
   cudaFree(ctx->d_i8);
   cudaFree(ctx->d_i32);
   cudaFree(ctx->d_i64);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return NUTS_OK;
 }
@@ -361,6 +376,7 @@ void* nuts_ctx_stream(nuts_ctx_t* ctx) { return (void*)ctx->stream; }
 int nuts_plane_alloc(nuts_ctx_t* ctx, nuts_plane_t** plane) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   nuts_plane* p = new nuts_plane();
+  p->ld = ctx->ld;
   int r = dev_alloc(&p->ptr, ctx->N * ctx->ld);
   if (r != NUTS_OK) {
     delete p;
@@ -400,7 +416,7 @@ int nuts_plane_write_to_host(nuts_ctx_t* ctx, const nuts_plane_t* src, double* d
   return plane_to_host(ctx, src->ptr, dst);
 }
 double* nuts_plane_device_ptr(nuts_plane_t* plane, uint64_t* row_stride_elems) {
-  (void)row_stride_elems;
+  if (row_stride_elems) *row_stride_elems = plane->ld;
   return plane->ptr;
 }
 
@@ -553,8 +569,18 @@ int nuts_logp_array(nuts_ctx_t* ctx, const nuts_plane_t* position, nuts_plane_t*
 int nuts_point_alloc(nuts_ctx_t* ctx, nuts_point_t** point) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   nuts_point* p = new nuts_point();
+  struct PointGuard {
+    nuts_ctx* c;
+    nuts_point* p;
+    ~PointGuard() {
+      if (p) nuts_point_free(c, p);
+    }
+  } guard{ctx, p};
   const size_t plane = ctx->N * ctx->ld;
-  for (int k = 0; k < 5; ++k) TRY(dev_alloc(&p->planes[k].ptr, plane));
+  for (int k = 0; k < 5; ++k) {
+    p->planes[k].ld = ctx->ld;
+    TRY(dev_alloc(&p->planes[k].ptr, plane));
+  }
   p->dev.x = p->planes[0].ptr;
   p->dev.gx = p->planes[1].ptr;
   p->dev.z = p->planes[2].ptr;
@@ -567,6 +593,7 @@ int nuts_point_alloc(nuts_ctx_t* ctx, nuts_point_t** point) {
   TRY(dev_alloc(&p->dev.e0, ctx->N));
   TRY(dev_alloc(&p->dev.tid, ctx->N));
   CUDA_TRY(cudaMemset(p->dev.tid, 0xff, ctx->N * sizeof(long long)));  // transform_id = -1 (transformed_hamiltonian.rs:376)
+  guard.p = nullptr;
   *point = p;
   return NUTS_OK;
 }
@@ -726,6 +753,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   }
 
   nuts_sampler* s = new nuts_sampler();
+  Guard<nuts_sampler, nuts_sampler_destroy> guard(s);  // every early return below releases what was allocated so far
   s->ctx = ctx;
   s->settings = *st;
   s->cfg = cfg;
@@ -735,7 +763,6 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   int blocks_per_sm = 0, cta_threads = 0, smf = 0;
   s->model_variant = ctx->model.kind == NUTS_LOGP_GAUSS_RANK1 ? 1 : ctx->model.kind == NUTS_LOGP_FUNNEL ? 2 : 0;
   if (!cfg->launch[s->model_variant] || !cfg->occupancy[s->model_variant]) {
-    delete s;
     return fail(NUTS_ERR_UNSUPPORTED, "engine %dx%d for model kind %d is not part of this build", cfg->tpc, cfg->ept, ctx->model.kind);
   }
   CUDA_TRY(cfg->occupancy[s->model_variant](&blocks_per_sm, &cta_threads, &smf));
@@ -744,7 +771,6 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   P.ld = (smf & SM_EXACT) ? (int)std::max<uint64_t>(ctx->ld, (uint64_t)cfg->tpc * cfg->ept) : (int)ctx->ld;
   const bool decoupled = cfg->minb >= 100;  // chain_engine_v2.cuh
   if (decoupled && st->maxdepth + st->extra_doublings > (uint64_t)V2_MAXD + 1) {
-    delete s;
     return fail(NUTS_ERR_UNSUPPORTED, "the decoupled engine needs maxdepth + extra_doublings <= %d", V2_MAXD + 1);
   }
   // checkpoint pool: 3 roles per pending level + the main tree's draw and its two ends; the decoupled engine hands slots out V2_K
@@ -780,7 +806,6 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   S.early_end = (uint64_t)(a.early_window * num_tune_f);
   S.final_step_size_window = st->num_tune >= step_size_window ? st->num_tune - step_size_window : 0;
   if (st->num_tune > 0 && !(S.early_end < st->num_tune)) {
-    delete s;
     return fail(NUTS_ERR_INVALID, "early_window must leave early_end < num_tune");
   }
   S.mm_switch_freq = a.mass_matrix_switch_freq;
@@ -810,10 +835,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   A((void**)&s->d_init, ctx->N * ctx->d * sizeof(double));
   A((void**)&s->d_status, ctx->N * sizeof(int));
   A((void**)&P.phase_clocks, 8 * sizeof(unsigned long long));
-  if (r != NUTS_OK) {
-    nuts_sampler_destroy(s);
-    return r;
-  }
+  if (r != NUTS_OK) return r;
   // chain scalars at construction: Strategy::new -> DualAverage::new(initial_step) (stepsize/adapt.rs:67-89),
   // DiagMassMatrix id -1 (diagonal.rs:81), GlobalStrategy flags (adapt_strategy.rs:87-97)
   std::vector<ChainState> cs(ctx->N);
@@ -838,9 +860,12 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   const int teams_per_cta = decoupled ? cfg->minb % 10 : cta_threads / cfg->tpc;  // decoupled tags end in the number of teams
   const uint64_t ctas_needed = (ctx->N + teams_per_cta - 1) / teams_per_cta;
   s->grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)blocks_per_sm * ctx->num_sms);
+  // NUTS_B200_GRID caps the persistent grid (tests / compute-sanitizer: forces draw migration between teams on small workloads)
+  if (const char* env = std::getenv("NUTS_B200_GRID")) s->grid = std::max(1, std::min(s->grid, std::atoi(env)));
   s->teams_per_cta = teams_per_cta;
   CUDA_TRY(cudaEventCreate(&s->ev0));
   CUDA_TRY(cudaEventCreate(&s->ev1));
+  guard.dismiss();
   *out = s;
   return NUTS_OK;
 }
@@ -853,21 +878,8 @@ int nuts_sampler_destroy(nuts_sampler_t* s) {
   auto F = [](void* p) {
     if (p) cudaFree(p);
   };
-  F(s->d_stats.depth);
-  F(s->d_stats.maxdepth_reached);
-  F(s->d_stats.index_in_trajectory);
-  F(s->d_stats.logp);
-  F(s->d_stats.energy);
-  F(s->d_stats.energy_error);
-  F(s->d_stats.diverging);
-  F(s->d_stats.step_size);
-  F(s->d_stats.step_size_bar);
-  F(s->d_stats.mean_tree_accept);
-  F(s->d_stats.mean_tree_accept_sym);
-  F(s->d_stats.n_steps);
-  F(s->d_stats.max_energy_error);
-  F(s->d_stats.tuning);
-  F(s->d_stats.fisher_distance);
+  F(s->d_stats_blob);
+  if (s->h_stats_blob) cudaFreeHost(s->h_stats_blob);
   F(s->d_draws);
   if (s->h_pinned) cudaFreeHost(s->h_pinned);
   if (s->ev0) cudaEventDestroy(s->ev0);
@@ -910,25 +922,44 @@ int nuts_set_position(nuts_sampler_t* s, const double* position, int32_t* status
   return NUTS_OK;
 }
 
+// element size of statistic k, in nuts_stats_t / StatsDev member order
+static const size_t kStatElem[15] = {8, 1, 8, 8, 8, 8, 1, 8, 8, 8, 8, 8, 8, 1, 8};
+
 static int ensure_stats(nuts_sampler* s, uint64_t n_draws) {
   if (n_draws <= s->stats_capacity) return NUTS_OK;
   const size_t n = n_draws * s->ctx->N;
+  s->stats_capacity = 0;  // nothing usable until the regrow below has succeeded
+  s->d_stats = StatsDev{};
+  if (s->d_stats_blob) CUDA_TRY(cudaFree(s->d_stats_blob));
+  s->d_stats_blob = nullptr;
+  if (s->h_stats_blob) CUDA_TRY(cudaFreeHost(s->h_stats_blob));
+  s->h_stats_blob = nullptr;
+  size_t off = 0;
+  for (int k = 0; k < 15; ++k) {
+    s->stats_offset[k] = off;
+    off += (n * kStatElem[k] + 255) / 256 * 256;
+  }
+  s->stats_blob_bytes = off;
+  CUDA_TRY(cudaMalloc((void**)&s->d_stats_blob, off));
+  CUDA_TRY(cudaMemset(s->d_stats_blob, 0, off));
+  CUDA_TRY(cudaHostAlloc((void**)&s->h_stats_blob, off, cudaHostAllocDefault));
+  unsigned char* b = s->d_stats_blob;
   StatsDev& d = s->d_stats;
-  TRY(grow(&d.depth, n));
-  TRY(grow(&d.maxdepth_reached, n));
-  TRY(grow(&d.index_in_trajectory, n));
-  TRY(grow(&d.logp, n));
-  TRY(grow(&d.energy, n));
-  TRY(grow(&d.energy_error, n));
-  TRY(grow(&d.diverging, n));
-  TRY(grow(&d.step_size, n));
-  TRY(grow(&d.step_size_bar, n));
-  TRY(grow(&d.mean_tree_accept, n));
-  TRY(grow(&d.mean_tree_accept_sym, n));
-  TRY(grow(&d.n_steps, n));
-  TRY(grow(&d.max_energy_error, n));
-  TRY(grow(&d.tuning, n));
-  TRY(grow(&d.fisher_distance, n));
+  d.depth = (uint64_t*)(b + s->stats_offset[0]);
+  d.maxdepth_reached = (uint8_t*)(b + s->stats_offset[1]);
+  d.index_in_trajectory = (long long*)(b + s->stats_offset[2]);
+  d.logp = (double*)(b + s->stats_offset[3]);
+  d.energy = (double*)(b + s->stats_offset[4]);
+  d.energy_error = (double*)(b + s->stats_offset[5]);
+  d.diverging = (uint8_t*)(b + s->stats_offset[6]);
+  d.step_size = (double*)(b + s->stats_offset[7]);
+  d.step_size_bar = (double*)(b + s->stats_offset[8]);
+  d.mean_tree_accept = (double*)(b + s->stats_offset[9]);
+  d.mean_tree_accept_sym = (double*)(b + s->stats_offset[10]);
+  d.n_steps = (uint64_t*)(b + s->stats_offset[11]);
+  d.max_energy_error = (double*)(b + s->stats_offset[12]);
+  d.tuning = (uint8_t*)(b + s->stats_offset[13]);
+  d.fisher_distance = (double*)(b + s->stats_offset[14]);
   s->stats_capacity = n_draws;
   return NUTS_OK;
 }
@@ -963,7 +994,8 @@ static int run_draws(nuts_sampler* s, uint64_t n_draws, double* draws_dev, bool 
 int nuts_draw_device(nuts_sampler_t* s, uint64_t n_draws, double* draws_dev) {
   CUDA_TRY(cudaSetDevice(s->ctx->device));
   s->last_launches = 0;
-  return run_draws(s, n_draws, draws_dev, false);
+  // the statistics are produced like in nuts_draw (the whole output of Chain::draw); they stay in the sampler's device buffers
+  return run_draws(s, n_draws, draws_dev, true);
 }
 
 int nuts_draw(nuts_sampler_t* s, uint64_t n_draws, double* draws_out, const nuts_stats_t* stats) {
@@ -982,6 +1014,8 @@ int nuts_draw(nuts_sampler_t* s, uint64_t n_draws, double* draws_out, const nuts
     if (cudaPointerGetAttributes(&attr, draws_out) == cudaSuccess) {
       if ((attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged) && attr.devicePointer) direct = (double*)attr.devicePointer;
       else if (attr.type == cudaMemoryTypeDevice && attr.device == ctx->device) direct = draws_out;
+      else if (attr.type == cudaMemoryTypeDevice)
+        return fail(NUTS_ERR_INVALID, "nuts_draw: draws_out is memory of device %d, the sampler runs on device %d", attr.device, ctx->device);
     } else {
       cudaGetLastError();
     }
@@ -994,29 +1028,21 @@ int nuts_draw(nuts_sampler_t* s, uint64_t n_draws, double* draws_out, const nuts
   s->last_direct = direct != nullptr;
   if (draws_out && !direct)
     CUDA_TRY(cudaMemcpyAsync(draws_out, s->d_draws, n_draws * per_draw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (stats) {
+  if (stats) {  // into the page-locked mirror: real asynchronous DMA, no pageable staging by the driver
     const size_t n = n_draws * ctx->N;
-    const StatsDev& d = s->d_stats;
-#define COPY_STAT(name) \
-  if (stats->name) CUDA_TRY(cudaMemcpyAsync(stats->name, d.name, n * sizeof(*stats->name), cudaMemcpyDeviceToHost, ctx->stream));
-    COPY_STAT(depth)
-    COPY_STAT(maxdepth_reached)
-    COPY_STAT(index_in_trajectory)
-    COPY_STAT(logp)
-    COPY_STAT(energy)
-    COPY_STAT(energy_error)
-    COPY_STAT(diverging)
-    COPY_STAT(step_size)
-    COPY_STAT(step_size_bar)
-    COPY_STAT(mean_tree_accept)
-    COPY_STAT(mean_tree_accept_sym)
-    COPY_STAT(n_steps)
-    COPY_STAT(max_energy_error)
-    COPY_STAT(tuning)
-    COPY_STAT(fisher_distance)
-#undef COPY_STAT
+    for (int k = 0; k < 15; ++k)
+      CUDA_TRY(cudaMemcpyAsync(s->h_stats_blob + s->stats_offset[k], s->d_stats_blob + s->stats_offset[k], n * kStatElem[k],
+                               cudaMemcpyDeviceToHost, ctx->stream));
   }
   TRY(sync(ctx));
+  if (stats) {
+    const size_t n = n_draws * ctx->N;
+    void* const dst[15] = {stats->depth, stats->maxdepth_reached, stats->index_in_trajectory, stats->logp, stats->energy,
+                           stats->energy_error, stats->diverging, stats->step_size, stats->step_size_bar, stats->mean_tree_accept,
+                           stats->mean_tree_accept_sym, stats->n_steps, stats->max_energy_error, stats->tuning, stats->fisher_distance};
+    for (int k = 0; k < 15; ++k)
+      if (dst[k]) std::memcpy(dst[k], s->h_stats_blob + s->stats_offset[k], n * kStatElem[k]);
+  }
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
   s->last_kernel_ms = ms;
@@ -1081,6 +1107,133 @@ int nuts_sampler_get_state(nuts_sampler_t* s, double* position, double* step_siz
       if (rng_counter) rng_counter[c] = cs[c].rng_counter;
     }
   }
+  return NUTS_OK;
+}
+
+// The whole state a chain carries from one draw to the next (include/nuts_b200.h nuts_chain_state_t).  Between two launches all
+// of it lives in global memory: the planes of EngineParams + one ChainState record per chain.
+int nuts_sampler_get_chain_state(nuts_sampler_t* s, const nuts_chain_state_t* o) {
+  nuts_ctx* ctx = s->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!o) return fail(NUTS_ERR_INVALID, "nuts_sampler_get_chain_state: out is NULL");
+  const EngineParams& P = s->P;
+  const size_t N = ctx->N;
+  std::vector<ChainState> cs(N);
+  CUDA_TRY(cudaMemcpyAsync(cs.data(), P.cs, N * sizeof(ChainState), cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(sync(ctx));
+  auto plane = [&](const double* src, double* dst) { return dst ? plane_to_host(ctx, src, dst, P.ld) : NUTS_OK; };
+  TRY(plane(P.x, o->position));
+  TRY(plane(P.gx, o->gradient));
+  TRY(plane(P.z, o->transformed_position));
+  TRY(plane(P.gz, o->transformed_gradient));
+  TRY(plane(P.stds, o->stds));
+  TRY(plane(P.inv_stds, o->inv_stds));
+  TRY(plane(P.mean, o->mean));
+  // estimators: est[chain][set][4][ld]; the foreground set is chain-dependent (a switch flips the index), so gather per chain
+  double* est_out[2][4] = {{o->draw_mean, o->draw_var, o->grad_mean, o->grad_var},
+                           {o->draw_mean_bg, o->draw_var_bg, o->grad_mean_bg, o->grad_var_bg}};
+  for (int bg = 0; bg < 2; ++bg)
+    for (int w = 0; w < 4; ++w)
+      if (est_out[bg][w])
+        for (size_t c = 0; c < N; ++c) {
+          const int set = bg ? 1 - cs[c].fg_set : cs[c].fg_set;
+          CUDA_TRY(cudaMemcpyAsync(est_out[bg][w] + c * ctx->d, P.est + ((c * 2 + set) * 4 + w) * (size_t)P.ld, ctx->d * sizeof(double),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+        }
+  TRY(sync(ctx));
+  for (size_t c = 0; c < N; ++c) {
+    const ChainState& k = cs[c];
+#define PUT(field, val) \
+  if (o->field) o->field[c] = (val)
+    PUT(logp, k.logp);
+    PUT(point_logdet, k.pt_logdet);
+    PUT(point_transform_id, k.pt_transform_id);
+    PUT(mass_matrix_logdet, k.mm_logdet);
+    PUT(mass_matrix_id, k.mm_id);
+    PUT(step_size, k.step_size);
+    PUT(da_log_step, k.da_log_step);
+    PUT(da_log_step_adapted, k.da_log_step_adapted);
+    PUT(da_hbar, k.da_hbar);
+    PUT(da_mu, k.da_mu);
+    PUT(da_count, k.da_count);
+    PUT(foreground_count, k.fg_count);
+    PUT(background_count, k.bg_count);
+    PUT(tuning, (uint8_t)(k.tuning != 0));
+    PUT(has_initial_mass_matrix, (uint8_t)(k.has_initial_mass_matrix != 0));
+    PUT(last_update, k.last_update);
+    PUT(current_window_size, k.current_window_size);
+    PUT(draw_count, k.draw_count);
+    PUT(rng_counter, k.rng_counter);
+    PUT(total_leapfrogs, k.total_leapfrogs);
+    PUT(alive, (uint8_t)(k.alive != 0));
+#undef PUT
+  }
+  return NUTS_OK;
+}
+
+int nuts_sampler_set_chain_state(nuts_sampler_t* s, const nuts_chain_state_t* in) {
+  nuts_ctx* ctx = s->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!in) return fail(NUTS_ERR_INVALID, "nuts_sampler_set_chain_state: in is NULL");
+  const void* const* members = reinterpret_cast<const void* const*>(in);
+  for (size_t k = 0; k < sizeof(nuts_chain_state_t) / sizeof(void*); ++k)
+    if (!members[k]) return fail(NUTS_ERR_INVALID, "nuts_sampler_set_chain_state: member %zu of nuts_chain_state_t is NULL", k);
+  EngineParams& P = s->P;
+  const size_t N = ctx->N;
+  RowArgs ra = ctx->row_args();
+  ra.ld = P.ld;  // rows keep their zero padding: k_pack only writes the first d elements
+  auto plane = [&](const double* src, double* dst) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_dense, src, N * ctx->d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_pack<<<(unsigned)N, PK_THREADS, 0, ctx->stream>>>(ra, ctx->d_dense, dst);
+    CHECK_LAUNCH();
+    return sync(ctx);
+  };
+  TRY(plane(in->position, P.x));
+  TRY(plane(in->gradient, P.gx));
+  TRY(plane(in->transformed_position, P.z));
+  TRY(plane(in->transformed_gradient, P.gz));
+  TRY(plane(in->stds, P.stds));
+  TRY(plane(in->inv_stds, P.inv_stds));
+  TRY(plane(in->mean, P.mean));
+  std::vector<ChainState> cs(N);
+  CUDA_TRY(cudaMemcpyAsync(cs.data(), P.cs, N * sizeof(ChainState), cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(sync(ctx));
+  const double* est_in[2][4] = {{in->draw_mean, in->draw_var, in->grad_mean, in->grad_var},
+                                {in->draw_mean_bg, in->draw_var_bg, in->grad_mean_bg, in->grad_var_bg}};
+  for (size_t c = 0; c < N; ++c) {
+    ChainState& k = cs[c];
+    k.fg_set = 0;  // restored estimators: foreground in set 0, background in set 1
+    for (int bg = 0; bg < 2; ++bg)
+      for (int w = 0; w < 4; ++w)
+        CUDA_TRY(cudaMemcpyAsync(P.est + ((c * 2 + bg) * 4 + w) * (size_t)P.ld, est_in[bg][w] + c * ctx->d, ctx->d * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    k.logp = in->logp[c];
+    k.pt_logdet = in->point_logdet[c];
+    k.pt_transform_id = in->point_transform_id[c];
+    k.mm_logdet = in->mass_matrix_logdet[c];
+    k.mm_id = in->mass_matrix_id[c];
+    k.step_size = in->step_size[c];
+    k.da_log_step = in->da_log_step[c];
+    k.da_log_step_adapted = in->da_log_step_adapted[c];
+    k.da_hbar = in->da_hbar[c];
+    k.da_mu = in->da_mu[c];
+    k.da_count = in->da_count[c];
+    k.fg_count = in->foreground_count[c];
+    k.bg_count = in->background_count[c];
+    k.tuning = in->tuning[c] ? 1 : 0;
+    k.has_initial_mass_matrix = in->has_initial_mass_matrix[c] ? 1 : 0;
+    k.last_update = in->last_update[c];
+    k.current_window_size = in->current_window_size[c];
+    k.draw_count = in->draw_count[c];
+    k.rng_counter = in->rng_counter[c];
+    k.total_leapfrogs = in->total_leapfrogs[c];
+    k.alive = in->alive[c] ? 1 : 0;
+  }
+  CUDA_TRY(cudaMemcpyAsync(P.cs, cs.data(), N * sizeof(ChainState), cudaMemcpyHostToDevice, ctx->stream));
+  TRY(sync(ctx));
+  s->positioned = true;
+  s->draws_done = 0;
+  for (size_t c = 0; c < N; ++c) s->draws_done = std::max<uint64_t>(s->draws_done, in->draw_count[c]);
   return NUTS_OK;
 }
 

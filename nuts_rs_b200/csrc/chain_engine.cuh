@@ -1832,7 +1832,7 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
   E.cs.draw_count += 1;
   if (!ok) {
     E.hs_alive = 0;
-    if (P.draws_out) cold_fill_dead(P, chain, tid, TPC, t + 1);
+    cold_fill_dead(P, chain, tid, TPC, t + 1);
   }
   if (tid == 0) {
     const StatsDev& st = P.stats;
@@ -1883,11 +1883,34 @@ __device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, 
   return status;
 }
 
+// Draws t0.. of this launch that a dead chain never produces: NaN positions, and statistics that say "nothing happened"
+// (0 leapfrogs, depth 0, NaN floats) instead of whatever the buffers held before.
 static __device__ __noinline__ void cold_fill_dead(const EngineParams& P, int chain, int tid, int tpc, uint64_t t0) {
   const double nan = __longlong_as_double(-1ll);
   for (uint64_t t = t0; t < P.n_draws; ++t) {
-    double* dst = P.draws_out + (t * (size_t)P.N + chain) * (size_t)P.d;
-    for (int i = tid; i < P.d; i += tpc) dst[i] = nan;
+    if (P.draws_out) {
+      double* dst = P.draws_out + (t * (size_t)P.N + chain) * (size_t)P.d;
+      for (int i = tid; i < P.d; i += tpc) dst[i] = nan;
+    }
+    if (tid == 0) {
+      const StatsDev& st = P.stats;
+      const size_t k = (size_t)t * (size_t)P.N + chain;
+      if (st.depth) st.depth[k] = 0;
+      if (st.maxdepth_reached) st.maxdepth_reached[k] = 0;
+      if (st.index_in_trajectory) st.index_in_trajectory[k] = 0;
+      if (st.logp) st.logp[k] = nan;
+      if (st.energy) st.energy[k] = nan;
+      if (st.energy_error) st.energy_error[k] = nan;
+      if (st.diverging) st.diverging[k] = 0;
+      if (st.step_size) st.step_size[k] = nan;
+      if (st.step_size_bar) st.step_size_bar[k] = nan;
+      if (st.mean_tree_accept) st.mean_tree_accept[k] = nan;
+      if (st.mean_tree_accept_sym) st.mean_tree_accept_sym[k] = nan;
+      if (st.n_steps) st.n_steps[k] = 0;
+      if (st.max_energy_error) st.max_energy_error[k] = nan;
+      if (st.tuning) st.tuning[k] = 0;
+      if (st.fisher_distance) st.fisher_distance[k] = nan;
+    }
   }
 }
 
@@ -1950,7 +1973,7 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
           E.run_draw(t);  // a chain that dies here has its remaining draws NaN-filled by cold_adapt
         } else {
           // draws a dead chain never produced read NaN (the output buffer may be host memory the kernel writes directly)
-          if (t == 0 && P.draws_out) cold_fill_dead(P, chain, tid, TPC, 0);
+          if (t == 0) cold_fill_dead(P, chain, tid, TPC, 0);
           break;
         }
       }

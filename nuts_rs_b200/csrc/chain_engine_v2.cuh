@@ -502,7 +502,7 @@ __global__ void NB_KERNEL_BOUNDS(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(cons
         if (E.hs_alive) {
           E.run_draw_v2(t, cmd_seen);
         } else {
-          if (t == 0 && P.draws_out) cold_fill_dead(P, chain, tid, TPC, 0);
+          if (t == 0) cold_fill_dead(P, chain, tid, TPC, 0);
           break;
         }
       }

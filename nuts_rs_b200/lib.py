@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "nuts_sampler_create", "nuts_sampler_destroy", "nuts_set_position", "nuts_draw", "nuts_draw_device",
     "nuts_sampler_counters", "nuts_sampler_last_timing", "nuts_sampler_get_state", "nuts_sampler_set_step_size",
     "nuts_host_alloc", "nuts_host_free", "nuts_sampler_last_draw_direct",
+    "nuts_sampler_get_chain_state", "nuts_sampler_set_chain_state",
 ]
 
 
@@ -110,6 +111,8 @@ def load():
     L.nuts_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
     L.nuts_host_free.argtypes = [vp]
     L.nuts_sampler_last_draw_direct.argtypes = [vp, _abi.c_i32_p]
+    L.nuts_sampler_get_chain_state.argtypes = [vp, C.POINTER(_abi.ChainState)]
+    L.nuts_sampler_set_chain_state.argtypes = [vp, C.POINTER(_abi.ChainState)]
     _LIB = L
     return L
 
@@ -442,6 +445,12 @@ class Sampler:
     def draw(self, n_draws, want_draws=True, stats=True, out=None):
         draws = None
         if want_draws:
+            if out is not None:
+                # the kernel (or the D2H copy) writes n_draws * nchains * dim doubles straight to this pointer
+                if not isinstance(out, np.ndarray) or out.shape != (n_draws, self.nchains, self.dim) or out.dtype != np.float64 \
+                        or not out.flags.c_contiguous or not out.flags.writeable:
+                    raise NutsError(f"Sampler.draw: `out` must be a writeable C-contiguous float64 array of shape "
+                                    f"{(n_draws, self.nchains, self.dim)}")
             draws = out if out is not None else np.empty((n_draws, self.nchains, self.dim))
         st, arrays = (alloc_stats(n_draws, self.nchains) if stats else (None, {}))
         _check(load().nuts_draw(self.h, n_draws, _p(draws), C.byref(st) if stats else None))
@@ -483,6 +492,17 @@ class Sampler:
     def set_step_size(self, eps):
         eps = _f64(np.broadcast_to(eps, (self.nchains,)))
         _check(load().nuts_sampler_set_step_size(self.h, _p(eps)))
+
+    def chain_state(self):
+        """Everything the chains carry from one draw to the next (nuts_chain_state_t) as a dict of numpy arrays: a checkpoint."""
+        st, arrays = _abi.alloc_chain_state(self.nchains, self.dim)
+        _check(load().nuts_sampler_get_chain_state(self.h, C.byref(st)))
+        return arrays
+
+    def set_chain_state(self, arrays):
+        """Resume from a checkpoint taken with chain_state() (same model, settings, seed and chain_id_offset)."""
+        st, keep = _abi.alloc_chain_state(self.nchains, self.dim, arrays)
+        _check(load().nuts_sampler_set_chain_state(self.h, C.byref(st)))
 
     def close(self):
         if self.h:

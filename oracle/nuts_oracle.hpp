@@ -398,6 +398,38 @@ struct TransformedPoint {  // :56-77
 };
 using State = std::shared_ptr<TransformedPoint>;
 
+// src/dynamics/state.rs:11-116 — StatePool: a State that loses its last reference goes back to the free list of the pool it
+// came from and is handed out again by new_state() WITHOUT being cleared (every field is overwritten by whoever fills it:
+// leapfrog :532-588, init_state :645-647), so a leapfrog allocates nothing once the pool is warm.
+struct StatePool {
+  struct Storage {
+    size_t dim;
+    std::vector<TransformedPoint*> free_states;
+    ~Storage() {
+      for (TransformedPoint* p : free_states) delete p;
+    }
+  };
+  std::shared_ptr<Storage> storage;
+  StatePool(size_t dim, size_t capacity) : storage(std::make_shared<Storage>()) {  // state.rs:27-32
+    storage->dim = dim;
+    storage->free_states.reserve(capacity);
+  }
+  State new_state() const {  // state.rs:34-42
+    TransformedPoint* p;
+    if (!storage->free_states.empty()) {
+      p = storage->free_states.back();
+      storage->free_states.pop_back();
+    } else {
+      p = new TransformedPoint(storage->dim);
+    }
+    std::weak_ptr<Storage> reuser = storage;
+    return State(p, [reuser](TransformedPoint* q) {  // Drop for State, state.rs:105-116
+      if (auto st = reuser.lock()) st->free_states.push_back(q);
+      else delete q;
+    });
+  }
+};
+
 struct DivergenceInfo {  // hamiltonian.rs:26-35 (the fields the stats use)
   bool logp_error = false;
   int64_t start_idx = 0, end_idx = 0;
@@ -493,10 +525,11 @@ struct TransformedHamiltonian {
   Vec ones, zeros;
   double step_size = 0.;
   DiagMassMatrix transformation;
+  StatePool pool;  // :427 StatePool::new(math, 10)
   uint64_t n_logp_evals = 0, n_leapfrogs = 0;
 
   TransformedHamiltonian(LogpFunc* f)  // :420-436
-      : dim(f->dim), logp_func(f), ones(f->dim, 1.), zeros(f->dim, 0.), transformation(f->dim) {}
+      : dim(f->dim), logp_func(f), ones(f->dim, 1.), zeros(f->dim, 0.), transformation(f->dim), pool(f->dim, 10) {}
 
   double logp_array(const Vec& x, Vec& grad) {  // cpu_math.rs:126-141
     n_logp_evals += 1;
@@ -525,7 +558,7 @@ struct TransformedHamiltonian {
   LeapfrogResult leapfrog(const State& start, Direction dir, double step_size_factor, double energy_baseline,
                           double max_energy_error, Collector& collector) {
     n_leapfrogs += 1;
-    State out = std::make_shared<TransformedPoint>(dim);
+    State out = pool.new_state();  // :532 self.pool().new_state(math)
     TransformedPoint& o = *out;
     const TransformedPoint& s = *start;
     o.initial_energy = s.initial_energy;
@@ -575,7 +608,7 @@ struct TransformedHamiltonian {
 
   // :640-661
   State init_state(const double* init) {
-    State st = std::make_shared<TransformedPoint>(dim);
+    State st = pool.new_state();
     std::copy(init, init + dim, st->untransformed_position.begin());
     init_from_untransformed_position(*st);
     if (!st->check_all()) throw BadInitGrad();
@@ -583,7 +616,7 @@ struct TransformedHamiltonian {
   }
   // :663-685
   State init_state_untransformed(const double* x) {
-    State st = std::make_shared<TransformedPoint>(dim);
+    State st = pool.new_state();
     std::copy(x, x + dim, st->untransformed_position.begin());
     st->logp = logp_array(st->untransformed_position, st->untransformed_gradient);
     st->transform_id = -1;

@@ -96,6 +96,8 @@ def lib():
         L.orc_sampler_draw.argtypes = [C.c_void_p, C.c_uint64, dp, C.POINTER(_abi.Stats), C.c_int]
         L.orc_sampler_get_state.argtypes = [C.c_void_p, dp, dp, dp, dp, _abi.c_u64_p]
         L.orc_sampler_set_step_size.argtypes = [C.c_void_p, dp]
+        L.orc_sampler_get_chain_state.argtypes = [C.c_void_p, C.POINTER(_abi.ChainState)]
+        L.orc_sampler_set_chain_state.argtypes = [C.c_void_p, C.POINTER(_abi.ChainState)]
         L.orc_sampler_counters.argtypes = [C.c_void_p, _abi.c_u64_p, _abi.c_u64_p]
         L.orc_settings_default.argtypes = [C.POINTER(_abi.NutsSettings)]
         _LIB = L
@@ -351,6 +353,15 @@ class Sampler:
     def set_step_size(self, eps):
         eps = _f64(np.broadcast_to(eps, (self.nchains,)))
         lib().orc_sampler_set_step_size(self.h, _p(eps))
+
+    def chain_state(self):
+        st, arrays = _abi.alloc_chain_state(self.nchains, self.dim)
+        lib().orc_sampler_get_chain_state(self.h, C.byref(st))
+        return arrays
+
+    def set_chain_state(self, arrays):
+        st, keep = _abi.alloc_chain_state(self.nchains, self.dim, arrays)
+        lib().orc_sampler_set_chain_state(self.h, C.byref(st))
 
     def counters(self):
         a = C.c_uint64()

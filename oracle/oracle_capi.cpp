@@ -379,6 +379,117 @@ void orc_sampler_get_state(void* sp, double* position, double* step_size, double
     if (rng_counter) rng_counter[c] = ch.rng.counter;
   }
 }
+// The complete state a NutsChain carries between two draws (include/nuts_b200.h nuts_chain_state_t): read it out / overwrite
+// it.  Teacher-forced parity tests inject the GPU's state after draw t here and compare draw t+1.
+void orc_sampler_get_chain_state(void* sp, const nuts_chain_state_t* o) {
+  auto* s = (Sampler*)sp;
+  const size_t d = s->dim;
+  auto putv = [&](double* dst, uint64_t c, const Vec& v) {
+    if (dst) std::copy(v.begin(), v.end(), dst + c * d);
+  };
+  for (uint64_t c = 0; c < s->nchains; ++c) {
+    NutsChain& ch = *s->chains[c];
+    const TransformedPoint& p = *ch.state;
+    const DiagMassMatrix& m = ch.hamiltonian.transformation;
+    const DiagAdaptStrategy& a = ch.strategy.mass_matrix_adapt;
+    putv(o->position, c, p.untransformed_position);
+    putv(o->gradient, c, p.untransformed_gradient);
+    putv(o->transformed_position, c, p.transformed_position);
+    putv(o->transformed_gradient, c, p.transformed_gradient);
+    putv(o->stds, c, m.stds);
+    putv(o->inv_stds, c, m.inv_stds);
+    putv(o->mean, c, m.mean);
+    putv(o->draw_mean, c, a.exp_variance_draw.mean);
+    putv(o->draw_var, c, a.exp_variance_draw.variance);
+    putv(o->grad_mean, c, a.exp_variance_grad.mean);
+    putv(o->grad_var, c, a.exp_variance_grad.variance);
+    putv(o->draw_mean_bg, c, a.exp_variance_draw_bg.mean);
+    putv(o->draw_var_bg, c, a.exp_variance_draw_bg.variance);
+    putv(o->grad_mean_bg, c, a.exp_variance_grad_bg.mean);
+    putv(o->grad_var_bg, c, a.exp_variance_grad_bg.variance);
+#define PUT(field, val) \
+  if (o->field) o->field[c] = (val)
+    PUT(logp, p.logp);
+    PUT(point_logdet, p.logdet);
+    PUT(point_transform_id, p.transform_id);
+    PUT(mass_matrix_logdet, m.logdet);
+    PUT(mass_matrix_id, m.id);
+    PUT(step_size, ch.hamiltonian.step_size);
+    const auto& da = ch.strategy.step_size.adaptation;
+    PUT(da_log_step, da ? da->log_step : 0.);
+    PUT(da_log_step_adapted, da ? da->log_step_adapted : 0.);
+    PUT(da_hbar, da ? da->hbar : 0.);
+    PUT(da_mu, da ? da->mu : 0.);
+    PUT(da_count, da ? da->count : 0);
+    PUT(foreground_count, a.exp_variance_draw.count);
+    PUT(background_count, a.exp_variance_draw_bg.count);
+    PUT(tuning, (uint8_t)ch.strategy.tuning);
+    PUT(has_initial_mass_matrix, (uint8_t)ch.strategy.has_initial_mass_matrix);
+    PUT(last_update, ch.strategy.last_update);
+    PUT(current_window_size, ch.strategy.current_window_size);
+    PUT(draw_count, ch.draw_count);
+    PUT(rng_counter, ch.rng.counter);
+    PUT(total_leapfrogs, ch.hamiltonian.n_leapfrogs);
+    PUT(alive, (uint8_t)s->alive[c]);
+#undef PUT
+  }
+}
+void orc_sampler_set_chain_state(void* sp, const nuts_chain_state_t* in) {
+  auto* s = (Sampler*)sp;
+  const size_t d = s->dim;
+  auto getv = [&](Vec& v, const double* src, uint64_t c) { std::copy(src + c * d, src + (c + 1) * d, v.begin()); };
+  for (uint64_t c = 0; c < s->nchains; ++c) {
+    NutsChain& ch = *s->chains[c];
+    ch.state = ch.hamiltonian.pool.new_state();  // never write through a State that a collector may still share
+    TransformedPoint& p = *ch.state;
+    DiagMassMatrix& m = ch.hamiltonian.transformation;
+    DiagAdaptStrategy& a = ch.strategy.mass_matrix_adapt;
+    getv(p.untransformed_position, in->position, c);
+    getv(p.untransformed_gradient, in->gradient, c);
+    getv(p.transformed_position, in->transformed_position, c);
+    getv(p.transformed_gradient, in->transformed_gradient, c);
+    std::fill(p.velocity.begin(), p.velocity.end(), 0.);
+    p.logp = in->logp[c];
+    p.logdet = in->point_logdet[c];
+    p.transform_id = in->point_transform_id[c];
+    p.index_in_trajectory = 0;
+    p.kinetic_energy = 0.;
+    p.initial_energy = 0.;
+    p.step_size_factor = 1.0;
+    getv(m.stds, in->stds, c);
+    getv(m.inv_stds, in->inv_stds, c);
+    getv(m.mean, in->mean, c);
+    m.logdet = in->mass_matrix_logdet[c];
+    m.id = in->mass_matrix_id[c];
+    ch.hamiltonian.step_size = in->step_size[c];
+    auto& da = ch.strategy.step_size.adaptation;
+    if (da) {
+      da->log_step = in->da_log_step[c];
+      da->log_step_adapted = in->da_log_step_adapted[c];
+      da->hbar = in->da_hbar[c];
+      da->mu = in->da_mu[c];
+      da->count = in->da_count[c];
+    }
+    getv(a.exp_variance_draw.mean, in->draw_mean, c);
+    getv(a.exp_variance_draw.variance, in->draw_var, c);
+    getv(a.exp_variance_grad.mean, in->grad_mean, c);
+    getv(a.exp_variance_grad.variance, in->grad_var, c);
+    getv(a.exp_variance_draw_bg.mean, in->draw_mean_bg, c);
+    getv(a.exp_variance_draw_bg.variance, in->draw_var_bg, c);
+    getv(a.exp_variance_grad_bg.mean, in->grad_mean_bg, c);
+    getv(a.exp_variance_grad_bg.variance, in->grad_var_bg, c);
+    a.exp_variance_draw.count = a.exp_variance_grad.count = in->foreground_count[c];
+    a.exp_variance_draw_bg.count = a.exp_variance_grad_bg.count = in->background_count[c];
+    ch.strategy.tuning = in->tuning[c] != 0;
+    ch.strategy.has_initial_mass_matrix = in->has_initial_mass_matrix[c] != 0;
+    ch.strategy.last_update = in->last_update[c];
+    ch.strategy.current_window_size = in->current_window_size[c];
+    ch.draw_count = in->draw_count[c];
+    ch.rng.counter = in->rng_counter[c];
+    ch.hamiltonian.n_leapfrogs = in->total_leapfrogs[c];
+    s->alive[c] = in->alive[c] ? 1 : 0;
+  }
+}
 void orc_sampler_set_step_size(void* sp, const double* step_size) {
   auto* s = (Sampler*)sp;
   for (uint64_t c = 0; c < s->nchains; ++c) s->chains[c]->hamiltonian.step_size = step_size[c];

@@ -1,10 +1,13 @@
 """BASELINE.json configs 2-5 at full size on one B200, checked through size-independent properties (the oracle cannot run
 1024 x 1000-dim chains for 1400 draws inside a test): posterior moments, adapted scales, tree invariants, reproducibility,
-stat consistency; plus an oracle comparison on a slice of the same run (first chains, first draws)."""
+stat consistency; plus, for every config, an ORACLE SLICE of the same full-size run: the first 4 chains followed one draw
+ahead (teacher forced, tests/test_gpu_teacher_forced.py) through the first draws of the warm-up and again late in the schedule,
+every draw and the whole adaptation state within 1e-9 with identical tree shapes."""
 import numpy as np
 import pytest
 
 from nuts_rs_b200 import _abi
+from test_gpu_teacher_forced import teacher_forced
 
 pytestmark = pytest.mark.gpu
 
@@ -139,3 +142,33 @@ def test_leapfrog_counter_matches_n_steps(L):
     assert done == 25 and after - before == int(stats["n_steps"].sum())
     S.close()
     m.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Oracle slices at full size: the GPU runs the whole BASELINE config (all chains resident / scheduled as in the bench), the
+# oracle follows chains 0..3 one draw ahead.  Two windows per config: the first draws of the warm-up (initial mass matrix, early
+# window switches, the step-size re-search) and a window late in the schedule that crosses the end of the tuning phase.
+# ---------------------------------------------------------------------------------------------------------------------------
+SLICES = {
+    "config2": dict(kind=_abi.NUTS_LOGP_GAUSS_DIAG, N=1024, d=1000, tune=400, early=24, late=(388, 24),
+                    mk=lambda d: dict(mu=0.5, sigma=np.exp(np.linspace(-1, 1, d)))),
+    "config3": dict(kind=_abi.NUTS_LOGP_FUNNEL, N=8192, d=10, tune=400, early=60, late=(380, 60), rtol=1e-8, knife=4,
+                    mk=lambda d: dict(funnel_scale=3.0)),
+    "config4": dict(kind=_abi.NUTS_LOGP_GAUSS_DIAG, N=256, d=10000, tune=1000, early=16, late=(990, 16),
+                    mk=lambda d: dict(mu=0.0, sigma=10.0 ** np.linspace(-3, 3, d))),
+    "config5": dict(kind=_abi.NUTS_LOGP_GAUSS_RANK1, N=8192, d=100, tune=400, early=24, late=(388, 24),
+                    mk=lambda d: dict(mu=0.0, rank1_scale=0.5)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SLICES))
+def test_oracle_slice_of_full_size_config(L, orc, name):
+    c = SLICES[name]
+    s = L.DiagNutsSettings(num_tune=c["tune"], seed=42)
+    kw = dict(rtol=c.get("rtol", 1e-9), max_knife_edge=c.get("knife", 1), oracle_chains=4)
+    mk = c["mk"](c["d"])
+    teacher_forced(L, orc, c["kind"], c["N"], c["d"], s, c["early"], 42, mk, **kw)
+    skip, n = c["late"]
+    stats = teacher_forced(L, orc, c["kind"], c["N"], c["d"], s, n, 42, mk, skip_draws=skip, **kw)
+    k = c["tune"] - skip
+    assert stats["tuning"][:k].all() and not stats["tuning"][k:].any()

@@ -171,3 +171,32 @@ def test_funnel_produces_divergences_and_depth_spread(orc):
     _, st = S.draw(400)
     assert st["diverging"].sum() > 0
     assert st["depth"].max() - st["depth"].min() >= 3
+
+
+def test_chain_state_round_trip_continues_bit_identically(orc):
+    """orc_sampler_get/set_chain_state (the injection point of the teacher-forced GPU tests): a sampler restored from the
+    complete chain state continues exactly like the one it was read from."""
+    d, N = 50, 3
+    s = _abi.default_settings()
+    s.num_tune = 60
+    s.maxdepth = 6
+    m = orc.Model(_abi.NUTS_LOGP_GAUSS_DIAG, d, mu=0.5, sigma=np.exp(np.linspace(-1, 1, d)))
+    x0 = np.random.default_rng(0).normal(size=(N, d))
+    a = orc.Sampler(m, s, seed=5, nchains=N)
+    a.set_position(x0)
+    a.draw(25)  # in the middle of the warm-up, after window switches and the step-size re-search
+    ckpt = a.chain_state()
+    da, sa = a.draw(50)
+    b = orc.Sampler(m, s, seed=5, nchains=N)
+    b.set_position(x0 + 1.0)
+    b.draw(3)
+    b.set_chain_state(ckpt)
+    db, sb = b.draw(50)
+    assert np.array_equal(da, db)
+    for k in sa:
+        if not k.startswith("_"):
+            assert np.array_equal(sa[k], sb[k]), k
+    fa, fb = a.chain_state(), b.chain_state()
+    for k in fa:
+        assert np.array_equal(fa[k], fb[k]), k
+    assert (fa["draw_count"] == 75).all() and (fa["tuning"] == 0).all()

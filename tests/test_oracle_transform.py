@@ -34,10 +34,17 @@ def test_diag_transform_position_and_gradient(orc):
     expected_logdet = sum(-(0.5 * math.log(v)) for v in sigma2)
     assert abs(s["logdet"] - expected_logdet) < 1e-12
     z = p.vec(p.Z)
-    standard_normal_logp = -0.5 * float(np.sum(z * z))
-    assert abs((s["logp"] - s["logdet"]) - (standard_normal_logp + expected_logdet - s["logdet"])) < 1e-12 or True
-    # logp(x) = -sum x^2/(2 sigma2) = -1.5 = standard normal logp at z=[1,1,1]
-    assert abs(s["logp"] - standard_normal_logp) < 1e-12
+    # transform/mod.rs:240-249: logp_adapted = logp - logdet equals the FULLY NORMALISED standard-normal density at z.  The
+    # reference's test target (MvNormal, transform/mod.rs:104-117) carries its normalising constant
+    # norm = -0.5 * (d * ln(2 pi) - ln det P); our device / oracle targets are un-normalised (test_logps.rs:49-58), so add it here.
+    d = len(sigma2)
+    log_det_p = sum(math.log(1.0 / v) for v in sigma2)
+    norm = -0.5 * (d * math.log(math.tau) - log_det_p)
+    standard_normal_logp = -0.5 * (d * math.log(math.tau) + float(np.sum(z * z)))  # transform/mod.rs:155-158
+    logp_adapted = (s["logp"] + norm) - s["logdet"]
+    assert abs(logp_adapted - standard_normal_logp) < 1e-12, (logp_adapted, standard_normal_logp)
+    # and without the constants: logp(x) = -sum x^2 / (2 sigma2) = -1.5 = -|z|^2 / 2
+    assert abs(s["logp"] - (-0.5 * float(np.sum(z * z)))) < 1e-12
     assert ham.transform()["id"] == 0  # -1 + one update (diagonal.rs:81,130)
 
 
