@@ -813,7 +813,15 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   S.mm_update_freq = a.mass_matrix_update_freq;
   S.mm_window_growth = a.mass_matrix_window_growth;
 
+  // persistent grid: one wave of resident CTAs
+  const int teams_per_cta = decoupled ? cfg->minb % 10 : cta_threads / cfg->tpc;  // decoupled tags end in the number of teams
+  const uint64_t ctas_needed = (ctx->N + teams_per_cta - 1) / teams_per_cta;
+  s->grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)blocks_per_sm * ctx->num_sms);
+  // NUTS_B200_GRID caps the persistent grid (tests / compute-sanitizer: forces draw migration between teams on small workloads)
+  if (const char* env = std::getenv("NUTS_B200_GRID")) s->grid = std::max(1, std::min(s->grid, std::atoi(env)));
+  s->teams_per_cta = teams_per_cta;
   const size_t plane = ctx->N * (size_t)P.ld * sizeof(double);
+  const size_t team_plane = (size_t)s->grid * teams_per_cta * (size_t)P.ld * sizeof(double);  // one row per resident team
   int r = NUTS_OK;
   auto A = [&](void** p, size_t bytes) {
     if (r == NUTS_OK) r = sampler_alloc(s, p, bytes);
@@ -827,8 +835,8 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   A((void**)&P.inv_stds, plane);
   A((void**)&P.mean, plane);
   A((void**)&P.est, plane * 8);
-  A((void**)&P.slots, plane * 2 * (size_t)P.P);
-  A((void**)&P.ends, plane * 3 * NB_END_BUFFERS);
+  A((void**)&P.slots, team_plane * 2 * (size_t)P.P);  // checkpoints live inside one draw on one team: pools per TEAM, not per chain
+  A((void**)&P.ends, team_plane * 3 * NB_END_BUFFERS);
   A((void**)&P.cs, ctx->N * sizeof(ChainState));
   A((void**)&P.queue, sizeof(unsigned int));
   A((void**)&P.done, ctx->N * sizeof(unsigned int));
@@ -856,13 +864,6 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
     c.alive = 0;
   }
   CUDA_TRY(cudaMemcpy(P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice));
-  // persistent grid: one wave of resident CTAs
-  const int teams_per_cta = decoupled ? cfg->minb % 10 : cta_threads / cfg->tpc;  // decoupled tags end in the number of teams
-  const uint64_t ctas_needed = (ctx->N + teams_per_cta - 1) / teams_per_cta;
-  s->grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)blocks_per_sm * ctx->num_sms);
-  // NUTS_B200_GRID caps the persistent grid (tests / compute-sanitizer: forces draw migration between teams on small workloads)
-  if (const char* env = std::getenv("NUTS_B200_GRID")) s->grid = std::max(1, std::min(s->grid, std::atoi(env)));
-  s->teams_per_cta = teams_per_cta;
   CUDA_TRY(cudaEventCreate(&s->ev0));
   CUDA_TRY(cudaEventCreate(&s->ev1));
   guard.dismiss();
@@ -1137,6 +1138,12 @@ int nuts_sampler_get_chain_state(nuts_sampler_t* s, const nuts_chain_state_t* o)
       if (est_out[bg][w])
         for (size_t c = 0; c < N; ++c) {
           const int set = bg ? 1 - cs[c].fg_set : cs[c].fg_set;
+          // an estimator without samples is a fresh RunningVariance (zeros, transform/adapt/diagonal.rs:24-30): after a window switch the
+          // engine just resets the count, the planes are overwritten by the first sample
+          if ((bg ? cs[c].bg_count : cs[c].fg_count) == 0) {
+            std::memset(est_out[bg][w] + c * ctx->d, 0, ctx->d * sizeof(double));
+            continue;
+          }
           CUDA_TRY(cudaMemcpyAsync(est_out[bg][w] + c * ctx->d, P.est + ((c * 2 + set) * 4 + w) * (size_t)P.ld, ctx->d * sizeof(double),
                                    cudaMemcpyDeviceToHost, ctx->stream));
         }

@@ -36,7 +36,7 @@ namespace nb {
 
 constexpr int MAX_DOUBLING_DEPTH = 19;  // deepest new half has 2^19 leaves (checkpoint pool: 3 per level + 6 <= MAX_SLOTS)
 constexpr int MAX_SLOTS = 64;
-constexpr int ACC_RING = 32;  // leaves whose acceptance statistics are evaluated together (one exp per lane)
+constexpr int ACC_RING = 32;  // leaves whose acceptance statistics are evaluated together (one exp per lane; = warp size)
 constexpr int NB_END_BUFFERS = 3;  // main-tree endpoint buffers per chain: left, right + one pending (decoupled engine)
 
 struct SettingsDev {
@@ -100,8 +100,8 @@ struct EngineParams {
   double *x, *gx, *z, *gz, *v0;     // chain point planes [N][ld]
   double *stds, *inv_stds, *mean;   // DiagMassMatrix planes [N][ld]
   double* est;                      // [N][2 sets][4: draw_mean, draw_var, grad_mean, grad_var][ld]
-  double* slots;                    // [N][P][2: z, v][ld]   leaf checkpoints of the half under construction
-  double* ends;                     // [N][NB_END_BUFFERS][3: z, v, grad_z][ld]   main-tree endpoints (v1: 0 left, 1 right)
+  double* slots;                    // [teams][P][2: z, v][ld]   leaf checkpoints of the half under construction (one pool per resident team)
+  double* ends;                     // [teams][NB_END_BUFFERS][3: z, v, grad_z][ld]   main-tree endpoints (v1: 0 left, 1 right)
   ChainState* cs;
   unsigned int* queue;              // persistent work-unit queue
   unsigned int* done;               // [N] work units (blocks of draws) of this launch each chain has completed
@@ -192,7 +192,8 @@ struct V2Ctl {
   unsigned long long acc_count, rng_out;
   int depth, draw_slot, draw_idx, reached_maxdepth, diverging;
   // leader lane's pending sub-trees, one per level (the leader is the only reader and writer)
-  double A_ls[V2_NT], A_draw_energy[V2_NT];
+  double A_ls[V2_NT], A_draw_energy[V2_NT];  // A_ls: linear weights (LeaderLane::lin) or log sizes
+  double A_log0;                              // log weight of the single leaf pending at level 0 (exact, for the switch to the log domain)
   int A_draw_idx[V2_NT];
   signed char A_first[V2_NT], A_last[V2_NT], A_draw[V2_NT];
   // vector side: first / last checkpoint slot of the pending sub-trees, one private copy per warp
@@ -210,6 +211,7 @@ struct MultiCtx {
   unsigned off_ctl;    // V2Ctl of the team
   unsigned off_ring;   // double [V2_K][W][V2_NV]
   int bar_id, warp;    // the team's named barrier, this warp's index inside the team
+  int pool;            // index of the team's checkpoint pool (blockIdx.x * teams per CTA + team)
 };
 
 // volatile load of a flag word in SHARED memory (a plain volatile access through a generic pointer would be a generic LD)
@@ -228,32 +230,29 @@ struct TreeTables {
   double A_ls[MAX_DOUBLING_DEPTH], A_draw_energy[MAX_DOUBLING_DEPTH];
   int A_draw_idx[MAX_DOUBLING_DEPTH];
   signed char A_first[MAX_DOUBLING_DEPTH], A_last[MAX_DOUBLING_DEPTH], A_draw[MAX_DOUBLING_DEPTH];
-  // deferred AcceptanceRateCollector: energy differences of the leaves not yet accumulated, and the batch of their statistics
-  double acc_diff[ACC_RING], acc_e[ACC_RING], acc_s[ACC_RING];
 };
 
-// Evaluate the acceptance statistics of the n pending leaves (TreeTables::acc_diff) and add them in leaf order.
+// Evaluate the acceptance statistics of the n pending leaves and add them in leaf order.  The batch lives in REGISTERS: lane k of
+// every warp of the team holds the energy difference of pending leaf k (`mine`), so each warp evaluates the whole batch on its own -
+// one exp per lane - and walks through it with shuffles: no shared memory, no traffic between the warps of a team.
 struct AccSums {
   double sum, sym, max_err;
 };
-static __device__ __noinline__ AccSums accept_batch(TreeTables* T, int n, double acc_sum, double acc_sym_sum, double max_energy_error) {
+static __device__ __noinline__ AccSums accept_batch(double mine, int n, double acc_sum, double acc_sym_sum, double max_energy_error) {
   const int lane = threadIdx.x & 31;
-  if (lane < n) {  // every warp of the team evaluates the whole batch (identical values; no cross-warp traffic)
-    const double diff = T->acc_diff[lane];
-    const double ed = exp(diff);
-    const double e = diff < 0. ? ed : 1.0;  // == exp(min(diff, 0)) bit for bit (diff is finite here), one exp instead of two
-    T->acc_e[lane] = e;
-    T->acc_s[lane] = 2. * e / (1. + ed);
+  double e = 0.0, s = 0.0;
+  if (lane < n) {
+    const double ed = accept_exp(mine);
+    e = mine < 0. ? ed : 1.0;  // == exp(min(diff, 0)) bit for bit (diff is finite here), one exp instead of two
+    s = 2. * e / (1. + ed);
   }
-  __syncwarp();
   AccSums r{acc_sum, acc_sym_sum, max_energy_error};
   for (int k = 0; k < n; ++k) {
-    r.sum += T->acc_e[k];
-    r.sym += T->acc_s[k];
-    const double diff = T->acc_diff[k];
+    r.sum += __shfl_sync(0xffffffffu, e, k);
+    r.sym += __shfl_sync(0xffffffffu, s, k);
+    const double diff = __shfl_sync(0xffffffffu, mine, k);
     if (fabs(diff) > fabs(r.max_err)) r.max_err = diff;
   }
-  __syncwarp();  // the batch is consumed before any lane records the next leaf
   return r;
 }
 
@@ -315,7 +314,11 @@ struct Engine {
   uint64_t acc_count;
 
   // ---- main tree ----
+  // Tree weights: linear domain (`lin`, see device_common.cuh): ls_main = sum of exp(-energy error) over the main tree's leaves,
+  // TreeTables::A_ls[l >= 1] the same for the pending sub-trees, A_ls[0] the LOG weight of a single pending leaf (two leaves are
+  // exponentiated together when they merge).  Reference log domain (!lin): log_size everywhere.
   double ls_main;
+  bool lin;
   int depth;
   int idx_left, idx_right;                 // index_in_trajectory of the two ends
   bool init_left, init_right;              // the end still is the initial point
@@ -335,7 +338,8 @@ struct Engine {
   __device__ __forceinline__ Engine(const EngineParams& p, int chain_, int tid_, double* scratch, double* team_smem, TreeTables& tables,
                                     const MultiCtx* mc_ = nullptr)
       : P(p), chain(chain_), tid(tid_), red(scratch), mc(mc_), d(p.d), ld(p.ld), row((size_t)chain_ * p.ld),
-        slots_base(p.slots + (size_t)chain_ * p.P * 2 * p.ld), ends_base(p.ends + (size_t)chain_ * NB_END_BUFFERS * 3 * p.ld), sm_sig(team_smem),
+        slots_base(p.slots + (size_t)pool_index(mc_) * p.P * 2 * p.ld), ends_base(p.ends + (size_t)pool_index(mc_) * NB_END_BUFFERS * 3 * p.ld),
+        sm_sig(team_smem),
         sm_mu(team_smem + (MMS ? TPC * EPT : 0)), sm_mmu(team_smem + (MMS ? 2 : 0) * TPC * EPT),
         sm_mprec(team_smem + ((MMS ? 2 : 0) + (MODS ? 1 : 0)) * TPC * EPT),
         sm_g(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0)) * TPC * EPT), T(tables) {
@@ -355,6 +359,13 @@ struct Engine {
   V2Ctl* v2_ctl;    // MULTI only
   double* v2_ring;
   int v2_warp;
+  // Checkpoints and end buffers only live inside one draw, which runs on one team from start to end (draw_finish materialises the
+  // chain point into the x / z planes): the pools belong to the resident TEAM, not to the chain (EngineParams::slots / ends are
+  // sized grid * teams per CTA).
+  static __device__ __forceinline__ int pool_index(const MultiCtx* m) {
+    if (MULTI) return m->pool;
+    return (int)blockIdx.x * ((int)blockDim.x / TPC) + (int)threadIdx.x / TPC;
+  }
   __device__ __forceinline__ double sg(int j) const { return MMS ? sm_sig[tid + j * TPC] : sig[MMS ? 0 : j]; }
   __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[tid + j * TPC] : mu[MMS ? 0 : j]; }
   // model parameters of element i = tid + j*TPC
@@ -866,13 +877,13 @@ struct Engine {
   // difference; ACC_RING of them are evaluated together - one exp per lane - and then added in leaf order, so the sums are
   // bit-identical to the reference's sequential accumulation.
   int acc_pending = 0;
+  double acc_mine = 0.0;  // energy difference of pending leaf (lane & 31)
   __device__ __forceinline__ void register_leapfrog(double energy, bool divergent) {
     if (divergent) {
       flush_accept();
       max_energy_error = -INFINITY;
     } else {
-      // every thread of the team stores the same value: a thread reads back what it (also) wrote, no barrier needed here
-      T.acc_diff[acc_pending] = E0 - energy;
+      if ((int)(threadIdx.x & 31) == acc_pending) acc_mine = E0 - energy;
       acc_pending += 1;
       if (acc_pending == ACC_RING) flush_accept();
     }
@@ -881,11 +892,24 @@ struct Engine {
   __device__ __forceinline__ void flush_accept() {
     if (acc_pending == 0) return;
     // by value: a member function that is not inlined would take `this` and pin the whole engine in local memory
-    const AccSums r = accept_batch(&T, acc_pending, acc_sum, acc_sym_sum, max_energy_error);
+    const AccSums r = accept_batch(acc_mine, acc_pending, acc_sum, acc_sym_sum, max_energy_error);
     acc_sum = r.sum;
     acc_sym_sum = r.sym;
     max_energy_error = r.max_err;
     acc_pending = 0;
+  }
+
+  // Leave the linear domain for the rest of this draw (a leaf weight could overflow / underflow): the pending sub-trees of the
+  // half under construction (levels = the set bits of the leaf index i; level 0 is a log weight already) and the main tree.
+  __device__ __forceinline__ void weights_to_log_domain(uint32_t i) {
+    lin = false;
+    ls_main = log(ls_main);
+    tsync();
+    if (tid == 0)
+      for (int l = 1; l < MAX_DOUBLING_DEPTH; ++l)
+        if ((i >> l) & 1u) T.A_ls[l] = log(T.A_ls[l]);
+    tsync();
+    if (TPC > 32) red.barrier();
   }
 
   // ------------------------------------------------------------------ NutsTree::extend for the MAIN tree (nuts.rs:108-170)
@@ -896,6 +920,7 @@ struct Engine {
   // is also the reference's RNG order.  An inner Turning / Diverging discards the whole half (nuts.rs:131-136).
   __device__ __forceinline__ int extend(int dir, bool check) {
     NB_T0(tq);
+    tsync();  // warp teams: every lane has finished reading the tables of the previous doubling
     const int D = depth;
     const uint32_t nleaf = 1u << D;
     const double eps = dir ? hs_step : -hs_step;
@@ -1001,11 +1026,12 @@ struct Engine {
       rc_add(s, 3);  // roles: first-of-B, draw-of-B, last-of-B (the newest leaf)
       B_first = s;
       B_draw = s;
-      B_ls = -energy_error;
+      B_ls = -energy_error;  // log weight of the leaf
       B_draw_energy = energy;
       B_draw_idx = idx_cur;
       int t = __ffs(~i) - 1;  // trailing ones of i
       if (t > D) t = D;
+      if (lin && fabs(B_ls) > LIN_WEIGHT_LIMIT) weights_to_log_domain(i);  // rare: the weight could leave the double range
       NB_ACC(2, tq);
       for (int l = 0; l < t; ++l) {
         const int Af = T.A_first[l], Al = T.A_last[l];
@@ -1017,8 +1043,22 @@ struct Engine {
                                     slot_ptr(B_first, 1), l > 0, dir);
         }
         // merge_into, non-main (nuts.rs:172-207): self_log_size = log_size of the merged tree
-        double total = logaddexp(T.A_ls[l], B_ls);
-        bool take_B = (B_ls >= total) || (rng_f64() < exp(B_ls - total));
+        double total;
+        bool take_B;
+        if (lin) {
+          double WA = T.A_ls[l], WB = B_ls;
+          if (l == 0) {  // two single leaves: both exponentials in one basic block
+            WA = exp_small(WA);
+            WB = exp_small(WB);
+          }
+          total = WA + WB;
+          // P(draw from B) = WB / (WA + WB); the reference's `other.log_size >= log_size` shortcut only exists for WA << WB
+          if (WA >= WB * 0x1p-40) take_B = rng_f64() * total < WB;
+          else take_B = lin_reference_shortcut(WA, WB) || (rng_f64() * total < WB);
+        } else {
+          total = logaddexp(T.A_ls[l], B_ls);
+          take_B = (B_ls >= total) || (rng_f64() < exp(B_ls - total));
+        }
         if (take_B) {
           unref(T.A_draw[l]);
         } else {
@@ -1051,8 +1091,16 @@ struct Engine {
     if (check) {
       turning = merge_turning(farZ, farV, nearZ, nearV, slot_ptr(B_first, 0), slot_ptr(B_first, 1), D > 0, dir);
     }
-    double total = logaddexp(ls_main, B_ls);
-    bool take = (B_ls >= ls_main) || (rng_f64() < exp(B_ls - ls_main));  // is_main: self_log_size = old log_size
+    double total;
+    bool take;  // is_main: self_log_size = old log_size (nuts.rs:190)
+    if (lin) {
+      const double WB = D == 0 ? exp_small(B_ls) : B_ls;  // a single leaf still carries its log weight
+      take = (WB >= ls_main) || (rng_f64() * ls_main < WB);
+      total = ls_main + WB;
+    } else {
+      total = logaddexp(ls_main, B_ls);
+      take = (B_ls >= ls_main) || (rng_f64() < exp(B_ls - ls_main));
+    }
     if (take) {
       draw_slot = B_draw;
       draw_energy = B_draw_energy;
@@ -1400,8 +1448,9 @@ struct Engine {
     NB_T0(tw);
     draw_begin();
     NB_ACC(0, td);
-    // NutsTree::new (nuts.rs:94-105)
-    ls_main = 0.;
+    // NutsTree::new (nuts.rs:94-105): log_size 0 = weight 1
+    lin = true;
+    ls_main = 1.;
     depth = 0;
     idx_left = idx_right = 0;
     init_left = init_right = true;

@@ -68,8 +68,9 @@ struct LeaderLane {
   // AcceptanceRateCollector
   double acc_sum, acc_sym_sum, max_ee;
   uint64_t acc_count;
-  // main tree
+  // main tree (weights: linear domain while `lin`, see device_common.cuh; the reference's log sizes otherwise)
   double ls_main, draw_energy;
+  bool lin;
   int depth, idx_left, idx_right, draw_slot, draw_idx;
   int end_slot_left, end_slot_right;  // checkpoint slots that hold the two ends of the main tree (-1: the initial point)
   uint64_t free_mask, rc_lo, rc_hi;
@@ -105,19 +106,30 @@ struct LeaderLane {
     return t;
   }
 
-  // AcceptanceRateCollector::register_leapfrog (dual_avg.rs:131-158)
-  __device__ __forceinline__ void register_leapfrog(double energy, bool divergent) {
+  // AcceptanceRateCollector::register_leapfrog (dual_avg.rs:131-158); returns exp(E0 - energy) = the leaf's linear weight
+  __device__ __forceinline__ double register_leapfrog(double energy, bool divergent) {
+    double ed = 0.;
     if (divergent) {
       max_ee = -INFINITY;
     } else {
       double diff = E0 - energy;
-      const double ed = exp(diff);
+      ed = accept_exp(diff);
       const double e = diff < 0. ? ed : 1.0;
       acc_sum += e;
       acc_sym_sum += 2. * e / (1. + ed);
       if (fabs(diff) > fabs(max_ee)) max_ee = diff;
     }
     acc_count += 1;
+    return ed;
+  }
+  __device__ __forceinline__ double next_f64() { return v2_stream_f64(P.seed, stream, rng++); }
+  // leave the linear domain for the rest of this draw (chain_engine.cuh weights_to_log_domain): pending levels = set bits of i
+  __device__ __forceinline__ void weights_to_log_domain() {
+    lin = false;
+    ls_main = log(ls_main);
+    if (i & 1u) c.A_ls[0] = c.A_log0;
+    for (int l = 1; l < V2_NT; ++l)
+      if ((i >> l) & 1u) c.A_ls[l] = log(c.A_ls[l]);
   }
 
   __device__ __forceinline__ void command(int kind, int accepted) {
@@ -199,7 +211,8 @@ struct LeaderLane {
     acc_sym_sum = 0.;
     acc_count = 0;
     max_ee = 0.;
-    ls_main = 0.;
+    lin = true;
+    ls_main = 1.;  // log_size 0
     depth = 0;
     idx_left = idx_right = 0;
     draw_slot = -1;
@@ -244,7 +257,7 @@ struct LeaderLane {
     const double energy = ke_new - (logp_new + pt_logdet);
     const double energy_error = energy - E0;
     const bool divergent = (energy_error > P.s.max_energy_error) | !isfinite(energy_error);
-    register_leapfrog(energy, divergent);
+    const double leaf_w = register_leapfrog(energy, divergent);
     if (divergent) {
       doubling_done(EXT_DIVERGING, 0);
       return;
@@ -253,7 +266,9 @@ struct LeaderLane {
     const int s = c.slot_ring[i & 7];
     rc_add(s, 3);  // roles: first-of-B, draw-of-B, last-of-B (the newest leaf)
     int B_first = s, B_draw = s, B_draw_idx = idx_cur;
-    double B_ls = -energy_error, B_draw_energy = energy;
+    const double leaf_ls = -energy_error;  // log weight of the leaf
+    if (lin && fabs(leaf_ls) > LIN_WEIGHT_LIMIT) weights_to_log_domain();
+    double B_ls = lin ? leaf_w : leaf_ls, B_draw_energy = energy;
     int t = __ffs(~i) - 1;
     if (t > D) t = D;
     int g = 0;
@@ -271,10 +286,19 @@ struct LeaderLane {
         }
       }
       // merge_into, non-main (nuts.rs:172-207): self_log_size = log_size of the merged tree
-      const V2Merge mg = v2_merge_into(c.A_ls[l], B_ls, false, P.seed, stream, rng);
-      rng += (uint64_t)mg.consumed;
-      const bool take_B = mg.take_other != 0;
-      const double total = mg.total;
+      bool take_B;
+      double total;
+      if (lin) {  // same arithmetic as chain_engine.cuh extend()
+        const double WA = c.A_ls[l], WB = B_ls;
+        total = WA + WB;
+        if (WA >= WB * 0x1p-40) take_B = next_f64() * total < WB;
+        else take_B = lin_reference_shortcut(WA, WB) || (next_f64() * total < WB);
+      } else {
+        const V2Merge mg = v2_merge_into(c.A_ls[l], B_ls, false, P.seed, stream, rng);
+        rng += (uint64_t)mg.consumed;
+        take_B = mg.take_other != 0;
+        total = mg.total;
+      }
       if (take_B) {
         unref(c.A_draw[l]);
       } else {
@@ -296,6 +320,7 @@ struct LeaderLane {
       c.A_first[t] = (signed char)B_first;
       c.A_last[t] = (signed char)s;  // the last-of-B reference moves to the pending sub-tree
       c.A_ls[t] = B_ls;
+      if (t == 0) c.A_log0 = leaf_ls;
       c.A_draw[t] = (signed char)B_draw;
       c.A_draw_energy[t] = B_draw_energy;
       c.A_draw_idx[t] = B_draw_idx;
@@ -313,10 +338,17 @@ struct LeaderLane {
       turning = v2_turn_eval(val(e, o), val(e, o + 1), dir);
       if (D > 0) turning = turning | v2_turn_eval(val(e, o + 2), val(e, o + 3), dir) | v2_turn_eval(val(e, o + 4), val(e, o + 5), dir);
     }
-    const V2Merge mg = v2_merge_into(ls_main, B_ls, true, P.seed, stream, rng);  // is_main: self_log_size = old log_size
-    rng += (uint64_t)mg.consumed;
-    const bool take = mg.take_other != 0;
-    const double total = mg.total;
+    bool take;  // is_main: self_log_size = old log_size
+    double total;
+    if (lin) {
+      take = (B_ls >= ls_main) || (next_f64() * ls_main < B_ls);
+      total = ls_main + B_ls;
+    } else {
+      const V2Merge mg = v2_merge_into(ls_main, B_ls, true, P.seed, stream, rng);
+      rng += (uint64_t)mg.consumed;
+      take = mg.take_other != 0;
+      total = mg.total;
+    }
     if (take) {
       draw_slot = B_draw;
       draw_energy = B_draw_energy;
@@ -461,6 +493,7 @@ __global__ void NB_KERNEL_BOUNDS(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(cons
   mc.off_ctl = (unsigned)(L::off_ctl + (size_t)team * L::ctl_bytes);
   mc.off_ring = (unsigned)(L::off_ring + (size_t)team * L::ring_bytes);
   mc.bar_id = 1 + team;
+  mc.pool = (int)blockIdx.x * C + team;
   mc.warp = (warp - NL) % W;
   unsigned cmd_seen = 0;
   // work units as in nuts_chain_kernel: one chain for set_position, ONE DRAW of one chain (draw-major) for draws

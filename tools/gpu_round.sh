@@ -1,12 +1,14 @@
 #!/bin/bash
-# One GPU visit.  Usage: tools/gpu_round.sh TAG [what...]   what = tests | tf | bench | ref | ncu | configs | sanitize   (default: tests bench)
+# One GPU visit.  Usage: tools/gpu_round.sh TAG [what...]
+#   what = tests | tf | engines | bench | ref | ncu | configs | v2 | sanitize | phase        (default: tests bench)
 TAG=${1:-r2x}; shift
 WHAT=${@:-tests bench}
 export PYTHONDONTWRITEBYTECODE=1
 mkdir -p gpurun_out
 for w in $WHAT; do
   case $w in
-    tf) timeout 1500 python -m pytest tests/test_gpu_teacher_forced.py -x -q > gpurun_out/pytest_tf_$TAG.log 2>&1; echo "tf rc=$?"; tail -15 gpurun_out/pytest_tf_$TAG.log;;
+    tf) timeout 1500 python -m pytest tests/test_gpu_teacher_forced.py -q > gpurun_out/pytest_tf_$TAG.log 2>&1; echo "tf rc=$?"; tail -15 gpurun_out/pytest_tf_$TAG.log;;
+    engines) timeout 1500 python -m pytest tests/test_gpu_engines.py tests/test_gpu_sampler.py -x -q > gpurun_out/pytest_eng_$TAG.log 2>&1; echo "engines rc=$?"; tail -8 gpurun_out/pytest_eng_$TAG.log;;
     tests) timeout 2400 python -m pytest tests -m gpu -x -q --durations=15 > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_$TAG.log;;
     bench) timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err;;
     ref) timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_ref_$TAG.json;;
@@ -14,6 +16,8 @@ for w in $WHAT; do
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1; echo "ncu list rc=$?"
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 3 -c 1 -f -o gpurun_out/prof_$TAG python tools/prof_run.py > gpurun_out/prof_$TAG.log 2>&1; echo "ncu full rc=$?"; tail -2 gpurun_out/prof_$TAG.log;;
     configs) for c in c2 c3 c4 c5; do timeout 300 python tools/quick.py $c 2>&1 | tail -1; done | tee gpurun_out/configs_$TAG.log;;
+    v2) for e in 64,16,107; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/v2_$TAG.log;;
+    phase) NUTS_B200_LIB=$PWD/nuts_rs_b200/libnuts_b200_phase.so timeout 300 python tools/phase_timing.py 2>&1 | tee gpurun_out/phase_$TAG.log;;
     sanitize)
       for c in c1 migrate large funnel rank1; do
         for tool in racecheck memcheck; do
