@@ -1244,6 +1244,43 @@ int nuts_sampler_set_chain_state(nuts_sampler_t* s, const nuts_chain_state_t* in
   return NUTS_OK;
 }
 
+// test hook: the branch-free division / square root of device_common.cuh next to the library operators, element by element
+// (tests/test_gpu_primitives.py checks bit-equality wherever the range test `ok` holds).  Host arrays of n doubles.
+__global__ void k_debug_fast_math(const double* a, const double* b, double* q_fast, double* q_ref, double* r_fast, double* r_ref,
+                                  unsigned char* ok_div, unsigned char* ok_sqrt, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool okd = true, oks = true;
+  q_fast[i] = div_fast(a[i], b[i], okd);
+  q_ref[i] = a[i] / b[i];
+  r_fast[i] = sqrt_fast(a[i], oks);
+  r_ref[i] = sqrt(a[i]);
+  ok_div[i] = okd;
+  ok_sqrt[i] = oks;
+}
+extern "C" int nuts_debug_fast_math(const double* a, const double* b, double* q_fast, double* q_ref, double* r_fast, double* r_ref,
+                                    uint8_t* ok_div, uint8_t* ok_sqrt, uint64_t n) {
+  TRY(check_device());
+  double* d[6] = {};
+  unsigned char* u[2] = {};
+  int rc = NUTS_OK;
+  for (int k = 0; k < 6 && rc == NUTS_OK; ++k) rc = dev_alloc(&d[k], n);
+  for (int k = 0; k < 2 && rc == NUTS_OK; ++k) rc = dev_alloc(&u[k], n);
+  if (rc == NUTS_OK && (cudaMemcpy(d[0], a, n * 8, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(d[1], b, n * 8, cudaMemcpyHostToDevice) != cudaSuccess))
+    rc = fail(NUTS_ERR_CUDA, "nuts_debug_fast_math: H2D failed");
+  if (rc == NUTS_OK) {
+    k_debug_fast_math<<<(unsigned)((n + 255) / 256), 256>>>(d[0], d[1], d[2], d[3], d[4], d[5], u[0], u[1], n);
+    double* out[4] = {q_fast, q_ref, r_fast, r_ref};
+    for (int k = 0; k < 4; ++k)
+      if (cudaMemcpy(out[k], d[2 + k], n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(NUTS_ERR_CUDA, "nuts_debug_fast_math: D2H failed");
+    if (cudaMemcpy(ok_div, u[0], n, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(ok_sqrt, u[1], n, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = fail(NUTS_ERR_CUDA, "nuts_debug_fast_math: D2H failed");
+  }
+  for (double* p : d) cudaFree(p);
+  for (unsigned char* p : u) cudaFree(p);
+  return rc;
+}
+
 // debug: per-phase clock totals of NB_PHASE_TIMING builds (zeros otherwise); resets the counters
 extern "C" int nuts_debug_phase_clocks(nuts_sampler_t* s, unsigned long long* out8) {
   CUDA_TRY(cudaSetDevice(s->ctx->device));

@@ -779,6 +779,47 @@ struct Engine {
     }
   }
 
+  // Large tiles of the decoupled engine (dim ~ 10^4: z and v alone fill 2/3 of the thread's registers): the once-per-draw vector
+  // code must not hold further vectors in registers - unrolled over EPT elements it spilled 2.3 KB per thread, and that local
+  // traffic (L1 is carved out for shared memory) was 1.4 x the checkpoint traffic of the whole draw.  ROLL: those passes run as
+  // rolled loops from and to the global planes, CH elements in flight per thread; the gradient of the chain point stays in its
+  // plane (the first half-step of a doubling reads it from there).
+  static constexpr bool ROLL = MULTI && EPT > 16 && MODEL == LOGP_GAUSS_DIAG;
+  __device__ __forceinline__ double model_mu_at(int i) const { return MSH ? sm_mmu[i] : __ldg(P.model.mu + i); }
+  __device__ __forceinline__ double model_prec_at(int i) const { return MSH ? sm_mprec[i] : __ldg(P.model.prec + i); }
+  // whiten_from_planes() from plane to plane (x, gx -> z, gz); sigma / mean are in shared memory (SM_MASS)
+  __device__ __forceinline__ bool whiten_planes_rolled() {
+    const double *xp = P.x + row, *gp = P.gx + row, *ip = P.inv_stds + row;
+    double *zp = P.z + row, *gzp = P.gz + row;
+    double bad[1] = {0.0};
+#pragma unroll 1
+    for (int j0 = 0; j0 < EPT; j0 += CH) {
+      double x[CH], gx[CH], is[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int i = tid + (j0 + q) * TPC;
+        const bool live = (j0 + q < EPT) && i < d;
+        x[q] = live ? xp[i] : 0.0;
+        gx[q] = live ? gp[i] : 0.0;
+        is[q] = live ? ip[i] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int i = tid + (j0 + q) * TPC;
+        if ((j0 + q < EPT) && i < d) {
+          const double t = fma(-1.0, sm_mu[i], x[q]);  // axpy_out(mean, x, -1)
+          const double zz = is[q] * t;                 // multiply_inplace(z, inv_stds): out = x*out
+          const double gg = gx[q] * sm_sig[i];
+          if (!(isfinite(zz) && isfinite(gg) && (gg != 0.0) && isfinite(gx[q]) && isfinite(x[q]))) bad[0] = 1.0;
+          zp[i] = zz;
+          gzp[i] = gg;
+        }
+      }
+    }
+    red.allreduce(bad);
+    return bad[0] == 0.0;
+  }
+
   // compute_transformed_position / _gradient (diagonal.rs:233-246, 258-265) of the chain point from the x, gx planes
   // into the z, g registers; also refreshes the z / gz planes.  Returns check_all() (transformed_hamiltonian.rs:310-324).
   __device__ __forceinline__ bool whiten_from_planes() {
@@ -1216,99 +1257,149 @@ struct Engine {
     return true;
   }
 
-  // ------------------------------------------------------------------ RunningVariance::add_sample x4 (transform/adapt/diagonal.rs:32-44,134-141)
-  // Operands are loaded in batches (all loads of a vector pass issued before the first store): the compiler may not move a load of
-  // one estimator plane above a store to another one, and a read-modify-write per element would serialise 64 global round trips.
-  __device__ __forceinline__ void add_sample_set(int set, uint64_t new_count, const double (&x)[EPT], const double (&gx)[EPT]) {
-    double* dm = est_ptr(set, 0);
-    double* dv = est_ptr(set, 1);
-    double* gm = est_ptr(set, 2);
-    double* gv = est_ptr(set, 3);
-    if (new_count == 1) {
-#pragma unroll
-      for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
-        if (i < d) {
-          dm[i] = x[j];
-          dv[i] = 0.0;
-          gm[i] = gx[j];
-          gv[i] = 0.0;
-        }
-      }
-    } else {
-      const double scale = 1.0 / (double)new_count;
-      double m0[EPT], q0[EPT], m1[EPT], q1[EPT];
-      load(dm, m0);
-      load(dv, q0);
-      load(gm, m1);
-      load(gv, q1);
-#pragma unroll
-      for (int j = 0; j < EPT; ++j) {
-        // array_update_variance (cpu_math.rs:605-631): both terms use the OLD mean
-        const double diff = x[j] - m0[j];
-        m0[j] = m0[j] + diff * scale;
-        q0[j] = q0[j] + diff * diff;
-        const double diff1 = gx[j] - m1[j];
-        m1[j] = m1[j] + diff1 * scale;
-        q1[j] = q1[j] + diff1 * diff1;
-      }
-      store(dm, m0);
-      store(dv, q0);
-      store(gm, m1);
-      store(gv, q1);
+  // ------------------------------------------------------------------ the vector work of GlobalStrategy::adapt in ONE pass
+  // RunningVariance::add_sample x4 (transform/adapt/diagonal.rs:32-44,134-141; array_update_variance cpu_math.rs:605-631) and
+  // Strategy::adapt -> DiagMassMatrix::update_diag_draw_grad / update_diag_draw (transform/diagonal.rs:85-131,
+  // cpu_math.rs:633-708) share their operands: the mass matrix is computed from the estimator values this draw has just updated.
+  //   upd:      add the draw's (x, grad_x) to estimator sets 0 and 1, whose counts become n0 / n1 (count 1 = first sample)
+  //   do_mm:    update stds / inv_stds / mean / logdet from set `mm_set` (the foreground set AFTER a window switch)
+  // The elements of a thread are processed in chunks of CH: all loads of a chunk are issued before its first store (the compiler
+  // may not move a load of one plane above a store to another), and the 2 divisions + 3 square roots per element run through the
+  // branch-free fast paths of device_common.cuh so that the CH dependency chains interleave - with the library operators every
+  // call ends in a slow-path branch and the elements of a thread run one after the other (the round-1 tuning phase spent 58 k of
+  // its 100 k adaptation cycles per draw there).  sum ln(inv_std) is accumulated as ln(product) per chunk: one log instead of CH.
+  static constexpr int CH = EPT < 4 ? EPT : 4;
+  static __device__ __noinline__ void mass_matrix_element_slow(double dv, double gv, double scale, bool grad_based, double& s_new, double& is_new) {
+    double val = grad_based ? sqrt(dv / gv) : dv * scale;  // cpu_math.rs:695 / :658
+    if (!((!isfinite(val)) | (val == 0.0))) {               // fill_invalid = None: leave untouched
+      val = clampd(val, 1e-20, 1e20);
+      s_new = sqrt(val);
+      is_new = sqrt(1.0 / val);
     }
   }
-
-  // Strategy::adapt (transform/adapt/diagonal.rs:161-196) -> DiagMassMatrix::update_diag_draw_grad / update_diag_draw
-  __device__ __forceinline__ bool mass_matrix_adapt() {
-    if (cs.fg_count < 3) return false;
-    const int set = cs.fg_set;
+  __device__ __forceinline__ void adapt_vector_pass(bool upd, uint64_t n0, uint64_t n1, int mm_set, bool do_mm, uint64_t fg_count) {
+    const double* xp = P.x + row;
+    const double* gp = P.gx + row;
     double* sd = P.stds + row;
     double* isd = P.inv_stds + row;
     double* mn = P.mean + row;
+    const uint64_t nn[2] = {n0, n1};
+    const double sc[2] = {1.0 / (double)n0, 1.0 / (double)n1};
+    const double mscale = 1.0 / (double)fg_count;
+    const bool grad_based = P.s.use_grad_based != 0;
     double ld[1] = {0.0};
-    const double scale = 1.0 / (double)cs.fg_count;
-    double s_new[EPT];
-    {
-      double dv[EPT], gv[EPT], is_new[EPT];
-      load(est_ptr(set, 1), dv);
-      load(est_ptr(set, 3), gv);
-      load(sd, s_new);
-      load(isd, is_new);
+#pragma unroll 1
+    for (int j0 = 0; j0 < EPT; j0 += CH) {
+      double x[CH], gx[CH], e[2][4][CH], s_new[CH], is_new[CH];
+      bool live[CH];
+      // ---- every load of the chunk
 #pragma unroll
-      for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
-        if (i < d) {
-          double val = P.s.use_grad_based ? sqrt(dv[j] / gv[j]) : dv[j] * scale;  // cpu_math.rs:695 / :658
-          if (!((!isfinite(val)) | (val == 0.0))) {                               // fill_invalid = None: leave untouched
-            val = clampd(val, 1e-20, 1e20);
-            s_new[j] = sqrt(val);
-            is_new[j] = sqrt(1.0 / val);
+      for (int q = 0; q < CH; ++q) {
+        const int i = tid + (j0 + q) * TPC;
+        live[q] = (j0 + q < EPT) && (i < d);
+        x[q] = (upd && live[q]) ? xp[i] : 0.0;
+        gx[q] = (upd && live[q]) ? gp[i] : 0.0;
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+          const bool need = (upd && nn[st] > 1) || (do_mm && st == mm_set);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) e[st][w][q] = (need && live[q]) ? est_ptr(st, w)[i] : 0.0;
+        }
+        s_new[q] = (do_mm && live[q]) ? sd[i] : 0.0;
+        is_new[q] = (do_mm && live[q]) ? isd[i] : 1.0;
+      }
+      // ---- RunningVariance::add_sample for the four estimators of both sets
+      if (upd) {
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+          if (nn[st] == 1) {
+#pragma unroll
+            for (int q = 0; q < CH; ++q) {
+              e[st][0][q] = x[q];
+              e[st][1][q] = 0.0;
+              e[st][2][q] = gx[q];
+              e[st][3][q] = 0.0;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < CH; ++q) {
+              // array_update_variance (cpu_math.rs:605-631): both terms use the OLD mean
+              const double diff = x[q] - e[st][0][q];
+              e[st][0][q] = e[st][0][q] + diff * sc[st];
+              e[st][1][q] = e[st][1][q] + diff * diff;
+              const double diff1 = gx[q] - e[st][2][q];
+              e[st][2][q] = e[st][2][q] + diff1 * sc[st];
+              e[st][3][q] = e[st][3][q] + diff1 * diff1;
+            }
           }
-          ld[0] += log(is_new[j]);            // array_sum_ln(inv_stds)
-        }
-      }
-      store(sd, s_new);
-      store(isd, is_new);
-    }
-    {
-      double dm[EPT], gm[EPT];
-      load(est_ptr(set, 0), dm);
-      if (P.s.use_grad_based) {
-        load(est_ptr(set, 2), gm);
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-          const double var = s_new[j] * s_new[j];  // array_mult(stds, stds, var)
-          const double m = var * gm[j];             // array_mult(var, grad_mean, mean)
-          dm[j] = fma(1.0, dm[j], m);               // axpy(draw_mean, mean, 1.0)
+          for (int q = 0; q < CH; ++q) {
+            const int i = tid + (j0 + q) * TPC;
+            if (live[q]) {
+#pragma unroll
+              for (int w = 0; w < 4; ++w) est_ptr(st, w)[i] = e[st][w][q];
+            }
+          }
         }
       }
-      store(mn, dm);
+      // ---- DiagMassMatrix::update_diag_draw_grad / update_diag_draw from set mm_set
+      if (do_mm) {
+        bool ok = true;
+        double cand_s[CH], cand_is[CH];
+        bool valid[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const double dv = mm_set ? e[1][1][q] : e[0][1][q], gv = mm_set ? e[1][3][q] : e[0][3][q];
+          double val = grad_based ? sqrt_fast(div_fast(dv, gv, ok), ok) : dv * mscale;  // cpu_math.rs:695 / :658
+          valid[q] = !((!isfinite(val)) | (val == 0.0));                               // fill_invalid = None: leave untouched
+          val = clampd(val, 1e-20, 1e20);
+          cand_s[q] = sqrt_fast(val, ok);
+          cand_is[q] = sqrt_fast(div_fast(1.0, val, ok), ok);
+        }
+        // the range tests only speak for operands that are used: an invalid val (NaN, inf, 0) fails them by construction
+        bool all_ok = true;
+#pragma unroll
+        for (int q = 0; q < CH; ++q) all_ok = all_ok & (!live[q] | !valid[q] | ok);
+        if (all_ok) {
+#pragma unroll
+          for (int q = 0; q < CH; ++q)
+            if (valid[q]) {
+              s_new[q] = cand_s[q];
+              is_new[q] = cand_is[q];
+            }
+        } else {  // denormal / huge operands somewhere in the chunk: the library operators, element by element
+#pragma unroll 1
+          for (int q = 0; q < CH; ++q) {
+            const double dv = mm_set ? e[1][1][q] : e[0][1][q], gv = mm_set ? e[1][3][q] : e[0][3][q];
+            if (live[q]) mass_matrix_element_slow(dv, gv, mscale, grad_based, s_new[q], is_new[q]);
+          }
+        }
+        double prod = 1.0;  // inv_std in [1e-10, 1e10] after the clamp (or the initial 1 / sqrt|grad| clamp): no overflow for CH <= 4
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const int i = tid + (j0 + q) * TPC;
+          const double dm = mm_set ? e[1][0][q] : e[0][0][q], gm = mm_set ? e[1][2][q] : e[0][2][q];
+          double mean = dm;
+          if (grad_based) {
+            const double var = s_new[q] * s_new[q];  // array_mult(stds, stds, var)
+            const double m = var * gm;               // array_mult(var, grad_mean, mean)
+            mean = fma(1.0, dm, m);                  // axpy(draw_mean, mean, 1.0)
+          }
+          if (live[q]) {
+            sd[i] = s_new[q];
+            isd[i] = is_new[q];
+            mn[i] = mean;
+            prod *= is_new[q];
+          }
+        }
+        ld[0] += log(prod);  // array_sum_ln(inv_stds)
+      }
     }
-    red.allreduce(ld);
-    hs_mm_logdet = ld[0];
-    hs_mm_id += 1;
-    return true;
+    if (do_mm) {
+      red.allreduce(ld);
+      hs_mm_logdet = ld[0];
+      hs_mm_id += 1;
+    }
   }
 
   // ------------------------------------------------------------------ GlobalStrategy::adapt (adapt_strategy.rs:121-222)
@@ -1329,17 +1420,12 @@ struct Engine {
       if (!is_early && draw == S.early_end) cs.current_window_size = max(cs.current_window_size, cs.bg_count);
       const uint64_t switch_freq = is_early ? S.early_mm_switch_freq : cs.current_window_size;
       NB_COLD_T(1);
-      if (cs.is_good) {  // update_estimators
-        double x[EPT], gx[EPT];
-        load(P.x + row, x);
-        load(P.gx + row, gx);
+      const bool upd = cs.is_good != 0;  // update_estimators (transform/adapt/diagonal.rs:134-141): counted here, added in the pass below
+      if (upd) {
         cs.fg_count += 1;
         cs.bg_count += 1;
-        add_sample_set(cs.fg_set, cs.fg_count, x, gx);
-        NB_COLD_T(2);
-        add_sample_set(1 - cs.fg_set, cs.bg_count, x, gx);
       }
-      NB_COLD_T(3);
+      const uint64_t n_set0 = cs.fg_set == 0 ? cs.fg_count : cs.bg_count, n_set1 = cs.fg_set == 0 ? cs.bg_count : cs.fg_count;
       const bool could_switch = cs.bg_count >= switch_freq;
       const uint64_t next_window_size =
           is_early ? S.early_mm_switch_freq
@@ -1353,8 +1439,9 @@ struct Engine {
         force_update = true;
         if (!is_early) cs.current_window_size = next_window_size;
       }
-      bool did_change = false;
-      if (force_update | (draw - cs.last_update >= S.mm_update_freq)) did_change = mass_matrix_adapt();
+      // Strategy::adapt needs three samples in the (new) foreground estimator (transform/adapt/diagonal.rs:166-168)
+      const bool did_change = (force_update | (draw - cs.last_update >= S.mm_update_freq)) && cs.fg_count >= 3;
+      if (upd | did_change) adapt_vector_pass(upd, n_set0, n_set1, cs.fg_set, did_change, cs.fg_count);
       NB_COLD_T(4);
       if (did_change) cs.last_update = draw;
       if (is_late) da_advance(cs.last_sym_mean_tree_accept);
@@ -1375,7 +1462,14 @@ struct Engine {
   // initialize_trajectory (transformed_hamiltonian.rs:687-736) + collector.register_init (dual_avg.rs:160-165)
   __device__ __forceinline__ void draw_begin() {
     load_mass_matrix();
-    if (hs_mm_id != hs_pt_tid) {
+    if (ROLL) {
+      if (hs_mm_id != hs_pt_tid) {
+        whiten_planes_rolled();  // inv_transform_normalize: no logp evaluation
+        hs_pt_logdet = hs_mm_logdet;
+        hs_pt_tid = hs_mm_id;
+      }
+      load(P.z + row, z);  // the gradient stays in the gz plane
+    } else if (hs_mm_id != hs_pt_tid) {
       whiten_from_planes();  // inv_transform_normalize: no logp evaluation
       hs_pt_logdet = hs_mm_logdet;
       hs_pt_tid = hs_mm_id;
@@ -1403,7 +1497,52 @@ struct Engine {
     const size_t N = (size_t)P.N;
     NB_T0(tm);
     double fisher[1] = {0.0};
-    if (draw_slot >= 0) {
+    if (ROLL) {
+      // plane to plane: z of the selected leaf -> (x, gx, z, gz) planes + the draw; logp and the Fisher distance ride along
+      const bool moved = draw_slot >= 0;
+      const double* zs = moved ? slot_ptr(draw_slot, 0) : P.z + row;
+      double* out = P.draws_out ? P.draws_out + (t * N + chain) * (size_t)d : nullptr;
+      double lp[1] = {0.0};
+#pragma unroll 1
+      for (int j0 = 0; j0 < EPT; j0 += CH) {
+        double zz[CH], g0[CH], x0[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const int i = tid + (j0 + q) * TPC;
+          const bool live = (j0 + q < EPT) && i < d;
+          zz[q] = live ? __ldcg(zs + i) : 0.0;
+          g0[q] = (!moved && live) ? P.gz[row + i] : 0.0;
+          x0[q] = (!moved && live) ? P.x[row + i] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const int i = tid + (j0 + q) * TPC;
+          if ((j0 + q < EPT) && i < d) {
+            double gn = g0[q], xn = x0[q];
+            if (moved) {
+              const double sgm = sm_sig[i];
+              const double tt = zz[q] * sgm;
+              xn = fma(1.0, sm_mu[i], tt);
+              const double diff = xn - model_mu_at(i);
+              const double pd = diff * model_prec_at(i);
+              lp[0] -= diff * pd / 2.;
+              const double gxn = -pd;
+              gn = gxn * sgm;
+              P.x[row + i] = xn;
+              P.gx[row + i] = gxn;
+              P.z[row + i] = zz[q];
+              P.gz[row + i] = gn;
+            }
+            if (out) out[i] = xn;
+            fisher[0] += (zz[q] + gn) * (zz[q] + gn);  // sq_norm_sum (cpu_math.rs:235-243)
+          }
+        }
+      }
+      if (moved) {
+        red.allreduce(lp);
+        hs_logp = lp[0];
+      }
+    } else if (draw_slot >= 0) {
       double x[EPT], gx[EPT];
       load_cg(slot_ptr(draw_slot, 0), z);
 #pragma unroll
@@ -1428,8 +1567,10 @@ struct Engine {
         store(P.draws_out + (t * N + chain) * (size_t)d, x);
       }
     }
+    if (!ROLL) {
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) fisher[0] += (z[j] + G(j)) * (z[j] + G(j));  // sq_norm_sum (cpu_math.rs:235-243)
+      for (int j = 0; j < EPT; ++j) fisher[0] += (z[j] + G(j)) * (z[j] + G(j));  // sq_norm_sum (cpu_math.rs:235-243)
+    }
     red.allreduce(fisher);
     NB_ACC(5, tm);
     // ---- adaptation + statistics: cold, through global memory
@@ -1642,9 +1783,12 @@ struct Engine {
       // start from the initial point of the draw: first half-step with the gradient draw_begin() loaded (after a mass-matrix
       // change it is not a function of z, see whiten_from_planes)
       const double eps_half = eps / 2.;
-      if (!(dir ? vt.holds_right : vt.holds_left)) {
+      const bool held = dir ? vt.holds_right : vt.holds_left;
+      if (!held) {
         load_cg(P.z + row, z);
         load_cg(P.v0 + row, v);
+      }
+      if (!held || ROLL) {  // ROLL: the gradient of the chain point is never held in registers
         const double* gp = P.gz + row;
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
@@ -1820,8 +1964,7 @@ struct Engine {
     cs.fg_set = 0;
     cs.fg_count = 1;
     cs.bg_count = 1;
-    add_sample_set(0, 1, x, gx);
-    add_sample_set(1, 1, x, gx);
+    adapt_vector_pass(true, 1, 1, 0, false, 1);  // reads the x / gx planes stored above
     double ld[1] = {0.0};
     {
       double* sd = P.stds + row;

@@ -301,3 +301,35 @@ def test_init_state_rejects_bad_points(L):
     _, status = m.init_state(x)
     np.testing.assert_array_equal(status, [0, 3, 3])
     m.close()
+
+
+def test_branch_free_division_and_sqrt_are_ieee_exact(L):
+    """device_common.cuh div_fast / sqrt_fast (the fast paths of the compiler's own sequences, used by the per-draw mass-matrix
+    update so that the elements of a thread overlap): wherever their range test holds the result is bit-identical to `/` and
+    sqrt(), i.e. to the reference's f64 arithmetic (src/math/cpu_math.rs:671-708); where it fails the engine falls back."""
+    import ctypes as C
+
+    lib = L.load()
+    rng = np.random.default_rng(7)
+    n = 1 << 20
+    mags = 10.0 ** rng.uniform(-300, 300, size=n)
+    a = np.concatenate([rng.normal(size=n) * mags, 10.0 ** rng.uniform(-25, 25, size=n), any_f64(rng, n // 4)])
+    b = np.concatenate([rng.normal(size=n) * 10.0 ** rng.uniform(-300, 300, size=n), 10.0 ** rng.uniform(-25, 25, size=n), any_f64(rng, n // 4)])
+    a[:n] = np.abs(a[:n])  # sqrt operands
+    m = a.size
+    out = [np.empty(m) for _ in range(4)]
+    okd, oks = np.empty(m, dtype=np.uint8), np.empty(m, dtype=np.uint8)
+    dp = _abi.c_double_p
+    lib.nuts_debug_fast_math.argtypes = [dp] * 6 + [_abi.c_u8_p, _abi.c_u8_p, C.c_uint64]
+    rc = lib.nuts_debug_fast_math(a.ctypes.data_as(dp), b.ctypes.data_as(dp), *[o.ctypes.data_as(dp) for o in out],
+                                  okd.ctypes.data_as(_abi.c_u8_p), oks.ctypes.data_as(_abi.c_u8_p), m)
+    assert rc == 0, lib.nuts_last_error()
+    qf, qr, rf, rr = out
+    d, s = okd.astype(bool), oks.astype(bool)
+    assert d[n:2 * n].all() and s[n:2 * n].all()  # the whole range the mass-matrix update works in takes the fast path
+    assert d.mean() > 0.5 and s.mean() > 0.5
+    assert np.array_equal(qf[d].view(np.uint64), qr[d].view(np.uint64))
+    assert np.array_equal(rf[s].view(np.uint64), rr[s].view(np.uint64))
+    with np.errstate(all="ignore"):
+        assert np.array_equal(qr[d].view(np.uint64), (a[d] / b[d]).view(np.uint64))  # and the CPU's IEEE division
+        assert np.array_equal(rr[s].view(np.uint64), np.sqrt(a[s]).view(np.uint64))

@@ -107,19 +107,26 @@ def teacher_forced(L, orc, kind, N, d, settings, n_draws, seed, model_kwargs, rt
             assert e <= 1.0, f"{where}: position off by {e * rtol:.3e} relative"
             worst = max(worst, e)
             escale = max(1.0, abs(os_["energy"][0, c]))
+            # Energies are sums of d terms; GPU and oracle add them in different orders and agree to ~1e-13 of their magnitude
+            # (1e-9 * 1e-4).  exp(E0 - E) turns that ABSOLUTE error into a relative one, so the acceptance statistics - and what
+            # dual averaging derives from them - are only determined to 1e-13 |E|: visible in the first draws of config 4, where
+            # |E| ~ 1e9 before the mass matrix has adapted (x0 ~ N(0,1) against sigma = 1e-3).
+            ascale = max(1.0, 1e-4 * escale)
             for k in FLOATS:
                 scale = max(1.0, abs(os_[k][0, c]))
                 if k in ("energy_error", "max_energy_error"):
                     scale = 10 * escale  # differences of O(d) energies
                 if k == "fisher_distance":
                     scale = 10 * max(1.0, abs(os_[k][0, c]), escale)
+                if k in ("mean_tree_accept", "mean_tree_accept_sym", "step_size", "step_size_bar"):
+                    scale = scale * ascale
                 e = _close(gs[k][0, c], os_[k][0, c], rtol, scale)
                 assert e <= 1.0, f"{where}: statistic {k}: {gs[k][0, c]!r} vs {os_[k][0, c]!r}"
             # ---- the state after the draw: every branch of GlobalStrategy::adapt
             for k in STATE_EXACT:
                 assert post[k][c] == opost[k][c], f"{where}: state {k}: {post[k][c]} vs {opost[k][c]}"
             for k in STATE_SCALARS:
-                e = _close(post[k][c], opost[k][c], rtol, max(1.0, abs(opost[k][c])))
+                e = _close(post[k][c], opost[k][c], rtol, max(1.0, abs(opost[k][c])) * (1.0 if k == "logp" else ascale))
                 assert e <= 1.0, f"{where}: state {k}: {post[k][c]!r} vs {opost[k][c]!r}"
             for k in STATE_VECTORS:
                 e = _close(post[k][c], opost[k][c], rtol, np.maximum(np.abs(opost[k][c]), 1e-300) if k in ("stds", "inv_stds")
