@@ -290,6 +290,25 @@ typedef struct {
 int nuts_sampler_get_chain_state(nuts_sampler_t*, const nuts_chain_state_t* out);
 int nuts_sampler_set_chain_state(nuts_sampler_t*, const nuts_chain_state_t* in);
 
+/* ===================== Multi-GPU: gather of the draws (the only exchange of the path) ====================
+ * Chains are independent (reference src/sampler.rs:1094-1126: one Math / RNG stream / adaptation per chain), so a job is split
+ * into contiguous blocks of chains, one sampler per GPU, with chain_id_offset = first global chain id of the block; nothing is
+ * exchanged while sampling.  What the reference does with its shared trace (src/sampler.rs:1065) is here an NCCL all-gather of
+ * the per-rank draw buffers over NVLink, issued on the communicator's OWN stream so that it overlaps the next batch of draws:
+ *     nuts_draw_device(s, n, buf[k & 1]);                       // batch k on the sampler's stream
+ *     nuts_gather_draws_begin(s, comm, buf[k & 1], all[k & 1], count);   // waits (event) for batch k only, then runs beside batch k+1
+ *     ... next batch ...      nuts_gather_draws_end(comm, &ms);  // before buf[k & 1] / all[k & 1] are reused
+ * libnccl is loaded at run time (dlopen "libnccl.so.2": the copy a host process such as PyTorch already carries is used);
+ * without it the calls fail with NUTS_ERR_UNSUPPORTED.  One process per GPU; the 128-byte id travels by any host channel. */
+typedef struct nuts_comm nuts_comm_t;
+int nuts_comm_unique_id(uint8_t id[128]); /* rank 0 */
+int nuts_comm_create(nuts_comm_t** comm, int device_id, const uint8_t id[128], int nranks, int rank);
+int nuts_comm_destroy(nuts_comm_t* comm);
+/* all-gather `count` doubles per rank: gathered_dev = [nranks][count] (rank-major) on every rank; both DEVICE pointers. */
+int nuts_gather_draws_begin(nuts_sampler_t*, nuts_comm_t* comm, const double* local_dev, double* gathered_dev, uint64_t count);
+/* wait for the gather in flight; elapsed_ms (optional) = its device time on the communicator's stream. */
+int nuts_gather_draws_end(nuts_comm_t* comm, double* elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

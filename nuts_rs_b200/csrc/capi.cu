@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <string>
 #include <vector>
 
@@ -30,6 +31,7 @@ NB_DECL(32, 32, 8)
 NB_DECL(32, 32, 7)
 NB_DECL(64, 16, 4)
 NB_DECL(64, 16, 54)  // SM_EXACT variant of 64x16x4 (rows padded to 1024)
+NB_DECL(64, 16, 58)  // SM_EXACT + SM_STAGE, model parameters through the read-only path (no shared-memory copy)
 NB_DECL(64, 16, 55)  // + SM_NOGRAD, 5 resident CTAs per SM
 NB_DECL(64, 16, 57)  // SM_EXACT + gradient in shared memory, 200 registers: 5 resident CTAs per SM
 NB_DECL(64, 16, 56)  // + SM_NOGRAD, 6 resident CTAs per SM
@@ -102,7 +104,7 @@ const EngineConfig kDecoupledLarge[] = {
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 58), NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 
@@ -842,7 +844,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   A((void**)&P.done, ctx->N * sizeof(unsigned int));
   A((void**)&s->d_init, ctx->N * ctx->d * sizeof(double));
   A((void**)&s->d_status, ctx->N * sizeof(int));
-  A((void**)&P.phase_clocks, 8 * sizeof(unsigned long long));
+  A((void**)&P.phase_clocks, 16 * sizeof(unsigned long long));
   if (r != NUTS_OK) return r;
   // chain scalars at construction: Strategy::new -> DualAverage::new(initial_step) (stepsize/adapt.rs:67-89),
   // DiagMassMatrix id -1 (diagonal.rs:81), GlobalStrategy flags (adapt_strategy.rs:87-97)
@@ -1244,6 +1246,122 @@ int nuts_sampler_set_chain_state(nuts_sampler_t* s, const nuts_chain_state_t* in
   return NUTS_OK;
 }
 
+// ============================================================ multi-GPU gather of the draws (NCCL, loaded at run time)
+namespace {
+struct NcclId {  // ncclUniqueId: 128 opaque bytes, passed by value
+  char internal[128];
+};
+struct NcclApi {  // the five entry points used, with their (stable) C signatures
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int load_nccl() {
+  if (g_nccl.handle) return NUTS_OK;
+  void* h = nullptr;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(NUTS_ERR_UNSUPPORTED, "libnccl.so.2 not found (%s): the draw gather needs NCCL", dlerror());
+  NcclApi a;
+  a.handle = h;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+  a.AllGather = (decltype(a.AllGather))dlsym(h, "ncclAllGather");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy) return fail(NUTS_ERR_UNSUPPORTED, "libnccl lacks an expected symbol");
+  g_nccl = a;
+  return NUTS_OK;
+}
+#define NCCL_TRY(expr)                                                                                                         \
+  do {                                                                                                                         \
+    int _r = (expr);                                                                                                           \
+    if (_r != 0) return fail(NUTS_ERR_CUDA, "%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "nccl error"); \
+  } while (0)
+}  // namespace
+
+struct nuts_comm {
+  void* comm = nullptr;
+  int device = 0, nranks = 1, rank = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ready = nullptr, t0 = nullptr, t1 = nullptr;
+  bool in_flight = false;
+};
+
+int nuts_comm_unique_id(uint8_t id[128]) {
+  TRY(load_nccl());
+  NcclId u;
+  NCCL_TRY(g_nccl.GetUniqueId(&u));
+  std::memcpy(id, u.internal, 128);
+  return NUTS_OK;
+}
+int nuts_comm_create(nuts_comm_t** out, int device_id, const uint8_t id[128], int nranks, int rank) {
+  TRY(check_device());
+  TRY(load_nccl());
+  if (!out || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(NUTS_ERR_INVALID, "nuts_comm_create: bad arguments");
+  CUDA_TRY(cudaSetDevice(device_id));
+  nuts_comm* c = new nuts_comm();
+  Guard<nuts_comm, nuts_comm_destroy> guard(c);
+  c->device = device_id;
+  c->nranks = nranks;
+  c->rank = rank;
+  NcclId u;
+  std::memcpy(u.internal, id, 128);
+  NCCL_TRY(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreate(&c->t0));
+  CUDA_TRY(cudaEventCreate(&c->t1));
+  guard.dismiss();
+  *out = c;
+  return NUTS_OK;
+}
+int nuts_comm_destroy(nuts_comm_t* c) {
+  if (!c) return NUTS_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->ready) cudaEventDestroy(c->ready);
+  if (c->t0) cudaEventDestroy(c->t0);
+  if (c->t1) cudaEventDestroy(c->t1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return NUTS_OK;
+}
+int nuts_gather_draws_begin(nuts_sampler_t* s, nuts_comm_t* c, const double* local_dev, double* gathered_dev, uint64_t count) {
+  if (!s || !c || !local_dev || !gathered_dev) return fail(NUTS_ERR_INVALID, "nuts_gather_draws_begin: NULL argument");
+  if (c->in_flight) return fail(NUTS_ERR_INVALID, "nuts_gather_draws_begin: a gather is in flight; call nuts_gather_draws_end first");
+  CUDA_TRY(cudaSetDevice(c->device));
+  // ordered after the draws already enqueued on the sampler's stream, but not after anything enqueued later
+  CUDA_TRY(cudaEventRecord(c->ready, s->ctx->stream));
+  CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ready, 0));
+  CUDA_TRY(cudaEventRecord(c->t0, c->stream));
+  NCCL_TRY(g_nccl.AllGather(local_dev, gathered_dev, (size_t)count, /* ncclFloat64 */ 8, c->comm, c->stream));
+  CUDA_TRY(cudaEventRecord(c->t1, c->stream));
+  c->in_flight = true;
+  return NUTS_OK;
+}
+int nuts_gather_draws_end(nuts_comm_t* c, double* elapsed_ms) {
+  if (!c) return fail(NUTS_ERR_INVALID, "nuts_gather_draws_end: comm is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (elapsed_ms) *elapsed_ms = 0.0;
+  if (!c->in_flight) return NUTS_OK;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->in_flight = false;
+  if (elapsed_ms) {
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->t0, c->t1));
+    *elapsed_ms = ms;
+  }
+  return NUTS_OK;
+}
+
 // test hook: the branch-free division / square root of device_common.cuh next to the library operators, element by element
 // (tests/test_gpu_primitives.py checks bit-equality wherever the range test `ok` holds).  Host arrays of n doubles.
 __global__ void k_debug_fast_math(const double* a, const double* b, double* q_fast, double* q_ref, double* r_fast, double* r_ref,
@@ -1282,11 +1400,11 @@ extern "C" int nuts_debug_fast_math(const double* a, const double* b, double* q_
 }
 
 // debug: per-phase clock totals of NB_PHASE_TIMING builds (zeros otherwise); resets the counters
-extern "C" int nuts_debug_phase_clocks(nuts_sampler_t* s, unsigned long long* out8) {
+extern "C" int nuts_debug_phase_clocks(nuts_sampler_t* s, unsigned long long* out16) {
   CUDA_TRY(cudaSetDevice(s->ctx->device));
   CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
-  CUDA_TRY(cudaMemcpy(out8, s->P.phase_clocks, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemset(s->P.phase_clocks, 0, 8 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemcpy(out16, s->P.phase_clocks, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(s->P.phase_clocks, 0, 16 * sizeof(unsigned long long)));
   return NUTS_OK;
 }
 

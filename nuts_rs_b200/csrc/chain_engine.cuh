@@ -115,7 +115,7 @@ struct EngineParams {
   double* draws_out;                // [n_draws][N][d] device (may be null)
   StatsDev stats;
   uint64_t stats_offset;            // unused draws before this call inside the stats arrays (always 0 for now)
-  unsigned long long* phase_clocks; // [8] debug phase timing (NB_PHASE_TIMING builds), else unused
+  unsigned long long* phase_clocks; // [16] debug phase timing (NB_PHASE_TIMING / NB_PHASE_TIMING_COLD builds), else unused
 };
 
 enum { EXT_OK = 0, EXT_TURNING = 1, EXT_DIVERGING = 2 };
@@ -225,7 +225,7 @@ __device__ __forceinline__ unsigned v2_ld(const volatile unsigned* p) {
 // all resident threads exceed L1).  Every thread computes the same values; thread 0 of the team stores them.  An entry
 // written after leaf i is first read during leaf i+1's merges, i.e. after the barrier / __syncwarp of that leaf's leapfrog
 // reduction, and entries of different levels never alias, so no extra synchronisation is needed for CTA teams.
-struct TreeTables {
+struct alignas(16) TreeTables {  // (16: the teams' shared-memory slices follow each other and hold double2-accessed vectors)
   // pending sub-trees of the half under construction, one per level
   double A_ls[MAX_DOUBLING_DEPTH], A_draw_energy[MAX_DOUBLING_DEPTH];
   int A_draw_idx[MAX_DOUBLING_DEPTH];
@@ -264,10 +264,13 @@ static __device__ __noinline__ AccSums accept_batch(double mine, int n, double a
 // point from z (5 flops per element) - 2*EPT registers less per thread, i.e. more resident teams per SM.
 // SM_MODEL_GLOBAL (decoupled engine): no CTA-wide shared-memory copy of the model parameters (they do not fit for dim ~ 10^4);
 // they are read through the read-only path from global memory, where capi.cu pads them with zeros to a multiple of 1024.
-enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32 };
+// SM_STAGE: four more vectors of shared memory into which cp.async (LDGSTS, 16 bytes per pair) stages the OLDEST operand of the
+// upcoming U-turn checks - (z, v) of the first leaf of the pending sub-tree (buffer X), of the far end of the main tree (buffer Y)
+// - while the leapfrog of the leaf that triggers the check is still running; see Engine::stage_pair().
+enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32, SM_STAGE = 64 };
 template <int SMF>
 __host__ __device__ constexpr int smem_vectors() {
-  return ((SMF & SM_MASS) ? 2 : 0) + ((SMF & SM_MODEL) ? 2 : 0) + ((SMF & SM_GRAD) ? 1 : 0);
+  return ((SMF & SM_MASS) ? 2 : 0) + ((SMF & SM_MODEL) ? 2 : 0) + ((SMF & SM_GRAD) ? 1 : 0) + ((SMF & SM_STAGE) ? 4 : 0);
 }
 template <int TPC, int EPT, int SMF>
 __host__ __device__ constexpr size_t team_smem_bytes() {
@@ -290,13 +293,21 @@ struct Engine {
   static constexpr bool MMS = (SMF & SM_MASS) != 0, MODS = (SMF & SM_MODEL) != 0, GS = (SMF & SM_GRAD) != 0, EXACT = (SMF & SM_EXACT) != 0,
                         NOG = (SMF & SM_NOGRAD) != 0 && MODEL == LOGP_GAUSS_DIAG,
                         MSH = MODS || (MULTI && (SMF & SM_MODEL_GLOBAL) == 0);  // model parameters are read from shared memory
-  static_assert(!EXACT || ((MODS || MULTI) && MMS), "SM_EXACT needs zero-padded copies of the model parameters and the mass matrix");
+  static constexpr bool STAGE = (SMF & SM_STAGE) != 0 && (EPT % 2) == 0 && !MULTI;
+  // (capi.cu pads the global model parameter arrays with zeros up to the largest tile)
+  static_assert(!EXACT || MMS, "SM_EXACT needs a zero-padded copy of the mass matrix");
   __device__ __forceinline__ bool inb(int i) const { return EXACT || i < d; }  // element i exists (or is zero padding that may be touched)
+  // Element -> thread mapping of every vector.  Even EPT: a thread owns PAIRS of adjacent elements (2*tid, 2*tid + 1, then the
+  // same 2*TPC further on), so its accesses to planes, checkpoints and shared memory are 16-byte (double2: LDG.E.128 / STG.E.128 /
+  // LDS.128, cp.async 16 B) and one Box-Muller pair of the momentum belongs to one thread.  Odd EPT (EPT = 1): element tid + j*TPC.
+  static constexpr bool PAIR = (EPT % 2) == 0;
+  static constexpr int NP = EPT / 2;
+  __device__ __forceinline__ int eidx(int j) const { return PAIR ? (j >> 1) * (2 * TPC) + 2 * tid + (j & 1) : tid + j * TPC; }
   double z[EPT], v[EPT];  // current phase-space point: whitened position, velocity
   double g_reg[GS ? 1 : EPT];  // whitened gradient: registers, or shared memory (GS) to fit more chains per SM
   // this chain's DiagMassMatrix (stds, mean): registers, or shared memory when MMS
   double sig[MMS ? 1 : EPT], mu[MMS ? 1 : EPT];
-  double *sm_sig, *sm_mu, *sm_mmu, *sm_mprec, *sm_g;
+  double *sm_sig, *sm_mu, *sm_mmu, *sm_mprec, *sm_g, *sm_stage;
   TreeTables& T;
 
   // Chain scalars used on the hot path are plain members (registers).  `cs` is only touched by the cold functions, which
@@ -304,7 +315,8 @@ struct Engine {
   // whole engine object in local memory (measured: 2 local accesses per counter update per leapfrog).
   double hs_step, hs_logp, hs_pt_logdet, hs_mm_logdet;
   long long hs_pt_tid, hs_mm_id;
-  uint64_t hs_rng, hs_total_lf, hs_tree_lf;
+  uint64_t hs_rng, hs_total_lf, hs_tree_lf, hs_draw_count;
+  double hs_da_lsa;  // DualAverage::log_step_adapted (read-only on the hot path: the step size after tuning)
   int hs_alive;
   ChainState cs;  // cold path only
   uint64_t stream;
@@ -342,7 +354,8 @@ struct Engine {
         sm_sig(team_smem),
         sm_mu(team_smem + (MMS ? TPC * EPT : 0)), sm_mmu(team_smem + (MMS ? 2 : 0) * TPC * EPT),
         sm_mprec(team_smem + ((MMS ? 2 : 0) + (MODS ? 1 : 0)) * TPC * EPT),
-        sm_g(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0)) * TPC * EPT), T(tables) {
+        sm_g(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0)) * TPC * EPT),
+        sm_stage(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0) + (GS ? 1 : 0)) * TPC * EPT), T(tables) {
     stream = p.chain_offset + (uint64_t)chain_ + 1;  // reference src/sampler.rs:1106 set_stream(chain_id + 1)
     if (MULTI) {  // several teams per CTA: named barrier, per-team reduction scratch, CTA-wide copy of the model parameters
       red.bar_id = mc->bar_id;
@@ -366,19 +379,39 @@ struct Engine {
     if (MULTI) return m->pool;
     return (int)blockIdx.x * ((int)blockDim.x / TPC) + (int)threadIdx.x / TPC;
   }
-  __device__ __forceinline__ double sg(int j) const { return MMS ? sm_sig[tid + j * TPC] : sig[MMS ? 0 : j]; }
-  __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[tid + j * TPC] : mu[MMS ? 0 : j]; }
+  __device__ __forceinline__ double sg(int j) const { return MMS ? sm_sig[eidx(j)] : sig[MMS ? 0 : j]; }
+  __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[eidx(j)] : mu[MMS ? 0 : j]; }
   // model parameters of element i = tid + j*TPC
   // (MULTI: one copy per CTA shared by all its teams, filled by the kernel prologue)
-  __device__ __forceinline__ double model_mu(int j, int i) const { return MSH ? sm_mmu[tid + j * TPC] : __ldg(P.model.mu + i); }
-  __device__ __forceinline__ double model_prec(int j, int i) const { return MSH ? sm_mprec[tid + j * TPC] : __ldg(P.model.prec + i); }
+  __device__ __forceinline__ double model_mu(int j, int i) const { return MSH ? sm_mmu[eidx(j)] : __ldg(P.model.mu + i); }
+  __device__ __forceinline__ double model_prec(int j, int i) const { return MSH ? sm_mprec[eidx(j)] : __ldg(P.model.prec + i); }
   // element j of the whitened gradient (each thread only touches its own entries: no synchronisation)
-  __device__ __forceinline__ double& G(int j) { return GS ? sm_g[tid + j * TPC] : g_reg[GS ? 0 : j]; }
+  __device__ __forceinline__ double& G(int j) { return GS ? sm_g[eidx(j)] : g_reg[GS ? 0 : j]; }
+  // The four per-element constants of the diagonal Gaussian leapfrog (sigma, mean of the mass matrix; mu, precision of the
+  // model) for elements j, j + 1 of a PAIR (j even): one 16-byte access per vector instead of two 8-byte ones.
+  struct PairConsts {
+    double sg[2], mn[2], mm[2], pr[2];
+  };
+  __device__ __forceinline__ void pair_consts(int j, PairConsts& c) const {
+    const int i0 = eidx(j);
+    if (MMS) {
+      const double2 a = *reinterpret_cast<const double2*>(sm_sig + i0), b = *reinterpret_cast<const double2*>(sm_mu + i0);
+      c.sg[0] = a.x, c.sg[1] = a.y, c.mn[0] = b.x, c.mn[1] = b.y;
+    } else {
+      c.sg[0] = sig[MMS ? 0 : j], c.sg[1] = sig[MMS ? 0 : j + 1], c.mn[0] = mu[MMS ? 0 : j], c.mn[1] = mu[MMS ? 0 : j + 1];
+    }
+    double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+    if (inb(i0)) {  // the partner of an odd last element reads the zero padding of the parameter arrays
+      if (MSH) a = *reinterpret_cast<const double2*>(sm_mmu + i0), b = *reinterpret_cast<const double2*>(sm_mprec + i0);
+      else a = __ldg(reinterpret_cast<const double2*>(P.model.mu + i0)), b = __ldg(reinterpret_cast<const double2*>(P.model.prec + i0));
+    }
+    c.mm[0] = a.x, c.mm[1] = a.y, c.pr[0] = b.x, c.pr[1] = b.y;
+  }
   __device__ __forceinline__ void load_model_params() {
     if (MODS && !MULTI) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         sm_mmu[i] = i < d ? P.model.mu[i] : 0.0;
         sm_mprec[i] = i < d ? P.model.prec[i] : 0.0;
       }
@@ -388,48 +421,102 @@ struct Engine {
   __device__ __forceinline__ void tsync() const {
     if (TPC == 32) __syncwarp();
   }
-  // checkpoint traffic bypasses L1 (ld.cg / st.cg): it is streamed once, L1 is kept for the model parameters and tables
+  // checkpoint traffic bypasses L1 (ld.cg / st.cg): it is streamed once, L1 is kept for the model parameters and tables.
+  // PAIR mapping: 16-byte accesses (rows start on 128-byte lines and the first element of a pair has an even index; the
+  // partner of an odd last element is zero padding of the row, which is never overwritten).
   __device__ __forceinline__ void load_cg(const double* __restrict__ src, double (&a)[EPT]) const {
+    if (PAIR) {
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
-      a[j] = inb(i) ? __ldcg(src + i) : 0.0;
+      for (int p = 0; p < NP; ++p) {
+        const int i0 = eidx(2 * p);
+        double2 t = make_double2(0.0, 0.0);
+        if (inb(i0)) t = __ldcg(reinterpret_cast<const double2*>(src + i0));
+        a[2 * p] = t.x;
+        a[2 * p + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = eidx(j);
+        a[j] = inb(i) ? __ldcg(src + i) : 0.0;
+      }
     }
   }
   __device__ __forceinline__ void store_cg(double* __restrict__ dst, const double (&a)[EPT]) const {
+    if (PAIR) {
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
-      if (inb(i)) __stcg(dst + i, a[j]);
+      for (int p = 0; p < NP; ++p) {
+        const int i0 = eidx(2 * p);
+        if (EXACT || i0 + 1 < d) __stcg(reinterpret_cast<double2*>(dst + i0), make_double2(a[2 * p], a[2 * p + 1]));
+        else if (i0 < d) __stcg(dst + i0, a[2 * p]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = eidx(j);
+        if (inb(i)) __stcg(dst + i, a[j]);
+      }
     }
   }
 
-  // ------------------------------------------------------------------ vector helpers
+  // ------------------------------------------------------------------ vector helpers (rows of the [N][ld] planes)
   __device__ __forceinline__ void load(const double* __restrict__ src, double (&a)[EPT]) const {
+    if (PAIR) {
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
-      a[j] = i < d ? src[i] : 0.0;
+      for (int p = 0; p < NP; ++p) {
+        const int i0 = eidx(2 * p);
+        double2 t = make_double2(0.0, 0.0);
+        if (i0 < d) t = *reinterpret_cast<const double2*>(src + i0);
+        a[2 * p] = t.x;
+        a[2 * p + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = eidx(j);
+        a[j] = i < d ? src[i] : 0.0;
+      }
     }
   }
   __device__ __forceinline__ void store(double* __restrict__ dst, const double (&a)[EPT]) const {
+    if (PAIR) {
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
-      if (i < d) dst[i] = a[j];
+      for (int p = 0; p < NP; ++p) {
+        const int i0 = eidx(2 * p);
+        if (i0 + 1 < d) *reinterpret_cast<double2*>(dst + i0) = make_double2(a[2 * p], a[2 * p + 1]);
+        else if (i0 < d) dst[i0] = a[2 * p];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = eidx(j);
+        if (i < d) dst[i] = a[j];
+      }
+    }
+  }
+  // a row of the dense [n_draws][N][d] output (stride d: 16-byte aligned only for even d)
+  __device__ __forceinline__ void store_dense(double* __restrict__ dst, const double (&a)[EPT]) const {
+    if (PAIR && (d & 1) == 0) {
+      store(dst, a);
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = eidx(j);
+        if (i < d) dst[i] = a[j];
+      }
     }
   }
   __device__ __forceinline__ void load_g(const double* __restrict__ src, bool cg) {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
+      int i = eidx(j);
       G(j) = i < d ? (cg ? __ldcg(src + i) : src[i]) : 0.0;
     }
   }
   __device__ __forceinline__ void store_g(double* __restrict__ dst, bool cg) {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
+      int i = eidx(j);
       if (i < d) {
         if (cg) __stcg(dst + i, G(j));
         else dst[i] = G(j);
@@ -455,6 +542,8 @@ struct Engine {
     hs_total_lf = __ldcg((const unsigned long long*)&g->total_leapfrogs);
     hs_tree_lf = __ldcg((const unsigned long long*)&g->tree_leapfrogs);
     hs_alive = __ldcg(&g->alive);
+    hs_draw_count = __ldcg((const unsigned long long*)&g->draw_count);
+    hs_da_lsa = __ldcg(&g->da_log_step_adapted);
   }
   __device__ __forceinline__ void team_sync() const {
     if (TPC > 32) red.barrier();
@@ -526,35 +615,37 @@ struct Engine {
   }
   // array_gaussian(rng, v, ones): v[i] = 1.0 * normal   (cpu_math.rs:561-577)
   __device__ __forceinline__ void sample_velocity() {
-    // Elements 2p and 2p+1 (one Box-Muller pair) belong to threads t (even) and t+1 at the same j.  Even threads evaluate the
-    // pairs of even j, odd threads those of odd j, and the partner's normal travels through one shuffle: EPT/2 Box-Mullers
-    // per thread instead of EPT.  Values are exactly those of stream_normal().
-    // The loop is ROLLED (the Box-Muller body is ~250 instructions; unrolled it would sweep 30 KB of code through the 32 KB
-    // instruction cache once per draw): the normals go to the chain's v0 plane - where initialize_trajectory stores the fresh
-    // velocity anyway - and every thread reads back the elements it wrote itself.
+    // Elements 2p and 2p+1 are one Box-Muller pair.  PAIR mapping: both belong to the same thread; values are exactly those of
+    // stream_normal().  The loop is ROLLED (the Box-Muller body is ~250 instructions; unrolled over EPT it would sweep 30 KB of
+    // code through the 32 KB instruction cache once per draw) with NB_BM_STEP (2) independent pairs per iteration, so that their
+    // dependency chains (log, sin / cos polynomials, square root) interleave.  The normals go to the chain's v0 plane - where
+    // initialize_trajectory stores the fresh velocity anyway - and every thread reads back the elements it wrote itself.
     double* v0 = P.v0 + row;
-    if (EPT % 2 == 0) {
+    if (PAIR) {
+#ifndef NB_BM_STEP
+#define NB_BM_STEP 2
+#endif
+      constexpr int STEP = (NP % NB_BM_STEP == 0) ? NB_BM_STEP : ((NP % 2 == 0) ? 2 : 1);
 #pragma unroll 1
-      for (int j = 0; j < EPT; j += 2) {
-        const int jj = j + (tid & 1);              // the j this thread evaluates
-        const int i_even = (tid & ~1) + jj * TPC;  // even element of that pair
-        double n0 = 0.0, n1 = 0.0;
-        if (i_even < d) stream_normal_pair(P.seed, stream, hs_rng, (uint32_t)i_even, n0, n1);
-        // mine: component (tid & 1) of my pair goes to element jj; the other component belongs to the neighbour's element at jj
-        const double keep = (tid & 1) ? n1 : n0;
-        const double give = (tid & 1) ? n0 : n1;
-        const double got = __shfl_xor_sync(0xffffffffu, give, 1);  // the neighbour evaluated j + 1 - (tid&1): the j I still need
+      for (int p = 0; p < NP; p += STEP) {
+        double n[STEP][2];
+        int i0[STEP];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int i = tid + (j + q) * TPC;
-          const double val = (q == (tid & 1)) ? keep : got;
-          if (i < d) v0[i] = 1.0 * val;
+        for (int u = 0; u < STEP; ++u) {
+          i0[u] = eidx(2 * (p + u));
+          // a pair beyond dim (or the odd last element's partner) is computed and dropped: no branch inside the chains
+          stream_normal_pair(P.seed, stream, hs_rng, (uint32_t)(i0[u] < d ? i0[u] : 0), n[u][0], n[u][1]);
+        }
+#pragma unroll
+        for (int u = 0; u < STEP; ++u) {
+          if (i0[u] < d) v0[i0[u]] = 1.0 * n[u][0];
+          if (i0[u] + 1 < d) v0[i0[u] + 1] = 1.0 * n[u][1];
         }
       }
     } else {
 #pragma unroll 1
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         if (i < d) v0[i] = 1.0 * stream_normal(P.seed, stream, hs_rng, (uint32_t)i);
       }
     }
@@ -573,7 +664,7 @@ struct Engine {
       double s[1] = {0.0};
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         if (i < d) s[0] += x[j] - model_mu(j, i);
       }
       red.allreduce(s);
@@ -582,7 +673,7 @@ struct Engine {
       double s[2] = {0.0, 0.0};
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         if (i < d) {
           if (i == 0) s[1] = x[j];
           else s[0] = fma(x[j], x[j], s[0]);
@@ -601,7 +692,7 @@ struct Engine {
     if (false /* ISO is served by the DIAG code path with prec = 1 */) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         gx[j] = 0.0;
         if (i < d) {
           double diff = x[j] - model_mu(j, i);
@@ -612,7 +703,7 @@ struct Engine {
     } else if (MODEL == LOGP_GAUSS_DIAG) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         gx[j] = 0.0;
         if (i < d) {
           double diff = x[j] - model_mu(j, i);
@@ -624,7 +715,7 @@ struct Engine {
     } else if (MODEL == LOGP_GAUSS_RANK1) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         gx[j] = 0.0;
         if (i < d) {
           double diff = x[j] - model_mu(j, i);
@@ -641,7 +732,7 @@ struct Engine {
       double half_ev_S = 0.5 * ev * a1;
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         gx[j] = 0.0;
         if (i < d) {
           if (i == 0) gx[j] = -vv * m.funnel_inv_var - 0.5 * nm1 + half_ev_S;
@@ -667,19 +758,21 @@ struct Engine {
   __device__ __forceinline__ void leapfrog_partials(double eps, double (&part)[4]) {
     const double eps_half = eps / 2.;
     part[0] = part[1] = part[2] = part[3] = 0.0;
+    PairConsts pc;
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      const int i = tid + j * TPC;
+      const int i = eidx(j);
+      if (PAIR && (j & 1) == 0) pair_consts(j, pc);
       const double zp = z[j], vp = v[j];
       const double vh = fma(eps_half, G(j), vp);   // first_velocity_halfstep :178-184  axpy_out(grad, v, eps/2)
       const double zn = fma(eps, vh, zp);          // position_step :220-225            axpy_out(v', z, eps)
-      const double sgm = sg(j);
+      const double sgm = PAIR ? pc.sg[j & 1] : sg(j);
       const double t = zn * sgm;                   // compute_untransformed_position    diagonal.rs:253-255
-      const double xn = fma(1.0, mn(j), t);
+      const double xn = fma(1.0, PAIR ? pc.mn[j & 1] : mn(j), t);
       double gxn = 0.0;
       if (inb(i)) {
-        const double diff = xn - model_mu(j, i);
-        const double pd = diff * model_prec(j, i);
+        const double diff = xn - (PAIR ? pc.mm[j & 1] : model_mu(j, i));
+        const double pd = diff * (PAIR ? pc.pr[j & 1] : model_prec(j, i));
         part[0] -= diff * pd / 2.;
         gxn = -pd;
       }
@@ -764,7 +857,7 @@ struct Engine {
     if (MMS) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         sm_sig[i] = i < d ? P.stds[row + i] : 0.0;
         sm_mu[i] = i < d ? P.mean[row + i] : 0.0;
       }
@@ -772,7 +865,7 @@ struct Engine {
     } else {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         sig[MMS ? 0 : j] = i < d ? P.stds[row + i] : 0.0;
         mu[MMS ? 0 : j] = i < d ? P.mean[row + i] : 0.0;
       }
@@ -797,15 +890,15 @@ struct Engine {
       double x[CH], gx[CH], is[CH];
 #pragma unroll
       for (int q = 0; q < CH; ++q) {
-        const int i = tid + (j0 + q) * TPC;
-        const bool live = (j0 + q < EPT) && i < d;
-        x[q] = live ? xp[i] : 0.0;
-        gx[q] = live ? gp[i] : 0.0;
-        is[q] = live ? ip[i] : 0.0;
+        const int i = eidx(j0 + q);
+        const int ii = ((j0 + q < EPT) && i < d) ? i : 0;  // unconditional loads (a lane without an element re-reads element 0)
+        x[q] = xp[ii];
+        gx[q] = gp[ii];
+        is[q] = ip[ii];
       }
 #pragma unroll
       for (int q = 0; q < CH; ++q) {
-        const int i = tid + (j0 + q) * TPC;
+        const int i = eidx(j0 + q);
         if ((j0 + q < EPT) && i < d) {
           const double t = fma(-1.0, sm_mu[i], x[q]);  // axpy_out(mean, x, -1)
           const double zz = is[q] * t;                 // multiply_inplace(z, inv_stds): out = x*out
@@ -830,7 +923,7 @@ struct Engine {
     double bad[1] = {0.0};
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
+      int i = eidx(j);
       double t = fma(-1.0, mn(j), x[j]);  // axpy_out(mean, x, -1)
       z[j] = is[j] * t;                   // multiply_inplace(z, inv_stds): out = x*out
       G(j) = gx[j] * sg(j);
@@ -865,6 +958,42 @@ struct Engine {
     if (rc_get(s) == 0) free_mask |= (1ull << s);
   }
 
+  // ------------------------------------------------------------------ cp.async staging of checkpoint pairs (SM_STAGE)
+  // Buffer b (0 = X, 1 = Y) holds (z, v) of one checkpoint: sm_stage[(2b + which) * TPC*EPT + element].  Every thread copies
+  // exactly the 16-byte pairs it owns under the engine's element mapping and later reads only those, so - like everywhere in this
+  // engine - no barrier is involved: completion is the thread's own cp.async.wait_all.  stg_src[b] remembers what was staged.
+  const double* stg_src[2] = {nullptr, nullptr};
+  __device__ __forceinline__ const double* stage_buf(int b, int which) const { return sm_stage + (size_t)(2 * b + which) * (TPC * EPT); }
+  __device__ __forceinline__ void stage_pair(int b, const double* zsrc, const double* vsrc) {
+    if (!STAGE) return;
+    stg_src[b] = zsrc;
+    const unsigned dz = (unsigned)__cvta_generic_to_shared(stage_buf(b, 0)), dv = (unsigned)__cvta_generic_to_shared(stage_buf(b, 1));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int i0 = eidx(2 * p);
+      if (inb(i0)) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dz + 8u * (unsigned)i0), "l"(zsrc + i0) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dv + 8u * (unsigned)i0), "l"(vsrc + i0) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void stage_wait() const {
+    if (STAGE) asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  // (z, v) of a checkpoint from a staging buffer into the registers (the start state of a doubling after a change of direction)
+  __device__ __forceinline__ void load_staged(int b) {
+    stage_wait();
+    const double *zs = stage_buf(b, 0), *vs = stage_buf(b, 1);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int i0 = eidx(2 * p);
+      double2 a = make_double2(0.0, 0.0), c = make_double2(0.0, 0.0);
+      if (inb(i0)) a = *reinterpret_cast<const double2*>(zs + i0), c = *reinterpret_cast<const double2*>(vs + i0);
+      z[2 * p] = a.x, z[2 * p + 1] = a.y, v[2 * p] = c.x, v[2 * p + 1] = c.y;
+    }
+  }
+
   // ------------------------------------------------------------------ U-turn products (is_turning :617-638 -> scalar_prods3)
   // pair (P = earlier built, Q = later built): delta = zQ - zP ; sP = delta . vP ; sQ = delta . vQ.
   // Forward: turning <=> sP < 0 | sQ < 0.  Backward the reference orders the pair the other way round, which negates
@@ -879,7 +1008,7 @@ struct Engine {
       double s[2] = {0.0, 0.0};
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         if (inb(i)) {
           double delta = (z[j] + 0.0) - __ldcg(Afz + i);
           s[0] = fma(delta, __ldcg(Afv + i), s[0]);
@@ -889,23 +1018,17 @@ struct Engine {
       red.allreduce(s);
       return turn_eval(s[0], s[1], dir);
     }
-    double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
-      if (inb(i)) {
-        double afz = __ldcg(Afz + i), afv = __ldcg(Afv + i), alz = __ldcg(Alz + i), alv = __ldcg(Alv + i), bfz = __ldcg(Bfz + i),
-               bfv = __ldcg(Bfv + i);
-        double d1 = (z[j] + 0.0) - afz;
-        s[0] = fma(d1, afv, s[0]);
-        s[1] = fma(d1, v[j], s[1]);
-        double d2 = (z[j] + 0.0) - alz;
-        s[2] = fma(d2, alv, s[2]);
-        s[3] = fma(d2, v[j], s[3]);
-        double d3 = (bfz + 0.0) - afz;
-        s[4] = fma(d3, afv, s[4]);
-        s[5] = fma(d3, bfv, s[5]);
+    double s[6];
+    if (STAGE) {  // (z, v) of A.first come from shared memory: prefetched by extend(), or staged now when nothing was
+      int b = stg_src[0] == Afz ? 0 : (stg_src[1] == Afz ? 1 : -1);
+      if (b < 0) {
+        b = 0;
+        stage_pair(0, Afz, Afv);
       }
+      stage_wait();
+      merge_products<true>(stage_buf(b, 0), stage_buf(b, 1), Alz, Alv, Bfz, Bfv, true, s);
+    } else {
+      merge_products<false>(Afz, Afv, Alz, Alv, Bfz, Bfv, true, s);
     }
     red.allreduce(s);
     if (!full) return turn_eval(s[0], s[1], dir);
@@ -983,6 +1106,9 @@ struct Engine {
     const double* nearV = near_init ? P.v0 + row : slot_ptr(es_near, 1);
     const double* farZ = far_init ? P.z + row : slot_ptr(es_far, 0);
     const double* farV = far_init ? P.v0 + row : slot_ptr(es_far, 1);
+    // staging buffers: X is per merge; Y keeps an end of the main tree across doublings (its checkpoint stays out of the pool)
+    stg_src[0] = nullptr;
+    if (stg_src[1] != farZ && stg_src[1] != nearZ) stg_src[1] = nullptr;
     bool half_done = false;  // NOG: v already holds the first half-step of leaf 0 (done with the stored gradient of the initial point)
     if (NOG) {
       if (near_init) {
@@ -993,7 +1119,7 @@ struct Engine {
           const double* gp = P.gz + row;
 #pragma unroll
           for (int j = 0; j < EPT; ++j) {
-            const int i = tid + j * TPC;
+            const int i = eidx(j);
             const double gl = inb(i) ? __ldcg(gp + i) : 0.0;
             v[j] = fma(eps_half, gl, v[j]);
           }
@@ -1007,14 +1133,18 @@ struct Engine {
         load_cg(nearV, v);
       }
     } else if (!(dir ? holds_right : holds_left)) {
-      load_cg(nearZ, z);
-      load_cg(nearV, v);
+      if (STAGE && stg_src[1] == nearZ) {  // the other end was staged for the last top-level check
+        load_staged(1);
+      } else {
+        load_cg(nearZ, z);
+        load_cg(nearV, v);
+      }
       if (near_init) {
         load_g(P.gz + row, true);
       } else if (MODEL == LOGP_GAUSS_DIAG) {
         // elementwise target: the gradient of a leaf is a function of its z (the leapfrog's own instruction sequence)
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) G(j) = grad_z_at(z[j], j, tid + j * TPC);
+        for (int j = 0; j < EPT; ++j) G(j) = grad_z_at(z[j], j, eidx(j));
       } else {
         load_g(end_ptr(dir, 2), true);
       }
@@ -1032,6 +1162,12 @@ struct Engine {
       NB_ACC(4, tq);
       // odd leaves merge with their predecessor first (level 0): its U-turn products come out of the leapfrog itself
       const bool fuse0 = kFusedPrevCheck && check && (i & 1u);
+      if (STAGE && check) {
+        // operands of the checks this leaf will trigger, fetched while its leapfrog runs: A.first of the level-1 merge (its slot
+        // is known from the tables: the merges a leaf completes follow from its index), the far end for the top-level check
+        if ((i & 3u) == 3u && D >= 2) stage_pair(0, slot_ptr(T.A_first[1], 0), slot_ptr(T.A_first[1], 1));
+        if (i + 1 == nleaf && stg_src[1] != farZ) stage_pair(1, farZ, farV);
+      }
       if (NOG) {
         double part[4];
         leapfrog_partials_nog(eps, half_done, part);
@@ -1114,6 +1250,7 @@ struct Engine {
         B_ls = total;
         if (turning) return EXT_TURNING;  // inner turn: the old tree is returned unchanged (nuts.rs:131-133)
       }
+      stg_src[0] = nullptr;  // buffer X only lives from the prefetch to the merges of the same leaf (slots are re-used afterwards)
       NB_ACC(3, tq);
       if (i + 1 < nleaf) {
         if (tid == 0) {
@@ -1269,13 +1406,15 @@ struct Engine {
   // call ends in a slow-path branch and the elements of a thread run one after the other (the round-1 tuning phase spent 58 k of
   // its 100 k adaptation cycles per draw there).  sum ln(inv_std) is accumulated as ln(product) per chunk: one log instead of CH.
   static constexpr int CH = EPT < 4 ? EPT : 4;
-  static __device__ __noinline__ void mass_matrix_element_slow(double dv, double gv, double scale, bool grad_based, double& s_new, double& is_new) {
+  // (everything by value and statically indexed at the call sites: a reference parameter or a rolled loop over the chunk would
+  // move the chunk's register arrays to local memory)
+  static __device__ __noinline__ double2 mass_matrix_element_slow(double dv, double gv, double scale, bool grad_based, double s_old, double is_old) {
     double val = grad_based ? sqrt(dv / gv) : dv * scale;  // cpu_math.rs:695 / :658
     if (!((!isfinite(val)) | (val == 0.0))) {               // fill_invalid = None: leave untouched
       val = clampd(val, 1e-20, 1e20);
-      s_new = sqrt(val);
-      is_new = sqrt(1.0 / val);
+      return make_double2(sqrt(val), sqrt(1.0 / val));
     }
+    return make_double2(s_old, is_old);
   }
   __device__ __forceinline__ void adapt_vector_pass(bool upd, uint64_t n0, uint64_t n1, int mm_set, bool do_mm, uint64_t fg_count) {
     const double* xp = P.x + row;
@@ -1292,21 +1431,20 @@ struct Engine {
     for (int j0 = 0; j0 < EPT; j0 += CH) {
       double x[CH], gx[CH], e[2][4][CH], s_new[CH], is_new[CH];
       bool live[CH];
-      // ---- every load of the chunk
+      // ---- every load of the chunk, unconditionally (a lane without an element re-reads element 0: no branch per load)
 #pragma unroll
       for (int q = 0; q < CH; ++q) {
-        const int i = tid + (j0 + q) * TPC;
+        const int i = eidx(j0 + q);
         live[q] = (j0 + q < EPT) && (i < d);
-        x[q] = (upd && live[q]) ? xp[i] : 0.0;
-        gx[q] = (upd && live[q]) ? gp[i] : 0.0;
+        const int ii = live[q] ? i : 0;
+        x[q] = xp[ii];
+        gx[q] = gp[ii];
 #pragma unroll
-        for (int st = 0; st < 2; ++st) {
-          const bool need = (upd && nn[st] > 1) || (do_mm && st == mm_set);
+        for (int st = 0; st < 2; ++st)
 #pragma unroll
-          for (int w = 0; w < 4; ++w) e[st][w][q] = (need && live[q]) ? est_ptr(st, w)[i] : 0.0;
-        }
-        s_new[q] = (do_mm && live[q]) ? sd[i] : 0.0;
-        is_new[q] = (do_mm && live[q]) ? isd[i] : 1.0;
+          for (int w = 0; w < 4; ++w) e[st][w][q] = est_ptr(st, w)[ii];
+        s_new[q] = sd[ii];
+        is_new[q] = isd[ii];
       }
       // ---- RunningVariance::add_sample for the four estimators of both sets
       if (upd) {
@@ -1334,7 +1472,7 @@ struct Engine {
           }
 #pragma unroll
           for (int q = 0; q < CH; ++q) {
-            const int i = tid + (j0 + q) * TPC;
+            const int i = eidx(j0 + q);
             if (live[q]) {
 #pragma unroll
               for (int w = 0; w < 4; ++w) est_ptr(st, w)[i] = e[st][w][q];
@@ -1344,22 +1482,21 @@ struct Engine {
       }
       // ---- DiagMassMatrix::update_diag_draw_grad / update_diag_draw from set mm_set
       if (do_mm) {
-        bool ok = true;
         double cand_s[CH], cand_is[CH];
         bool valid[CH];
+        bool all_ok = true;
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
           const double dv = mm_set ? e[1][1][q] : e[0][1][q], gv = mm_set ? e[1][3][q] : e[0][3][q];
-          double val = grad_based ? sqrt_fast(div_fast(dv, gv, ok), ok) : dv * mscale;  // cpu_math.rs:695 / :658
-          valid[q] = !((!isfinite(val)) | (val == 0.0));                               // fill_invalid = None: leave untouched
+          bool ok1 = true, ok2 = true;
+          double val = grad_based ? sqrt_fast(div_fast(dv, gv, ok1), ok1) : dv * mscale;  // cpu_math.rs:695 / :658
+          valid[q] = !((!isfinite(val)) | (val == 0.0));                                 // fill_invalid = None: leave untouched
           val = clampd(val, 1e-20, 1e20);
-          cand_s[q] = sqrt_fast(val, ok);
-          cand_is[q] = sqrt_fast(div_fast(1.0, val, ok), ok);
+          cand_s[q] = sqrt_fast(val, ok2);
+          cand_is[q] = sqrt_fast(div_fast(1.0, val, ok2), ok2);
+          // a failed range test only matters where its result is used: an invalid val (NaN, inf, 0) is discarded anyway
+          all_ok = all_ok & (!live[q] | (ok1 & (!valid[q] | ok2)));
         }
-        // the range tests only speak for operands that are used: an invalid val (NaN, inf, 0) fails them by construction
-        bool all_ok = true;
-#pragma unroll
-        for (int q = 0; q < CH; ++q) all_ok = all_ok & (!live[q] | !valid[q] | ok);
         if (all_ok) {
 #pragma unroll
           for (int q = 0; q < CH; ++q)
@@ -1368,16 +1505,20 @@ struct Engine {
               is_new[q] = cand_is[q];
             }
         } else {  // denormal / huge operands somewhere in the chunk: the library operators, element by element
-#pragma unroll 1
+#pragma unroll
           for (int q = 0; q < CH; ++q) {
             const double dv = mm_set ? e[1][1][q] : e[0][1][q], gv = mm_set ? e[1][3][q] : e[0][3][q];
-            if (live[q]) mass_matrix_element_slow(dv, gv, mscale, grad_based, s_new[q], is_new[q]);
+            if (live[q]) {
+              const double2 r = mass_matrix_element_slow(dv, gv, mscale, grad_based, s_new[q], is_new[q]);
+              s_new[q] = r.x;
+              is_new[q] = r.y;
+            }
           }
         }
         double prod = 1.0;  // inv_std in [1e-10, 1e10] after the clamp (or the initial 1 / sqrt|grad| clamp): no overflow for CH <= 4
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
-          const int i = tid + (j0 + q) * TPC;
+          const int i = eidx(j0 + q);
           const double dm = mm_set ? e[1][0][q] : e[0][0][q], gm = mm_set ? e[1][2][q] : e[0][2][q];
           double mean = dm;
           if (grad_based) {
@@ -1508,15 +1649,15 @@ struct Engine {
         double zz[CH], g0[CH], x0[CH];
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
-          const int i = tid + (j0 + q) * TPC;
-          const bool live = (j0 + q < EPT) && i < d;
-          zz[q] = live ? __ldcg(zs + i) : 0.0;
-          g0[q] = (!moved && live) ? P.gz[row + i] : 0.0;
-          x0[q] = (!moved && live) ? P.x[row + i] : 0.0;
+          const int i = eidx(j0 + q);
+          const int ii = ((j0 + q < EPT) && i < d) ? i : 0;  // unconditional loads
+          zz[q] = __ldcg(zs + ii);
+          g0[q] = P.gz[row + ii];
+          x0[q] = P.x[row + ii];
         }
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
-          const int i = tid + (j0 + q) * TPC;
+          const int i = eidx(j0 + q);
           if ((j0 + q < EPT) && i < d) {
             double gn = g0[q], xn = x0[q];
             if (moved) {
@@ -1557,14 +1698,14 @@ struct Engine {
       store(P.gx + row, gx);
       store(P.z + row, z);
       store_g(P.gz + row, false);
-      if (P.draws_out) store(P.draws_out + (t * N + chain) * (size_t)d, x);
+      if (P.draws_out) store_dense(P.draws_out + (t * N + chain) * (size_t)d, x);
     } else {
       load(P.z + row, z);
       load_g(P.gz + row, false);
       if (P.draws_out) {
         double x[EPT];
         load(P.x + row, x);
-        store(P.draws_out + (t * N + chain) * (size_t)d, x);
+        store_dense(P.draws_out + (t * N + chain) * (size_t)d, x);
       }
     }
     if (!ROLL) {
@@ -1573,6 +1714,49 @@ struct Engine {
     }
     red.allreduce(fisher);
     NB_ACC(5, tm);
+    // ---- after the tuning phase GlobalStrategy::adapt only copies the collector statistics and draws the next jittered step size
+    // (adapt_strategy.rs:126-137 -> stepsize/adapt.rs:201-209, 235-267): done right here, without the round trip of the whole
+    // ChainState through the cold function (same arithmetic, same random stream: bit-identical to the cold path)
+    if (hs_draw_count >= P.s.num_tune) {
+      const double mta = acc_sum / (double)acc_count, msa = acc_sym_sum / (double)acc_count;
+      const double step_bar = P.s.method != 0 ? P.s.fixed_step : exp(hs_da_lsa);
+      if (P.s.has_jitter) {
+        const double lo = 1.0 - P.s.jitter, hi = 1.0 + P.s.jitter;
+        hs_step = step_bar * fma(hi - lo, rng_f64(), lo);
+      } else {
+        hs_step = step_bar;
+      }
+      if (tid == 0) {
+        ChainState* g = P.cs + chain;
+        g->last_mean_tree_accept = mta;
+        g->last_sym_mean_tree_accept = msa;
+        g->last_n_steps = acc_count;
+        g->last_max_energy_error = max_energy_error;
+        g->is_good = (diverging ? (abs(draw_idx) > 4) : (draw_idx != 0)) ? 1 : 0;
+        g->tuning = 0;
+        g->draw_count = hs_draw_count + 1;
+        const StatsDev& st = P.stats;
+        const size_t k = (size_t)t * N + chain;
+        if (st.depth) st.depth[k] = (uint64_t)depth;
+        if (st.maxdepth_reached) st.maxdepth_reached[k] = reached_maxdepth ? 1 : 0;
+        if (st.index_in_trajectory) st.index_in_trajectory[k] = draw_idx;
+        if (st.logp) st.logp[k] = hs_logp;
+        if (st.energy) st.energy[k] = draw_energy;
+        if (st.energy_error) st.energy_error[k] = draw_energy - E0;
+        if (st.diverging) st.diverging[k] = diverging ? 1 : 0;
+        if (st.step_size) st.step_size[k] = hs_step;
+        if (st.step_size_bar) st.step_size_bar[k] = step_bar;
+        if (st.mean_tree_accept) st.mean_tree_accept[k] = mta;
+        if (st.mean_tree_accept_sym) st.mean_tree_accept_sym[k] = msa;
+        if (st.n_steps) st.n_steps[k] = acc_count;
+        if (st.max_energy_error) st.max_energy_error[k] = max_energy_error;
+        if (st.tuning) st.tuning[k] = 0;
+        if (st.fisher_distance) st.fisher_distance[k] = fisher[0];
+      }
+      store_hot();
+      NB_ACC(6, tm);
+      return;
+    }
     // ---- adaptation + statistics: cold, through global memory
     store_hot();
     const int ret = cold_adapt<TPC, EPT, SMF, MODEL, MULTI>(P, chain, tid, red.scratch, sm_sig, mc, red.parity, t, acc_sum, acc_sym_sum, acc_count,
@@ -1590,6 +1774,7 @@ struct Engine {
     draw_begin();
     NB_ACC(0, td);
     // NutsTree::new (nuts.rs:94-105): log_size 0 = weight 1
+    stg_src[0] = stg_src[1] = nullptr;
     lin = true;
     ls_main = 1.;
     depth = 0;
@@ -1648,13 +1833,15 @@ struct Engine {
   __device__ __forceinline__ double* endbuf_ptr(int buf, int which) const { return ends_base + (size_t)((buf * 3 + which) * ld); }
 
   // U-turn products of one merge, per-thread partials (no reduction): (Af, cur) always; when `full` also (Al, cur), (Af, Bf).
+  // AF_SMEM: Afz / Afv point into a staging buffer (shared memory) instead of the checkpoint pool
+  template <bool AF_SMEM>
   __device__ __forceinline__ void merge_products(const double* Afz, const double* Afv, const double* Alz, const double* Alv,
                                                  const double* Bfz, const double* Bfv, bool full, double (&s)[6]) {
     s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.0;
     if (!full) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         if (inb(i)) {
           double delta = (z[j] + 0.0) - __ldcg(Afz + i);
           s[0] = fma(delta, __ldcg(Afv + i), s[0]);
@@ -1663,23 +1850,39 @@ struct Engine {
       }
       return;
     }
+    if (PAIR) {  // 16-byte checkpoint reads; the partner of an odd last element is zero padding on both sides (adds +0.0)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int i0 = eidx(2 * p);
+        if (inb(i0)) {
+          const double2 afz = AF_SMEM ? *reinterpret_cast<const double2*>(Afz + i0) : __ldcg(reinterpret_cast<const double2*>(Afz + i0)),
+                        afv = AF_SMEM ? *reinterpret_cast<const double2*>(Afv + i0) : __ldcg(reinterpret_cast<const double2*>(Afv + i0)),
+                        alz = __ldcg(reinterpret_cast<const double2*>(Alz + i0)), alv = __ldcg(reinterpret_cast<const double2*>(Alv + i0)),
+                        bfz = __ldcg(reinterpret_cast<const double2*>(Bfz + i0)), bfv = __ldcg(reinterpret_cast<const double2*>(Bfv + i0));
+          merge_element(z[2 * p], v[2 * p], afz.x, afv.x, alz.x, alv.x, bfz.x, bfv.x, s);
+          merge_element(z[2 * p + 1], v[2 * p + 1], afz.y, afv.y, alz.y, alv.y, bfz.y, bfv.y, s);
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
-      if (inb(i)) {
-        double afz = __ldcg(Afz + i), afv = __ldcg(Afv + i), alz = __ldcg(Alz + i), alv = __ldcg(Alv + i), bfz = __ldcg(Bfz + i),
-               bfv = __ldcg(Bfv + i);
-        double d1 = (z[j] + 0.0) - afz;
-        s[0] = fma(d1, afv, s[0]);
-        s[1] = fma(d1, v[j], s[1]);
-        double d2 = (z[j] + 0.0) - alz;
-        s[2] = fma(d2, alv, s[2]);
-        s[3] = fma(d2, v[j], s[3]);
-        double d3 = (bfz + 0.0) - afz;
-        s[4] = fma(d3, afv, s[4]);
-        s[5] = fma(d3, bfv, s[5]);
-      }
+      int i = eidx(j);
+      if (inb(i)) merge_element(z[j], v[j], __ldcg(Afz + i), __ldcg(Afv + i), __ldcg(Alz + i), __ldcg(Alv + i), __ldcg(Bfz + i), __ldcg(Bfv + i), s);
     }
+  }
+  // the six U-turn products of one element: pairs (Af, cur), (Al, cur), (Af, Bf)
+  static __device__ __forceinline__ void merge_element(double zc, double vc, double afz, double afv, double alz, double alv, double bfz,
+                                                       double bfv, double (&s)[6]) {
+    const double d1 = (zc + 0.0) - afz;
+    s[0] = fma(d1, afv, s[0]);
+    s[1] = fma(d1, vc, s[1]);
+    const double d2 = (zc + 0.0) - alz;
+    s[2] = fma(d2, alv, s[2]);
+    s[3] = fma(d2, vc, s[3]);
+    const double d3 = (bfz + 0.0) - afz;
+    s[4] = fma(d3, afv, s[4]);
+    s[5] = fma(d3, bfv, s[5]);
   }
 
   // gradient of the diagonal Gaussian in the whitened space at whitened position zz, element j: the very instruction sequence
@@ -1703,15 +1906,17 @@ struct Engine {
   __device__ __forceinline__ void leapfrog_partials_nog(double eps, bool half_done, double (&part)[4]) {
     const double eps_half = eps / 2.;
     part[0] = part[1] = part[2] = part[3] = 0.0;
+    PairConsts pc;
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      const int i = tid + j * TPC;
+      const int i = eidx(j);
+      if (PAIR && (j & 1) == 0) pair_consts(j, pc);
       const double zp = z[j], vp = v[j];
-      const double sgm = sg(j), mnj = mn(j);
+      const double sgm = PAIR ? pc.sg[j & 1] : sg(j), mnj = PAIR ? pc.mn[j & 1] : mn(j);
       double mmu = 0.0, mprec = 0.0;
       if (inb(i)) {
-        mmu = model_mu(j, i);
-        mprec = model_prec(j, i);
+        mmu = PAIR ? pc.mm[j & 1] : model_mu(j, i);
+        mprec = PAIR ? pc.pr[j & 1] : model_prec(j, i);
       }
       double g0;
       {
@@ -1792,7 +1997,7 @@ struct Engine {
         const double* gp = P.gz + row;
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
-          const int i = tid + j * TPC;
+          const int i = eidx(j);
           const double gl = inb(i) ? __ldcg(gp + i) : 0.0;
           v[j] = fma(eps_half, gl, v[j]);
         }
@@ -1850,7 +2055,7 @@ struct Engine {
           lv = es_near < 0 ? P.v0 + row : slot_ptr(es_near, 1);
         }
         double sp[6];
-        merge_products(az, av, lz, lv, slot_ptr(Bf, 0), slot_ptr(Bf, 1), true, sp);
+        merge_products<false>(az, av, lz, lv, slot_ptr(Bf, 0), slot_ptr(Bf, 1), true, sp);
         const double mine = warp_reduce_scatter8<6>(sp);
         if (lane < 6) e[4 + 6 * m + lane] = mine;
       }
@@ -1947,13 +2152,17 @@ struct Engine {
   // ------------------------------------------------------------------ Chain::set_position (chain.rs:137-149)
   __device__ __forceinline__ int run_set_position() {
     double x[EPT], gx[EPT];
-    load(P.init_position + (size_t)chain * d, x);
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {  // dense [N][d] rows: not 16-byte aligned for odd d
+      const int i = eidx(j);
+      x[j] = i < d ? P.init_position[(size_t)chain * d + i] : 0.0;
+    }
     // GlobalStrategy::init -> init_state_untransformed (transformed_hamiltonian.rs:663-685)
     hs_logp = eval_at_position(x, gx);
     double bad[1] = {0.0};
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      int i = tid + j * TPC;
+      int i = eidx(j);
       if (i < d && !(isfinite(x[j]) && isfinite(gx[j]))) bad[0] = 1.0;
     }
     red.allreduce(bad);
@@ -1972,7 +2181,7 @@ struct Engine {
       double* mn = P.mean + row;
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        int i = tid + j * TPC;
+        int i = eidx(j);
         if (i < d) {
           double val = 1.0 / clampd(fabs(gx[j]), 1e-20, 1e20);  // cpu_math.rs:710-738
           if (!isfinite(val)) val = 1.0;
@@ -2047,17 +2256,15 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
   }
   E.cold_store();
 #ifdef NB_PHASE_TIMING_COLD
-  if (tid == 0 && P.phase_clocks) {  // 0 cold_load..estimators, 1 first set, 2 second set, 3 mass matrix, 4 rest, 7 total
+  if (tid == 0 && P.phase_clocks) {  // [8] cold_load .. schedule, [9] the vector pass, [10] dual averaging / step size / stats / cold_store, [15] total
     const long long t_end = clock64();
     const long long* c = E.cold_t;
     if (c[1]) {
-      atomicAdd(P.phase_clocks + 0, (unsigned long long)(c[1] - cold_t0));
-      atomicAdd(P.phase_clocks + 1, (unsigned long long)((c[2] ? c[2] : c[3]) - c[1]));
-      atomicAdd(P.phase_clocks + 2, (unsigned long long)(c[3] - (c[2] ? c[2] : c[3])));
-      atomicAdd(P.phase_clocks + 3, (unsigned long long)(c[4] - c[3]));
-      atomicAdd(P.phase_clocks + 4, (unsigned long long)(t_end - c[4]));
+      atomicAdd(P.phase_clocks + 8, (unsigned long long)(c[1] - cold_t0));
+      atomicAdd(P.phase_clocks + 9, (unsigned long long)(c[4] - c[1]));
+      atomicAdd(P.phase_clocks + 10, (unsigned long long)(t_end - c[4]));
     }
-    atomicAdd(P.phase_clocks + 7, (unsigned long long)(t_end - cold_t0));
+    atomicAdd(P.phase_clocks + 15, (unsigned long long)(t_end - cold_t0));
   }
 #endif
   return E.red.parity & 1;

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "nuts_sampler_counters", "nuts_sampler_last_timing", "nuts_sampler_get_state", "nuts_sampler_set_step_size",
     "nuts_host_alloc", "nuts_host_free", "nuts_sampler_last_draw_direct",
     "nuts_sampler_get_chain_state", "nuts_sampler_set_chain_state",
+    "nuts_comm_unique_id", "nuts_comm_create", "nuts_comm_destroy", "nuts_gather_draws_begin", "nuts_gather_draws_end",
 ]
 
 
@@ -113,6 +114,11 @@ def load():
     L.nuts_sampler_last_draw_direct.argtypes = [vp, _abi.c_i32_p]
     L.nuts_sampler_get_chain_state.argtypes = [vp, C.POINTER(_abi.ChainState)]
     L.nuts_sampler_set_chain_state.argtypes = [vp, C.POINTER(_abi.ChainState)]
+    L.nuts_comm_unique_id.argtypes = [_abi.c_u8_p]
+    L.nuts_comm_create.argtypes = [C.POINTER(vp), C.c_int, _abi.c_u8_p, C.c_int, C.c_int]
+    L.nuts_comm_destroy.argtypes = [vp]
+    L.nuts_gather_draws_begin.argtypes = [vp, vp, vp, vp, C.c_uint64]
+    L.nuts_gather_draws_end.argtypes = [vp, dp]
     _LIB = L
     return L
 
@@ -507,4 +513,33 @@ class Sampler:
     def close(self):
         if self.h:
             load().nuts_sampler_destroy(self.h)
+            self.h = None
+
+
+class Comm:
+    """NCCL communicator of the draw gather (nuts_comm_*): one per process / GPU.  `exchange(id_bytes_or_None) -> bytes` moves the
+    128-byte id from rank 0 to every rank over any host channel (e.g. torch.distributed.broadcast_object_list)."""
+
+    def __init__(self, device, nranks, rank, exchange):
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            _check(load().nuts_comm_unique_id(ident))
+        raw = exchange(bytes(ident) if rank == 0 else None)
+        ident = (C.c_uint8 * 128).from_buffer_copy(raw)
+        h = C.c_void_p()
+        _check(load().nuts_comm_create(C.byref(h), device, ident, nranks, rank))
+        self.h = h
+        self.nranks, self.rank = nranks, rank
+
+    def gather_begin(self, sampler, local_dev_ptr, gathered_dev_ptr, count):
+        _check(load().nuts_gather_draws_begin(sampler.h, self.h, local_dev_ptr, gathered_dev_ptr, count))
+
+    def gather_end(self):
+        ms = C.c_double()
+        _check(load().nuts_gather_draws_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            load().nuts_comm_destroy(self.h)
             self.h = None

@@ -17,7 +17,11 @@ for w in $WHAT; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 3 -c 1 -f -o gpurun_out/prof_$TAG python tools/prof_run.py > gpurun_out/prof_$TAG.log 2>&1; echo "ncu full rc=$?"; tail -2 gpurun_out/prof_$TAG.log;;
     configs) for c in c2 c3 c4 c5; do timeout 300 python tools/quick.py $c 2>&1 | tail -1; done | tee gpurun_out/configs_$TAG.log;;
     v2) for e in 64,16,107; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/v2_$TAG.log;;
-    phase) NUTS_B200_LIB=$PWD/nuts_rs_b200/libnuts_b200_phase.so timeout 300 python tools/phase_timing.py 2>&1 | tee gpurun_out/phase_$TAG.log;;
+    phase) for c in c2 c5; do NUTS_B200_LIB=$PWD/nuts_rs_b200/libnuts_b200_phase.so timeout 300 python tools/phase_timing.py $c; done 2>&1 | tee gpurun_out/phase_$TAG.log;;
+    variants) for e in 64,16,54 64,16,55 64,16,57 64,16,56 64,16,58 64,16,107; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/variants_$TAG.log;;
+    stage) for e in 64,16,54 64,16,58; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/stage_$TAG.log
+           NUTS_B200_ENGINE=64,16,58 NUTS_B200_LIB=$PWD/nuts_rs_b200/libnuts_b200_phase.so timeout 300 python tools/phase_timing.py c2 2>&1 | tee -a gpurun_out/stage_$TAG.log
+           NUTS_B200_ENGINE=64,16,58 timeout 600 python -m pytest tests/test_gpu_teacher_forced.py -q -k "config2 or checkpoint" 2>&1 | tail -3 | tee -a gpurun_out/stage_$TAG.log;;
     sanitize)
       for c in c1 migrate large funnel rank1; do
         for tool in racecheck memcheck; do
