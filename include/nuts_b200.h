@@ -49,7 +49,9 @@ enum {
   NUTS_LOGP_GAUSS_ISO = 0,   /* logp = -sum (x-mu)^2/2          reference src/math/test_logps.rs:49-58, benches/sample.rs:49-62 */
   NUTS_LOGP_GAUSS_DIAG = 1,  /* logp = -sum (x-mu_i)^2/(2 s_i^2) diagonal generalisation of the above                           */
   NUTS_LOGP_GAUSS_RANK1 = 2, /* Sigma = I + s*11^T              reference tests/sample_normal.rs:29-96                           */
-  NUTS_LOGP_FUNNEL = 3       /* Neal's funnel: x0=v~N(0,fs^2), x_i~N(0,e^v)  (BASELINE.json config 3; not in the reference)      */
+  NUTS_LOGP_FUNNEL = 3,      /* Neal's funnel: x0=v~N(0,fs^2), x_i~N(0,e^v)  (BASELINE.json config 3; not in the reference)      */
+  NUTS_LOGP_USER = 4         /* the density compiled in from a user header: include/nuts_user_logp.cuh (CpuLogpFunc::logp,
+                                reference src/math/cpu_math.rs:885-970, incl. the recoverable / fatal LogpError channel)          */
 };
 
 typedef struct {
@@ -60,6 +62,8 @@ typedef struct {
   const double* sigma;  /* GAUSS_DIAG: host pointer [dim] of standard deviations (required) */
   double rank1_scale;   /* GAUSS_RANK1: s */
   double funnel_scale;  /* FUNNEL: prior sd of v (3.0 in BASELINE) */
+  const double* user_params; /* USER: host pointer [n_user_params], copied to the device and handed to NutsUserLogp */
+  uint64_t n_user_params;
 } nuts_logp_desc_t;
 
 /* ---- settings: NutsSettings<EuclideanAdaptOptions<DiagAdaptExpSettings>> field for field --------------------

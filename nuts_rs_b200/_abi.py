@@ -11,6 +11,7 @@ NUTS_LOGP_GAUSS_ISO = 0
 NUTS_LOGP_GAUSS_DIAG = 1
 NUTS_LOGP_GAUSS_RANK1 = 2
 NUTS_LOGP_FUNNEL = 3
+NUTS_LOGP_USER = 4
 
 NUTS_STEPSIZE_DUAL_AVERAGE = 0
 NUTS_STEPSIZE_FIXED = 2
@@ -39,6 +40,8 @@ class LogpDesc(C.Structure):
         ("sigma", c_double_p),
         ("rank1_scale", C.c_double),
         ("funnel_scale", C.c_double),
+        ("user_params", c_double_p),
+        ("n_user_params", C.c_uint64),
     ]
 
 
@@ -216,7 +219,7 @@ def default_settings() -> NutsSettings:
     return s
 
 
-def make_logp_desc(kind, dim, mu=None, sigma=None, rank1_scale=0.0, funnel_scale=3.0):
+def make_logp_desc(kind, dim, mu=None, sigma=None, rank1_scale=0.0, funnel_scale=3.0, user_params=None):
     """Build a LogpDesc; returns (desc, keepalive) — keep `keepalive` referenced while the desc is in use."""
     import numpy as np
 
@@ -239,4 +242,9 @@ def make_logp_desc(kind, dim, mu=None, sigma=None, rank1_scale=0.0, funnel_scale
         d.sigma = sg.ctypes.data_as(c_double_p)
     d.rank1_scale = float(rank1_scale)
     d.funnel_scale = float(funnel_scale)
+    if user_params is not None:
+        up = np.ascontiguousarray(user_params, dtype=np.float64).ravel()
+        keep.append(up)
+        d.user_params = up.ctypes.data_as(c_double_p)
+        d.n_user_params = up.size
     return d, keep

@@ -21,7 +21,7 @@ using namespace nb;
 #define NB_DECL1(TPC, EPT, MINB, MODEL)                                                                                                      \
   extern "C" __attribute__((weak)) cudaError_t nb_launch_chain_##TPC##_##EPT##_##MINB##_##MODEL(const EngineParams* p, int grid, cudaStream_t s); \
   extern "C" __attribute__((weak)) cudaError_t nb_occupancy_chain_##TPC##_##EPT##_##MINB##_##MODEL(int* blocks_per_sm, int* cta_threads, int* smf);
-#define NB_DECL(TPC, EPT, MINB) NB_DECL1(TPC, EPT, MINB, 1) NB_DECL1(TPC, EPT, MINB, 2) NB_DECL1(TPC, EPT, MINB, 3)
+#define NB_DECL(TPC, EPT, MINB) NB_DECL1(TPC, EPT, MINB, 1) NB_DECL1(TPC, EPT, MINB, 2) NB_DECL1(TPC, EPT, MINB, 3) NB_DECL1(TPC, EPT, MINB, 4)
 NB_DECL(32, 1, 16)
 NB_DECL(32, 2, 16)
 NB_DECL(32, 4, 16)
@@ -78,29 +78,31 @@ int fail(int code, const char* fmt, ...) {
 
 struct EngineConfig {
   int tpc, ept, minb, max_d;
-  // indexed by model variant - 1 (1 diagonal/isotropic Gaussian, 2 rank-1 Gaussian, 3 funnel)
-  cudaError_t (*launch[3])(const EngineParams*, int, cudaStream_t);
-  cudaError_t (*occupancy[3])(int*, int*, int*);
+  // indexed by model variant - 1 (1 diagonal/isotropic Gaussian, 2 rank-1 Gaussian, 3 funnel, 4 user density)
+  cudaError_t (*launch[4])(const EngineParams*, int, cudaStream_t);
+  cudaError_t (*occupancy[4])(int*, int*, int*);
   int min_d = 0;  // kDecoupledLarge only: chosen for min_d < dim <= max_d
 };
 #define NB_CFG(TPC, EPT, MINB)                                                                                                             \
   {                                                                                                                                        \
     TPC, EPT, MINB, TPC* EPT,                                                                                                              \
-        {nb_launch_chain_##TPC##_##EPT##_##MINB##_1, nb_launch_chain_##TPC##_##EPT##_##MINB##_2, nb_launch_chain_##TPC##_##EPT##_##MINB##_3}, \
+        {nb_launch_chain_##TPC##_##EPT##_##MINB##_1, nb_launch_chain_##TPC##_##EPT##_##MINB##_2, nb_launch_chain_##TPC##_##EPT##_##MINB##_3, \
+         nb_launch_chain_##TPC##_##EPT##_##MINB##_4},                                                                                      \
     {                                                                                                                                      \
-      nb_occupancy_chain_##TPC##_##EPT##_##MINB##_1, nb_occupancy_chain_##TPC##_##EPT##_##MINB##_2, nb_occupancy_chain_##TPC##_##EPT##_##MINB##_3 \
+      nb_occupancy_chain_##TPC##_##EPT##_##MINB##_1, nb_occupancy_chain_##TPC##_##EPT##_##MINB##_2, nb_occupancy_chain_##TPC##_##EPT##_##MINB##_3, \
+          nb_occupancy_chain_##TPC##_##EPT##_##MINB##_4                                                                                    \
     }                                                                                                                                      \
   }
 #define NB_CFG1(TPC, EPT, MINB) \
-  { TPC, EPT, MINB, TPC* EPT, {nb_launch_chain_##TPC##_##EPT##_##MINB##_1, nullptr, nullptr}, {nb_occupancy_chain_##TPC##_##EPT##_##MINB##_1, nullptr, nullptr} }
+  { TPC, EPT, MINB, TPC* EPT, {nb_launch_chain_##TPC##_##EPT##_##MINB##_1, nullptr, nullptr, nullptr}, {nb_occupancy_chain_##TPC##_##EPT##_##MINB##_1, nullptr, nullptr, nullptr} }
 // default choice: the first entry whose capacity (tpc*ept) covers dim.  Warp-per-chain up to dim 1024 (no barrier in
 // the whole kernel, all 1024 chains of config 2 resident at once); CTA-per-chain above.
 const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32, 4, 16),  NB_CFG(32, 8, 12),   NB_CFG(32, 16, 8),   NB_CFG(64, 16, 4),
                                  NB_CFG(256, 8, 2), NB_CFG(512, 8, 1), NB_CFG(1024, 8, 1), NB_CFG(1024, 10, 1), NB_CFG(1024, 16, 1)};
 // decoupled engine for large dims (chosen for min_d < dim <= max_d, elementwise targets)
 const EngineConfig kDecoupledLarge[] = {
-    {480, 18, 181, 480 * 18, {nb_launch_chain_480_18_181_1, nullptr, nullptr}, {nb_occupancy_chain_480_18_181_1, nullptr, nullptr}, 4096},
-    {480, 21, 171, 480 * 21, {nb_launch_chain_480_21_171_1, nullptr, nullptr}, {nb_occupancy_chain_480_21_171_1, nullptr, nullptr}, 480 * 18}};
+    {480, 18, 181, 480 * 18, {nb_launch_chain_480_18_181_1, nullptr, nullptr, nullptr}, {nb_occupancy_chain_480_18_181_1, nullptr, nullptr, nullptr}, 4096},
+    {480, 21, 171, 480 * 21, {nb_launch_chain_480_21_171_1, nullptr, nullptr, nullptr}, {nb_occupancy_chain_480_21_171_1, nullptr, nullptr, nullptr}, 480 * 18}};
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
@@ -121,6 +123,7 @@ struct nuts_ctx {
   ModelDev model{};
   double* d_model_mu = nullptr;
   double* d_model_prec = nullptr;
+  double* d_model_user = nullptr;  // NUTS_LOGP_USER: device copy of user_params
   // Tier-2 transformation (one DiagMassMatrix per chain)
   TransformDev T{};
   // scratch
@@ -321,6 +324,13 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
     case NUTS_LOGP_FUNNEL:
       ctx->model.funnel_inv_var = 1.0 / (model->funnel_scale * model->funnel_scale);
       break;
+    case NUTS_LOGP_USER:  // the density compiled in from the user header (include/nuts_user_logp.cuh)
+      if (model->n_user_params > 0 && !model->user_params) return fail(NUTS_ERR_INVALID, "NUTS_LOGP_USER: user_params is NULL");
+      TRY(dev_alloc(&ctx->d_model_user, std::max<size_t>(model->n_user_params, 1)));
+      if (model->n_user_params > 0)
+        CUDA_TRY(cudaMemcpy(ctx->d_model_user, model->user_params, model->n_user_params * sizeof(double), cudaMemcpyHostToDevice));
+      ctx->model.user = ctx->d_model_user;
+      break;
     default:
       return fail(NUTS_ERR_INVALID, "unknown logp kind %d", model->kind);
   }
@@ -355,6 +365,7 @@ int nuts_ctx_destroy(nuts_ctx_t* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_model_mu);
   cudaFree(ctx->d_model_prec);
+  cudaFree(ctx->d_model_user);
   cudaFree(ctx->T.stds);
   cudaFree(ctx->T.inv_stds);
   cudaFree(ctx->T.mean);
@@ -744,7 +755,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
     // dim ~ 10^4: a chain's (z, v, sigma, mu) plus the redundant scalar state of the register-resident engine no longer fit one SM
     // (1024x10 runs at 64 registers per thread and spills 2.5 KB); the decoupled engine keeps the scalar state in ONE leader warp
     for (const EngineConfig& c : kDecoupledLarge)
-      if (ctx->model.kind != NUTS_LOGP_GAUSS_RANK1 && ctx->model.kind != NUTS_LOGP_FUNNEL && c.launch[0] && ctx->d > (uint64_t)c.min_d &&
+      if (ctx->model.kind != NUTS_LOGP_GAUSS_RANK1 && ctx->model.kind != NUTS_LOGP_FUNNEL && ctx->model.kind != NUTS_LOGP_USER && c.launch[0] && ctx->d > (uint64_t)c.min_d &&
           ctx->d <= (uint64_t)c.max_d && st->maxdepth + st->extra_doublings <= (uint64_t)V2_MAXD + 1) {
         cfg = &c;
         break;
@@ -763,7 +774,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   P.N = (int)ctx->N;
   P.d = (int)ctx->d;
   int blocks_per_sm = 0, cta_threads = 0, smf = 0;
-  s->model_variant = ctx->model.kind == NUTS_LOGP_GAUSS_RANK1 ? 1 : ctx->model.kind == NUTS_LOGP_FUNNEL ? 2 : 0;
+  s->model_variant = ctx->model.kind == NUTS_LOGP_GAUSS_RANK1 ? 1 : ctx->model.kind == NUTS_LOGP_FUNNEL ? 2 : ctx->model.kind == NUTS_LOGP_USER ? 3 : 0;
   if (!cfg->launch[s->model_variant] || !cfg->occupancy[s->model_variant]) {
     return fail(NUTS_ERR_UNSUPPORTED, "engine %dx%d for model kind %d is not part of this build", cfg->tpc, cfg->ept, ctx->model.kind);
   }

@@ -594,9 +594,9 @@ struct Engine {
     uint64_t off = hs_rng - pc_base;
     if (off >= 32ull) {  // warp-uniform
       pc_base = hs_rng;
-      const PhiloxBlock b = philox4x32_10(P.seed, stream, hs_rng + (uint64_t)(threadIdx.x & 31));
-      pc_r0 = b.r0;
-      pc_r1 = b.r1;
+      const uint2 b = philox01(P.seed, stream, hs_rng + (uint64_t)(threadIdx.x & 31));
+      pc_r0 = b.x;
+      pc_r1 = b.y;
       off = 0;
     }
     r0 = __shfl_sync(0xffffffffu, pc_r0, (int)off);
@@ -682,8 +682,22 @@ struct Engine {
       red.allreduce(s);
       a0 = s[1];  // v
       a1 = s[0];  // S
+    } else if (MODEL == LOGP_USER && NutsUserLogp::NUM_SUMS > 0) {  // the team-wide sums the user's element pass asks for
+      double s[2] = {0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = eidx(j);
+        if (i < d) NutsUserLogp::sums(i, d, x[j], m.user, s);
+      }
+      red.allreduce(s);
+      a0 = s[0];
+      a1 = s[1];
     }
   }
+  // LOGP_USER error channel (LogpError, reference src/math/math.rs:9-13): what this thread's elements reported during the last
+  // model_phase_b, and the draw-level verdict after the team reduction
+  double ue_rec = 0.0, ue_fatal = 0.0;
+  bool user_fatal = false;
   // elementwise gradient; returns this thread's partial of logp (sum-type models)
   __device__ __forceinline__ double model_phase_b(const double (&x)[EPT], double (&gx)[EPT], double a0, double a1, double& ev_out) {
     const ModelDev& m = P.model;
@@ -724,6 +738,21 @@ struct Engine {
           lp -= 0.5 * diff * ptd;
         }
       }
+    } else if (MODEL == LOGP_USER) {
+      const double sums[2] = {a0, a1};
+      ue_rec = 0.0;
+      ue_fatal = 0.0;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        int i = eidx(j);
+        gx[j] = 0.0;
+        if (i < d) {
+          int status = NUTS_USER_OK;
+          lp += NutsUserLogp::element(i, d, x[j], sums, m.user, gx[j], status);
+          if (status == NUTS_USER_RECOVERABLE) ue_rec = 1.0;
+          if (status == NUTS_USER_FATAL) ue_fatal = 1.0;
+        }
+      }
     } else {  // funnel
       double vv = a0;
       double ev = exp(-vv);
@@ -749,7 +778,17 @@ struct Engine {
       double half_ev_S = 0.5 * ev * a1;
       return -0.5 * a0 * a0 * m.funnel_inv_var - 0.5 * nm1 * a0 - half_ev_S;
     }
+    if (MODEL == LOGP_USER) {
+      const double sums[2] = {a0, a1};
+      return lp_sum + NutsUserLogp::finish(d, sums, m.user);
+    }
     return lp_sum;
+  }
+  // LOGP_USER: fold the team's error flags (reduced next to logp) into the result: any error makes logp NaN - the leapfrog is then
+  // a divergence (non-finite energy, transformed_hamiltonian.rs:562-565, 590-597) - and a fatal one also ends the chain
+  __device__ __forceinline__ double user_verdict(double logp, double n_rec, double n_fatal) {
+    if (n_fatal > 0.0) user_fatal = true;
+    return (n_rec > 0.0 || n_fatal > 0.0) ? __longlong_as_double(0x7ff8000000000000ll) : logp;
   }
 
   // One velocity-Verlet step of the diagonal Gaussian WITHOUT the team reduction: (z, v, g) advance in place, part = this thread's
@@ -834,9 +873,16 @@ struct Engine {
       v[j] = fma(eps_half, G(j), v[j]);
       part[1] = fma(v[j], v[j], part[1]);
     }
-    red.allreduce(part);
-    logp_out = model_finish(part[0], a0, a1, ev);
-    ke_out = 0.5 * part[1];
+    if (MODEL == LOGP_USER) {
+      double p4[4] = {part[0], part[1], ue_rec, ue_fatal};
+      red.allreduce(p4);
+      logp_out = user_verdict(model_finish(p4[0], a0, a1, ev), p4[2], p4[3]);
+      ke_out = 0.5 * p4[1];
+    } else {
+      red.allreduce(part);
+      logp_out = model_finish(part[0], a0, a1, ev);
+      ke_out = 0.5 * part[1];
+    }
     sP = 0.0;
     sQ = 0.0;
   }
@@ -849,6 +895,11 @@ struct Engine {
     model_phase_a(x, a0, a1);
     double part[1];
     part[0] = model_phase_b(x, gx, a0, a1, ev);
+    if (MODEL == LOGP_USER) {
+      double p3[3] = {part[0], ue_rec, ue_fatal};
+      red.allreduce(p3);
+      return user_verdict(model_finish(p3[0], a0, a1, ev), p3[1], p3[2]);
+    }
     red.allreduce(part);
     return model_finish(part[0], a0, a1, ev);
   }
@@ -1067,11 +1118,13 @@ struct Engine {
   // half under construction (levels = the set bits of the leaf index i; level 0 is a log weight already) and the main tree.
   __device__ __forceinline__ void weights_to_log_domain(uint32_t i) {
     lin = false;
-    ls_main = log(ls_main);
+    ls_main = log_noinline(ls_main);
     tsync();
-    if (tid == 0)
+    if (tid == 0) {
+#pragma unroll 1
       for (int l = 1; l < MAX_DOUBLING_DEPTH; ++l)
-        if ((i >> l) & 1u) T.A_ls[l] = log(T.A_ls[l]);
+        if ((i >> l) & 1u) T.A_ls[l] = log_noinline(T.A_ls[l]);
+    }
     tsync();
     if (TPC > 32) red.barrier();
   }
@@ -1233,8 +1286,9 @@ struct Engine {
           if (WA >= WB * 0x1p-40) take_B = rng_f64() * total < WB;
           else take_B = lin_reference_shortcut(WA, WB) || (rng_f64() * total < WB);
         } else {
-          total = logaddexp(T.A_ls[l], B_ls);
-          take_B = (B_ls >= total) || (rng_f64() < exp(B_ls - total));
+          const LogMerge mg = log_domain_merge(T.A_ls[l], B_ls, false);
+          total = mg.total;
+          take_B = mg.shortcut || (rng_f64() < mg.p);
         }
         if (take_B) {
           unref(T.A_draw[l]);
@@ -1276,8 +1330,9 @@ struct Engine {
       take = (WB >= ls_main) || (rng_f64() * ls_main < WB);
       total = ls_main + WB;
     } else {
-      total = logaddexp(ls_main, B_ls);
-      take = (B_ls >= ls_main) || (rng_f64() < exp(B_ls - ls_main));
+      const LogMerge mg = log_domain_merge(ls_main, B_ls, true);
+      total = mg.total;
+      take = mg.shortcut || (rng_f64() < mg.p);
     }
     if (take) {
       draw_slot = B_draw;
@@ -1821,6 +1876,16 @@ struct Engine {
       }
     }
     flush_accept();
+    if (MODEL == LOGP_USER && user_fatal) {
+      // LogpError::is_recoverable() == false: NutsError::LogpFailure ends the chain (nuts.rs:231); this draw and all later ones of
+      // the launch read NaN / "nothing happened", the chain is reported dead (nuts_chain_state_t::alive = 0)
+      hs_alive = 0;
+      store_hot();
+      if (tid == 0) P.cs[chain].alive = 0;
+      team_sync();
+      cold_fill_dead(P, chain, tid, TPC, t);
+      return;
+    }
     draw_finish(t, diverging, reached_maxdepth);
     NB_ACC(7, tw);
   }
@@ -2167,6 +2232,7 @@ struct Engine {
     }
     red.allreduce(bad);
     if (bad[0] != 0.0) return 3;
+    if (MODEL == LOGP_USER && !isfinite(hs_logp)) return 3;  // the user density reported an error at the initial point
     store(P.x + row, x);
     store(P.gx + row, gx);
     // mass_matrix_adapt.init (transform/adapt/diagonal.rs:209-231): seed all four estimators, update_diag_grad

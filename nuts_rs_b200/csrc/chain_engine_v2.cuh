@@ -25,10 +25,7 @@ __device__ __forceinline__ bool v2_turn_eval(double sP, double sQ, int dir) {
 
 // The leader's transcendental / RNG work goes through ONE copy of each routine (the kernel's hot code has to stay inside the
 // 32 KB instruction cache next to the unrolled vector loops).
-static __device__ __noinline__ uint2 v2_philox01(uint64_t seed, uint64_t stream, uint64_t counter) {  // words 0, 1 of the block
-  const PhiloxBlock b = philox4x32_10(seed, stream, counter);
-  return make_uint2(b.r0, b.r1);
-}
+__device__ __forceinline__ uint2 v2_philox01(uint64_t seed, uint64_t stream, uint64_t counter) { return philox01(seed, stream, counter); }
 __device__ __forceinline__ double v2_stream_f64(uint64_t seed, uint64_t stream, uint64_t counter) {  // == stream_f64
   const uint2 b = v2_philox01(seed, stream, counter);
   return u53((uint64_t)b.x | ((uint64_t)b.y << 32));
@@ -126,10 +123,11 @@ struct LeaderLane {
   // leave the linear domain for the rest of this draw (chain_engine.cuh weights_to_log_domain): pending levels = set bits of i
   __device__ __forceinline__ void weights_to_log_domain() {
     lin = false;
-    ls_main = log(ls_main);
+    ls_main = log_noinline(ls_main);
     if (i & 1u) c.A_ls[0] = c.A_log0;
+#pragma unroll 1
     for (int l = 1; l < V2_NT; ++l)
-      if ((i >> l) & 1u) c.A_ls[l] = log(c.A_ls[l]);
+      if ((i >> l) & 1u) c.A_ls[l] = log_noinline(c.A_ls[l]);
   }
 
   __device__ __forceinline__ void command(int kind, int accepted) {

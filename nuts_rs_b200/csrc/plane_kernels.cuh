@@ -183,6 +183,23 @@ __device__ __forceinline__ double model_eval_row(const ModelDev& m, int d, const
     a0 = s[1];
     a1 = s[0];
   }
+  if (m.kind == LOGP_USER) {  // the user density (include/nuts_user_logp.cuh); an error of either kind makes logp NaN
+    double s[2] = {0.0, 0.0};
+    if (NutsUserLogp::NUM_SUMS > 0) {
+      for (int i = threadIdx.x; i < d; i += PK_THREADS) NutsUserLogp::sums(i, d, x[i], m.user, s);
+      red.allreduce(s);
+    }
+    double p2[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      int status = NUTS_USER_OK;
+      double g = 0.0;
+      p2[0] += NutsUserLogp::element(i, d, x[i], s, m.user, g, status);
+      gx[i] = g;
+      if (status != NUTS_USER_OK) p2[1] = 1.0;
+    }
+    red.allreduce(p2);
+    return p2[1] > 0.0 ? __longlong_as_double(0x7ff8000000000000ll) : p2[0] + NutsUserLogp::finish(d, s, m.user);
+  }
   double lp[1] = {0.0};
   if (m.kind == LOGP_FUNNEL) {
     double ev = exp(-a0), nm1 = (double)(d - 1), half_ev_S = 0.5 * ev * a1;

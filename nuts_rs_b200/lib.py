@@ -228,11 +228,11 @@ class Point:
 class CudaMath:
     """Batched `Math` backend on one B200: `nchains` independent chains of dimension `dim` with a device-side logp."""
 
-    def __init__(self, nchains, dim, kind, mu=None, sigma=None, rank1_scale=0.0, funnel_scale=3.0, device=0):
+    def __init__(self, nchains, dim, kind, mu=None, sigma=None, rank1_scale=0.0, funnel_scale=3.0, device=0, user_params=None):
         self.h = None
         self.nchains = int(nchains)
         self._dim = int(dim)
-        self.desc, self._keep = _abi.make_logp_desc(kind, dim, mu, sigma, rank1_scale, funnel_scale)
+        self.desc, self._keep = _abi.make_logp_desc(kind, dim, mu, sigma, rank1_scale, funnel_scale, user_params)
         h = C.c_void_p()
         _check(load().nuts_ctx_create(C.byref(h), device, nchains, dim, C.byref(self.desc)))
         self.h = h

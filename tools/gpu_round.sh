@@ -18,6 +18,12 @@ for w in $WHAT; do
     configs) for c in c2 c3 c4 c5; do timeout 300 python tools/quick.py $c 2>&1 | tail -1; done | tee gpurun_out/configs_$TAG.log;;
     v2) for e in 64,16,107; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/v2_$TAG.log;;
     phase) for c in c2 c5; do NUTS_B200_LIB=$PWD/nuts_rs_b200/libnuts_b200_phase.so timeout 300 python tools/phase_timing.py $c; done 2>&1 | tee gpurun_out/phase_$TAG.log;;
+    ncutune) PROF_N=8192 PROF_TUNE_DRAWS=60 timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 1 -c 1 -f -o gpurun_out/prof_tune_c5_$TAG python tools/prof_run.py c5 tune > gpurun_out/prof_tune_c5_$TAG.log 2>&1; echo "ncu tune c5 rc=$?"; tail -2 gpurun_out/prof_tune_c5_$TAG.log
+             PROF_TUNE_DRAWS=60 timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 1 -c 1 -f -o gpurun_out/prof_tune_c2_$TAG python tools/prof_run.py c2 tune > gpurun_out/prof_tune_c2_$TAG.log 2>&1; echo "ncu tune c2 rc=$?"; tail -2 gpurun_out/prof_tune_c2_$TAG.log;;
+    ncuc5) timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 3 -c 1 -f -o gpurun_out/prof_c5_$TAG python tools/prof_run.py c5 > gpurun_out/prof_c5_$TAG.log 2>&1; echo "ncu c5 rc=$?"; tail -2 gpurun_out/prof_c5_$TAG.log;;
+    user) timeout 900 python -m pytest tests/test_gpu_user_logp.py -q > gpurun_out/pytest_user_$TAG.log 2>&1; echo "user rc=$?"; tail -15 gpurun_out/pytest_user_$TAG.log;;
+    ncusample) timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 3 -c 1 -f -o gpurun_out/prof_c2_$TAG python tools/prof_run.py c2 > gpurun_out/prof_c2_$TAG.log 2>&1; echo "ncu c2 rc=$?"; tail -2 gpurun_out/prof_c2_$TAG.log
+               timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 3 -c 1 -f -o gpurun_out/prof_c4_$TAG python tools/prof_run.py c4 > gpurun_out/prof_c4_$TAG.log 2>&1; echo "ncu c4 rc=$?"; tail -2 gpurun_out/prof_c4_$TAG.log;;
     variants) for e in 64,16,54 64,16,55 64,16,57 64,16,56 64,16,58 64,16,107; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/variants_$TAG.log;;
     stage) for e in 64,16,54 64,16,58; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/stage_$TAG.log
            NUTS_B200_ENGINE=64,16,58 NUTS_B200_LIB=$PWD/nuts_rs_b200/libnuts_b200_phase.so timeout 300 python tools/phase_timing.py c2 2>&1 | tee -a gpurun_out/stage_$TAG.log

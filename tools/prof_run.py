@@ -1,15 +1,27 @@
-"""Short driver for ncu: set_position, tuning, then a few draw launches of the bench workload."""
-import sys, os
+"""Short driver for ncu.  python tools/prof_run.py [config] [mode]
+  mode sample (default): set_position, tuning, then PROF_LAUNCHES sampling launches of 10 draws (profile with --launch-skip 3)
+  mode tune:             set_position, then ONE launch of PROF_TUNE_DRAWS tuning draws (profile with --launch-skip 1 -c 1)"""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import bench
-from nuts_rs_b200 import _abi, lib
-N = int(os.environ.get("PROF_N", bench.CHAINS_PER_GPU)); d = bench.DIM
-math = lib.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_DIAG, mu=0.5, sigma=bench.model_sigma())
-s = lib.Sampler(math, bench.settings(), seed=bench.SEED)
-assert (s.set_position(bench.initial_positions(N, 0)) == 0).all()
-s.draw_device(bench.NUM_TUNE)
-for _ in range(int(os.environ.get("PROF_LAUNCHES", 3))):
-    s.draw_device(10)
+from nuts_rs_b200 import lib
+
+name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+mode = sys.argv[2] if len(sys.argv) > 2 else "sample"
+cfg = bench.CONFIGS[name]
+N, d = int(os.environ.get("PROF_N", cfg["chains"])), cfg["dim"]
+math = lib.CudaMath(N, d, cfg["kind"], **cfg["model"](d))
+s = lib.Sampler(math, bench.config_settings(cfg), seed=bench.SEED)
+assert (s.set_position(bench.initial_positions(N, 0, d)) == 0).all()
+if mode == "tune":
+    s.draw_device(int(os.environ.get("PROF_TUNE_DRAWS", 100)))
     print(s.last_timing(), s.counters())
-s.close(); math.close()
+else:
+    s.draw_device(cfg["num_tune"])
+    for _ in range(int(os.environ.get("PROF_LAUNCHES", 3))):
+        s.draw_device(10)
+        print(s.last_timing(), s.counters())
+s.close()
+math.close()
