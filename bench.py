@@ -423,6 +423,48 @@ def main():
     clocks.window(e0, time.perf_counter())
     d2h = host_draws.nbytes + sum(a.nbytes for a in stats_arrays.values())
     e2e_direct = samp.last_draw_direct()
+
+    # ---------------- the only exchange of the path: NCCL all-gather of every step's draws over NVLink, behind the C ABI
+    # (nuts_gather_draws_*), on its own stream: the gather of step k runs beside the sampling of step k + 1
+    gather = None
+    try:
+        def exchange(raw):
+            box = [raw]
+            if world > 1:
+                dist.broadcast_object_list(box, src=0)
+            return box[0]
+
+        comm = lib.Comm(local_rank, world, rank, exchange)
+        bufs = [dev_draws, torch.empty_like(dev_draws)]
+        alls = [torch.empty((world,) + tuple(dev_draws.shape), dtype=torch.float64, device="cuda") for _ in range(2)]
+        count = dev_draws.numel()
+
+        def pipeline(nsteps):
+            for k in range(nsteps):
+                samp.draw_device(dps, bufs[k & 1].data_ptr())  # enqueued, not waited for
+                if k > 0:
+                    comm.gather_end()  # gather k-1 ran beside draw k
+                comm.gather_begin(samp, bufs[k & 1].data_ptr(), alls[k & 1].data_ptr(), count)
+            last_ms = comm.gather_end()
+            math.synchronize()
+            return last_ms
+
+        pipeline(max(2, args.warmup))
+        lfg0, _ = samp.counters()
+        barrier()
+        g0 = time.perf_counter()
+        gather_last_ms = pipeline(args.steps)
+        barrier()
+        gather_s = time.perf_counter() - g0
+        clocks.window(g0, time.perf_counter())
+        lfg1, _ = samp.counters()
+        same = bool(torch.equal(alls[(args.steps - 1) & 1][rank], bufs[(args.steps - 1) & 1]))
+        gather = {"wall_s": gather_s, "leapfrogs": lfg1 - lfg0, "last_gather_ms": gather_last_ms, "own_shard_intact": same,
+                  "bytes_received_per_rank_per_step": int(count * 8 * world)}
+        comm.close()
+        del bufs, alls
+    except Exception as e:  # libnccl missing on a host: the sampling numbers stand, the gather line says why it is absent
+        gather = {"error": str(e)[:200]}
     samp.close()
     math.close()
 
@@ -483,6 +525,9 @@ def main():
     if whole:
         tl += [whole["wall_s"] * 1e3, whole["tune_wall_s"] * 1e3]
         wl += [float(whole["leapfrogs"]), float(whole["tune_leapfrogs"])]
+    has_gather = gather is not None and "error" not in gather
+    tl += [gather["wall_s"] * 1e3 if has_gather else 0.0]
+    wl += [float(gather["leapfrogs"]) if has_gather else 0.0]
     t = torch.tensor(tl, dtype=torch.float64, device="cuda")
     w = torch.tensor(wl, dtype=torch.float64, device="cuda")
     if world > 1:
@@ -583,6 +628,18 @@ def main():
                                  "registers across leapfrogs, so algorithmic bytes are NOT DRAM bytes (frac > 1 is possible); see DESIGN.md"},
             "cpu_baseline": cpu,
         }
+        if has_gather:
+            line["config"]["draw_gather"] = {
+                "what": "every step's draws all-gathered to every rank with NCCL over NVLink through the C ABI (nuts_gather_draws_begin / "
+                        "_end) on the communicator's own stream, overlapping the sampling of the next step; wall clock over the K steps "
+                        "incl. the last gather, max over ranks",
+                "leapfrogs_per_s": w[-1] / (t[-1] * 1e-3), "ms_per_step": t[-1] / args.steps,
+                "ratio_to_value": w[-1] / (t[-1] * 1e-3) / value, "last_gather_device_ms_rank0": gather["last_gather_ms"],
+                "bytes_received_per_rank_per_step": gather["bytes_received_per_rank_per_step"],
+                "gather_GBps_per_rank": gather["bytes_received_per_rank_per_step"] / max(gather["last_gather_ms"], 1e-9) / 1e6,
+                "own_shard_intact_rank0": gather["own_shard_intact"]}
+        elif gather is not None:
+            line["config"]["draw_gather"] = gather
         line["config"]["microbench_fixed_step_no_turn_checks_rank0"] = micro
         line["config"]["other_configs"] = other_out
         if whole:

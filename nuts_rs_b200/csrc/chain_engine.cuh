@@ -1208,6 +1208,7 @@ struct Engine {
     // the sub-tree B that the newest leaf belongs to
     int B_first = -1, B_draw = -1, B_draw_idx = 0;
     double B_ls = 0., B_draw_energy = 0.;
+    bool top_turning = false;
 
     for (uint32_t i = 0; i < nleaf; ++i) {
       // single_step (nuts.rs:209-245): one leapfrog from the previous leaf; baseline = initial energy
@@ -1263,14 +1264,22 @@ struct Engine {
       if (t > D) t = D;
       if (lin && fabs(B_ls) > LIN_WEIGHT_LIMIT) weights_to_log_domain(i);  // rare: the weight could leave the double range
       NB_ACC(2, tq);
-      for (int l = 0; l < t; ++l) {
-        const int Af = T.A_first[l], Al = T.A_last[l];
+      // levels 0 .. t-1: merges inside the half; the last leaf goes on to level t = the top-level merge of the main tree (A) with
+      // the finished half (B) - through the SAME U-turn code (one inlined copy of the vector pass instead of two)
+      const bool last_leaf = i + 1 == nleaf;
+      for (int l = 0; l < t + (last_leaf ? 1 : 0); ++l) {
+        const bool top = l == t;
+        const int Af = top ? 0 : T.A_first[l], Al = top ? 0 : T.A_last[l];
         bool turning = false;
         if (check) {
-          if (l == 0 && fuse0) turning = turn_eval(sP0, sQ0, dir);
+          if (l == 0 && fuse0 && !top) turning = turn_eval(sP0, sQ0, dir);
           else
-            turning = merge_turning(slot_ptr(Af, 0), slot_ptr(Af, 1), slot_ptr(Al, 0), slot_ptr(Al, 1), slot_ptr(B_first, 0),
-                                    slot_ptr(B_first, 1), l > 0, dir);
+            turning = merge_turning(top ? farZ : slot_ptr(Af, 0), top ? farV : slot_ptr(Af, 1), top ? nearZ : slot_ptr(Al, 0),
+                                    top ? nearV : slot_ptr(Al, 1), slot_ptr(B_first, 0), slot_ptr(B_first, 1), top ? D > 0 : l > 0, dir);
+        }
+        if (top) {
+          top_turning = turning;
+          break;
         }
         // merge_into, non-main (nuts.rs:172-207): self_log_size = log_size of the merged tree
         double total;
@@ -1318,11 +1327,8 @@ struct Engine {
         tsync();
       }
     }
-    // top-level merge of the main tree (A) with the finished half (B)
-    bool turning = false;
-    if (check) {
-      turning = merge_turning(farZ, farV, nearZ, nearV, slot_ptr(B_first, 0), slot_ptr(B_first, 1), D > 0, dir);
-    }
+    // top-level merge of the main tree (A) with the finished half (B): its U-turn checks ran as the last pass of the level loop
+    const bool turning = top_turning;
     double total;
     bool take;  // is_main: self_log_size = old log_size (nuts.rs:190)
     if (lin) {
@@ -1460,7 +1466,10 @@ struct Engine {
   // branch-free fast paths of device_common.cuh so that the CH dependency chains interleave - with the library operators every
   // call ends in a slow-path branch and the elements of a thread run one after the other (the round-1 tuning phase spent 58 k of
   // its 100 k adaptation cycles per draw there).  sum ln(inv_std) is accumulated as ln(product) per chunk: one log instead of CH.
-  static constexpr int CH = EPT < 4 ? EPT : 4;
+#ifndef NB_ADAPT_CHUNK
+#define NB_ADAPT_CHUNK 4
+#endif
+  static constexpr int CH = EPT < 4 ? EPT : ((EPT % NB_ADAPT_CHUNK == 0 && !MULTI) ? NB_ADAPT_CHUNK : 4);
   // (everything by value and statically indexed at the call sites: a reference parameter or a rolled loop over the chunk would
   // move the chunk's register arrays to local memory)
   static __device__ __noinline__ double2 mass_matrix_element_slow(double dv, double gv, double scale, bool grad_based, double s_old, double is_old) {

@@ -55,12 +55,6 @@ def test_user_density_samples_like_the_builtin_and_the_oracle(L, orc, d, N):
         np.testing.assert_array_equal(su[name][:k], sb[name][:k], err_msg=name)
     np.testing.assert_allclose(du[:k], do[:k], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(du[:k], db[:k], rtol=1e-9, atol=1e-9)
-    if d == 1000:
-        # CTA teams (64 x 16): the generic two-pass leapfrog of the user variant adds the same per-thread partial sums in the same
-        # reduction tree as the fused diagonal-Gaussian path, so the whole run agrees bit for bit
-        assert np.array_equal(du, db)
-        for name in su:
-            assert np.array_equal(su[name], sb[name]), name
 
 
 def test_recoverable_error_is_a_divergence_and_fatal_error_stops_the_chain(L):
@@ -68,7 +62,8 @@ def test_recoverable_error_is_a_divergence_and_fatal_error_stops_the_chain(L):
     sigma = np.ones(d)
     s = L.DiagNutsSettings(num_tune=0, maxdepth=6)
     rng = np.random.default_rng(3)
-    x0 = rng.normal(size=(N, d)) * 0.5
+    # |x0_i| ~ 1: the initial mass matrix (1 / sqrt|grad|, no adaptation in this test) is then close to the identity
+    x0 = rng.choice([-1.0, 1.0], size=(N, d)) * rng.uniform(0.7, 1.3, size=(N, d))
     # limit 2.5 sigma: N(0,1) trajectories in 20 dims cross it regularly -> recoverable errors -> divergences, never fatal (25 sigma)
     st, draws, stats, state = _run(L, _abi.NUTS_LOGP_USER, N, d, s, 200, 5, x0, user_params=_params(0.0, sigma, limit=2.5))
     assert (st == 0).all()

@@ -27,8 +27,12 @@ for l in dis.splitlines():
 n = min(len(lines), len(sass))
 if len(lines) != len(sass): print(f"warning: {len(sass)} instructions in the report, {len(lines)} in the object; matching the first {n}")
 agg = collections.Counter(); inst = collections.Counter(); tot = 0
-for (f, ln), (src, s, ie) in zip(lines[:n], sass[:n]):
+why = collections.defaultdict(collections.Counter)
+body = [r for r in rows[2:] if len(r) >= len(h)]
+for (f, ln), (src, s, ie), r in zip(lines[:n], sass[:n], body[:n]):
     agg[(f, ln)] += s; inst[(f, ln)] += ie; tot += s
+    for c in stall_cols:
+        if "Not Issued" not in c and r[ix[c]] and r[ix[c]] != "0": why[(f, ln)][c[6:]] += int(r[ix[c]])
 print(f"total samples {tot}; stalls: " + ", ".join(f"{k[6:]} {100*v/max(1,sum(stalls.values())):.1f}%" for k, v in stalls.most_common(8)))
 srcs = {}
 for (f, ln), s in agg.most_common(top):
@@ -37,4 +41,5 @@ for (f, ln), s in agg.most_common(top):
         alt = os.path.join(os.path.dirname(os.path.abspath(obj)), "..", "..", "..", "include", f)
         srcs[f] = open(p).read().splitlines() if os.path.exists(p) else (open(alt).read().splitlines() if os.path.exists(alt) else [])
     text = srcs[f][ln - 1].strip()[:110] if 0 < ln <= len(srcs[f]) else ""
-    print(f"{100*s/max(tot,1):6.2f}%  {inst[(f, ln)]:>12}  {f}:{ln}: {text}")
+    top2 = ", ".join(f"{k} {v}" for k, v in why[(f, ln)].most_common(2))
+    print(f"{100*s/max(tot,1):6.2f}%  {inst[(f, ln)]:>12}  {f}:{ln}: {text}   [{top2}]")
