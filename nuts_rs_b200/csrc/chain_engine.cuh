@@ -168,6 +168,7 @@ constexpr int V2_MAXD = 10;              // deepest doubling (2^10 leaves): maxd
 constexpr int V2_NV = 4 + 6 * V2_MAXD;   // values per leaf entry and warp: leapfrog sums + 6 per bundled merge (<= V2_MAXD merges)
 constexpr int V2_NT = V2_MAXD + 2;       // per-level table size
 constexpr int V2_MAXW = 16;              // warps per team
+constexpr int V2_MRING = 4;              // stages of the model-parameter ring of the large-dim teams (one stage = one element per thread)
 enum { V2_CMD_DOUBLING = 1, V2_CMD_TREE_DONE = 2 };
 
 struct V2Ctl {
@@ -210,6 +211,7 @@ struct MultiCtx {
   unsigned off_model;  // [2][TPC*EPT] model mu | prec, one copy per CTA
   unsigned off_ctl;    // V2Ctl of the team
   unsigned off_ring;   // double [V2_K][W][V2_NV]
+  unsigned off_mring;  // double [V2_MRING][2][TPC]: cp.async ring of the model parameters (SM_MODEL_GLOBAL teams)
   int bar_id, warp;    // the team's named barrier, this warp's index inside the team
   int pool;            // index of the team's checkpoint pool (blockIdx.x * teams per CTA + team)
 };
@@ -366,12 +368,35 @@ struct Engine {
       // keep what the hot loops use in registers (*mc lives in local memory)
       v2_ctl = reinterpret_cast<V2Ctl*>(nb_dyn_smem + mc->off_ctl);
       v2_ring = reinterpret_cast<double*>(nb_dyn_smem + mc->off_ring);
+      sm_mring = reinterpret_cast<double*>(nb_dyn_smem + mc->off_mring);
       v2_warp = mc->warp;
     }
   }
   V2Ctl* v2_ctl;    // MULTI only
   double* v2_ring;
+  double* sm_mring = nullptr;
   int v2_warp;
+  // Large-dim teams (SM_MODEL_GLOBAL): the model's mu / precision (2 x 8*d bytes, the same for every leapfrog) do not fit on chip
+  // next to z, v (registers) and sigma, mean (shared memory) and come from L2 on every leapfrog.  Plain loads put that latency
+  // on the critical path of every element (the registers are full: few loads can be in flight); cp.async streams them through
+  // a small shared-memory ring V2_MRING - 1 elements ahead instead - every thread copies and reads only its own elements, so
+  // completion is its own cp.async.wait_group and no barrier is involved.
+  static constexpr bool MSTREAM = MULTI && (SMF & SM_MODEL_GLOBAL) != 0;
+  __device__ __forceinline__ void mstream_issue(int j) {
+    if (j < EPT) {
+      const int i = eidx(j);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(sm_mring + (size_t)((j % V2_MRING) * 2) * TPC + tid);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(P.model.mu + i) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * TPC), "l"(P.model.prec + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // (an empty group past the last element keeps the count uniform)
+  }
+  __device__ __forceinline__ void mstream_wait(int j, double& mmu, double& mprec) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(V2_MRING - 1) : "memory");
+    const double* st = sm_mring + (size_t)((j % V2_MRING) * 2) * TPC + tid;
+    mmu = st[0];
+    mprec = st[TPC];
+  }
   // Checkpoints and end buffers only live inside one draw, which runs on one team from start to end (draw_finish materialises the
   // chain point into the x / z planes): the pools belong to the resident TEAM, not to the chain (EngineParams::slots / ends are
   // sized grid * teams per CTA).
@@ -1208,7 +1233,6 @@ struct Engine {
     // the sub-tree B that the newest leaf belongs to
     int B_first = -1, B_draw = -1, B_draw_idx = 0;
     double B_ls = 0., B_draw_energy = 0.;
-    bool top_turning = false;
 
     for (uint32_t i = 0; i < nleaf; ++i) {
       // single_step (nuts.rs:209-245): one leapfrog from the previous leaf; baseline = initial energy
@@ -1264,22 +1288,14 @@ struct Engine {
       if (t > D) t = D;
       if (lin && fabs(B_ls) > LIN_WEIGHT_LIMIT) weights_to_log_domain(i);  // rare: the weight could leave the double range
       NB_ACC(2, tq);
-      // levels 0 .. t-1: merges inside the half; the last leaf goes on to level t = the top-level merge of the main tree (A) with
-      // the finished half (B) - through the SAME U-turn code (one inlined copy of the vector pass instead of two)
-      const bool last_leaf = i + 1 == nleaf;
-      for (int l = 0; l < t + (last_leaf ? 1 : 0); ++l) {
-        const bool top = l == t;
-        const int Af = top ? 0 : T.A_first[l], Al = top ? 0 : T.A_last[l];
+      for (int l = 0; l < t; ++l) {
+        const int Af = T.A_first[l], Al = T.A_last[l];
         bool turning = false;
         if (check) {
-          if (l == 0 && fuse0 && !top) turning = turn_eval(sP0, sQ0, dir);
+          if (l == 0 && fuse0) turning = turn_eval(sP0, sQ0, dir);
           else
-            turning = merge_turning(top ? farZ : slot_ptr(Af, 0), top ? farV : slot_ptr(Af, 1), top ? nearZ : slot_ptr(Al, 0),
-                                    top ? nearV : slot_ptr(Al, 1), slot_ptr(B_first, 0), slot_ptr(B_first, 1), top ? D > 0 : l > 0, dir);
-        }
-        if (top) {
-          top_turning = turning;
-          break;
+            turning = merge_turning(slot_ptr(Af, 0), slot_ptr(Af, 1), slot_ptr(Al, 0), slot_ptr(Al, 1), slot_ptr(B_first, 0),
+                                    slot_ptr(B_first, 1), l > 0, dir);
         }
         // merge_into, non-main (nuts.rs:172-207): self_log_size = log_size of the merged tree
         double total;
@@ -1327,8 +1343,13 @@ struct Engine {
         tsync();
       }
     }
-    // top-level merge of the main tree (A) with the finished half (B): its U-turn checks ran as the last pass of the level loop
-    const bool turning = top_turning;
+    // top-level merge of the main tree (A) with the finished half (B)
+    // (measured: routing this check through the level loop to save one inlined copy of the U-turn pass costs the warp-team
+    // configurations 7 % - pointer selects and a longer loop on every merge - for 8 % less code; not kept)
+    bool turning = false;
+    if (check) {
+      turning = merge_turning(farZ, farV, nearZ, nearV, slot_ptr(B_first, 0), slot_ptr(B_first, 1), D > 0, dir);
+    }
     double total;
     bool take;  // is_main: self_log_size = old log_size (nuts.rs:190)
     if (lin) {
@@ -1981,14 +2002,21 @@ struct Engine {
     const double eps_half = eps / 2.;
     part[0] = part[1] = part[2] = part[3] = 0.0;
     PairConsts pc;
+    if (MSTREAM) {
+#pragma unroll
+      for (int j = 0; j < V2_MRING - 1; ++j) mstream_issue(j);
+    }
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
       const int i = eidx(j);
-      if (PAIR && (j & 1) == 0) pair_consts(j, pc);
+      if (!MSTREAM && PAIR && (j & 1) == 0) pair_consts(j, pc);
       const double zp = z[j], vp = v[j];
-      const double sgm = PAIR ? pc.sg[j & 1] : sg(j), mnj = PAIR ? pc.mn[j & 1] : mn(j);
+      const double sgm = (!MSTREAM && PAIR) ? pc.sg[j & 1] : sg(j), mnj = (!MSTREAM && PAIR) ? pc.mn[j & 1] : mn(j);
       double mmu = 0.0, mprec = 0.0;
-      if (inb(i)) {
+      if (MSTREAM) {
+        mstream_issue(j + V2_MRING - 1);
+        mstream_wait(j, mmu, mprec);
+      } else if (inb(i)) {
         mmu = PAIR ? pc.mm[j & 1] : model_mu(j, i);
         mprec = PAIR ? pc.pr[j & 1] : model_prec(j, i);
       }

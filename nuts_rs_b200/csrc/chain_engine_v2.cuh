@@ -411,7 +411,10 @@ struct V2Layout {
   static constexpr size_t off_scratch = off_ctl + (size_t)C * ctl_bytes;
   static constexpr size_t scratch_bytes = 2 * (size_t)W * REDUCE_MAXK * sizeof(double);
   static constexpr size_t off_chain = off_scratch + (size_t)C * scratch_bytes;
-  static constexpr size_t total = off_chain + (size_t)C * 2 * sizeof(int);
+  // cp.async ring of the model parameters, one per team, only when they are not resident in shared memory
+  static constexpr size_t off_mring = (off_chain + (size_t)C * 2 * sizeof(int) + 15) / 16 * 16;
+  static constexpr size_t mring_bytes = MODEL_SHARED ? 0 : (size_t)V2_MRING * 2 * TPC * sizeof(double);
+  static constexpr size_t total = off_mring + (size_t)C * mring_bytes;
 };
 
 // One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).  Warps 0 .. NL-1 = leaders, then C teams of TPC threads.
@@ -490,6 +493,7 @@ __global__ void NB_KERNEL_BOUNDS(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(cons
   mc.off_model = (unsigned)L::off_model;
   mc.off_ctl = (unsigned)(L::off_ctl + (size_t)team * L::ctl_bytes);
   mc.off_ring = (unsigned)(L::off_ring + (size_t)team * L::ring_bytes);
+  mc.off_mring = (unsigned)(L::off_mring + (size_t)team * L::mring_bytes);
   mc.bar_id = 1 + team;
   mc.pool = (int)blockIdx.x * C + team;
   mc.warp = (warp - NL) % W;

@@ -14,6 +14,7 @@
 static constexpr int kSmf = nb::V2Layout<CFG_TPC, CFG_EPT, CFG_C>::SMF;
 static constexpr size_t kSmem = nb::V2Layout<CFG_TPC, CFG_EPT, CFG_C>::total;
 static constexpr int kThreads = 32 * CFG_NL + CFG_C * CFG_TPC;
+static_assert(kSmem <= 227 * 1024, "the layout exceeds the 227 KB of dynamic shared memory a CTA may use on sm_100");
 
 extern "C" cudaError_t NB_CAT(nb_launch_chain, CFG_TPC, CFG_EPT, CFG_TAG, CFG_MODEL)(const nb::EngineParams* p, int grid, cudaStream_t stream) {
   static bool configured = false;
