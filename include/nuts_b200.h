@@ -239,6 +239,10 @@ int nuts_sampler_create(nuts_ctx_t*, nuts_sampler_t** sampler, const nuts_settin
 int nuts_sampler_destroy(nuts_sampler_t* sampler);
 /* Chain::set_position for every chain: position HOST [N*d]; status[N] (0 ok, 3 bad initial point). */
 int nuts_set_position(nuts_sampler_t*, const double* position, int32_t* status);
+/* The same for the chains with mask[c] != 0 only (mask, status: HOST [N]; status entries of the other chains are left as they
+ * are): the retry of bad initial points - the reference draws a fresh init_position up to 500 times for a chain whose
+ * set_position fails (src/sampler.rs:1133-1143).  The chain starts over as a new NutsChain; its random stream continues. */
+int nuts_set_position_masked(nuts_sampler_t*, const double* position, const uint8_t* mask, int32_t* status);
 /* n_draws x Chain::draw for every chain.  draws_out: HOST [n_draws x N x d] (may be NULL); stats: HOST SoA (may be NULL).
  * Returns after the stream is synchronised. */
 int nuts_draw(nuts_sampler_t*, uint64_t n_draws, double* draws_out, const nuts_stats_t* stats);

@@ -10,14 +10,23 @@
 //   Chain::set_position(&init) -> Result<()>                Chains::set_position             (src/chain.rs:137-149; per-chain status)
 //   Chain::draw() -> (position, stats)  x n                 Chains::draw(n) -> Draws         (src/chain.rs:151-188, 215-231)
 //   NutsError::BadInitGrad / LogpFailure                    status 3 per chain; nuts_b200::Error for fatal library errors
+//   init retries of Sampler::new (500 fresh init points)    Chains::set_position_with_retries   (src/sampler.rs:1133-1143)
+//   Sampler::{pause, resume, progress, abort, wait}         nuts_b200::Sampler (batch granularity)   (src/sampler.rs:1253-1552)
+//   (no counterpart: chains live in one process)            Chains::checkpoint / restore = nuts_chain_state_t: stop and resume a run
+//   CpuLogpFunc implemented by the user                     CudaMath::user(..): the density compiled in from include/nuts_user_logp.cuh
 //
 // Chains::draw hands back the draws draw-major ([draw][chain][dim], what one kernel launch produces); Draws::position(chain, draw)
 // and the statistics accessors give the reference's per-chain view.  With `pinned = true` the draws live in page-locked memory and
 // are written by the kernel directly.  There is no CPU fallback: without an sm_100 device every call throws Error(NUTS_ERR_NO_DEVICE).
 #pragma once
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
+#include <functional>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -71,6 +80,14 @@ class CudaMath {
     nuts_logp_desc_t m{};
     m.kind = NUTS_LOGP_FUNNEL;
     m.funnel_scale = scale;
+    return CudaMath(nchains, dim, m, device);
+  }
+  // the user-supplied device density the library was built with (include/nuts_user_logp.cuh; `make USER_LOGP=my_model.cuh`)
+  static CudaMath user(uint64_t nchains, uint64_t dim, const std::vector<double>& params, int device = 0) {
+    nuts_logp_desc_t m{};
+    m.kind = NUTS_LOGP_USER;
+    m.user_params = params.data();
+    m.n_user_params = params.size();
     return CudaMath(nchains, dim, m, device);
   }
   CudaMath(uint64_t nchains, uint64_t dim, const nuts_logp_desc_t& model, int device = 0) : nchains_(nchains), dim_(dim) {
@@ -164,6 +181,44 @@ class Draws {
   std::vector<double> pageable_;
 };
 
+// Everything the chains carry from one draw to the next (nuts_chain_state_t), owning its arrays: a checkpoint of a run.
+struct ChainState {
+  uint64_t nchains = 0, dim = 0;
+  std::vector<double> position, gradient, transformed_position, transformed_gradient, logp, point_logdet, stds, inv_stds, mean,
+      mass_matrix_logdet, step_size, da_log_step, da_log_step_adapted, da_hbar, da_mu, draw_mean, draw_var, grad_mean, grad_var,
+      draw_mean_bg, draw_var_bg, grad_mean_bg, grad_var_bg;
+  std::vector<int64_t> point_transform_id, mass_matrix_id;
+  std::vector<uint64_t> da_count, foreground_count, background_count, last_update, current_window_size, draw_count, rng_counter,
+      total_leapfrogs;
+  std::vector<uint8_t> tuning, has_initial_mass_matrix, alive;
+  ChainState(uint64_t n, uint64_t d) : nchains(n), dim(d) {
+    for (auto* v : {&position, &gradient, &transformed_position, &transformed_gradient, &stds, &inv_stds, &mean, &draw_mean, &draw_var,
+                    &grad_mean, &grad_var, &draw_mean_bg, &draw_var_bg, &grad_mean_bg, &grad_var_bg})
+      v->resize(n * d);
+    for (auto* v : {&logp, &point_logdet, &mass_matrix_logdet, &step_size, &da_log_step, &da_log_step_adapted, &da_hbar, &da_mu}) v->resize(n);
+    for (auto* v : {&point_transform_id, &mass_matrix_id}) v->resize(n);
+    for (auto* v : {&da_count, &foreground_count, &background_count, &last_update, &current_window_size, &draw_count, &rng_counter,
+                    &total_leapfrogs})
+      v->resize(n);
+    for (auto* v : {&tuning, &has_initial_mass_matrix, &alive}) v->resize(n);
+  }
+  nuts_chain_state_t view() {
+    nuts_chain_state_t s{};
+    s.position = position.data(), s.gradient = gradient.data(), s.transformed_position = transformed_position.data();
+    s.transformed_gradient = transformed_gradient.data(), s.logp = logp.data(), s.point_logdet = point_logdet.data();
+    s.point_transform_id = point_transform_id.data(), s.stds = stds.data(), s.inv_stds = inv_stds.data(), s.mean = mean.data();
+    s.mass_matrix_logdet = mass_matrix_logdet.data(), s.mass_matrix_id = mass_matrix_id.data(), s.step_size = step_size.data();
+    s.da_log_step = da_log_step.data(), s.da_log_step_adapted = da_log_step_adapted.data(), s.da_hbar = da_hbar.data();
+    s.da_mu = da_mu.data(), s.da_count = da_count.data(), s.draw_mean = draw_mean.data(), s.draw_var = draw_var.data();
+    s.grad_mean = grad_mean.data(), s.grad_var = grad_var.data(), s.draw_mean_bg = draw_mean_bg.data(), s.draw_var_bg = draw_var_bg.data();
+    s.grad_mean_bg = grad_mean_bg.data(), s.grad_var_bg = grad_var_bg.data(), s.foreground_count = foreground_count.data();
+    s.background_count = background_count.data(), s.tuning = tuning.data(), s.has_initial_mass_matrix = has_initial_mass_matrix.data();
+    s.last_update = last_update.data(), s.current_window_size = current_window_size.data(), s.draw_count = draw_count.data();
+    s.rng_counter = rng_counter.data(), s.total_leapfrogs = total_leapfrogs.data(), s.alive = alive.data();
+    return s;
+  }
+};
+
 // All chains of one GPU: `settings.new_chain(chain_id, math, rng)` for chain ids chain_id_offset .. chain_id_offset + nchains - 1
 // (random streams are keyed by the global chain id, src/sampler.rs:1105-1106, so shards reproduce the unsharded run).
 class Chains {
@@ -186,6 +241,39 @@ class Chains {
   std::vector<int32_t> set_position(const std::vector<double>& positions) {
     if (positions.size() != nchains_ * dim_) throw Error(NUTS_ERR_INVALID, "set_position: need nchains x dim values");
     return set_position(positions.data());
+  }
+  // The chain start of the reference's Sampler (src/sampler.rs:1133-1143): `init(chain_id, out[dim])` is asked for a fresh initial
+  // point for every chain whose set_position failed, up to max_tries times; returns the final per-chain status.
+  std::vector<int32_t> set_position_with_retries(const std::function<void(uint64_t, double*)>& init, uint64_t chain_id_offset = 0,
+                                                 int max_tries = 500) {
+    std::vector<double> pos(nchains_ * dim_);
+    for (uint64_t c = 0; c < nchains_; ++c) init(chain_id_offset + c, pos.data() + c * dim_);
+    std::vector<int32_t> status = set_position(pos);
+    for (int t = 1; t < max_tries; ++t) {
+      std::vector<uint8_t> mask(nchains_, 0);
+      bool any = false;
+      for (uint64_t c = 0; c < nchains_; ++c)
+        if (status[c] != 0) {
+          mask[c] = 1, any = true;
+          init(chain_id_offset + c, pos.data() + c * dim_);
+        }
+      if (!any) break;
+      check(nuts_set_position_masked(s_, pos.data(), mask.data(), status.data()));
+    }
+    return status;
+  }
+  // checkpoint / resume: the complete state between two draws; restore() on a fresh Chains (same model, settings, seed, offset)
+  // continues bit-identically
+  ChainState checkpoint() {
+    ChainState st(nchains_, dim_);
+    nuts_chain_state_t v = st.view();
+    check(nuts_sampler_get_chain_state(s_, &v));
+    return st;
+  }
+  void restore(ChainState& st) {
+    if (st.nchains != nchains_ || st.dim != dim_) throw Error(NUTS_ERR_INVALID, "restore: checkpoint of a different shape");
+    nuts_chain_state_t v = st.view();
+    check(nuts_sampler_set_chain_state(s_, &v));
   }
   // n x Chain::draw for every chain
   Draws draw(uint64_t n_draws, bool pinned = true) {
@@ -210,6 +298,97 @@ class Chains {
  private:
   nuts_sampler_t* s_ = nullptr;
   uint64_t nchains_, dim_;
+};
+
+// What the reference's Sampler offers around its chains (src/sampler.rs:1253-1552): run in the background, pause / resume, progress,
+// abort - here at the granularity of one batch of draws (one nuts_draw call for all chains of the GPU).  Every finished batch is
+// handed to `sink` (the reference writes into its trace storage there); the sampler owns nothing but the control flow.
+struct Progress {  // per-sampler view of src/sampler.rs:165-174 + ChainProgress :1554-1660
+  uint64_t finished_draws = 0, total_draws = 0, tuning_draws = 0, divergences = 0, leapfrogs = 0;
+  bool tuning = true, paused = false, finished = false;
+};
+class Sampler {
+ public:
+  using Sink = std::function<void(const Draws&, uint64_t first_draw)>;
+  Sampler(Chains& chains, const DiagNutsSettings& settings, Sink sink, uint64_t batch = 50)
+      : chains_(chains), total_(settings.num_tune + settings.num_draws), num_tune_(settings.num_tune), batch_(batch), sink_(std::move(sink)) {
+    progress_.total_draws = total_;
+    progress_.tuning_draws = num_tune_;
+    worker_ = std::thread([this] { run(); });
+  }
+  ~Sampler() {
+    abort();
+    if (worker_.joinable()) worker_.join();
+  }
+  void pause() {  // takes effect after the batch in flight (Sampler::pause, src/sampler.rs:1469-1485)
+    std::lock_guard<std::mutex> l(m_);
+    paused_ = true;
+  }
+  void resume() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      paused_ = false;
+    }
+    cv_.notify_all();
+  }
+  void abort() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      abort_ = true;
+      paused_ = false;
+    }
+    cv_.notify_all();
+  }
+  Progress progress() {
+    std::lock_guard<std::mutex> l(m_);
+    Progress p = progress_;
+    p.paused = paused_;
+    return p;
+  }
+  // blocks until all draws are done (or abort()); rethrows an error of the worker (Sampler::wait_timeout / finish)
+  void wait() {
+    if (worker_.joinable()) worker_.join();
+    if (error_) std::rethrow_exception(error_);
+  }
+
+ private:
+  void run() {
+    try {
+      uint64_t done = 0;
+      while (done < total_) {
+        {
+          std::unique_lock<std::mutex> l(m_);
+          cv_.wait(l, [this] { return !paused_ || abort_; });
+          if (abort_) break;
+        }
+        const uint64_t n = std::min<uint64_t>(batch_, total_ - done);
+        Draws d = chains_.draw(n);
+        uint64_t div = 0;
+        for (uint8_t f : d.diverging) div += f;
+        const uint64_t lf = chains_.counters().first;
+        if (sink_) sink_(d, done);
+        done += n;
+        std::lock_guard<std::mutex> l(m_);
+        progress_.finished_draws = done;
+        progress_.divergences += div;
+        progress_.leapfrogs = lf;
+        progress_.tuning = done < num_tune_;
+      }
+      std::lock_guard<std::mutex> l(m_);
+      progress_.finished = progress_.finished_draws >= total_;
+    } catch (...) {
+      error_ = std::current_exception();
+    }
+  }
+  Chains& chains_;
+  uint64_t total_, num_tune_, batch_;
+  Sink sink_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  bool paused_ = false, abort_ = false;
+  Progress progress_;
+  std::exception_ptr error_;
+  std::thread worker_;
 };
 
 }  // namespace nuts_b200

@@ -40,6 +40,10 @@ NB_DECL(64, 16, 6)
 NB_DECL(64, 16, 7)
 NB_DECL(64, 16, 8)
 NB_DECL(128, 8, 5)
+NB_DECL(128, 8, 53)  // SM_EXACT, 3 CTAs per SM (168 registers)
+NB_DECL(128, 8, 52)  // SM_EXACT, 2 CTAs per SM
+NB_DECL(256, 4, 62)  // SM_EXACT, 2 CTAs per SM
+NB_DECL(256, 4, 61)  // SM_EXACT, 1 CTA per SM
 NB_DECL(128, 8, 4)
 NB_DECL(256, 8, 2)
 NB_DECL(512, 8, 1)
@@ -106,7 +110,7 @@ const EngineConfig kDecoupledLarge[] = {
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 58), NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(128, 8, 53), NB_CFG(128, 8, 52), NB_CFG(256, 4, 62), NB_CFG(256, 4, 61), NB_CFG(64, 16, 58), NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 
@@ -723,6 +727,27 @@ static int sampler_alloc(nuts_sampler* s, void** p, size_t bytes) {
   return NUTS_OK;
 }
 
+// chain scalars at construction: Strategy::new -> DualAverage::new(initial_step) (stepsize/adapt.rs:67-89), DiagMassMatrix id -1
+// (diagonal.rs:81), GlobalStrategy flags (adapt_strategy.rs:87-97)
+static ChainState fresh_chain_state(const SettingsDev& S) {
+  ChainState c;
+  std::memset(&c, 0, sizeof(c));
+  c.step_size = 0.0;
+  c.pt_transform_id = -1;
+  c.mm_id = -1;
+  c.da_log_step = std::log(S.initial_step);
+  c.da_log_step_adapted = std::log(S.initial_step);
+  c.da_hbar = 0.0;
+  c.da_mu = std::log(10.0 * S.initial_step);
+  c.da_count = 1;
+  c.tuning = 1;
+  c.has_initial_mass_matrix = 1;
+  c.current_window_size = S.mm_switch_freq;
+  c.is_good = 1;
+  c.alive = 0;
+  return c;
+}
+
 int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settings_t* st, uint64_t seed, uint64_t chain_id_offset) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (!st) return fail(NUTS_ERR_INVALID, "nuts_sampler_create: settings is NULL");
@@ -857,25 +882,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   A((void**)&s->d_status, ctx->N * sizeof(int));
   A((void**)&P.phase_clocks, 16 * sizeof(unsigned long long));
   if (r != NUTS_OK) return r;
-  // chain scalars at construction: Strategy::new -> DualAverage::new(initial_step) (stepsize/adapt.rs:67-89),
-  // DiagMassMatrix id -1 (diagonal.rs:81), GlobalStrategy flags (adapt_strategy.rs:87-97)
-  std::vector<ChainState> cs(ctx->N);
-  for (auto& c : cs) {
-    std::memset(&c, 0, sizeof(c));
-    c.step_size = 0.0;
-    c.pt_transform_id = -1;
-    c.mm_id = -1;
-    c.da_log_step = std::log(S.initial_step);
-    c.da_log_step_adapted = std::log(S.initial_step);
-    c.da_hbar = 0.0;
-    c.da_mu = std::log(10.0 * S.initial_step);
-    c.da_count = 1;
-    c.tuning = 1;
-    c.has_initial_mass_matrix = 1;
-    c.current_window_size = S.mm_switch_freq;
-    c.is_good = 1;
-    c.alive = 0;
-  }
+  std::vector<ChainState> cs(ctx->N, fresh_chain_state(S));
   CUDA_TRY(cudaMemcpy(P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaEventCreate(&s->ev0));
   CUDA_TRY(cudaEventCreate(&s->ev1));
@@ -913,11 +920,31 @@ static int launch_engine(nuts_sampler* s) {
   return NUTS_OK;
 }
 
-int nuts_set_position(nuts_sampler_t* s, const double* position, int32_t* status) {
+int nuts_set_position(nuts_sampler_t* s, const double* position, int32_t* status) { return nuts_set_position_masked(s, position, nullptr, status); }
+
+int nuts_set_position_masked(nuts_sampler_t* s, const double* position, const uint8_t* mask, int32_t* status) {
   nuts_ctx* ctx = s->ctx;
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (!position) return fail(NUTS_ERR_INVALID, "nuts_set_position: position is NULL");
+  if (mask && !s->positioned) return fail(NUTS_ERR_INVALID, "nuts_set_position_masked: call nuts_set_position for all chains first");
   CUDA_TRY(cudaMemcpyAsync(s->d_init, position, ctx->N * ctx->d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  s->P.init_mask = nullptr;
+  if (mask) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_u8, mask, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    s->P.init_mask = ctx->d_u8;
+    // a chain that is initialised again starts from a fresh NutsChain (Settings::new_chain, sampler.rs:745-772): reset its record
+    std::vector<ChainState> cs(ctx->N);
+    CUDA_TRY(cudaMemcpyAsync(cs.data(), s->P.cs, cs.size() * sizeof(ChainState), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync(ctx));
+    for (uint64_t c = 0; c < ctx->N; ++c)
+      if (mask[c]) {
+        const uint64_t rng = cs[c].rng_counter;  // the chain's random stream goes on (the reference re-draws from the same rng)
+        cs[c] = fresh_chain_state(s->P.s);
+        cs[c].rng_counter = rng;
+      }
+    CUDA_TRY(cudaMemcpyAsync(s->P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice, ctx->stream));
+    if (status) CUDA_TRY(cudaMemcpyAsync(s->d_status, status, ctx->N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
   s->P.mode = 0;
   s->P.init_position = s->d_init;
   s->P.status_out = s->d_status;

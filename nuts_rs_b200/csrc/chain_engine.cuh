@@ -108,6 +108,7 @@ struct EngineParams {
   // mode 0: set_position ; mode 1: draw
   int mode, _pad;
   const double* init_position;      // [N][d] device
+  const unsigned char* init_mask;   // [N] device or null: set_position only for chains with a non-zero entry (retry of bad initial points)
   int* status_out;                  // [N]
   uint64_t n_draws;
   uint32_t draws_per_unit;          // work unit of a draw launch = this many consecutive draws of one chain (>= 1)
@@ -1488,7 +1489,7 @@ struct Engine {
   // call ends in a slow-path branch and the elements of a thread run one after the other (the round-1 tuning phase spent 58 k of
   // its 100 k adaptation cycles per draw there).  sum ln(inv_std) is accumulated as ln(product) per chunk: one log instead of CH.
 #ifndef NB_ADAPT_CHUNK
-#define NB_ADAPT_CHUNK 4
+#define NB_ADAPT_CHUNK 2
 #endif
   static constexpr int CH = EPT < 4 ? EPT : ((EPT % NB_ADAPT_CHUNK == 0 && !MULTI) ? NB_ADAPT_CHUNK : 4);
   // (everything by value and statically indexed at the call sites: a reference parameter or a rolled loop over the chunk would
@@ -2453,8 +2454,10 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
     const unsigned blk = unit / (unsigned)P.N;  // block of B consecutive draws (a few draws per unit amortise the hand-over)
     Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
     if (P.mode == 0) {
-      const int status = cold_set_position<TPC, EPT, SMF, MODEL, false>(P, chain, tid, scratch, team_smem, nullptr);
-      if (tid == 0 && P.status_out) P.status_out[chain] = status;
+      if (P.init_mask == nullptr || P.init_mask[chain] != 0) {
+        const int status = cold_set_position<TPC, EPT, SMF, MODEL, false>(P, chain, tid, scratch, team_smem, nullptr);
+        if (tid == 0 && P.status_out) P.status_out[chain] = status;
+      }
     } else {
       if (blk > 0) {
         if (tid == 0) {

@@ -516,8 +516,10 @@ __global__ void NB_KERNEL_BOUNDS(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(cons
     const unsigned blk = unit / (unsigned)P.N;
     Engine<TPC, EPT, SMF, MODEL, true> E(P, chain, tid, scratch, team_smem, tables, &mc);
     if (P.mode == 0) {
-      const int status = cold_set_position<TPC, EPT, SMF, MODEL, true>(P, chain, tid, scratch, team_smem, &mc);
-      if (tid == 0 && P.status_out) P.status_out[chain] = status;
+      if (P.init_mask == nullptr || P.init_mask[chain] != 0) {
+        const int status = cold_set_position<TPC, EPT, SMF, MODEL, true>(P, chain, tid, scratch, team_smem, &mc);
+        if (tid == 0 && P.status_out) P.status_out[chain] = status;
+      }
     } else {
       if (blk > 0) {
         if (tid == 0) {

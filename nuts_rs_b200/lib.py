@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "nuts_sampler_counters", "nuts_sampler_last_timing", "nuts_sampler_get_state", "nuts_sampler_set_step_size",
     "nuts_host_alloc", "nuts_host_free", "nuts_sampler_last_draw_direct",
     "nuts_sampler_get_chain_state", "nuts_sampler_set_chain_state",
-    "nuts_comm_unique_id", "nuts_comm_create", "nuts_comm_destroy", "nuts_gather_draws_begin", "nuts_gather_draws_end",
+    "nuts_set_position_masked", "nuts_comm_unique_id", "nuts_comm_create", "nuts_comm_destroy", "nuts_gather_draws_begin", "nuts_gather_draws_end",
 ]
 
 
@@ -103,6 +103,7 @@ def load():
     L.nuts_sampler_create.argtypes = [vp, C.POINTER(vp), C.POINTER(_abi.NutsSettings), C.c_uint64, C.c_uint64]
     L.nuts_sampler_destroy.argtypes = [vp]
     L.nuts_set_position.argtypes = [vp, dp, _abi.c_i32_p]
+    L.nuts_set_position_masked.argtypes = [vp, dp, _abi.c_u8_p, _abi.c_i32_p]
     L.nuts_draw.argtypes = [vp, C.c_uint64, dp, C.POINTER(_abi.Stats)]
     L.nuts_draw_device.argtypes = [vp, C.c_uint64, vp]
     L.nuts_sampler_counters.argtypes = [vp, _abi.c_u64_p, _abi.c_u64_p]
@@ -447,6 +448,23 @@ class Sampler:
         status = np.zeros(self.nchains, dtype=np.int32)
         _check(load().nuts_set_position(self.h, _p(position), status.ctypes.data_as(_abi.c_i32_p)))
         return status
+
+    def set_position_with_retries(self, init_position, max_tries=500):
+        """The reference's chain start (src/sampler.rs:1133-1143): `init_position(chain_ids) -> [len(chain_ids), dim]` is asked for a
+        fresh starting point for every chain whose set_position failed (NutsError::BadInitGrad), up to `max_tries` times.
+        Returns (status, tries): status 3 is left for chains that never found a valid point."""
+        ids = np.arange(self.nchains)
+        position = _f64(init_position(ids + self.chain_id_offset)).reshape(self.nchains, self.dim)
+        status = self.set_position(position)
+        tries = 1
+        while (status != 0).any() and tries < max_tries:
+            bad = np.nonzero(status != 0)[0]
+            position[bad] = _f64(init_position(bad + self.chain_id_offset)).reshape(len(bad), self.dim)
+            mask = np.zeros(self.nchains, dtype=np.uint8)
+            mask[bad] = 1
+            _check(load().nuts_set_position_masked(self.h, _p(position), mask.ctypes.data_as(_abi.c_u8_p), status.ctypes.data_as(_abi.c_i32_p)))
+            tries += 1
+        return status, tries
 
     def draw(self, n_draws, want_draws=True, stats=True, out=None):
         draws = None

@@ -13,14 +13,24 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _build(tmp_path_factory, name):
+    out = tmp_path_factory.mktemp("cpp") / name
+    libdir = os.path.join(ROOT, "nuts_rs_b200")
+    cmd = ["g++", "-std=c++17", "-pthread", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", name + ".cpp"), "-L", libdir, "-lnuts_b200", "-Wl,-rpath," + libdir, "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return str(out)
+
+
 @pytest.fixture(scope="module")
 def exe(tmp_path_factory):
-    out = tmp_path_factory.mktemp("cpp") / "sample_normal"
-    libdir = os.path.join(ROOT, "nuts_rs_b200")
-    cmd = ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "sample_normal.cpp"),
-           "-L", libdir, "-lnuts_b200", "-Wl,-rpath," + libdir, "-o", str(out)]
-    subprocess.run(cmd, check=True, capture_output=True)
-    return str(out)
+    return _build(tmp_path_factory, "sample_normal")
+
+
+@pytest.fixture(scope="module")
+def exe_control(tmp_path_factory):
+    return _build(tmp_path_factory, "sampler_control")
 
 
 def test_cpp_example_builds_and_has_no_cpu_fallback(exe):
@@ -58,3 +68,23 @@ def test_cpp_example_matches_python_mirror(exe):
         checksum += v
     assert float(got["checksum"]) == checksum
     assert int(got["leapfrogs"]) == int(stats["n_steps"].sum())
+
+
+def test_cpp_sampler_control_builds_and_has_no_cpu_fallback(exe_control):
+    from nuts_rs_b200 import lib
+
+    if lib.device_available():
+        pytest.skip("a device is visible: covered by the gpu test")
+    r = subprocess.run([exe_control], capture_output=True, text=True)
+    assert r.returncode == 77, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_cpp_sampler_pause_resume_progress_checkpoint(exe_control):
+    """nuts_b200::Sampler (the reference's Sampler::pause / resume / progress / wait, src/sampler.rs:1253-1552, at batch
+    granularity), the init-retry loop (src/sampler.rs:1133-1143) and checkpoint / restore through the C ABI."""
+    r = subprocess.run([exe_control], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    fields = r.stdout.split()
+    got = {fields[i]: fields[i + 1] for i in range(0, len(fields), 2)}
+    assert int(got["resumed_identical"]) == 1 and int(got["leapfrogs"]) > 0

@@ -322,3 +322,48 @@ def test_draw_trace_schema_on_device(L):
     assert (a["sample_stats"]["draw"][0] == np.arange(7)).all() and (b["sample_stats"]["draw"][0] == np.arange(7, 11)).all()
     assert a["sample_stats"]["tuning"][:, :5].all() and not a["sample_stats"]["tuning"][:, 5:].any() and not b["sample_stats"]["tuning"].any()
     assert (a["sample_stats"]["n_steps"] >= 1).all() and np.isfinite(a["sample_stats"]["logp"]).all()
+
+
+def test_bad_initial_points_are_retried_like_the_reference_sampler(L, orc):
+    """src/sampler.rs:1133-1143: a chain whose set_position fails asks for a fresh init_position (up to 500 times).  The chains
+    that were fine keep their state bit for bit; a retried chain starts over as a new chain on its own random stream."""
+    N, d = 6, 10
+    s = _settings(L, num_tune=20, maxdepth=4)
+    rng = np.random.default_rng(4)
+    good = rng.normal(size=(N, d))
+    calls = []
+
+    def init_position(chain_ids):
+        calls.append(np.array(chain_ids))
+        x = good[chain_ids].copy()
+        if len(calls) == 1:
+            x[1, 3] = np.nan        # chain 1: non-finite start
+            x[4, :] = 3.0           # chain 4: exactly at the mode (zero gradient => BadInitGrad)
+        elif len(calls) == 2:
+            x[list(chain_ids).index(4), :] = 3.0  # chain 4 fails a second time
+        return x
+
+    math = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_ISO, mu=3.0)
+    samp = L.Sampler(math, s, seed=1)
+    status, tries = samp.set_position_with_retries(init_position)
+    assert (status == 0).all() and tries == 3
+    assert [list(c) for c in calls] == [[0, 1, 2, 3, 4, 5], [1, 4], [4]]
+    draws, stats = samp.draw(30)
+    assert np.isfinite(draws).all()
+    # chains 0, 2, 3, 5 never failed: identical to a run without any bad point
+    m2 = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_ISO, mu=3.0)
+    s2 = L.Sampler(m2, s, seed=1)
+    assert (s2.set_position(good) == 0).all()
+    d2, _ = s2.draw(30)
+    ok = [0, 2, 3, 5]
+    assert np.array_equal(draws[:, ok], d2[:, ok])
+    # a chain that exhausts its tries stays dead (status 3) and produces NaN draws
+    samp2 = L.Sampler(m2, s, seed=1)
+    status, tries = samp2.set_position_with_retries(lambda ids: np.where(np.asarray(ids)[:, None] == 2, 3.0, good[ids]), max_tries=4)
+    assert tries == 4 and status[2] == 3 and (np.delete(status, 2) == 0).all()
+    d3, _ = samp2.draw(5)
+    assert np.isnan(d3[:, 2]).all() and np.isfinite(np.delete(d3, 2, axis=1)).all()
+    for x in (samp, s2, samp2):
+        x.close()
+    for x in (math, m2):
+        x.close()

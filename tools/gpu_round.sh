@@ -25,6 +25,8 @@ for w in $WHAT; do
     ncusample) timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 3 -c 1 -f -o gpurun_out/prof_c2_$TAG python tools/prof_run.py c2 > gpurun_out/prof_c2_$TAG.log 2>&1; echo "ncu c2 rc=$?"; tail -2 gpurun_out/prof_c2_$TAG.log
                timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 3 -c 1 -f -o gpurun_out/prof_c4_$TAG python tools/prof_run.py c4 > gpurun_out/prof_c4_$TAG.log 2>&1; echo "ncu c4 rc=$?"; tail -2 gpurun_out/prof_c4_$TAG.log;;
     bsweep) for c in c2 c5 c3; do for b in 1 2 4 8; do NUTS_B200_DRAWS_PER_UNIT=$b timeout 300 python tools/quick.py $c 400 40 3 2>&1 | tail -1 | sed "s/^/B=$b /"; done; done | tee gpurun_out/bsweep_$TAG.log;;
+    wide) for e in 64,16,54 128,8,53 128,8,52 256,4,62 256,4,61; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/wide_$TAG.log
+          for c in c2 c5; do NUTS_B200_LIB=$PWD/nuts_rs_b200/libnuts_b200_phase.so timeout 300 python tools/quick.py $c 2>&1 | tail -1 | sed "s/^/chunk2 /"; done | tee -a gpurun_out/wide_$TAG.log;;
     variants) for e in 64,16,54 64,16,55 64,16,57 64,16,56 64,16,58 64,16,107; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/variants_$TAG.log;;
     stage) for e in 64,16,54 64,16,58; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/stage_$TAG.log
            NUTS_B200_ENGINE=64,16,58 NUTS_B200_LIB=$PWD/nuts_rs_b200/libnuts_b200_phase.so timeout 300 python tools/phase_timing.py c2 2>&1 | tee -a gpurun_out/stage_$TAG.log
