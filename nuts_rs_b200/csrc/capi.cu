@@ -59,6 +59,9 @@ NB_DECL1(480, 21, 171, 1)
 NB_DECL1(480, 18, 181, 1)
 NB_DECL1(64, 16, 155, 1)
 NB_DECL1(64, 16, 127, 1)
+// cluster engine (engine_cl_inst.cu): the team spans the CTAs of a thread-block cluster
+NB_DECL(1024, 10, 41)      // 4 CTAs x 256 threads, all model variants
+NB_DECL1(768, 14, 42, 1)   // 2 CTAs x 384 threads (experiments)
 
 namespace {
 
@@ -107,10 +110,12 @@ const EngineConfig kConfigs[] = {NB_CFG(32, 1, 16), NB_CFG(32, 2, 16), NB_CFG(32
 const EngineConfig kDecoupledLarge[] = {
     {480, 18, 181, 480 * 18, {nb_launch_chain_480_18_181_1, nullptr, nullptr, nullptr}, {nb_occupancy_chain_480_18_181_1, nullptr, nullptr, nullptr}, 4096},
     {480, 21, 171, 480 * 21, {nb_launch_chain_480_21_171_1, nullptr, nullptr, nullptr}, {nb_occupancy_chain_480_21_171_1, nullptr, nullptr, nullptr}, 480 * 18}};
+// cluster engine (a team = the 4 CTAs of a thread-block cluster): default for the non-elementwise targets at 4096 < dim <= 10240
+const EngineConfig kClusterLarge = NB_CFG(1024, 10, 41);
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(128, 8, 53), NB_CFG(128, 8, 52), NB_CFG(256, 4, 62), NB_CFG(256, 4, 61), NB_CFG(64, 16, 58), NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(1024, 10, 41), NB_CFG1(768, 14, 42), NB_CFG(128, 8, 53), NB_CFG(128, 8, 52), NB_CFG(256, 4, 62), NB_CFG(256, 4, 61), NB_CFG(64, 16, 58), NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 
@@ -153,6 +158,7 @@ struct nuts_sampler {
   int model_variant = 0;  // index into cfg->launch
   int grid = 0;
   int teams_per_cta = 1;
+  uint64_t resident_teams = 1;
   std::vector<void*> allocations;
   double* d_init = nullptr;
   int* d_status = nullptr;
@@ -727,6 +733,8 @@ static int sampler_alloc(nuts_sampler* s, void** p, size_t bytes) {
   return NUTS_OK;
 }
 
+static int cluster_size_of(int smf) { return (smf & SM_CL4) ? 4 : ((smf & SM_CL2) ? 2 : 1); }
+
 // chain scalars at construction: Strategy::new -> DualAverage::new(initial_step) (stepsize/adapt.rs:67-89), DiagMassMatrix id -1
 // (diagonal.rs:81), GlobalStrategy flags (adapt_strategy.rs:87-97)
 static ChainState fresh_chain_state(const SettingsDev& S) {
@@ -759,6 +767,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
     return fail(NUTS_ERR_UNSUPPORTED, "maxdepth + extra_doublings must be <= %d", MAX_DOUBLING_DEPTH);
   if (st->adapt_options.mass_matrix_window_growth < 1.0) return fail(NUTS_ERR_INVALID, "mass_matrix_window_growth must be >= 1");
   const EngineConfig* cfg = nullptr;
+  const int s_variant = ctx->model.kind == NUTS_LOGP_GAUSS_RANK1 ? 1 : ctx->model.kind == NUTS_LOGP_FUNNEL ? 2 : ctx->model.kind == NUTS_LOGP_USER ? 3 : 0;
   if (const char* env = std::getenv("NUTS_B200_ENGINE")) {
     int tpc = 0, ept = 0, minb = 0;
     if (std::sscanf(env, "%d,%d,%d", &tpc, &ept, &minb) == 3) {
@@ -785,6 +794,11 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
         cfg = &c;
         break;
       }
+    // rank-1 / funnel / user targets at dim ~ 10^4: the register-resident single-CTA tilings (1024 x 8 / 10) run at 64 registers per
+    // thread and spill 2.5 KB; the cluster engine spreads the chain over the four SMs of a thread-block cluster (255 registers)
+    if (ctx->model.kind != NUTS_LOGP_GAUSS_ISO && ctx->model.kind != NUTS_LOGP_GAUSS_DIAG && ctx->d > 4096 &&
+        ctx->d <= (uint64_t)kClusterLarge.max_d && kClusterLarge.launch[s_variant])
+      cfg = &kClusterLarge;
     // same tiling without bounds checks (SM_EXACT: rows zero-padded to tpc*ept) when the padding costs at most 7 % more traffic
     for (const EngineConfig& c : kExactConfigs)
       if (c.tpc == cfg->tpc && c.ept == cfg->ept && c.launch[0] && (uint64_t)c.max_d - ctx->d <= ctx->d * 7 / 100) cfg = &c;
@@ -804,6 +818,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
     return fail(NUTS_ERR_UNSUPPORTED, "engine %dx%d for model kind %d is not part of this build", cfg->tpc, cfg->ept, ctx->model.kind);
   }
   CUDA_TRY(cfg->occupancy[s->model_variant](&blocks_per_sm, &cta_threads, &smf));
+  const int blocks_per_sm_raw = blocks_per_sm;
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   // SM_EXACT engines run their hot loops without bounds checks: every sampler row is zero-padded to tpc*ept elements
   P.ld = (smf & SM_EXACT) ? (int)std::max<uint64_t>(ctx->ld, (uint64_t)cfg->tpc * cfg->ept) : (int)ctx->ld;
@@ -852,14 +867,25 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   S.mm_window_growth = a.mass_matrix_window_growth;
 
   // persistent grid: one wave of resident CTAs
-  const int teams_per_cta = decoupled ? cfg->minb % 10 : cta_threads / cfg->tpc;  // decoupled tags end in the number of teams
-  const uint64_t ctas_needed = (ctx->N + teams_per_cta - 1) / teams_per_cta;
-  s->grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)blocks_per_sm * ctx->num_sms);
-  // NUTS_B200_GRID caps the persistent grid (tests / compute-sanitizer: forces draw migration between teams on small workloads)
-  if (const char* env = std::getenv("NUTS_B200_GRID")) s->grid = std::max(1, std::min(s->grid, std::atoi(env)));
+  const int cluster = cluster_size_of(smf);  // CTAs per team (thread-block cluster engines), else 1
+  const int teams_per_cta = cluster > 1 ? 1 : (decoupled ? cfg->minb % 10 : cta_threads / cfg->tpc);  // decoupled tags end in the number of teams
+  uint64_t resident_teams;
+  if (cluster > 1) {
+    // the occupancy hook of a cluster engine reports MINUS the number of clusters the device can hold at once
+    resident_teams = std::min<uint64_t>(ctx->N, (uint64_t)std::max(1, -blocks_per_sm_raw));
+    if (const char* env = std::getenv("NUTS_B200_GRID")) resident_teams = std::max<uint64_t>(1, std::min<uint64_t>(resident_teams, std::atoi(env)));
+    s->grid = (int)resident_teams * cluster;
+  } else {
+    const uint64_t ctas_needed = (ctx->N + teams_per_cta - 1) / teams_per_cta;
+    s->grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)blocks_per_sm * ctx->num_sms);
+    // NUTS_B200_GRID caps the persistent grid (tests / compute-sanitizer: forces draw migration between teams on small workloads)
+    if (const char* env = std::getenv("NUTS_B200_GRID")) s->grid = std::max(1, std::min(s->grid, std::atoi(env)));
+    resident_teams = (uint64_t)s->grid * teams_per_cta;
+  }
   s->teams_per_cta = teams_per_cta;
+  s->resident_teams = resident_teams;
   const size_t plane = ctx->N * (size_t)P.ld * sizeof(double);
-  const size_t team_plane = (size_t)s->grid * teams_per_cta * (size_t)P.ld * sizeof(double);  // one row per resident team
+  const size_t team_plane = resident_teams * (size_t)P.ld * sizeof(double);  // one row per resident team
   int r = NUTS_OK;
   auto A = [&](void** p, size_t bytes) {
     if (r == NUTS_OK) r = sampler_alloc(s, p, bytes);
@@ -1017,7 +1043,7 @@ static int run_draws(nuts_sampler* s, uint64_t n_draws, double* draws_dev, bool 
   {
     // draws per work unit: the whole call when every chain has its own team (no hand-over at all), else one draw - or a few
     // for tiny dims; NUTS_B200_DRAWS_PER_UNIT overrides (experiments)
-    const uint64_t teams = (uint64_t)s->grid * (uint64_t)s->teams_per_cta;
+    const uint64_t teams = s->resident_teams;
     // (measured: blocks of draws pay for tiny dims, where the hand-over is a large part of a draw: config 3 +4 % sampling, +10 %
     // tuning; config 5 shard (dim 100) -5 %; config 2 +-0)
     uint64_t b = ctx->N <= teams ? n_draws : (ctx->d <= 32 ? std::max<uint64_t>(1, std::min<uint64_t>(8, n_draws / 8)) : 1);

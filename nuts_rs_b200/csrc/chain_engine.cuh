@@ -270,14 +270,20 @@ static __device__ __noinline__ AccSums accept_batch(double mine, int n, double a
 // SM_STAGE: four more vectors of shared memory into which cp.async (LDGSTS, 16 bytes per pair) stages the OLDEST operand of the
 // upcoming U-turn checks - (z, v) of the first leaf of the pending sub-tree (buffer X), of the far end of the main tree (buffer Y)
 // - while the leapfrog of the leaf that triggers the check is still running; see Engine::stage_pair().
-enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32, SM_STAGE = 64 };
+// SM_CL2 / SM_CL4: the team spans the 2 / 4 CTAs of a thread-block cluster (TPC = threads of the whole team): every CTA holds its
+// threads' elements of the shared-memory vectors, reductions go through distributed shared memory (TeamReduce, CL > 1).
+enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32, SM_STAGE = 64, SM_CL2 = 128, SM_CL4 = 256 };
+template <int SMF>
+__host__ __device__ constexpr int cluster_size() {
+  return (SMF & SM_CL4) ? 4 : ((SMF & SM_CL2) ? 2 : 1);
+}
 template <int SMF>
 __host__ __device__ constexpr int smem_vectors() {
   return ((SMF & SM_MASS) ? 2 : 0) + ((SMF & SM_MODEL) ? 2 : 0) + ((SMF & SM_GRAD) ? 1 : 0) + ((SMF & SM_STAGE) ? 4 : 0);
 }
 template <int TPC, int EPT, int SMF>
 __host__ __device__ constexpr size_t team_smem_bytes() {
-  return smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double) + sizeof(TreeTables);
+  return smem_vectors<SMF>() * (size_t)(TPC / cluster_size<SMF>()) * EPT * sizeof(double) + sizeof(TreeTables);  // per CTA
 }
 
 template <int TPC, int EPT, int SMF, int MODEL, bool MULTI = false>
@@ -285,7 +291,11 @@ struct Engine {
   const EngineParams& P;
   const int chain;
   const int tid;  // thread index inside the team
-  TeamReduce<TPC, MULTI> red;
+  static constexpr int CL = cluster_size<SMF>();  // CTAs the team spans (thread-block cluster)
+  static constexpr int LT = TPC / CL;             // the team's threads in THIS CTA
+  static_assert(CL == 1 || !MULTI, "cluster teams use the register-resident engine");
+  const int ltid;                                 // thread index inside the CTA's share of the team
+  TeamReduce<LT, MULTI, CL> red;
   const MultiCtx* const mc;  // MULTI only
   const int d, ld;
   const size_t row;  // chain * ld
@@ -306,6 +316,8 @@ struct Engine {
   static constexpr bool PAIR = (EPT % 2) == 0;
   static constexpr int NP = EPT / 2;
   __device__ __forceinline__ int eidx(int j) const { return PAIR ? (j >> 1) * (2 * TPC) + 2 * tid + (j & 1) : tid + j * TPC; }
+  // the same element in the CTA's shared-memory vectors (equal to eidx unless the team spans a cluster)
+  __device__ __forceinline__ int sidx(int j) const { return CL == 1 ? eidx(j) : (PAIR ? (j >> 1) * (2 * LT) + 2 * ltid + (j & 1) : ltid + j * LT); }
   double z[EPT], v[EPT];  // current phase-space point: whitened position, velocity
   double g_reg[GS ? 1 : EPT];  // whitened gradient: registers, or shared memory (GS) to fit more chains per SM
   // this chain's DiagMassMatrix (stds, mean): registers, or shared memory when MMS
@@ -352,13 +364,13 @@ struct Engine {
   // team_smem: this team's slice of dynamic shared memory (team_smem_bytes()); tables: where the TreeTables live
   __device__ __forceinline__ Engine(const EngineParams& p, int chain_, int tid_, double* scratch, double* team_smem, TreeTables& tables,
                                     const MultiCtx* mc_ = nullptr)
-      : P(p), chain(chain_), tid(tid_), red(scratch), mc(mc_), d(p.d), ld(p.ld), row((size_t)chain_ * p.ld),
+      : P(p), chain(chain_), tid(tid_), ltid(CL > 1 ? (int)threadIdx.x : tid_), red(scratch), mc(mc_), d(p.d), ld(p.ld), row((size_t)chain_ * p.ld),
         slots_base(p.slots + (size_t)pool_index(mc_) * p.P * 2 * p.ld), ends_base(p.ends + (size_t)pool_index(mc_) * NB_END_BUFFERS * 3 * p.ld),
         sm_sig(team_smem),
-        sm_mu(team_smem + (MMS ? TPC * EPT : 0)), sm_mmu(team_smem + (MMS ? 2 : 0) * TPC * EPT),
-        sm_mprec(team_smem + ((MMS ? 2 : 0) + (MODS ? 1 : 0)) * TPC * EPT),
-        sm_g(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0)) * TPC * EPT),
-        sm_stage(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0) + (GS ? 1 : 0)) * TPC * EPT), T(tables) {
+        sm_mu(team_smem + (MMS ? LT * EPT : 0)), sm_mmu(team_smem + (MMS ? 2 : 0) * LT * EPT),
+        sm_mprec(team_smem + ((MMS ? 2 : 0) + (MODS ? 1 : 0)) * LT * EPT),
+        sm_g(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0)) * LT * EPT),
+        sm_stage(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0) + (GS ? 1 : 0)) * LT * EPT), T(tables) {
     stream = p.chain_offset + (uint64_t)chain_ + 1;  // reference src/sampler.rs:1106 set_stream(chain_id + 1)
     if (MULTI) {  // several teams per CTA: named barrier, per-team reduction scratch, CTA-wide copy of the model parameters
       red.bar_id = mc->bar_id;
@@ -403,32 +415,33 @@ struct Engine {
   // sized grid * teams per CTA).
   static __device__ __forceinline__ int pool_index(const MultiCtx* m) {
     if (MULTI) return m->pool;
+    if (CL > 1) return (int)blockIdx.x / CL;  // one team per cluster
     return (int)blockIdx.x * ((int)blockDim.x / TPC) + (int)threadIdx.x / TPC;
   }
-  __device__ __forceinline__ double sg(int j) const { return MMS ? sm_sig[eidx(j)] : sig[MMS ? 0 : j]; }
-  __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[eidx(j)] : mu[MMS ? 0 : j]; }
+  __device__ __forceinline__ double sg(int j) const { return MMS ? sm_sig[sidx(j)] : sig[MMS ? 0 : j]; }
+  __device__ __forceinline__ double mn(int j) const { return MMS ? sm_mu[sidx(j)] : mu[MMS ? 0 : j]; }
   // model parameters of element i = tid + j*TPC
   // (MULTI: one copy per CTA shared by all its teams, filled by the kernel prologue)
-  __device__ __forceinline__ double model_mu(int j, int i) const { return MSH ? sm_mmu[eidx(j)] : __ldg(P.model.mu + i); }
-  __device__ __forceinline__ double model_prec(int j, int i) const { return MSH ? sm_mprec[eidx(j)] : __ldg(P.model.prec + i); }
+  __device__ __forceinline__ double model_mu(int j, int i) const { return MSH ? sm_mmu[sidx(j)] : __ldg(P.model.mu + i); }
+  __device__ __forceinline__ double model_prec(int j, int i) const { return MSH ? sm_mprec[sidx(j)] : __ldg(P.model.prec + i); }
   // element j of the whitened gradient (each thread only touches its own entries: no synchronisation)
-  __device__ __forceinline__ double& G(int j) { return GS ? sm_g[eidx(j)] : g_reg[GS ? 0 : j]; }
+  __device__ __forceinline__ double& G(int j) { return GS ? sm_g[sidx(j)] : g_reg[GS ? 0 : j]; }
   // The four per-element constants of the diagonal Gaussian leapfrog (sigma, mean of the mass matrix; mu, precision of the
   // model) for elements j, j + 1 of a PAIR (j even): one 16-byte access per vector instead of two 8-byte ones.
   struct PairConsts {
     double sg[2], mn[2], mm[2], pr[2];
   };
   __device__ __forceinline__ void pair_consts(int j, PairConsts& c) const {
-    const int i0 = eidx(j);
+    const int i0 = eidx(j), s0 = sidx(j);
     if (MMS) {
-      const double2 a = *reinterpret_cast<const double2*>(sm_sig + i0), b = *reinterpret_cast<const double2*>(sm_mu + i0);
+      const double2 a = *reinterpret_cast<const double2*>(sm_sig + s0), b = *reinterpret_cast<const double2*>(sm_mu + s0);
       c.sg[0] = a.x, c.sg[1] = a.y, c.mn[0] = b.x, c.mn[1] = b.y;
     } else {
       c.sg[0] = sig[MMS ? 0 : j], c.sg[1] = sig[MMS ? 0 : j + 1], c.mn[0] = mu[MMS ? 0 : j], c.mn[1] = mu[MMS ? 0 : j + 1];
     }
     double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
     if (inb(i0)) {  // the partner of an odd last element reads the zero padding of the parameter arrays
-      if (MSH) a = *reinterpret_cast<const double2*>(sm_mmu + i0), b = *reinterpret_cast<const double2*>(sm_mprec + i0);
+      if (MSH) a = *reinterpret_cast<const double2*>(sm_mmu + s0), b = *reinterpret_cast<const double2*>(sm_mprec + s0);
       else a = __ldg(reinterpret_cast<const double2*>(P.model.mu + i0)), b = __ldg(reinterpret_cast<const double2*>(P.model.prec + i0));
     }
     c.mm[0] = a.x, c.mm[1] = a.y, c.pr[0] = b.x, c.pr[1] = b.y;
@@ -438,8 +451,8 @@ struct Engine {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = eidx(j);
-        sm_mmu[i] = i < d ? P.model.mu[i] : 0.0;
-        sm_mprec[i] = i < d ? P.model.prec[i] : 0.0;
+        sm_mmu[sidx(j)] = i < d ? P.model.mu[i] : 0.0;
+        sm_mprec[sidx(j)] = i < d ? P.model.prec[i] : 0.0;
       }
     }
   }
@@ -935,8 +948,8 @@ struct Engine {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = eidx(j);
-        sm_sig[i] = i < d ? P.stds[row + i] : 0.0;
-        sm_mu[i] = i < d ? P.mean[row + i] : 0.0;
+        sm_sig[sidx(j)] = i < d ? P.stds[row + i] : 0.0;
+        sm_mu[sidx(j)] = i < d ? P.mean[row + i] : 0.0;
       }
       // each thread only ever reads back the entries it wrote itself: no barrier needed
     } else {
@@ -1040,7 +1053,7 @@ struct Engine {
   // exactly the 16-byte pairs it owns under the engine's element mapping and later reads only those, so - like everywhere in this
   // engine - no barrier is involved: completion is the thread's own cp.async.wait_all.  stg_src[b] remembers what was staged.
   const double* stg_src[2] = {nullptr, nullptr};
-  __device__ __forceinline__ const double* stage_buf(int b, int which) const { return sm_stage + (size_t)(2 * b + which) * (TPC * EPT); }
+  __device__ __forceinline__ const double* stage_buf(int b, int which) const { return sm_stage + (size_t)(2 * b + which) * (LT * EPT); }
   __device__ __forceinline__ void stage_pair(int b, const double* zsrc, const double* vsrc) {
     if (!STAGE) return;
     stg_src[b] = zsrc;
@@ -1146,13 +1159,13 @@ struct Engine {
     lin = false;
     ls_main = log_noinline(ls_main);
     tsync();
-    if (tid == 0) {
+    if (ltid == 0) {  // (one writer per copy of the tables: every CTA of a cluster team keeps its own)
 #pragma unroll 1
       for (int l = 1; l < MAX_DOUBLING_DEPTH; ++l)
         if ((i >> l) & 1u) T.A_ls[l] = log_noinline(T.A_ls[l]);
     }
     tsync();
-    if (TPC > 32) red.barrier();
+    if (TPC > 32) red.local_barrier();
   }
 
   // ------------------------------------------------------------------ NutsTree::extend for the MAIN tree (nuts.rs:108-170)
@@ -1333,7 +1346,7 @@ struct Engine {
       stg_src[0] = nullptr;  // buffer X only lives from the prefetch to the merges of the same leaf (slots are re-used afterwards)
       NB_ACC(3, tq);
       if (i + 1 < nleaf) {
-        if (tid == 0) {
+        if (ltid == 0) {
           T.A_first[t] = (signed char)B_first;
           T.A_last[t] = (signed char)s;  // the last-of-B reference moves to the pending sub-tree
           T.A_ls[t] = B_ls;
@@ -1491,7 +1504,7 @@ struct Engine {
 #ifndef NB_ADAPT_CHUNK
 #define NB_ADAPT_CHUNK 2
 #endif
-  static constexpr int CH = EPT < 4 ? EPT : ((EPT % NB_ADAPT_CHUNK == 0 && !MULTI) ? NB_ADAPT_CHUNK : 4);
+  static constexpr int CH = EPT < 4 ? EPT : (EPT % NB_ADAPT_CHUNK == 0 ? NB_ADAPT_CHUNK : 4);  // (the same for both engines: bit-identical results)
   // (everything by value and statically indexed at the call sites: a reference parameter or a rolled loop over the chunk would
   // move the chunk's register arrays to local memory)
   static __device__ __noinline__ double2 mass_matrix_element_slow(double dv, double gv, double scale, bool grad_based, double s_old, double is_old) {
@@ -1845,10 +1858,11 @@ struct Engine {
     }
     // ---- adaptation + statistics: cold, through global memory
     store_hot();
-    const int ret = cold_adapt<TPC, EPT, SMF, MODEL, MULTI>(P, chain, tid, red.scratch, sm_sig, mc, red.parity, t, acc_sum, acc_sym_sum, acc_count,
+    const int ret = cold_adapt<TPC, EPT, SMF, MODEL, MULTI>(P, chain, tid, red.scratch, sm_sig, mc, (red.parity & 1) | ((red.xparity & 1) << 1), t, acc_sum, acc_sym_sum, acc_count,
                                               max_energy_error, diverging ? (abs(draw_idx) > 4) : (draw_idx != 0), depth, reached_maxdepth,
                                               diverging, draw_idx, draw_energy, draw_energy - E0, fisher[0]);
     red.parity = ret & 1;
+    red.xparity = (ret >> 1) & 1;
     // the chain scalars now live in ChainState again; the next work unit (possibly on another team) reloads them
     NB_ACC(6, tm);
   }
@@ -2323,9 +2337,10 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
                                        uint64_t t, double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
                                        int depth, bool reached_maxdepth, bool diverging, int draw_idx, double pt_energy,
                                        double pt_energy_error, double fisher) {
-  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)(TPC / cluster_size<SMF>()) * EPT * sizeof(double)));
   Engine<TPC, EPT, SMF, MODEL, MULTI> E(P, chain, tid, scratch, team_smem, tables, mc);
-  E.red.parity = parity;
+  E.red.parity = parity & 1;
+  E.red.xparity = (parity >> 1) & 1;
   NB_COLD_T0;
   E.cold_load();
   E.acc_sum = acc_sum;
@@ -2371,13 +2386,13 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
     atomicAdd(P.phase_clocks + 15, (unsigned long long)(t_end - cold_t0));
   }
 #endif
-  return E.red.parity & 1;
+  return (E.red.parity & 1) | ((E.red.xparity & 1) << 1);
 }
 
 // Chain::set_position for one chain; returns the per-chain status (0 ok, 3 bad initial point).
 template <int TPC, int EPT, int SMF, int MODEL, bool MULTI>
 __device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc) {
-  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)(TPC / cluster_size<SMF>()) * EPT * sizeof(double)));
   Engine<TPC, EPT, SMF, MODEL, MULTI> E(P, chain, tid, scratch, team_smem, tables, mc);
   E.cold_load();
   const int status = E.run_set_position();
@@ -2429,7 +2444,7 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
   const int tid = threadIdx.x % TPC;
   unsigned char* my_smem = dyn_smem + (size_t)team * team_smem_bytes<TPC, EPT, SMF>();
   double* team_smem = reinterpret_cast<double*>(my_smem);
-  TreeTables& tables = *reinterpret_cast<TreeTables*>(my_smem + (smem_vectors<SMF>() * (size_t)TPC * EPT * sizeof(double)));
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(my_smem + (smem_vectors<SMF>() * (size_t)(TPC / cluster_size<SMF>()) * EPT * sizeof(double)));
   {  // model parameters: the same for every chain, loaded once per team
     Engine<TPC, EPT, SMF, MODEL> E0(P, 0, tid, scratch, team_smem, tables);
     E0.load_model_params();
@@ -2495,6 +2510,83 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
     if (tid == 0 && P.phase_clocks)
       for (int k = 0; k < 8; ++k) atomicAdd(P.phase_clocks + k, (unsigned long long)E.phase[k]);
 #endif
+  }
+}
+
+// The same engine with the team spread over the CL CTAs of a thread-block cluster (SM_CL2 / SM_CL4): CL SMs work on ONE chain.
+// For dim ~ 10^4 a single SM cannot hold a chain's vectors (z, v, sigma, mean, model parameters: 6 x 80 KB); a cluster of four
+// holds all of them in registers and shared memory, every leapfrog touches HBM only for its checkpoint, and the register file
+// leaves room for the redundant scalar state again (no leader warp, no spills).  Work units as in nuts_chain_kernel, fetched by
+// CTA 0 of the cluster and handed to the peers through distributed shared memory.
+// Launched with cluster dimension CL (cudaLaunchKernelEx); blockDim = TPC / CL; grid = clusters * CL.
+template <int TPC, int EPT, int SMF, int MODEL>
+__global__ void __launch_bounds__(TPC / cluster_size<SMF>(), 1) nuts_chain_kernel_cluster(const __grid_constant__ EngineParams P) {
+  constexpr int CL = cluster_size<SMF>();
+  constexpr int LT = TPC / CL;
+  static_assert(CL > 1 && LT % 32 == 0 && LT > 32, "cluster teams: at least two warps per CTA");
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ double scratch[TeamReduce<LT, false, CL>::SCRATCH_DOUBLES];
+  __shared__ unsigned next_unit;
+  const unsigned crank = cluster_ctarank();
+  const int tid = (int)crank * LT + (int)threadIdx.x;
+  double* team_smem = reinterpret_cast<double*>(dyn_smem);
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(dyn_smem + (smem_vectors<SMF>() * (size_t)LT * EPT * sizeof(double)));
+  {
+    Engine<TPC, EPT, SMF, MODEL> E0(P, 0, tid, scratch, team_smem, tables);
+    E0.load_model_params();
+  }
+  const unsigned B = P.draws_per_unit;
+  const unsigned blocks = P.mode == 0 ? 1u : ((unsigned)P.n_draws + B - 1u) / B;
+  const unsigned total_units = (unsigned)P.N * blocks;
+  for (;;) {
+    if (tid == 0) {
+      const unsigned u = atomicAdd(P.queue, 1u);
+#pragma unroll
+      for (int r = 0; r < CL; ++r) st_cluster_u32(&next_unit, (unsigned)r, u);
+    }
+    cluster_barrier();
+    const unsigned unit = next_unit;
+    cluster_barrier();  // everybody has read it before CTA 0 fetches the next one
+    if (unit >= total_units) break;
+    const int chain = (int)(unit % (unsigned)P.N);
+    const unsigned blk = unit / (unsigned)P.N;
+    Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
+    if (P.mode == 0) {
+      if (P.init_mask == nullptr || P.init_mask[chain] != 0) {
+        const int status = cold_set_position<TPC, EPT, SMF, MODEL, false>(P, chain, tid, scratch, team_smem, nullptr);
+        if (tid == 0 && P.status_out) P.status_out[chain] = status;
+      }
+    } else {
+      if (blk > 0) {
+        if (tid == 0) {
+          unsigned dn;
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(P.done + chain) : "memory");
+            if (dn >= blk) break;
+            __nanosleep(200);
+          }
+        }
+        cluster_barrier();
+        __threadfence();
+      }
+      const uint64_t t_end = min((uint64_t)(blk + 1u) * B, (uint64_t)P.n_draws);
+      for (uint64_t t = (uint64_t)blk * B; t < t_end; ++t) {
+        E.load_hot();
+        if (E.hs_alive) {
+          E.run_draw(t);
+        } else {
+          if (t == 0) cold_fill_dead(P, chain, tid, TPC, 0);
+          break;
+        }
+      }
+      __threadfence();
+      cluster_barrier();
+      if (tid == 0) {
+        const unsigned dn = blk + 1u;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.done + chain), "r"(dn) : "memory");
+      }
+    }
+    cluster_barrier();
   }
 }
 

@@ -367,3 +367,32 @@ def test_bad_initial_points_are_retried_like_the_reference_sampler(L, orc):
         x.close()
     for x in (math, m2):
         x.close()
+
+
+LARGE_DIMS = [(5000, 2, 16), (9000, 2, 12), (10240, 2, 10)]
+
+
+@pytest.mark.parametrize("d,N,draws", LARGE_DIMS)
+@pytest.mark.parametrize("kind", [_abi.NUTS_LOGP_GAUSS_RANK1, _abi.NUTS_LOGP_FUNNEL])
+def test_large_dim_cluster_engine_non_elementwise_targets(L, orc, kind, d, N, draws):
+    """dim ~ 10^4 for the targets that need a team-wide reduction inside every leapfrog (rank-1 Gaussian, funnel): by default the
+    cluster engine (the team = the 4 CTAs of a thread-block cluster, reductions through distributed shared memory); fixed step
+    size and mass matrix, every draw within 1e-9 of the oracle with identical tree shapes."""
+    s = _no_adapt(L, maxdepth=5)
+    if kind == _abi.NUTS_LOGP_FUNNEL:
+        # the funnel's neck is chaotic: start every chain inside the bulk (v = 0) and require exact agreement on a prefix
+        x0 = np.random.default_rng(d).normal(size=(N, d))
+        x0[:, 0] = 0.1
+        compare_run(L, orc, kind, N, d, s, draws, seed=d, x0=x0, strict=4, min_common=6, rtol=1e-8)
+    else:
+        compare_run(L, orc, kind, N, d, s, draws, seed=d, strict=6, min_common=8)
+
+
+@pytest.mark.parametrize("d,N,draws", LARGE_DIMS[:2])
+def test_large_dim_cluster_engine_diag_with_adaptation(L, orc, monkeypatch, d, N, draws):
+    """The cluster engine on the elementwise target (selected explicitly; the decoupled engine is the default there), warm-up on."""
+    monkeypatch.setenv("NUTS_B200_ENGINE", "1024,10,41")
+    s = _settings(L, num_tune=draws // 2, maxdepth=6)
+    compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_DIAG, N, d, s, draws, seed=d, strict=1, min_common=5, loose=1e-6)
+    s = _no_adapt(L, maxdepth=6)
+    compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_DIAG, N, d, s, draws, seed=d + 1)
