@@ -162,6 +162,7 @@ struct nuts_sampler {
   std::vector<void*> allocations;
   double* d_init = nullptr;
   int* d_status = nullptr;
+  unsigned int* d_ring_template = nullptr;  // 0, 1, 2, ..: the ready ring's sequence numbers at the start of a launch
   // device stats buffers (grown on demand): ONE allocation holding the 15 arrays + a page-locked host mirror, so the statistics
   // of a nuts_draw call leave in a single D2H copy
   uint64_t stats_capacity = 0;  // in draws
@@ -902,14 +903,27 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   A((void**)&P.slots, team_plane * 2 * (size_t)P.P);  // checkpoints live inside one draw on one team: pools per TEAM, not per chain
   A((void**)&P.ends, team_plane * 3 * NB_END_BUFFERS);
   A((void**)&P.cs, ctx->N * sizeof(ChainState));
-  A((void**)&P.queue, sizeof(unsigned int));
+  // ready queue of the work units (chain_engine.cuh, unit_pop / unit_push): two tickets, the per-chain unit counters, and a ring
+  // of a power of two >= N slots whose sequence numbers are reset from a template before every launch
+  size_t ring = 1;
+  while (ring < (size_t)ctx->N) ring *= 2;
+  P.ring_mask = (unsigned)(ring - 1);
+  A((void**)&P.queue, 2 * sizeof(unsigned int));
   A((void**)&P.done, ctx->N * sizeof(unsigned int));
+  A((void**)&P.ring_seq, ring * sizeof(unsigned int));
+  A((void**)&P.ring_chain, ring * sizeof(unsigned int));
+  A((void**)&s->d_ring_template, ring * sizeof(unsigned int));
   A((void**)&s->d_init, ctx->N * ctx->d * sizeof(double));
   A((void**)&s->d_status, ctx->N * sizeof(int));
   A((void**)&P.phase_clocks, 16 * sizeof(unsigned long long));
   if (r != NUTS_OK) return r;
   std::vector<ChainState> cs(ctx->N, fresh_chain_state(S));
   CUDA_TRY(cudaMemcpy(P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice));
+  {
+    std::vector<unsigned int> seq(ring);
+    for (size_t i = 0; i < ring; ++i) seq[i] = (unsigned)i;
+    CUDA_TRY(cudaMemcpy(s->d_ring_template, seq.data(), ring * sizeof(unsigned int), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaEventCreate(&s->ev0));
   CUDA_TRY(cudaEventCreate(&s->ev1));
   guard.dismiss();
@@ -937,8 +951,9 @@ int nuts_sampler_destroy(nuts_sampler_t* s) {
 
 static int launch_engine(nuts_sampler* s) {
   nuts_ctx* ctx = s->ctx;
-  CUDA_TRY(cudaMemsetAsync(s->P.queue, 0, sizeof(unsigned int), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(s->P.queue, 0, 2 * sizeof(unsigned int), ctx->stream));
   CUDA_TRY(cudaMemsetAsync(s->P.done, 0, ctx->N * sizeof(unsigned int), ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->P.ring_seq, s->d_ring_template, ((size_t)s->P.ring_mask + 1) * sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
   CUDA_TRY(cudaEventRecord(s->ev0, ctx->stream));
   CUDA_TRY(s->cfg->launch[s->model_variant](&s->P, s->grid, ctx->stream));
   CUDA_TRY(cudaEventRecord(s->ev1, ctx->stream));

@@ -103,8 +103,11 @@ struct EngineParams {
   double* slots;                    // [teams][P][2: z, v][ld]   leaf checkpoints of the half under construction (one pool per resident team)
   double* ends;                     // [teams][NB_END_BUFFERS][3: z, v, grad_z][ld]   main-tree endpoints (v1: 0 left, 1 right)
   ChainState* cs;
-  unsigned int* queue;              // persistent work-unit queue
+  unsigned int* queue;              // [2] ready queue of this launch: pop tickets taken, push tickets taken
   unsigned int* done;               // [N] work units (blocks of draws) of this launch each chain has completed
+  unsigned int* ring_seq;           // [ring_mask + 1] ready ring, slot sequence numbers (reset to 0, 1, 2, .. before every launch)
+  unsigned int* ring_chain;         // [ring_mask + 1] ready ring, chain ids
+  unsigned int ring_mask;           // ring size - 1; the ring holds a power of two >= N entries
   // mode 0: set_position ; mode 1: draw
   int mode, _pad;
   const double* init_position;      // [N][d] device
@@ -2432,6 +2435,51 @@ static __device__ __noinline__ void cold_fill_dead(const EngineParams& P, int ch
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- work units
+// set_position: one unit per chain.  Draws: a unit is draws_per_unit consecutive draws of one chain; a chain's state lives in
+// global memory between units, so ANY team can run a chain's next unit.  Units are handed out through a ready queue: the first
+// N pop tickets are the chains themselves (unit 0 of every chain), and a team that completes a unit of a chain that has more
+// to do pushes the chain into a bounded multi-producer / multi-consumer ring (a sequence number per slot); pop ticket N + T
+// takes what push ticket T delivered.  First in, first out keeps the launch draw-major (all chains advance together, the launch
+// ends after total_units / teams rounds rather than ceil(N / teams) whole chains), but a team never waits for one PARTICULAR
+// chain: with the trees of the warm-up phase ranging from 1 to 1023 leapfrogs, the fixed order unit u = (draw u / N, chain u % N)
+// of round 1 left the team that drew the successor of a long draw asleep until that draw ended (12 - 15 % of the tuning phase
+// of config 2 in the ncu stall samples).  Release / acquire at gpu scope on the slot's sequence number orders the chain's planes
+// (the engine's global loads bypass L1: -dlcm=cg).  Both functions are called by ONE thread of the team.
+__device__ __forceinline__ unsigned unit_pop(const EngineParams& P, unsigned total_units, unsigned& blk) {
+  const unsigned h = atomicAdd(P.queue, 1u);
+  blk = 0;
+  if (h >= total_units) return ~0u;
+  if (h < (unsigned)P.N) return h;
+  const unsigned T = h - (unsigned)P.N, slot = T & P.ring_mask;
+  for (;;) {
+    unsigned sq;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(sq) : "l"(P.ring_seq + slot) : "memory");
+    if (sq == T + 1u) break;
+    __nanosleep(100);
+  }
+  const unsigned chain = *reinterpret_cast<volatile unsigned*>(P.ring_chain + slot);
+  blk = *reinterpret_cast<volatile unsigned*>(P.done + chain);
+  const unsigned freed = T + P.ring_mask + 1u;  // the slot now waits for push ticket T + ring size
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.ring_seq + slot), "r"(freed) : "memory");
+  return chain;
+}
+// (the caller has made the team's stores visible: __threadfence by every thread, then a team barrier)
+__device__ __forceinline__ void unit_push(const EngineParams& P, unsigned chain, unsigned blocks_done, unsigned blocks) {
+  *reinterpret_cast<volatile unsigned*>(P.done + chain) = blocks_done;
+  if (blocks_done >= blocks) return;  // the chain's last unit of this launch
+  const unsigned T = atomicAdd(P.queue + 1, 1u), slot = T & P.ring_mask;
+  for (;;) {  // never spins in practice: at most N chains are in flight and the ring has >= N slots
+    unsigned sq;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(sq) : "l"(P.ring_seq + slot) : "memory");
+    if (sq == T) break;
+    __nanosleep(100);
+  }
+  *reinterpret_cast<volatile unsigned*>(P.ring_chain + slot) = chain;
+  const unsigned filled = T + 1u;
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.ring_seq + slot), "r"(filled) : "memory");
+}
+
 // One kernel for both Chain::set_position (mode 0) and n_draws x Chain::draw (mode 1).
 // Dynamic shared memory: TEAMS x team_smem_bytes<TPC, EPT, SMF>().
 template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, int SMF, int MODEL>
@@ -2439,7 +2487,7 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
   constexpr int TEAMS = CTA_THREADS / TPC;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ double scratch[TPC > 32 ? 2 * (TPC / 32) * REDUCE_MAXK : 1];
-  __shared__ int next_chain[TEAMS];
+  __shared__ int next_chain[TEAMS][2];
   const int team = threadIdx.x / TPC;
   const int tid = threadIdx.x % TPC;
   unsigned char* my_smem = dyn_smem + (size_t)team * team_smem_bytes<TPC, EPT, SMF>();
@@ -2449,24 +2497,22 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
     Engine<TPC, EPT, SMF, MODEL> E0(P, 0, tid, scratch, team_smem, tables);
     E0.load_model_params();
   }
-  // Work units.  set_position: one chain.  Draws: ONE DRAW of one chain, in draw-major order (unit u = draw u / N of chain u % N):
-  // a chain's state lives in global memory between draws anyway, so any team can run its next draw, and with more chains than
-  // resident teams (config 2: 1024 chains, 592 teams) the launch ends after total_work / teams instead of ceil(N / teams) whole
-  // chains.  Draw t of a chain waits for its draw t-1 (P.done, release / acquire at gpu scope; the engine's global loads bypass
-  // L1: -dlcm=cg, so data written by another SM is read from L2).
   const unsigned B = P.draws_per_unit;
   const unsigned blocks = P.mode == 0 ? 1u : ((unsigned)P.n_draws + B - 1u) / B;
   const unsigned total_units = (unsigned)P.N * blocks;
   for (;;) {
-    if (tid == 0) next_chain[team] = (int)atomicAdd(P.queue, 1u);
+    if (tid == 0) {
+      unsigned b;
+      next_chain[team][0] = (int)unit_pop(P, total_units, b);
+      next_chain[team][1] = (int)b;
+    }
     if (TPC > 32) __syncthreads();
     else __syncwarp();
-    const unsigned unit = (unsigned)next_chain[team];
+    const int chain = next_chain[team][0];
+    const unsigned blk = (unsigned)next_chain[team][1];  // block of B consecutive draws (a few draws per unit amortise the hand-over)
     if (TPC > 32) __syncthreads();
     else __syncwarp();
-    if (unit >= total_units) break;
-    const int chain = (int)(unit % (unsigned)P.N);
-    const unsigned blk = unit / (unsigned)P.N;  // block of B consecutive draws (a few draws per unit amortise the hand-over)
+    if (chain < 0) break;
     Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
     if (P.mode == 0) {
       if (P.init_mask == nullptr || P.init_mask[chain] != 0) {
@@ -2474,18 +2520,7 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
         if (tid == 0 && P.status_out) P.status_out[chain] = status;
       }
     } else {
-      if (blk > 0) {
-        if (tid == 0) {
-          unsigned dn;
-          for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(P.done + chain) : "memory");
-            if (dn >= blk) break;
-            __nanosleep(200);
-          }
-        }
-        E.team_sync();
-        __threadfence();
-      }
+      if (blk > 0) __threadfence();  // (thread 0 acquired the chain in unit_pop; the team barrier above ordered the others after it)
       const uint64_t t_end = min((uint64_t)(blk + 1u) * B, (uint64_t)P.n_draws);
       for (uint64_t t = (uint64_t)blk * B; t < t_end; ++t) {
         E.load_hot();
@@ -2499,10 +2534,7 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
       }
       __threadfence();
       E.team_sync();
-      if (tid == 0) {
-        const unsigned dn = blk + 1u;
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.done + chain), "r"(dn) : "memory");
-      }
+      if (tid == 0) unit_push(P, (unsigned)chain, blk + 1u, blocks);
     }
     if (TPC > 32) __syncthreads();
     else __syncwarp();
@@ -2526,7 +2558,7 @@ __global__ void __launch_bounds__(TPC / cluster_size<SMF>(), 1) nuts_chain_kerne
   static_assert(CL > 1 && LT % 32 == 0 && LT > 32, "cluster teams: at least two warps per CTA");
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ double scratch[TeamReduce<LT, false, CL>::SCRATCH_DOUBLES];
-  __shared__ unsigned next_unit;
+  __shared__ unsigned next_unit[2];
   const unsigned crank = cluster_ctarank();
   const int tid = (int)crank * LT + (int)threadIdx.x;
   double* team_smem = reinterpret_cast<double*>(dyn_smem);
@@ -2540,16 +2572,19 @@ __global__ void __launch_bounds__(TPC / cluster_size<SMF>(), 1) nuts_chain_kerne
   const unsigned total_units = (unsigned)P.N * blocks;
   for (;;) {
     if (tid == 0) {
-      const unsigned u = atomicAdd(P.queue, 1u);
+      unsigned b;
+      const unsigned c = unit_pop(P, total_units, b);
 #pragma unroll
-      for (int r = 0; r < CL; ++r) st_cluster_u32(&next_unit, (unsigned)r, u);
+      for (int r = 0; r < CL; ++r) {
+        st_cluster_u32(&next_unit[0], (unsigned)r, c);
+        st_cluster_u32(&next_unit[1], (unsigned)r, b);
+      }
     }
     cluster_barrier();
-    const unsigned unit = next_unit;
+    const int chain = (int)next_unit[0];
+    const unsigned blk = next_unit[1];
     cluster_barrier();  // everybody has read it before CTA 0 fetches the next one
-    if (unit >= total_units) break;
-    const int chain = (int)(unit % (unsigned)P.N);
-    const unsigned blk = unit / (unsigned)P.N;
+    if (chain < 0) break;
     Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
     if (P.mode == 0) {
       if (P.init_mask == nullptr || P.init_mask[chain] != 0) {
@@ -2557,18 +2592,7 @@ __global__ void __launch_bounds__(TPC / cluster_size<SMF>(), 1) nuts_chain_kerne
         if (tid == 0 && P.status_out) P.status_out[chain] = status;
       }
     } else {
-      if (blk > 0) {
-        if (tid == 0) {
-          unsigned dn;
-          for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(P.done + chain) : "memory");
-            if (dn >= blk) break;
-            __nanosleep(200);
-          }
-        }
-        cluster_barrier();
-        __threadfence();
-      }
+      if (blk > 0) __threadfence();
       const uint64_t t_end = min((uint64_t)(blk + 1u) * B, (uint64_t)P.n_draws);
       for (uint64_t t = (uint64_t)blk * B; t < t_end; ++t) {
         E.load_hot();
@@ -2581,10 +2605,7 @@ __global__ void __launch_bounds__(TPC / cluster_size<SMF>(), 1) nuts_chain_kerne
       }
       __threadfence();
       cluster_barrier();
-      if (tid == 0) {
-        const unsigned dn = blk + 1u;
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.done + chain), "r"(dn) : "memory");
-      }
+      if (tid == 0) unit_push(P, (unsigned)chain, blk + 1u, blocks);
     }
     cluster_barrier();
   }

@@ -504,16 +504,16 @@ __global__ void NB_KERNEL_BOUNDS(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(cons
   const unsigned total_units = (unsigned)P.N * blocks;
   for (;;) {
     if (tid == 0) {
-      const unsigned u = atomicAdd(P.queue, 1u);
-      next_chain[1] = (int)u;
-      next_chain[0] = u < total_units ? (int)(u % (unsigned)P.N) : -1;  // the leader lane reads the chain id from here
+      unsigned b;
+      const unsigned c = unit_pop(P, total_units, b);
+      next_chain[0] = (int)c;  // the leader lane reads the chain id from here (-1: no more work)
+      next_chain[1] = (int)b;
     }
     bar_sync(mc.bar_id, TPC);
-    const unsigned unit = (unsigned)next_chain[1];
+    const int chain = next_chain[0];
+    const unsigned blk = (unsigned)next_chain[1];
     bar_sync(mc.bar_id, TPC);
-    if (unit >= total_units) break;
-    const int chain = (int)(unit % (unsigned)P.N);
-    const unsigned blk = unit / (unsigned)P.N;
+    if (chain < 0) break;
     Engine<TPC, EPT, SMF, MODEL, true> E(P, chain, tid, scratch, team_smem, tables, &mc);
     if (P.mode == 0) {
       if (P.init_mask == nullptr || P.init_mask[chain] != 0) {
@@ -521,18 +521,7 @@ __global__ void NB_KERNEL_BOUNDS(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(cons
         if (tid == 0 && P.status_out) P.status_out[chain] = status;
       }
     } else {
-      if (blk > 0) {
-        if (tid == 0) {
-          unsigned dn;
-          for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(P.done + chain) : "memory");
-            if (dn >= blk) break;
-            __nanosleep(200);
-          }
-        }
-        bar_sync(mc.bar_id, TPC);
-        __threadfence();
-      }
+      if (blk > 0) __threadfence();
       const uint64_t t_end = min((uint64_t)(blk + 1u) * B, (uint64_t)P.n_draws);
       for (uint64_t t = (uint64_t)blk * B; t < t_end; ++t) {
         E.load_hot();
@@ -545,10 +534,7 @@ __global__ void NB_KERNEL_BOUNDS(32 * NL + C * TPC, 1) nuts_chain_kernel_v2(cons
       }
       __threadfence();
       bar_sync(mc.bar_id, TPC);
-      if (tid == 0) {
-        const unsigned dn = blk + 1u;
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.done + chain), "r"(dn) : "memory");
-      }
+      if (tid == 0) unit_push(P, (unsigned)chain, blk + 1u, blocks);
     }
     bar_sync(mc.bar_id, TPC);
 #ifdef NB_PHASE_TIMING_TEAM
