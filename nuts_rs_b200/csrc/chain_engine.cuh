@@ -146,6 +146,17 @@ enum { EXT_OK = 0, EXT_TURNING = 1, EXT_DIVERGING = 2 };
 // instance and exchange the chain scalars by value, so that the hot tree builder (run_draw -> extend -> leapfrog, all
 // force-inlined with one call site each) never has its address taken and its vectors really live in registers.
 struct MultiCtx;  // decoupled engine only (several teams per CTA), see below
+// The launch parameters as the cold functions see them: a private copy (COPY) or the kernel's own (see cold_adapt).
+template <bool COPY>
+struct ParamsCopy {
+  const EngineParams P;
+  __device__ __forceinline__ explicit ParamsCopy(const EngineParams& g) : P(g) {}
+};
+template <>
+struct ParamsCopy<false> {
+  const EngineParams& P;
+  __device__ __forceinline__ explicit ParamsCopy(const EngineParams& g) : P(g) {}
+};
 template <int TPC, int EPT, int SMF, int MODEL, bool MULTI>
 __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc, int parity,
                                        uint64_t t, double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
@@ -1524,6 +1535,8 @@ struct Engine {
     double* sd = P.stds + row;
     double* isd = P.inv_stds + row;
     double* mn = P.mean + row;
+    double* const est0 = est_ptr(0, 0);  // plane (set, which) = est0 + (4 * set + which) * pl; locals: a store cannot alias them
+    const size_t pl = (size_t)P.ld;
     const uint64_t nn[2] = {n0, n1};
     const double sc[2] = {1.0 / (double)n0, 1.0 / (double)n1};
     const double mscale = 1.0 / (double)fg_count;
@@ -1533,21 +1546,53 @@ struct Engine {
     for (int j0 = 0; j0 < EPT; j0 += CH) {
       double x[CH], gx[CH], e[2][4][CH], s_new[CH], is_new[CH];
       bool live[CH];
-      // ---- every load of the chunk, unconditionally (a lane without an element re-reads element 0: no branch per load)
+      // ---- every load of the chunk, unconditionally (a lane without an element re-reads element 0: no branch per load);
+      // PAIR mapping: the two elements of a pair in one 16-byte access (a row's padding is readable)
+      constexpr int VS = (PAIR && CH % 2 == 0) ? 2 : 1;
+      int at[CH];  // where element q is loaded from
+      auto ldv = [&](const double* __restrict__ p, double (&a)[CH]) {
+#pragma unroll
+        for (int q = 0; q < CH; q += VS) {
+          if constexpr (VS == 2) {
+            const double2 t = *reinterpret_cast<const double2*>(p + at[q]);
+            a[q] = t.x;
+            a[q + 1] = t.y;
+          } else {
+            a[q] = p[at[q]];
+          }
+        }
+      };
+      auto stv = [&](double* __restrict__ p, const double (&a)[CH]) {
+#pragma unroll
+        for (int q = 0; q < CH; q += VS) {
+          if constexpr (VS == 2) {
+            if (live[q + 1]) *reinterpret_cast<double2*>(p + at[q]) = make_double2(a[q], a[q + 1]);
+            else if (live[q]) p[at[q]] = a[q];
+          } else {
+            if (live[q]) p[at[q]] = a[q];
+          }
+        }
+      };
 #pragma unroll
       for (int q = 0; q < CH; ++q) {
         const int i = eidx(j0 + q);
         live[q] = (j0 + q < EPT) && (i < d);
-        const int ii = live[q] ? i : 0;
-        x[q] = xp[ii];
-        gx[q] = gp[ii];
-#pragma unroll
-        for (int st = 0; st < 2; ++st)
-#pragma unroll
-          for (int w = 0; w < 4; ++w) e[st][w][q] = est_ptr(st, w)[ii];
-        s_new[q] = sd[ii];
-        is_new[q] = isd[ii];
+        at[q] = (VS == 2 && (q & 1)) ? at[q - 1] + 1 : (live[q] ? i : 0);
       }
+      ldv(xp, x);
+      ldv(gp, gx);
+#pragma unroll
+      for (int st = 0; st < 2; ++st)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) ldv(est0 + (size_t)(4 * st + w) * pl, e[st][w]);
+      ldv(sd, s_new);
+      ldv(isd, is_new);
+#ifdef NB_PHASE_TIMING_COLD
+      const long long vp_a = clock64();
+      asm volatile("" ::"d"(x[0]), "d"(is_new[CH - 1]), "d"(e[1][3][CH - 1]), "d"(e[0][0][0]));  // wait for the chunk's loads
+      const long long vp_b = clock64();
+      cold_t[2] += vp_b - vp_a;
+#endif
       // ---- RunningVariance::add_sample for the four estimators of both sets
       if (upd) {
 #pragma unroll
@@ -1573,15 +1618,13 @@ struct Engine {
             }
           }
 #pragma unroll
-          for (int q = 0; q < CH; ++q) {
-            const int i = eidx(j0 + q);
-            if (live[q]) {
-#pragma unroll
-              for (int w = 0; w < 4; ++w) est_ptr(st, w)[i] = e[st][w][q];
-            }
-          }
+          for (int w = 0; w < 4; ++w) stv(est0 + (size_t)(4 * st + w) * pl, e[st][w]);
         }
       }
+#ifdef NB_PHASE_TIMING_COLD
+      const long long vp_c = clock64();
+      cold_t[3] += vp_c - vp_b;
+#endif
       // ---- DiagMassMatrix::update_diag_draw_grad / update_diag_draw from set mm_set
       if (do_mm) {
         double cand_s[CH], cand_is[CH];
@@ -1618,25 +1661,26 @@ struct Engine {
           }
         }
         double prod = 1.0;  // inv_std in [1e-10, 1e10] after the clamp (or the initial 1 / sqrt|grad| clamp): no overflow for CH <= 4
+        double mean[CH];
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
-          const int i = eidx(j0 + q);
           const double dm = mm_set ? e[1][0][q] : e[0][0][q], gm = mm_set ? e[1][2][q] : e[0][2][q];
-          double mean = dm;
+          mean[q] = dm;
           if (grad_based) {
             const double var = s_new[q] * s_new[q];  // array_mult(stds, stds, var)
             const double m = var * gm;               // array_mult(var, grad_mean, mean)
-            mean = fma(1.0, dm, m);                  // axpy(draw_mean, mean, 1.0)
+            mean[q] = fma(1.0, dm, m);               // axpy(draw_mean, mean, 1.0)
           }
-          if (live[q]) {
-            sd[i] = s_new[q];
-            isd[i] = is_new[q];
-            mn[i] = mean;
-            prod *= is_new[q];
-          }
+          if (live[q]) prod *= is_new[q];
         }
+        stv(sd, s_new);
+        stv(isd, is_new);
+        stv(mn, mean);
         ld[0] += log(prod);  // array_sum_ln(inv_stds)
       }
+#ifdef NB_PHASE_TIMING_COLD
+      cold_t[5] += clock64() - vp_c;
+#endif
     }
     if (do_mm) {
       red.allreduce(ld);
@@ -1739,6 +1783,20 @@ struct Engine {
   __device__ __forceinline__ void draw_finish(uint64_t t, bool diverging, bool reached_maxdepth) {
     const size_t N = (size_t)P.N;
     NB_T0(tm);
+    // While the mass matrix adapts, the pass at the end of this draw reads the chain's 8 estimator planes and 3 mass-matrix planes:
+    // last touched a whole draw ago, so they come from DRAM (all chains' planes + the checkpoint traffic of a draw exceed L2), one
+    // dependent round trip per chunk.  Ask L2 for them now; the materialisation below covers the latency.
+    if (!ROLL && hs_draw_count < P.s.final_step_size_window) {
+      const int lines = (d + 15) >> 4;  // rows start on 128-byte lines
+      for (int l = tid; l < lines; l += TPC) {
+        const size_t o = (size_t)l << 4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) prefetch_l2(est_ptr(k >> 2, k & 3) + o);
+        prefetch_l2(P.stds + row + o);
+        prefetch_l2(P.inv_stds + row + o);
+        prefetch_l2(P.mean + row + o);
+      }
+    }
     double fisher[1] = {0.0};
     if (ROLL) {
       // plane to plane: z of the selected leaf -> (x, gx, z, gz) planes + the draw; logp and the Fisher distance ride along
@@ -2336,10 +2394,16 @@ struct Engine {
 
 // GlobalStrategy::adapt + the statistics of Chain::expanded_draw for one chain; returns the reduction parity (bit 0).
 template <int TPC, int EPT, int SMF, int MODEL, bool MULTI>
-__device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc, int parity,
+__device__ __noinline__ int cold_adapt(const EngineParams& Pg, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc, int parity,
                                        uint64_t t, double acc_sum, double acc_sym_sum, uint64_t acc_count, double max_energy_error, bool is_good,
                                        int depth, bool reached_maxdepth, bool diverging, int draw_idx, double pt_energy,
                                        double pt_energy_error, double fisher) {
+  // A private copy of the launch parameters.  Through the reference (a generic pointer to the kernel's parameter space) every
+  // store in this function could alias them as far as the compiler knows, and each plane pointer was re-read - an L2 round trip,
+  // the loads bypass L1 - between two consecutive stores: 16 dependent round trips per chunk of the estimator pass, 15 in the
+  // statistics block (measured: 71 k + 16 k of the 100 k cycles a tuning draw of config 2 spent here).
+  const ParamsCopy<!MULTI> pc(Pg);
+  const EngineParams& P = pc.P;
   TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)(TPC / cluster_size<SMF>()) * EPT * sizeof(double)));
   Engine<TPC, EPT, SMF, MODEL, MULTI> E(P, chain, tid, scratch, team_smem, tables, mc);
   E.red.parity = parity & 1;
@@ -2355,7 +2419,7 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
   E.cs.draw_count += 1;
   if (!ok) {
     E.hs_alive = 0;
-    cold_fill_dead(P, chain, tid, TPC, t + 1);
+    cold_fill_dead(Pg, chain, tid, TPC, t + 1);  // (the reference: the copy's address must not escape)
   }
   if (tid == 0) {
     const StatsDev& st = P.stats;
@@ -2385,6 +2449,9 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
       atomicAdd(P.phase_clocks + 8, (unsigned long long)(c[1] - cold_t0));
       atomicAdd(P.phase_clocks + 9, (unsigned long long)(c[4] - c[1]));
       atomicAdd(P.phase_clocks + 10, (unsigned long long)(t_end - c[4]));
+      atomicAdd(P.phase_clocks + 11, (unsigned long long)c[2]);  // vector pass: waiting for a chunk's loads
+      atomicAdd(P.phase_clocks + 12, (unsigned long long)c[3]);  // vector pass: estimator updates + their stores
+      atomicAdd(P.phase_clocks + 13, (unsigned long long)c[5]);  // vector pass: mass-matrix elements + their stores
     }
     atomicAdd(P.phase_clocks + 15, (unsigned long long)(t_end - cold_t0));
   }
@@ -2394,7 +2461,9 @@ __device__ __noinline__ int cold_adapt(const EngineParams& P, int chain, int tid
 
 // Chain::set_position for one chain; returns the per-chain status (0 ok, 3 bad initial point).
 template <int TPC, int EPT, int SMF, int MODEL, bool MULTI>
-__device__ __noinline__ int cold_set_position(const EngineParams& P, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc) {
+__device__ __noinline__ int cold_set_position(const EngineParams& Pg, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc) {
+  const ParamsCopy<!MULTI> pc(Pg);  // as in cold_adapt
+  const EngineParams& P = pc.P;
   TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)(TPC / cluster_size<SMF>()) * EPT * sizeof(double)));
   Engine<TPC, EPT, SMF, MODEL, MULTI> E(P, chain, tid, scratch, team_smem, tables, mc);
   E.cold_load();

@@ -20,7 +20,7 @@ L = lib.load()
 L.nuts_debug_phase_clocks.argtypes = [C.c_void_p, C.c_void_p]
 L.nuts_debug_phase_clocks(s.h, out)
 names = ["init_traj", "leapfrog", "leaf+store", "merges", "doubling pro/epilogue", "materialise", "adapt (cold call)", "whole draw",
-         "cold: load + schedule", "cold: vector pass", "cold: dual avg / step / stats / store", "", "", "", "", "cold total"]
+         "cold: load + schedule", "cold: vector pass", "cold: dual avg / step / stats / store", "  pass: load wait", "  pass: estimators + stores", "  pass: mass matrix + stores", "", "cold total"]
 
 
 def report(label, draws):
