@@ -30,6 +30,13 @@ NB_DECL(32, 16, 8)
 NB_DECL(32, 32, 8)
 NB_DECL(32, 32, 7)
 NB_DECL(64, 16, 4)
+// SM_ALIGN (tag 21): all warp teams of an SM in ONE CTA, starting their work units together (chain_engine.cuh)
+NB_DECL(32, 1, 21)
+NB_DECL(32, 2, 21)
+NB_DECL(32, 4, 21)
+NB_DECL(32, 8, 21)
+NB_DECL(32, 16, 21)
+NB_DECL(64, 16, 44)   // SM_EXACT + SM_ALIGN: the 4 resident 64-thread teams of an SM in one 256-thread CTA
 NB_DECL(64, 16, 54)  // SM_EXACT variant of 64x16x4 (rows padded to 1024)
 NB_DECL(64, 16, 58)  // SM_EXACT + SM_STAGE, model parameters through the read-only path (no shared-memory copy)
 NB_DECL(64, 16, 55)  // + SM_NOGRAD, 5 resident CTAs per SM
@@ -112,10 +119,13 @@ const EngineConfig kDecoupledLarge[] = {
     {480, 21, 171, 480 * 21, {nb_launch_chain_480_21_171_1, nullptr, nullptr, nullptr}, {nb_occupancy_chain_480_21_171_1, nullptr, nullptr, nullptr}, 480 * 18}};
 // cluster engine (a team = the 4 CTAs of a thread-block cluster): default for the non-elementwise targets at 4096 < dim <= 10240
 const EngineConfig kClusterLarge = NB_CFG(1024, 10, 41);
+// SM_ALIGN variants of the warp tilings (tag 21): the default unless the target's tree depths vary wildly (funnel) or
+// NUTS_B200_ALIGN=0
+const EngineConfig kAlignedConfigs[] = {NB_CFG(32, 1, 21), NB_CFG(32, 2, 21), NB_CFG(32, 4, 21), NB_CFG(32, 8, 21), NB_CFG(32, 16, 21)};
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(1024, 10, 41), NB_CFG1(768, 14, 42), NB_CFG(128, 8, 53), NB_CFG(128, 8, 52), NB_CFG(256, 4, 62), NB_CFG(256, 4, 61), NB_CFG(64, 16, 58), NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 44), NB_CFG(32, 1, 21), NB_CFG(32, 2, 21), NB_CFG(32, 4, 21), NB_CFG(32, 8, 21), NB_CFG(32, 16, 21), NB_CFG(1024, 10, 41), NB_CFG1(768, 14, 42), NB_CFG(128, 8, 53), NB_CFG(128, 8, 52), NB_CFG(256, 4, 62), NB_CFG(256, 4, 61), NB_CFG(64, 16, 58), NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 
@@ -800,6 +810,16 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
     if (ctx->model.kind != NUTS_LOGP_GAUSS_ISO && ctx->model.kind != NUTS_LOGP_GAUSS_DIAG && ctx->d > 4096 &&
         ctx->d <= (uint64_t)kClusterLarge.max_d && kClusterLarge.launch[s_variant])
       cfg = &kClusterLarge;
+    // warp tilings: the aligned build.  Measured on diagonal / rank-1 Gaussians (dim 20 ... 500): tuning +23 ... +81 %, sampling
+    // +3 ... +30 % (instruction-fetch stalls were 21 % / 65 % of the samples); the funnel, whose trees range from 1 to 1023
+    // leapfrogs, loses 2 ... 8 % to the waiting and keeps the unaligned tiling.
+    {
+      const char* env = std::getenv("NUTS_B200_ALIGN");
+      const bool align = env ? std::atoi(env) != 0 : ctx->model.kind != NUTS_LOGP_FUNNEL;
+      if (align)
+        for (const EngineConfig& c : kAlignedConfigs)
+          if (c.tpc == cfg->tpc && c.ept == cfg->ept && c.launch[s_variant]) cfg = &c;
+    }
     // same tiling without bounds checks (SM_EXACT: rows zero-padded to tpc*ept) when the padding costs at most 7 % more traffic
     for (const EngineConfig& c : kExactConfigs)
       if (c.tpc == cfg->tpc && c.ept == cfg->ept && c.launch[0] && (uint64_t)c.max_d - ctx->d <= ctx->d * 7 / 100) cfg = &c;

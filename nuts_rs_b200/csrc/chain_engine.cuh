@@ -286,7 +286,9 @@ static __device__ __noinline__ AccSums accept_batch(double mine, int n, double a
 // - while the leapfrog of the leaf that triggers the check is still running; see Engine::stage_pair().
 // SM_CL2 / SM_CL4: the team spans the 2 / 4 CTAs of a thread-block cluster (TPC = threads of the whole team): every CTA holds its
 // threads' elements of the shared-memory vectors, reductions go through distributed shared memory (TeamReduce, CL > 1).
-enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32, SM_STAGE = 64, SM_CL2 = 128, SM_CL4 = 256 };
+// SM_ALIGN: the warp teams of a CTA start their work units together (a CTA barrier per unit): warps that run the same code at
+// the same time share the 32 KB instruction cache of the SM - the engine's per-draw instruction working set is 80 - 140 KB.
+enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32, SM_STAGE = 64, SM_CL2 = 128, SM_CL4 = 256, SM_ALIGN = 512 };
 template <int SMF>
 __host__ __device__ constexpr int cluster_size() {
   return (SMF & SM_CL4) ? 4 : ((SMF & SM_CL2) ? 2 : 1);
@@ -309,7 +311,10 @@ struct Engine {
   static constexpr int LT = TPC / CL;             // the team's threads in THIS CTA
   static_assert(CL == 1 || !MULTI, "cluster teams use the register-resident engine");
   const int ltid;                                 // thread index inside the CTA's share of the team
-  TeamReduce<LT, MULTI, CL> red;
+  // several CTA-sized teams in one CTA (SM_ALIGN with TPC > 32): the team synchronises on its own named barrier like the
+  // teams of the decoupled engine
+  static constexpr bool SUBT = (SMF & SM_ALIGN) != 0 && TPC > 32 && !MULTI && CL == 1;
+  TeamReduce<LT, MULTI || SUBT, CL> red;
   const MultiCtx* const mc;  // MULTI only
   const int d, ld;
   const size_t row;  // chain * ld
@@ -386,6 +391,10 @@ struct Engine {
         sm_g(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0)) * LT * EPT),
         sm_stage(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0) + (GS ? 1 : 0)) * LT * EPT), T(tables) {
     stream = p.chain_offset + (uint64_t)chain_ + 1;  // reference src/sampler.rs:1106 set_stream(chain_id + 1)
+    if (SUBT) {
+      red.bar_id = 1 + (int)threadIdx.x / TPC;
+      red.warp = ((int)threadIdx.x % TPC) >> 5;
+    }
     if (MULTI) {  // several teams per CTA: named barrier, per-team reduction scratch, CTA-wide copy of the model parameters
       red.bar_id = mc->bar_id;
       red.warp = mc->warp;
@@ -549,13 +558,18 @@ struct Engine {
   }
   // a row of the dense [n_draws][N][d] output (stride d: 16-byte aligned only for even d)
   __device__ __forceinline__ void store_dense(double* __restrict__ dst, const double (&a)[EPT]) const {
+    // the draw output is written once and not read again by the engine: streaming (evict-first) stores
     if (PAIR && (d & 1) == 0) {
-      store(dst, a);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int i0 = eidx(2 * p);
+        if (i0 < d) __stcs(reinterpret_cast<double2*>(dst + i0), make_double2(a[2 * p], a[2 * p + 1]));
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         int i = eidx(j);
-        if (i < d) dst[i] = a[j];
+        if (i < d) __stcs(dst + i, a[j]);
       }
     }
   }
@@ -1550,43 +1564,57 @@ struct Engine {
       // PAIR mapping: the two elements of a pair in one 16-byte access (a row's padding is readable)
       constexpr int VS = (PAIR && CH % 2 == 0) ? 2 : 1;
       int at[CH];  // where element q is loaded from
-      auto ldv = [&](const double* __restrict__ p, double (&a)[CH]) {
+      // (STREAM: the estimator planes are touched once per draw - evict-first, so that they do not push the checkpoints of
+      // the running trees out of L2)
+      auto ldv = [&](const double* __restrict__ p, double (&a)[CH], auto stream) {
+        constexpr bool STREAM = decltype(stream)::value;
 #pragma unroll
         for (int q = 0; q < CH; q += VS) {
           if constexpr (VS == 2) {
-            const double2 t = *reinterpret_cast<const double2*>(p + at[q]);
+            const double2* p2 = reinterpret_cast<const double2*>(p + at[q]);
+            const double2 t = STREAM ? __ldcs(p2) : *p2;
             a[q] = t.x;
             a[q + 1] = t.y;
           } else {
-            a[q] = p[at[q]];
+            a[q] = STREAM ? __ldcs(p + at[q]) : p[at[q]];
           }
         }
       };
-      auto stv = [&](double* __restrict__ p, const double (&a)[CH]) {
+      auto stv = [&](double* __restrict__ p, const double (&a)[CH], auto stream) {
+        constexpr bool STREAM = decltype(stream)::value;
 #pragma unroll
         for (int q = 0; q < CH; q += VS) {
           if constexpr (VS == 2) {
-            if (live[q + 1]) *reinterpret_cast<double2*>(p + at[q]) = make_double2(a[q], a[q + 1]);
-            else if (live[q]) p[at[q]] = a[q];
+            if (live[q + 1]) {
+              if (STREAM) __stcs(reinterpret_cast<double2*>(p + at[q]), make_double2(a[q], a[q + 1]));
+              else *reinterpret_cast<double2*>(p + at[q]) = make_double2(a[q], a[q + 1]);
+            } else if (live[q]) {
+              p[at[q]] = a[q];
+            }
           } else {
-            if (live[q]) p[at[q]] = a[q];
+            if (live[q]) {
+              if (STREAM) __stcs(p + at[q], a[q]);
+              else p[at[q]] = a[q];
+            }
           }
         }
       };
+      constexpr std::true_type kStream{};
+      constexpr std::false_type kKeep{};
 #pragma unroll
       for (int q = 0; q < CH; ++q) {
         const int i = eidx(j0 + q);
         live[q] = (j0 + q < EPT) && (i < d);
         at[q] = (VS == 2 && (q & 1)) ? at[q - 1] + 1 : (live[q] ? i : 0);
       }
-      ldv(xp, x);
-      ldv(gp, gx);
+      ldv(xp, x, kKeep);
+      ldv(gp, gx, kKeep);
 #pragma unroll
       for (int st = 0; st < 2; ++st)
 #pragma unroll
-        for (int w = 0; w < 4; ++w) ldv(est0 + (size_t)(4 * st + w) * pl, e[st][w]);
-      ldv(sd, s_new);
-      ldv(isd, is_new);
+        for (int w = 0; w < 4; ++w) ldv(est0 + (size_t)(4 * st + w) * pl, e[st][w], kStream);
+      ldv(sd, s_new, kKeep);
+      ldv(isd, is_new, kKeep);
 #ifdef NB_PHASE_TIMING_COLD
       const long long vp_a = clock64();
       asm volatile("" ::"d"(x[0]), "d"(is_new[CH - 1]), "d"(e[1][3][CH - 1]), "d"(e[0][0][0]));  // wait for the chunk's loads
@@ -1618,7 +1646,7 @@ struct Engine {
             }
           }
 #pragma unroll
-          for (int w = 0; w < 4; ++w) stv(est0 + (size_t)(4 * st + w) * pl, e[st][w]);
+          for (int w = 0; w < 4; ++w) stv(est0 + (size_t)(4 * st + w) * pl, e[st][w], kStream);
         }
       }
 #ifdef NB_PHASE_TIMING_COLD
@@ -1673,9 +1701,9 @@ struct Engine {
           }
           if (live[q]) prod *= is_new[q];
         }
-        stv(sd, s_new);
-        stv(isd, is_new);
-        stv(mn, mean);
+        stv(sd, s_new, kKeep);
+        stv(isd, is_new, kKeep);
+        stv(mn, mean, kKeep);
         ld[0] += log(prod);  // array_sum_ln(inv_stds)
       }
 #ifdef NB_PHASE_TIMING_COLD
@@ -2555,10 +2583,18 @@ template <int TPC, int EPT, int CTA_THREADS, int MIN_BLOCKS, int SMF, int MODEL>
 __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(const __grid_constant__ EngineParams P) {
   constexpr int TEAMS = CTA_THREADS / TPC;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ double scratch[TPC > 32 ? 2 * (TPC / 32) * REDUCE_MAXK : 1];
+  static_assert(TEAMS == 1 || TPC <= 32 || (SMF & SM_ALIGN), "several CTA-sized teams per CTA: SM_ALIGN builds only");
+  constexpr int kScratch = TPC > 32 ? 2 * (TPC / 32) * REDUCE_MAXK : 1;
+  __shared__ double scratch_all[TEAMS * kScratch];
   __shared__ int next_chain[TEAMS][2];
   const int team = threadIdx.x / TPC;
   const int tid = threadIdx.x % TPC;
+  double* scratch = scratch_all + team * kScratch;
+  auto team_bar = [&]() {
+    if (TPC <= 32) __syncwarp();
+    else if (TEAMS > 1) bar_sync(1 + team, TPC);
+    else __syncthreads();
+  };
   unsigned char* my_smem = dyn_smem + (size_t)team * team_smem_bytes<TPC, EPT, SMF>();
   double* team_smem = reinterpret_cast<double*>(my_smem);
   TreeTables& tables = *reinterpret_cast<TreeTables*>(my_smem + (smem_vectors<SMF>() * (size_t)(TPC / cluster_size<SMF>()) * EPT * sizeof(double)));
@@ -2569,19 +2605,31 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
   const unsigned B = P.draws_per_unit;
   const unsigned blocks = P.mode == 0 ? 1u : ((unsigned)P.n_draws + B - 1u) / B;
   const unsigned total_units = (unsigned)P.N * blocks;
+  bool active = true;
   for (;;) {
+    if ((SMF & SM_ALIGN) && TEAMS > 1) {
+      // The barrier comes BEFORE the pop: a team waiting here holds no chain (it has pushed the one it finished), so a team whose
+      // pop has to wait for a push can never be waiting for a chain that is parked at a barrier.  Every team takes part until
+      // the queue is empty for all of them.
+      if (!__syncthreads_or(active)) break;
+      if (!active) continue;
+    }
     if (tid == 0) {
       unsigned b;
       next_chain[team][0] = (int)unit_pop(P, total_units, b);
       next_chain[team][1] = (int)b;
     }
-    if (TPC > 32) __syncthreads();
-    else __syncwarp();
+    team_bar();
     const int chain = next_chain[team][0];
     const unsigned blk = (unsigned)next_chain[team][1];  // block of B consecutive draws (a few draws per unit amortise the hand-over)
-    if (TPC > 32) __syncthreads();
-    else __syncwarp();
-    if (chain < 0) break;
+    team_bar();
+    if (chain < 0) {
+      if ((SMF & SM_ALIGN) && TEAMS > 1) {
+        active = false;
+        continue;
+      }
+      break;
+    }
     Engine<TPC, EPT, SMF, MODEL> E(P, chain, tid, scratch, team_smem, tables);
     if (P.mode == 0) {
       if (P.init_mask == nullptr || P.init_mask[chain] != 0) {
@@ -2605,8 +2653,7 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
       E.team_sync();
       if (tid == 0) unit_push(P, (unsigned)chain, blk + 1u, blocks);
     }
-    if (TPC > 32) __syncthreads();
-    else __syncwarp();
+    team_bar();
 #ifdef NB_PHASE_TIMING
     if (tid == 0 && P.phase_clocks)
       for (int k = 0; k < 8; ++k) atomicAdd(P.phase_clocks + k, (unsigned long long)E.phase[k]);

@@ -67,3 +67,46 @@ def test_engine_variants_bit_identical(L, engine, case):
     for k in ref[2]:
         assert np.array_equal(ref[2][k], got[2][k], equal_nan=True), k
     assert ref[2]["depth"].max() >= min(md, 3)
+
+
+def _run_aligned(L, align, kind, N, d, num_tune, n_draws, maxdepth, **mk):
+    old = os.environ.get("NUTS_B200_ALIGN")
+    os.environ["NUTS_B200_ALIGN"] = align
+    try:
+        m = L.CudaMath(N, d, kind, **mk)
+        s = L.Sampler(m, L.DiagNutsSettings(num_tune=num_tune, maxdepth=maxdepth), seed=11)
+        x0 = np.random.default_rng(2).normal(size=(N, d))
+        if kind == _abi.NUTS_LOGP_FUNNEL:
+            x0[:, 0] = 0.1
+        status = s.set_position(x0)
+        draws, stats = s.draw(n_draws)
+        lf, _ = s.counters()
+        s.close()
+        m.close()
+        return status, draws, stats, lf
+    finally:
+        if old is None:
+            os.environ.pop("NUTS_B200_ALIGN", None)
+        else:
+            os.environ["NUTS_B200_ALIGN"] = old
+
+
+@pytest.mark.parametrize("kind,d,N", [
+    (_abi.NUTS_LOGP_GAUSS_DIAG, 20, 5000), (_abi.NUTS_LOGP_GAUSS_DIAG, 50, 3000), (_abi.NUTS_LOGP_GAUSS_RANK1, 100, 3000),
+    (_abi.NUTS_LOGP_GAUSS_DIAG, 200, 2000), (_abi.NUTS_LOGP_GAUSS_DIAG, 500, 1400), (_abi.NUTS_LOGP_FUNNEL, 10, 5000),
+    (_abi.NUTS_LOGP_GAUSS_DIAG, 100, 7),
+])
+def test_aligned_warp_tilings_bit_identical(L, kind, d, N):
+    """The warp tilings exist in two builds: one warp team per CTA (tag 16 / 12 / 8), and all teams of an SM in one CTA that starts
+    its work units together (SM_ALIGN, tag 21: the default, NUTS_B200_ALIGN=0 selects the other).  Which team runs which draw
+    when does not enter the arithmetic: draws, statistics and leapfrog counts agree bit for bit - with more chains than resident
+    teams (hand-over through the ready queue, teams that run out of work while their CTA keeps going) and with fewer."""
+    mk = {_abi.NUTS_LOGP_GAUSS_DIAG: dict(mu=0.5, sigma=np.exp(np.linspace(-1, 1, d))),
+          _abi.NUTS_LOGP_GAUSS_RANK1: dict(mu=0.0, rank1_scale=0.5), _abi.NUTS_LOGP_FUNNEL: dict(funnel_scale=3.0)}[kind]
+    ref = _run_aligned(L, "0", kind, N, d, 12, 20, 6, **mk)
+    got = _run_aligned(L, "1", kind, N, d, 12, 20, 6, **mk)
+    assert np.array_equal(ref[0], got[0])
+    assert ref[3] == got[3], "leapfrog counters differ"
+    assert np.array_equal(ref[1], got[1], equal_nan=True), "draws differ"
+    for k in ref[2]:
+        assert np.array_equal(ref[2][k], got[2][k], equal_nan=True), k

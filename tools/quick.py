@@ -1,6 +1,6 @@
 """Quick device-arm throughput of one BASELINE config (or any shape) with the engine chosen by NUTS_B200_ENGINE.
 
-  python tools/quick.py c2|c3|c4|c5 [tune] [draws_per_launch] [launches]
+  python tools/quick.py c2|c3|c4|c5|diag:<dim>:<chains> [tune] [draws_per_launch] [launches]
 Prints the tuning-phase and sampling-phase leapfrog rates and a checksum of the draws (to compare engine variants)."""
 import os
 import sys
@@ -12,7 +12,11 @@ import bench
 from nuts_rs_b200 import lib
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
-cfg = bench.CONFIGS[name]
+if ":" in name:  # ad-hoc shape "diag:<dim>:<chains>": the config-2 target at another size
+    _, _d, _n = name.split(":")
+    cfg = dict(bench.CONFIGS["c2"], dim=int(_d), chains=int(_n))
+else:
+    cfg = bench.CONFIGS[name]
 tune = int(sys.argv[2]) if len(sys.argv) > 2 else cfg["num_tune"]
 dpl = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 launches = int(sys.argv[4]) if len(sys.argv) > 4 else 5
