@@ -424,6 +424,28 @@ def main():
     d2h = host_draws.nbytes + sum(a.nbytes for a in stats_arrays.values())
     e2e_direct = samp.last_draw_direct()
 
+    # ---------------- what the host side can absorb: every rank copies one step's draws device -> page-locked host at the same time
+    # (cudaMemcpyAsync, nothing else running).  e2e cannot deliver draws faster than this; at N > 1 the ranks share the host's
+    # PCIe root complexes and memory controllers.
+    sink_ms = float("nan")
+    try:
+        dev_buf = torch.empty(host_draws.nbytes, dtype=torch.uint8, device="cuda")
+        pin_buf = torch.empty(host_draws.nbytes, dtype=torch.uint8, pin_memory=True)
+        pin_buf.copy_(dev_buf, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(3):
+            pin_buf.copy_(dev_buf, non_blocking=True)
+        ev[1].record()
+        torch.cuda.synchronize()
+        sink_ms = ev[0].elapsed_time(ev[1]) / 3.0
+        barrier()
+        del dev_buf, pin_buf
+    except Exception as exc:  # pinned allocation can fail on a small host
+        print(f"host sink ceiling not measured: {exc}", file=sys.stderr)
+
     # ---------------- the only exchange of the path: NCCL all-gather of every step's draws over NVLink, behind the C ABI
     # (nuts_gather_draws_*), on its own stream: the gather of step k runs beside the sampling of step k + 1
     gather = None
@@ -526,7 +548,7 @@ def main():
         tl += [whole["wall_s"] * 1e3, whole["tune_wall_s"] * 1e3]
         wl += [float(whole["leapfrogs"]), float(whole["tune_leapfrogs"])]
     has_gather = gather is not None and "error" not in gather
-    tl += [gather["wall_s"] * 1e3 if has_gather else 0.0]
+    tl += [gather["wall_s"] * 1e3 if has_gather else 0.0, sink_ms if sink_ms == sink_ms else 0.0]
     wl += [float(gather["leapfrogs"]) if has_gather else 0.0]
     t = torch.tensor(tl, dtype=torch.float64, device="cuda")
     w = torch.tensor(wl, dtype=torch.float64, device="cuda")
@@ -615,6 +637,12 @@ def main():
                                         "ratio_to_sampling_rate": tune_lf_all / max(tune_ms_max * 1e-3, 1e-9) / value}},
             "e2e": {"value": steps_e2e_all / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
                     "d2h_GBps_per_rank": d2h * args.steps / (e2e_ms_max * 1e-3) / 1e9,
+                    "host_sink_ceiling": {
+                        "GBps_per_rank": (host_draws.nbytes / (t[-1] * 1e-3) / 1e9) if t[-1] > 0 else None,
+                        "leapfrogs_per_s_all_gpus": (steps_e2e_all / args.steps / (t[-1] * 1e-3)) if t[-1] > 0 else None,
+                        "what": "all ranks copy one step's draws device -> page-locked host at the same time with cudaMemcpyAsync and "
+                                "nothing else running (max over ranks): the rate at which this box's host side absorbs draws; e2e "
+                                "delivers the same bytes while sampling"},
                     "draws_path": "kernel writes the page-locked host buffer directly (posted PCIe writes overlapping the sampling)"
                                   if e2e_direct else "device staging buffer + cudaMemcpyAsync D2H after the kernel",
                     "note": "nuts_draw with page-locked host buffers: every draw [draws x chains x dim] f64 and all 15 statistics reach host "
@@ -633,8 +661,8 @@ def main():
                 "what": "every step's draws all-gathered to every rank with NCCL over NVLink through the C ABI (nuts_gather_draws_begin / "
                         "_end) on the communicator's own stream, overlapping the sampling of the next step; wall clock over the K steps "
                         "incl. the last gather, max over ranks",
-                "leapfrogs_per_s": w[-1] / (t[-1] * 1e-3), "ms_per_step": t[-1] / args.steps,
-                "ratio_to_value": w[-1] / (t[-1] * 1e-3) / value, "last_gather_device_ms_rank0": gather["last_gather_ms"],
+                "leapfrogs_per_s": w[-1] / (t[-2] * 1e-3), "ms_per_step": t[-2] / args.steps,
+                "ratio_to_value": w[-1] / (t[-2] * 1e-3) / value, "last_gather_device_ms_rank0": gather["last_gather_ms"],
                 "bytes_received_per_rank_per_step": gather["bytes_received_per_rank_per_step"],
                 "gather_GBps_per_rank": gather["bytes_received_per_rank_per_step"] / max(gather["last_gather_ms"], 1e-9) / 1e6,
                 "own_shard_intact_rank0": gather["own_shard_intact"]}

@@ -15,6 +15,7 @@ for w in $WHAT; do
     ncu)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1; echo "ncu list rc=$?"
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_chain_kernel --launch-skip 3 -c 1 -f -o gpurun_out/prof_$TAG python tools/prof_run.py > gpurun_out/prof_$TAG.log 2>&1; echo "ncu full rc=$?"; tail -2 gpurun_out/prof_$TAG.log;;
+    plane) timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_leapfrog --launch-skip 3 -c 3 --csv --log-file gpurun_out/plane_leapfrog_$TAG.csv python tools/plane_leapfrog_run.py > gpurun_out/plane_leapfrog_$TAG.log 2>&1; echo "plane rc=$?"; tail -2 gpurun_out/plane_leapfrog_$TAG.log;;
     configs) for c in c2 c3 c4 c5; do timeout 300 python tools/quick.py $c 2>&1 | tail -1; done | tee gpurun_out/configs_$TAG.log;;
     v2) for e in 64,16,107; do NUTS_B200_ENGINE=$e timeout 300 python tools/quick.py c2 2>&1 | tail -1; done | tee gpurun_out/v2_$TAG.log;;
     phase) for c in c2 c5; do NUTS_B200_LIB=$PWD/nuts_rs_b200/libnuts_b200_phase.so timeout 300 python tools/phase_timing.py $c; done 2>&1 | tee gpurun_out/phase_$TAG.log;;
@@ -32,7 +33,7 @@ for w in $WHAT; do
            NUTS_B200_ENGINE=64,16,58 NUTS_B200_LIB=$PWD/nuts_rs_b200/libnuts_b200_phase.so timeout 300 python tools/phase_timing.py c2 2>&1 | tee -a gpurun_out/stage_$TAG.log
            NUTS_B200_ENGINE=64,16,58 timeout 600 python -m pytest tests/test_gpu_teacher_forced.py -q -k "config2 or checkpoint" 2>&1 | tail -3 | tee -a gpurun_out/stage_$TAG.log;;
     sanitize)
-      for c in c1 migrate large funnel rank1; do
+      for c in ${SANITIZE_CASES:-c1 migrate large funnel rank1 cluster}; do
         for tool in racecheck memcheck; do
           NUTS_B200_GRID=3 timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_run.py $c > gpurun_out/sanitize_${tool}_${c}_$TAG.log 2>&1
           echo "sanitize $tool $c rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|ok:' gpurun_out/sanitize_${tool}_${c}_$TAG.log | tr '\n' ' ')"

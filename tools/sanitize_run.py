@@ -4,7 +4,7 @@ reductions (double-buffered shared scratch, one barrier), the decoupled engine's
 
   compute-sanitizer --tool racecheck python tools/sanitize_run.py <case>
 cases: c1 (warp teams, 4 chains x d=10), migrate (d=1000, 64x16 CTA teams, more chains than one wave of teams via NUTS_B200_GRID),
-       large (large-dim engine, d=5000), funnel, rank1"""
+       large (large-dim engine, d=5000), funnel, rank1, cluster (rank-1 at d=4200: one chain on the 4 CTAs of a cluster, DSMEM reductions)"""
 import os
 import sys
 
@@ -20,6 +20,7 @@ shapes = {
     "large": (_abi.NUTS_LOGP_GAUSS_DIAG, 3, 5000, dict(mu=0.0, sigma=np.exp(np.linspace(-1, 1, 5000))), 6, 3),
     "funnel": (_abi.NUTS_LOGP_FUNNEL, 64, 10, dict(funnel_scale=3.0), 10, 6),
     "rank1": (_abi.NUTS_LOGP_GAUSS_RANK1, 24, 100, dict(mu=0.0, rank1_scale=0.5), 8, 5),
+    "cluster": (_abi.NUTS_LOGP_GAUSS_RANK1, 3, 4200, dict(mu=0.0, rank1_scale=0.5), 4, 3),
 }
 kind, N, d, mk, tune, maxdepth = shapes[case]
 s = lib.DiagNutsSettings(num_tune=tune, maxdepth=maxdepth)
