@@ -220,6 +220,26 @@ int nuts_point_set_scalars(nuts_ctx_t*, nuts_point_t*, const int64_t* index_in_t
 /* DiagMassMatrix::set_transform (diagonal.rs:156-162): stds/mean HOST [N*d]; bumps id, recomputes inv_stds + logdet. */
 int nuts_set_transform(nuts_ctx_t*, const double* stds, const double* mean);
 int nuts_get_transform(nuts_ctx_t*, double* stds, double* inv_stds, double* mean, double* logdet /*[N]*/, int64_t* id /*[N]*/);
+/* ---- Low-rank mass matrix (reference src/transform/low_rank.rs, src/math/math.rs:127-144) -----------------------
+ * EigVectors + EigValues of every chain (Math::new_eig_vectors / new_eig_values, math.rs:150-160): chain c has rank[c] <= rank_max
+ * eigenvectors; vecs is HOST [N][rank_max][dim] (eigenvector k of chain c at vecs[(c * rank_max + k) * dim]), vals HOST [N][rank_max]
+ * (entries k >= rank[c] are ignored), rank HOST [N] or NULL for rank_max everywhere.  rank_max <= 64. */
+typedef struct nuts_eigs nuts_eigs_t;
+int nuts_eigs_create(nuts_ctx_t*, nuts_eigs_t** eigs, uint64_t rank_max, const double* vecs, const double* vals, const int32_t* rank);
+int nuts_eigs_free(nuts_ctx_t*, nuts_eigs_t* eigs);
+/* Math::apply_lowrank_transform (math.rs:131-137, cpu_math.rs:332-377): dest = (I + U (diag(vals) - I) U^T) rhs per chain; a chain
+ * without eigenvectors copies rhs.  _inplace (math.rs:139-144): rhs_and_dest is updated in place. */
+int nuts_apply_lowrank_transform(nuts_ctx_t*, const nuts_eigs_t* eigs, const nuts_plane_t* rhs, nuts_plane_t* dest);
+int nuts_apply_lowrank_transform_inplace(nuts_ctx_t*, const nuts_eigs_t* eigs, nuts_plane_t* rhs_and_dest);
+/* LowRankMassMatrix::update (low_rank.rs:158-190) for every chain: the Tier-2 transformation becomes
+ *   F(z) = sigma * ((I + U (sqrt(lambda) - 1) U^T) z + mean_low_rank) + mean,  logdet = sum ln(1 / sigma) - 1/2 sum ln(lambda).
+ * stds, mean, mean_low_rank: HOST [N*dim]; vals / vecs / rank as in nuts_eigs_create (vals = the raw eigenvalues lambda).
+ * A chain with a non-finite input keeps its old transformation (low_rank.rs:168-173) and gets accepted[c] = 0 (accepted may be
+ * NULL).  nuts_set_transform (diagonal) drops the correction again, like update_from_grad (low_rank.rs:143-156).
+ * nuts_init_state / nuts_initialize_trajectory / nuts_leapfrog use the transformation that is current. */
+int nuts_set_lowrank_transform(nuts_ctx_t*, const double* stds, const double* mean, uint64_t rank_max, const double* vals,
+                               const double* vecs, const int32_t* rank, const double* mean_low_rank, uint8_t* accepted);
+
 /* Hamiltonian::init_state (transformed_hamiltonian.rs:640-661): x -> logp, grad, z, grad_z; status 3 when check_all fails. */
 int nuts_init_state(nuts_ctx_t*, nuts_point_t* point, const double* position /*HOST [N*d]*/, int32_t* status);
 /* Hamiltonian::initialize_trajectory (:687-736): resample velocity from (seed, chain_offset+c+1, counter), re-whiten when the

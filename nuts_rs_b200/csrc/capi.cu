@@ -145,6 +145,11 @@ struct nuts_ctx {
   double* d_model_user = nullptr;  // NUTS_LOGP_USER: device copy of user_params
   // Tier-2 transformation (one DiagMassMatrix per chain)
   TransformDev T{};
+  // low-rank correction of the Tier-2 transformation (allocated by the first nuts_set_lowrank_transform)
+  double* lr_vecs = nullptr;
+  double *lr_vals_sqrt = nullptr, *lr_vals_sqrt_inv = nullptr, *lr_mu = nullptr;
+  int* lr_rank = nullptr;
+  int lr_rmax = 0;
   // scratch
   double* d_dense = nullptr;    // [N*d] staging for host <-> plane packing
   double* d_sc[4] = {nullptr, nullptr, nullptr, nullptr};  // [N] f64 scratch
@@ -392,6 +397,11 @@ int nuts_ctx_destroy(nuts_ctx_t* ctx) {
   cudaFree(ctx->T.mean);
   cudaFree(ctx->T.logdet);
   cudaFree(ctx->T.id);
+  cudaFree(ctx->lr_vecs);
+  cudaFree(ctx->lr_vals_sqrt);
+  cudaFree(ctx->lr_vals_sqrt_inv);
+  cudaFree(ctx->lr_mu);
+  cudaFree(ctx->lr_rank);
   cudaFree(ctx->d_dense);
   for (int k = 0; k < 4; ++k) cudaFree(ctx->d_sc[k]);
   cudaFree(ctx->d_u8);
@@ -677,8 +687,177 @@ int nuts_set_transform(nuts_ctx_t* ctx, const double* stds, const double* mean) 
   CUDA_TRY(cudaSetDevice(ctx->device));
   TRY(plane_from_host(ctx, ctx->T.stds, stds));
   TRY(plane_from_host(ctx, ctx->T.mean, mean));
-  k_set_transform<<<GRID>>>(ctx->row_args(), ctx->T);
+  if (ctx->lr_rank) CUDA_TRY(cudaMemsetAsync(ctx->lr_rank, 0xff, ctx->N * sizeof(int), ctx->stream));  // inner = None (rank -1)
+  k_set_transform<<<GRID>>>(ctx->row_args(), ctx->T, nullptr);
   CHECK_LAUNCH();
+  return sync(ctx);
+}
+
+// ---- low-rank mass matrix: EigVectors / EigValues of all chains, Math::apply_lowrank_transform, LowRankMassMatrix::update
+struct nuts_eigs {
+  double* vecs = nullptr;  // [N][rmax][ld]
+  double* vals = nullptr;  // [N][rmax]
+  int* rank = nullptr;     // [N]
+  int rmax = 0;
+};
+// host [N][rmax][d] -> device [N][rmax][ld] (rows padded with zeros like every plane)
+static int upload_vecs(nuts_ctx* ctx, double* dst, const double* vecs, uint64_t rmax) {
+  CUDA_TRY(cudaMemsetAsync(dst, 0, ctx->N * rmax * ctx->ld * sizeof(double), ctx->stream));
+  CUDA_TRY(cudaMemcpy2DAsync(dst, ctx->ld * sizeof(double), vecs, ctx->d * sizeof(double), ctx->d * sizeof(double), ctx->N * rmax,
+                             cudaMemcpyHostToDevice, ctx->stream));
+  return NUTS_OK;
+}
+int nuts_eigs_create(nuts_ctx_t* ctx, nuts_eigs_t** out, uint64_t rank_max, const double* vecs, const double* vals, const int32_t* rank) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!out || !vecs || !vals) return fail(NUTS_ERR_INVALID, "nuts_eigs_create: NULL argument");
+  if (rank_max == 0 || rank_max > (uint64_t)LR_MAX_RANK) return fail(NUTS_ERR_INVALID, "nuts_eigs_create: rank_max must be 1 .. %d", LR_MAX_RANK);
+  nuts_eigs* e = new nuts_eigs();
+  struct G {
+    nuts_ctx* c;
+    nuts_eigs* e;
+    ~G() {
+      if (e) nuts_eigs_free(c, e);
+    }
+  } guard{ctx, e};
+  e->rmax = (int)rank_max;
+  TRY(dev_alloc(&e->vecs, ctx->N * rank_max * ctx->ld));
+  TRY(dev_alloc(&e->vals, ctx->N * rank_max));
+  TRY(dev_alloc(&e->rank, ctx->N));
+  TRY(upload_vecs(ctx, e->vecs, vecs, rank_max));
+  CUDA_TRY(cudaMemcpyAsync(e->vals, vals, ctx->N * rank_max * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<int> rk(ctx->N, (int)rank_max);
+  if (rank)
+    for (uint64_t c = 0; c < ctx->N; ++c) {
+      if (rank[c] < 0 || (uint64_t)rank[c] > rank_max) return fail(NUTS_ERR_INVALID, "nuts_eigs_create: rank[%llu] = %d outside 0 .. rank_max", (unsigned long long)c, rank[c]);
+      rk[c] = rank[c];
+    }
+  CUDA_TRY(cudaMemcpyAsync(e->rank, rk.data(), ctx->N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  TRY(sync(ctx));
+  guard.e = nullptr;
+  *out = e;
+  return NUTS_OK;
+}
+int nuts_eigs_free(nuts_ctx_t* ctx, nuts_eigs_t* e) {
+  if (!e) return NUTS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(e->vecs);
+  cudaFree(e->vals);
+  cudaFree(e->rank);
+  delete e;
+  return NUTS_OK;
+}
+int nuts_apply_lowrank_transform(nuts_ctx_t* ctx, const nuts_eigs_t* e, const nuts_plane_t* rhs, nuts_plane_t* dest) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!e || !rhs || !dest) return fail(NUTS_ERR_INVALID, "nuts_apply_lowrank_transform: NULL argument");
+  k_lowrank_apply<<<GRID>>>(ctx->row_args(), e->vecs, e->vals, e->rank, e->rmax, rhs->ptr, dest->ptr);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_apply_lowrank_transform_inplace(nuts_ctx_t* ctx, const nuts_eigs_t* e, nuts_plane_t* rhs_and_dest) {
+  return nuts_apply_lowrank_transform(ctx, e, rhs_and_dest, rhs_and_dest);
+}
+int nuts_set_lowrank_transform(nuts_ctx_t* ctx, const double* stds, const double* mean, uint64_t rank_max, const double* vals,
+                               const double* vecs, const int32_t* rank, const double* mean_low_rank, uint8_t* accepted) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!stds || !mean || !mean_low_rank) return fail(NUTS_ERR_INVALID, "nuts_set_lowrank_transform: NULL argument");
+  if (rank_max > (uint64_t)LR_MAX_RANK) return fail(NUTS_ERR_INVALID, "nuts_set_lowrank_transform: rank_max must be <= %d", LR_MAX_RANK);
+  if (rank_max > 0 && (!vals || !vecs)) return fail(NUTS_ERR_INVALID, "nuts_set_lowrank_transform: vals / vecs are NULL");
+  const uint64_t N = ctx->N, d = ctx->d, R = std::max<uint64_t>(rank_max, 1);
+  if (!ctx->lr_rank || (uint64_t)ctx->lr_rmax < R) {  // (re)allocate for the larger rank
+    cudaFree(ctx->lr_vecs), cudaFree(ctx->lr_vals_sqrt), cudaFree(ctx->lr_vals_sqrt_inv), cudaFree(ctx->lr_mu), cudaFree(ctx->lr_rank);
+    ctx->lr_vecs = ctx->lr_vals_sqrt = ctx->lr_vals_sqrt_inv = ctx->lr_mu = nullptr;
+    ctx->lr_rank = nullptr;
+    TRY(dev_alloc(&ctx->lr_vecs, N * R * ctx->ld));
+    TRY(dev_alloc(&ctx->lr_vals_sqrt, N * R));
+    TRY(dev_alloc(&ctx->lr_vals_sqrt_inv, N * R));
+    TRY(dev_alloc(&ctx->lr_mu, N * ctx->ld));
+    TRY(dev_alloc(&ctx->lr_rank, N));
+    CUDA_TRY(cudaMemset(ctx->lr_rank, 0xff, N * sizeof(int)));  // -1: no inner matrix yet
+    ctx->lr_rmax = (int)R;
+  }
+  const uint64_t RM = (uint64_t)ctx->lr_rmax;
+  // per chain: finiteness (low_rank.rs:168-173), sqrt(lambda), 1 / sqrt(lambda), -1/2 sum ln(lambda) (low_rank.rs:55-71)
+  std::vector<uint8_t> ok(N, 1);
+  std::vector<int> rk(N, 0);
+  std::vector<double> vs(N * RM, 1.0), vi(N * RM, 1.0), contrib(N, 0.0);
+  auto finite = [](const double* p, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i)
+      if (!std::isfinite(p[i])) return false;
+    return true;
+  };
+  for (uint64_t c = 0; c < N; ++c) {
+    const int r = rank_max == 0 ? 0 : (rank ? rank[c] : (int)rank_max);
+    if (r < 0 || (uint64_t)r > rank_max) return fail(NUTS_ERR_INVALID, "nuts_set_lowrank_transform: rank[%llu] = %d outside 0 .. rank_max", (unsigned long long)c, r);
+    bool good = finite(stds + c * d, d) && finite(mean + c * d, d);
+    if (r > 0) good = good && finite(vals + c * rank_max, (uint64_t)r) && finite(vecs + c * rank_max * d, (uint64_t)r * d);
+    ok[c] = good ? 1 : 0;
+    rk[c] = r;
+    for (int k = 0; k < r; ++k) {
+      const double lam = vals[c * rank_max + k];
+      contrib[c] += -0.5 * std::log(lam);
+      const double sq = std::sqrt(lam);
+      vs[c * RM + k] = sq;
+      vi[c * RM + k] = 1.0 / sq;
+    }
+  }
+  bool all_ok = true;
+  for (uint8_t b : ok) all_ok = all_ok && b;
+  const uint8_t* d_mask = nullptr;
+  if (all_ok) {
+    TRY(plane_from_host(ctx, ctx->T.stds, stds));
+    TRY(plane_from_host(ctx, ctx->T.mean, mean));
+    TRY(plane_from_host(ctx, ctx->lr_mu, mean_low_rank));
+    if (rank_max > 0) {
+      CUDA_TRY(cudaMemsetAsync(ctx->lr_vecs, 0, N * RM * ctx->ld * sizeof(double), ctx->stream));
+      for (uint64_t c = 0; c < N; ++c)  // [c][rank_max][d] -> [c][RM][ld]
+        CUDA_TRY(cudaMemcpy2DAsync(ctx->lr_vecs + c * RM * ctx->ld, ctx->ld * sizeof(double), vecs + c * rank_max * d, d * sizeof(double),
+                                   d * sizeof(double), rank_max, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  } else {
+    // some chains keep their old transformation (low_rank.rs:168-173): row-by-row upload of the accepted ones, and the old rank,
+    // eigenvalues and log-determinant of the others stay what they are
+    std::vector<int> old_rank(N);
+    std::vector<double> old_vs(N * RM), old_vi(N * RM);
+    CUDA_TRY(cudaMemcpyAsync(old_rank.data(), ctx->lr_rank, N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(old_vs.data(), ctx->lr_vals_sqrt, N * RM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(old_vi.data(), ctx->lr_vals_sqrt_inv, N * RM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync(ctx));
+    for (uint64_t c = 0; c < N; ++c) {
+      if (!ok[c]) {
+        rk[c] = old_rank[c];
+        contrib[c] = 0.0;
+        std::copy(old_vs.begin() + c * RM, old_vs.begin() + (c + 1) * RM, vs.begin() + c * RM);
+        std::copy(old_vi.begin() + c * RM, old_vi.begin() + (c + 1) * RM, vi.begin() + c * RM);
+        continue;
+      }
+      const size_t row = c * ctx->ld;
+      CUDA_TRY(cudaMemcpyAsync(ctx->T.stds + row, stds + c * d, d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(cudaMemcpyAsync(ctx->T.mean + row, mean + c * d, d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(cudaMemcpyAsync(ctx->lr_mu + row, mean_low_rank + c * d, d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(cudaMemsetAsync(ctx->lr_vecs + c * RM * ctx->ld, 0, RM * ctx->ld * sizeof(double), ctx->stream));
+      if (rank_max > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(ctx->lr_vecs + c * RM * ctx->ld, ctx->ld * sizeof(double), vecs + c * rank_max * d, d * sizeof(double),
+                                   d * sizeof(double), rank_max, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_u8, ok.data(), N, cudaMemcpyHostToDevice, ctx->stream));
+    d_mask = ctx->d_u8;
+  }
+  CUDA_TRY(cudaMemcpyAsync(ctx->lr_vals_sqrt, vs.data(), N * RM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->lr_vals_sqrt_inv, vi.data(), N * RM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->lr_rank, rk.data(), N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_sc[3], contrib.data(), N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->T.lr_vecs = ctx->lr_vecs;
+  ctx->T.lr_vals_sqrt = ctx->lr_vals_sqrt;
+  ctx->T.lr_vals_sqrt_inv = ctx->lr_vals_sqrt_inv;
+  ctx->T.lr_mu = ctx->lr_mu;
+  ctx->T.lr_rank = ctx->lr_rank;
+  ctx->T.lr_rmax = ctx->lr_rmax;
+  k_set_transform<<<GRID>>>(ctx->row_args(), ctx->T, d_mask);  // diag.set_transform: inv_stds, sum ln(1 / sigma), id += 1
+  CHECK_LAUNCH();
+  k_add_logdet<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((int)N, ctx->T.logdet, ctx->d_sc[3]);
+  CHECK_LAUNCH();
+  if (accepted) std::memcpy(accepted, ok.data(), N);
   return sync(ctx);
 }
 int nuts_get_transform(nuts_ctx_t* ctx, double* stds, double* inv_stds, double* mean, double* logdet, int64_t* id) {

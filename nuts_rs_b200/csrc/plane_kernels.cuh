@@ -159,11 +159,71 @@ struct PointDev {  // batched TransformedPoint (transformed_hamiltonian.rs:56-77
   double *logp, *logdet, *ke, *e0;
   long long* tid;
 };
-struct TransformDev {  // batched DiagMassMatrix (transform/diagonal.rs:9-17)
+struct TransformDev {  // batched DiagMassMatrix (transform/diagonal.rs:9-17) + the optional low-rank correction of
+                       // LowRankMassMatrix (transform/low_rank.rs:25-41, 97-111): null / rank 0 = pure diagonal
   double *stds, *inv_stds, *mean;
   double* logdet;
   long long* id;
+  const double* lr_vecs;           // [N][lr_rmax][ld]: eigenvector k of chain c at ((c * lr_rmax + k) * ld)
+  const double* lr_vals_sqrt;      // [N][lr_rmax] lambda^{1/2}
+  const double* lr_vals_sqrt_inv;  // [N][lr_rmax] lambda^{-1/2}
+  const double* lr_mu;             // [N][ld]
+  const int* lr_rank;              // [N] number of eigenvectors of chain c (-1: the transformation of chain c is diagonal)
+  int lr_rmax;
 };
+constexpr int LR_MAX_RANK = 64;  // eigenvectors per chain the kernels hold coefficients for
+
+// Math::apply_lowrank_transform(_inplace) (math.rs:131-144, cpu_math.rs:332-425) for the row of one chain:
+//   out = in + U ((vals - 1) .* (U^T in)),  U = r eigenvectors of length d (rows of `vecs`, stride ld).  in == out is allowed.
+// Two passes over U (2 * r * d * 8 bytes from HBM / L2 per chain): the r dot products 8 at a time through the team reduction,
+// then the rank-r update with the coefficients in shared memory.
+__device__ __forceinline__ void lowrank_apply_row(const double* __restrict__ vecs, const double* __restrict__ vals, int r, int d, int ld,
+                                                  const double* in, double* out, TeamReduce<PK_THREADS>& red, double* coef) {
+  for (int k0 = 0; k0 < r; k0 += 8) {
+    double part[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      const double xi = in[i];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (k0 + q < r) part[q] = fma(vecs[(size_t)(k0 + q) * ld + i], xi, part[q]);
+    }
+    red.allreduce(part);
+    if (threadIdx.x < 8 && k0 + (int)threadIdx.x < r) coef[k0 + threadIdx.x] = part[threadIdx.x] * (vals[k0 + threadIdx.x] - 1.0);
+  }
+  __syncthreads();  // coefficients visible; every thread has finished reading `in` (in == out)
+  for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+    double acc = in[i];
+    for (int k = 0; k < r; ++k) acc = fma(vecs[(size_t)k * ld + i], coef[k], acc);
+    out[i] = acc;
+  }
+  __syncthreads();  // `out` complete before the caller's next pass reads other elements of it; coef free for the next call
+}
+// -1: the chain's transformation has no inner matrix (pure diagonal); >= 0: LowRankMassMatrix::update was called with that many
+// eigenvectors - with 0 of them the translation mu_lr still applies (low_rank.rs:337-345: `if let Some(inner)`)
+__device__ __forceinline__ int lowrank_rank(const TransformDev& T, int c) {
+  if (!T.lr_rank) return -1;
+  const int r = T.lr_rank[c];
+  return r < T.lr_rmax ? r : T.lr_rmax;
+}
+// z, gz of a chain from x, gx (LowRankMassMatrix::compute_transformed_position / _gradient, low_rank.rs:326-348, 380-398; with
+// rank 0 DiagMassMatrix's, diagonal.rs:233-265)
+__device__ __forceinline__ void whiten_row(const TransformDev& T, int c, size_t row, int d, int ld, const double* x, const double* gx, double* z,
+                                           double* gz, TeamReduce<PK_THREADS>& red, double* coef) {
+  const int r = lowrank_rank(T, c);
+  for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+    double t = fma(-1.0, T.mean[row + i], x[i]);
+    double zv = T.inv_stds[row + i] * t;
+    if (r >= 0) zv = fma(-1.0, T.lr_mu[row + i], zv);  // axpy(mu, z, -1)
+    z[i] = zv;
+    gz[i] = gx[i] * T.stds[row + i];
+  }
+  if (r > 0) {
+    __syncthreads();
+    const double* U = T.lr_vecs + (size_t)c * T.lr_rmax * ld;
+    lowrank_apply_row(U, T.lr_vals_sqrt_inv + (size_t)c * T.lr_rmax, r, d, ld, z, z, red, coef);
+    lowrank_apply_row(U, T.lr_vals_sqrt + (size_t)c * T.lr_rmax, r, d, ld, gz, gz, red, coef);
+  }
+}
 
 // strided model evaluation at x (row pointer): writes gx, returns logp to every thread
 __device__ __forceinline__ double model_eval_row(const ModelDev& m, int d, const double* x, double* gx, TeamReduce<PK_THREADS>& red) {
@@ -243,10 +303,9 @@ __global__ void __launch_bounds__(PK_THREADS) k_logp_array(RowArgs A, ModelDev m
 }
 
 // DiagMassMatrix::set_transform (diagonal.rs:156-162): stds/mean already written; inv_stds, logdet, id
-__global__ void __launch_bounds__(PK_THREADS) k_set_transform(RowArgs A, TransformDev T) {
+__global__ void __launch_bounds__(PK_THREADS) k_set_transform(RowArgs A, TransformDev T, const uint8_t* active) {
   __shared__ double scratch[2 * 32 * REDUCE_MAXK];
   TeamReduce<PK_THREADS> red(scratch);
-  const uint8_t* active = nullptr;
   NB_ROW_PROLOGUE
   double s[1] = {0.0};
   for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
@@ -267,15 +326,14 @@ __global__ void __launch_bounds__(PK_THREADS) k_init_state(RowArgs A, ModelDev m
   TeamReduce<PK_THREADS> red(scratch);
   const uint8_t* active = nullptr;
   NB_ROW_PROLOGUE
+  __shared__ double coef[LR_MAX_RANK];
   double lp = model_eval_row(m, A.d, p.x + row, p.gx + row, red);
   double bad[1] = {0.0};
+  __syncthreads();  // gx of the whole row written
+  whiten_row(T, c, row, A.d, A.ld, p.x + row, p.gx + row, p.z + row, p.gz + row, red, coef);
+  __syncthreads();
   for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
-    double xv = p.x[row + i], gxv = p.gx[row + i];
-    double t = fma(-1.0, T.mean[row + i], xv);
-    double zv = T.inv_stds[row + i] * t;
-    double gv = gxv * T.stds[row + i];
-    p.z[row + i] = zv;
-    p.gz[row + i] = gv;
+    double xv = p.x[row + i], gxv = p.gx[row + i], zv = p.z[row + i], gv = p.gz[row + i];
     if (!(isfinite(zv) && isfinite(gv) && (gv != 0.0) && isfinite(gxv) && isfinite(xv))) bad[0] = 1.0;
   }
   red.allreduce(bad);
@@ -295,18 +353,15 @@ __global__ void __launch_bounds__(PK_THREADS) k_initialize_trajectory(RowArgs A,
   const uint8_t* active = nullptr;
   NB_ROW_PROLOGUE
   const uint64_t stream = chain_offset + (uint64_t)c + 1;
+  __shared__ double coef[LR_MAX_RANK];
   const bool rewhiten = T.id[c] != p.tid[c];
   double s[1] = {0.0};
   for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
     double vv = resample ? 1.0 * stream_normal(seed, stream, counter, (uint32_t)i) : p.v[row + i];
     if (resample) p.v[row + i] = vv;
-    if (rewhiten) {
-      double t = fma(-1.0, T.mean[row + i], p.x[row + i]);
-      p.z[row + i] = T.inv_stds[row + i] * t;
-      p.gz[row + i] = p.gx[row + i] * T.stds[row + i];
-    }
     s[0] = fma(vv, vv, s[0]);
   }
+  if (rewhiten) whiten_row(T, c, row, A.d, A.ld, p.x + row, p.gx + row, p.z + row, p.gz + row, red, coef);  // inv_transform_normalize
   red.allreduce(s);
   if (threadIdx.x == 0) {
     if (rewhiten) {
@@ -335,7 +390,9 @@ __global__ void __launch_bounds__(PK_THREADS) k_leapfrog(RowArgs A, ModelDev m, 
   const double eps_half = eps / 2.;
   double part[2] = {0.0, 0.0};
   double lp;
-  const bool single_pass = (m.kind == LOGP_GAUSS_ISO) | (m.kind == LOGP_GAUSS_DIAG);
+  __shared__ double coef[LR_MAX_RANK];
+  const int lr = lowrank_rank(T, c);
+  const bool single_pass = ((m.kind == LOGP_GAUSS_ISO) | (m.kind == LOGP_GAUSS_DIAG)) && lr < 0;
   if (single_pass) {
     for (int i = threadIdx.x; i < d; i += PK_THREADS) {
       double sg = T.stds[row + i];
@@ -364,7 +421,7 @@ __global__ void __launch_bounds__(PK_THREADS) k_leapfrog(RowArgs A, ModelDev m, 
     }
     red.allreduce(part);
     lp = part[0];
-  } else {
+  } else if (lr < 0) {
     for (int i = threadIdx.x; i < d; i += PK_THREADS) {
       double vh = fma(eps_half, s.gz[row + i], s.v[row + i]);
       double zn = fma(eps, vh, s.z[row + i]);
@@ -378,6 +435,35 @@ __global__ void __launch_bounds__(PK_THREADS) k_leapfrog(RowArgs A, ModelDev m, 
       double gn = o.gx[row + i] * T.stds[row + i];
       double vn = fma(eps_half, gn, o.v[row + i]);
       o.gz[row + i] = gn;
+      o.v[row + i] = vn;
+      part[1] = fma(vn, vn, part[1]);
+    }
+    red.allreduce(part);
+  } else {
+    // low-rank transformation (low_rank.rs:350-398): x = ((I + U (sqrt(lambda) - 1) U^T) z + mu_lr) * sigma + mean,
+    // grad_z = (I + U (sqrt(lambda) - 1) U^T) (grad_x * sigma): two more passes with a team reduction each
+    const double* U = T.lr_vecs + (size_t)c * T.lr_rmax * A.ld;
+    const double* lam = T.lr_vals_sqrt + (size_t)c * T.lr_rmax;
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      double vh = fma(eps_half, s.gz[row + i], s.v[row + i]);
+      o.v[row + i] = vh;
+      o.z[row + i] = fma(eps, vh, s.z[row + i]);
+    }
+    __syncthreads();
+    lowrank_apply_row(U, lam, lr, d, A.ld, o.z + row, o.x + row, red, coef);
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      double xv = fma(1.0, T.lr_mu[row + i], o.x[row + i]);  // axpy(mu, x, 1)
+      xv = xv * T.stds[row + i];                             // array_mult_inplace(x, stds)
+      o.x[row + i] = fma(1.0, T.mean[row + i], xv);          // axpy(mean, x, 1)
+    }
+    __syncthreads();
+    lp = model_eval_row(m, d, o.x + row, o.gx + row, red);
+    __syncthreads();
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) o.gz[row + i] = o.gx[row + i] * T.stds[row + i];
+    __syncthreads();
+    lowrank_apply_row(U, lam, lr, d, A.ld, o.gz + row, o.gz + row, red, coef);
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      double vn = fma(eps_half, o.gz[row + i], o.v[row + i]);
       o.v[row + i] = vn;
       part[1] = fma(vn, vn, part[1]);
     }
@@ -397,6 +483,28 @@ __global__ void __launch_bounds__(PK_THREADS) k_leapfrog(RowArgs A, ModelDev m, 
     if (energy_error_out) energy_error_out[c] = ee;
     if (status) status[c] = ((ee > max_energy_error) | !isfinite(ee)) ? 1 : 0;
   }
+}
+
+// Math::apply_lowrank_transform / _inplace for every chain (Tier 1)
+__global__ void __launch_bounds__(PK_THREADS) k_lowrank_apply(RowArgs A, const double* vecs, const double* vals, const int* rank, int rmax,
+                                                               const double* in, double* out) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  __shared__ double coef[LR_MAX_RANK];
+  TeamReduce<PK_THREADS> red(scratch);
+  const uint8_t* active = nullptr;
+  NB_ROW_PROLOGUE
+  const int r = rank[c] < rmax ? rank[c] : rmax;
+  if (r == 0) {  // cpu_math.rs:339-342: no eigenvectors = copy
+    if (in != out)
+      for (int i = threadIdx.x; i < A.d; i += PK_THREADS) out[row + i] = in[row + i];
+    return;
+  }
+  lowrank_apply_row(vecs + (size_t)c * rmax * A.ld, vals + (size_t)c * rmax, r, A.d, A.ld, in + row, out + row, red, coef);
+}
+// LowRankMassMatrix::update (low_rank.rs:186-189): logdet = inner.logdet() + diag.logdet() for the chains whose update was accepted
+__global__ void k_add_logdet(int N, double* logdet, const double* contribution) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < N) logdet[c] = contribution[c] + logdet[c];
 }
 
 // Hamiltonian::is_turning (transformed_hamiltonian.rs:617-638)

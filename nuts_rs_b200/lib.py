@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "nuts_sampler_counters", "nuts_sampler_last_timing", "nuts_sampler_get_state", "nuts_sampler_set_step_size",
     "nuts_host_alloc", "nuts_host_free", "nuts_sampler_last_draw_direct",
     "nuts_sampler_get_chain_state", "nuts_sampler_set_chain_state",
+    "nuts_eigs_create", "nuts_eigs_free", "nuts_apply_lowrank_transform", "nuts_apply_lowrank_transform_inplace", "nuts_set_lowrank_transform",
     "nuts_set_position_masked", "nuts_comm_unique_id", "nuts_comm_create", "nuts_comm_destroy", "nuts_gather_draws_begin", "nuts_gather_draws_end",
 ]
 
@@ -96,6 +97,11 @@ def load():
     L.nuts_point_set_scalars.argtypes = [vp, vp, _abi.c_i64_p, dp, dp, dp, dp, _abi.c_i64_p]
     L.nuts_set_transform.argtypes = [vp, dp, dp]
     L.nuts_get_transform.argtypes = [vp, dp, dp, dp, dp, _abi.c_i64_p]
+    L.nuts_eigs_create.argtypes = [vp, C.POINTER(vp), C.c_uint64, dp, dp, _abi.c_i32_p]
+    L.nuts_eigs_free.argtypes = [vp, vp]
+    L.nuts_apply_lowrank_transform.argtypes = [vp, vp, vp, vp]
+    L.nuts_apply_lowrank_transform_inplace.argtypes = [vp, vp, vp]
+    L.nuts_set_lowrank_transform.argtypes = [vp, dp, dp, C.c_uint64, dp, dp, _abi.c_i32_p, dp, C.POINTER(C.c_uint8)]
     L.nuts_init_state.argtypes = [vp, vp, dp, _abi.c_i32_p]
     L.nuts_initialize_trajectory.argtypes = [vp, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]
     L.nuts_leapfrog.argtypes = [vp, vp, vp, dp, C.c_double, _abi.c_i8_p, dp, C.c_double, _abi.c_u8_p, _abi.c_i32_p, dp]
@@ -148,6 +154,28 @@ def DiagNutsSettings(**overrides) -> _abi.NutsSettings:
     for k, v in overrides.items():
         setattr(s, k, v)
     return s
+
+
+class Eigs:
+    """EigVectors + EigValues of all chains on the device (reference src/math/math.rs:17-18, 150-160)."""
+
+    def __init__(self, math, vecs, vals, rank=None):
+        N, d = math.nchains, math.dim
+        vals = np.asarray(vals, dtype=np.float64)
+        r = vals.shape[-1]
+        vals = _f64(np.broadcast_to(vals.reshape((-1, r)) if vals.ndim < 2 else vals, (N, r)))
+        vecs = np.asarray(vecs, dtype=np.float64)
+        vecs = _f64(np.broadcast_to(vecs.reshape((-1, r, d)) if vecs.ndim < 3 else vecs, (N, r, d)))
+        rk = None if rank is None else np.ascontiguousarray(np.broadcast_to(rank, (N,)), dtype=np.int32)
+        self.math = math
+        h = C.c_void_p()
+        _check(load().nuts_eigs_create(math.h, C.byref(h), r, _p(vecs), _p(vals), None if rk is None else rk.ctypes.data_as(_abi.c_i32_p)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.math.h:
+            load().nuts_eigs_free(self.math.h, self.h)
+            self.h = None
 
 
 class Plane:
@@ -352,6 +380,36 @@ class CudaMath:
         stds = _f64(np.broadcast_to(stds, (self.nchains, self.dim)))
         mean = _f64(np.broadcast_to(mean, (self.nchains, self.dim)))
         _check(load().nuts_set_transform(self.h, _p(stds), _p(mean)))
+
+    def set_lowrank_transform(self, stds, mean, vals, vecs, mean_low_rank, rank=None):
+        """LowRankMassMatrix::update (reference src/transform/low_rank.rs:158-190) for every chain.  vals: [N, r] (or [r], the same
+        for every chain), vecs: [N, r, dim] (or [r, dim]), rank: [N] eigenvectors actually used per chain (default r).  Returns the
+        per-chain `accepted` flags (False: a non-finite input, that chain keeps its old transformation)."""
+        N, d = self.nchains, self.dim
+        stds = _f64(np.broadcast_to(stds, (N, d)))
+        mean = _f64(np.broadcast_to(mean, (N, d)))
+        mu = _f64(np.broadcast_to(mean_low_rank, (N, d)))
+        vals = np.asarray(vals, dtype=np.float64)
+        r = vals.shape[-1] if vals.ndim else 0
+        vals = _f64(np.broadcast_to(vals.reshape((-1, r)) if vals.ndim < 2 else vals, (N, r)))
+        vecs = np.asarray(vecs, dtype=np.float64)
+        vecs = _f64(np.broadcast_to(vecs.reshape((-1, r, d)) if vecs.ndim < 3 else vecs, (N, r, d)))
+        rk = None if rank is None else np.ascontiguousarray(np.broadcast_to(rank, (N,)), dtype=np.int32)
+        ok = np.zeros(N, dtype=np.uint8)
+        _check(load().nuts_set_lowrank_transform(self.h, _p(stds), _p(mean), r, _p(vals) if r else None, _p(vecs) if r else None,
+                                                 None if rk is None else rk.ctypes.data_as(_abi.c_i32_p), _p(mu),
+                                                 ok.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return ok.astype(bool)
+
+    def new_eigs(self, vecs, vals, rank=None):
+        """Math::new_eig_vectors + new_eig_values for every chain: vecs [N, r, dim] (or [r, dim]), vals [N, r] (or [r])."""
+        return Eigs(self, vecs, vals, rank)
+
+    def apply_lowrank_transform(self, eigs, rhs, dest):
+        _check(load().nuts_apply_lowrank_transform(self.h, eigs.h, rhs.h, dest.h))
+
+    def apply_lowrank_transform_inplace(self, eigs, rhs_and_dest):
+        _check(load().nuts_apply_lowrank_transform_inplace(self.h, eigs.h, rhs_and_dest.h))
 
     def transform(self):
         N, d = self.nchains, self.dim

@@ -310,17 +310,71 @@ struct Funnel : LogpFunc {
 };
 
 // ------------------------------------------------------------------------------------------------
-// src/transform/diagonal.rs — DiagMassMatrix
+// src/math/cpu_math.rs:332-425 — apply_lowrank_transform(_inplace):  dest = rhs + U ((vals - 1) .* (U^T rhs))
+// vecs: r eigenvectors of length d, one after the other (the columns of the reference's d x r matrix).  faer's matmul leaves the
+// summation order open; here every dot product runs left to right with FMAs.  rhs == dest is allowed (the in-place form).
+// ------------------------------------------------------------------------------------------------
+inline void apply_lowrank_transform(const Vec& vecs, const Vec& vals, const double* rhs, double* dest, size_t d) {
+  const size_t r = vals.size();
+  if (r == 0) {  // :339-342
+    if (dest != rhs) std::copy(rhs, rhs + d, dest);
+    return;
+  }
+  Vec scratch(r);
+  for (size_t k = 0; k < r; ++k) {  // scratch = U^T rhs, then scratch[k] *= vals[k] - 1   (:353-366)
+    double acc = 0.;
+    for (size_t i = 0; i < d; ++i) acc = std::fma(vecs[k * d + i], rhs[i], acc);
+    scratch[k] = acc * (vals[k] - 1.0);
+  }
+  for (size_t i = 0; i < d; ++i) {  // dest = rhs + U scratch   (:368-377)
+    double acc = rhs[i];
+    for (size_t k = 0; k < r; ++k) acc = std::fma(vecs[k * d + i], scratch[k], acc);
+    dest[i] = acc;
+  }
+}
+
+// src/transform/low_rank.rs:25-91 — InnerMatrix: U, lambda^{1/2}, lambda^{-1/2}, -1/2 sum ln(lambda), mu
+struct LowRankInner {
+  Vec vecs, vals_sqrt, vals_sqrt_inv, mu;
+  double logdet_contribution = 0.;
+  LowRankInner(const Vec& vals, const Vec& vecs_, const Vec& mu_) : vecs(vecs_), vals_sqrt(vals), vals_sqrt_inv(vals), mu(mu_) {
+    for (double v : vals) logdet_contribution += -0.5 * std::log(v);   // :57
+    for (double& v : vals_sqrt) v = std::sqrt(v);                      // :66
+    for (size_t k = 0; k < vals.size(); ++k) vals_sqrt_inv[k] = 1.0 / vals_sqrt[k];  // :70
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// src/transform/diagonal.rs — DiagMassMatrix; with `inner` set it is the LowRankMassMatrix of src/transform/low_rank.rs:97-404
+// (diag + optional low-rank correction; every diagonal update drops the correction like update_from_grad, low_rank.rs:143-156)
 // ------------------------------------------------------------------------------------------------
 struct DiagMassMatrix {
   Vec mean, inv_stds, stds;
   double logdet = 0.;
   int64_t id = -1;
+  std::shared_ptr<LowRankInner> inner;
+  // LowRankMassMatrix::update (low_rank.rs:158-190): silently keeps the old transformation when an input is not finite
+  bool update_lowrank(const Vec& stds_, const Vec& mean_, const Vec& vals, const Vec& vecs, const Vec& mean_low_rank) {
+    auto finite = [](const Vec& v) {
+      for (double x : v)
+        if (!std::isfinite(x)) return false;
+      return true;
+    };
+    if (!finite(stds_) || !finite(mean_) || !finite(vals) || !finite(vecs)) return false;
+    const int64_t old_id = id;
+    set_transform(stds_, mean_);  // self.diag.set_transform
+    auto in = std::make_shared<LowRankInner>(vals, vecs, mean_low_rank);
+    logdet = in->logdet_contribution + logdet;  // :187
+    inner = in;
+    id = old_id + 1;
+    return true;
+  }
   explicit DiagMassMatrix(size_t d) : mean(d, 0.), inv_stds(d, 0.), stds(d, 0.) {}  // diagonal.rs:73-83
 
   // diagonal.rs:85-105
   void update_diag_draw(const Vec& draw_mean, const Vec& draw_var, double scale, std::optional<double> fill, double lo,
                         double hi) {
+    inner.reset();
     array_update_var_inv_std_draw(inv_stds, stds, draw_var, scale, fill, lo, hi);
     mean = draw_mean;
     logdet = array_sum_ln(inv_stds);
@@ -329,6 +383,7 @@ struct DiagMassMatrix {
   // diagonal.rs:107-131
   void update_diag_draw_grad(const Vec& draw_mean, const Vec& grad_mean, const Vec& draw_var, const Vec& grad_var,
                              std::optional<double> fill, double lo, double hi) {
+    inner.reset();
     array_update_var_inv_std_draw_grad(inv_stds, stds, draw_var, grad_var, fill, lo, hi);
     size_t d = stds.size();
     Vec var(d);
@@ -340,6 +395,7 @@ struct DiagMassMatrix {
   }
   // diagonal.rs:133-154
   void update_diag_grad(const Vec& position, const Vec& gradient, double fill, double lo, double hi) {
+    inner.reset();
     array_update_var_inv_std_grad(inv_stds, stds, gradient, fill, lo, hi);
     size_t d = stds.size();
     Vec var(d);
@@ -351,6 +407,7 @@ struct DiagMassMatrix {
   }
   // diagonal.rs:156-162
   void set_transform(const Vec& stds_, const Vec& mean_) {
+    inner.reset();
     stds = stds_;
     mean = mean_;
     for (size_t i = 0; i < stds.size(); ++i) inv_stds[i] = 1.0 / stds[i];
@@ -358,17 +415,31 @@ struct DiagMassMatrix {
     id += 1;
   }
   // diagonal.rs:233-246  z = (x - mu) * inv_std   (axpy_out with a=-1, then multiply_inplace)
+  // (low_rank.rs:326-348: then z -= mu_lr and the lambda^{-1/2} correction)
   void compute_transformed_position(const Vec& x, Vec& z) const {
     axpy_out(mean.data(), x.data(), -1.0, z.data(), x.size());
     multiply_inplace(z.data(), inv_stds.data(), x.size());
+    if (inner) {
+      axpy(inner->mu.data(), z.data(), -1.0, z.size());
+      apply_lowrank_transform(inner->vecs, inner->vals_sqrt_inv, z.data(), z.data(), z.size());
+    }
   }
-  // diagonal.rs:248-256  x = z*std ; x += mu
+  // diagonal.rs:248-256  x = z*std ; x += mu   (low_rank.rs:350-378: x = ((I + U(sqrt(lambda) - 1)U^T) z + mu_lr) * std + mean)
   void compute_untransformed_position(const Vec& z, Vec& x) const {
-    multiply(z.data(), stds.data(), x.data(), z.size());
+    if (inner) {
+      apply_lowrank_transform(inner->vecs, inner->vals_sqrt, z.data(), x.data(), z.size());
+      axpy(inner->mu.data(), x.data(), 1.0, z.size());
+      multiply_inplace(x.data(), stds.data(), z.size());
+    } else {
+      multiply(z.data(), stds.data(), x.data(), z.size());
+    }
     axpy(mean.data(), x.data(), 1.0, z.size());
   }
-  // diagonal.rs:258-265
-  void compute_transformed_gradient(const Vec& gx, Vec& gz) const { multiply(gx.data(), stds.data(), gz.data(), gx.size()); }
+  // diagonal.rs:258-265   (low_rank.rs:380-398: then the sqrt(lambda) correction)
+  void compute_transformed_gradient(const Vec& gx, Vec& gz) const {
+    multiply(gx.data(), stds.data(), gz.data(), gx.size());
+    if (inner) apply_lowrank_transform(inner->vecs, inner->vals_sqrt, gz.data(), gz.data(), gz.size());
+  }
 };
 
 // ------------------------------------------------------------------------------------------------

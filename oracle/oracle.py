@@ -70,6 +70,9 @@ def lib():
         L.orc_ham_destroy.argtypes = [C.c_void_p]
         L.orc_ham_set_step_size.argtypes = [C.c_void_p, C.c_double]
         L.orc_ham_set_transform.argtypes = [C.c_void_p, dp, dp]
+        L.orc_ham_set_lowrank_transform.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, C.c_uint64]
+        L.orc_ham_set_lowrank_transform.restype = C.c_int
+        L.orc_apply_lowrank_transform.argtypes = [dp, dp, dp, dp, C.c_uint64, C.c_uint64]
         L.orc_ham_update_diag_draw_grad.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_double]
         L.orc_ham_update_diag_grad.argtypes = [C.c_void_p, dp, dp, C.c_double, C.c_double, C.c_double]
         L.orc_ham_update_diag_draw.argtypes = [C.c_void_p, dp, dp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
@@ -137,6 +140,15 @@ def multiply(x, y):
     y = _f64(y)
     out = np.empty_like(x)
     lib().orc_multiply(_p(x), _p(y), _p(out), x.size)
+    return out
+
+
+def apply_lowrank_transform(vecs, vals, rhs):
+    """(I + U (diag(vals) - I) U^T) rhs  (src/math/cpu_math.rs:332-377); vecs: [r, d]."""
+    vals, rhs = _f64(vals), _f64(rhs)
+    vecs = _f64(np.asarray(vecs, dtype=np.float64).reshape(len(vals), len(rhs)))
+    out = np.empty_like(rhs)
+    lib().orc_apply_lowrank_transform(_p(vecs), _p(vals), _p(rhs), _p(out), len(rhs), len(vals))
     return out
 
 
@@ -252,6 +264,13 @@ class Hamiltonian:
     def set_transform(self, stds, mean):
         stds, mean = _f64(stds), _f64(mean)
         lib().orc_ham_set_transform(self.h, _p(stds), _p(mean))
+
+    def set_lowrank_transform(self, stds, mean, vals, vecs, mean_low_rank):
+        """LowRankMassMatrix::update (src/transform/low_rank.rs:158-190).  vecs: [r, dim] (row k = eigenvector k).  Returns False when an
+        input was not finite (the old transformation stays)."""
+        stds, mean, vals, mu = _f64(stds), _f64(mean), _f64(vals), _f64(mean_low_rank)
+        vecs = _f64(np.asarray(vecs, dtype=np.float64).reshape(len(vals), self.dim))
+        return bool(lib().orc_ham_set_lowrank_transform(self.h, _p(stds), _p(mean), _p(vals), _p(vecs), _p(mu), len(vals)))
 
     def update_diag_draw_grad(self, draw_mean, grad_mean, draw_var, grad_var, fill=None, clamp=(1e-20, 1e20)):
         a = list(map(_f64, (draw_mean, grad_mean, draw_var, grad_var)))

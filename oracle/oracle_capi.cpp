@@ -203,6 +203,17 @@ void orc_ham_set_transform(void* h, const double* stds, const double* mean) {
   auto& H = ((Ham*)h)->h;
   H.transformation.set_transform(Vec(stds, stds + H.dim), Vec(mean, mean + H.dim));
 }
+// LowRankMassMatrix::update (src/transform/low_rank.rs:158-190); vecs = r eigenvectors of length dim, one after the other
+int orc_ham_set_lowrank_transform(void* h, const double* stds, const double* mean, const double* vals, const double* vecs,
+                                  const double* mean_low_rank, uint64_t r) {
+  auto& H = ((Ham*)h)->h;
+  size_t d = H.dim;
+  return H.transformation.update_lowrank(Vec(stds, stds + d), Vec(mean, mean + d), Vec(vals, vals + r), Vec(vecs, vecs + r * d),
+                                         Vec(mean_low_rank, mean_low_rank + d)) ? 1 : 0;
+}
+void orc_apply_lowrank_transform(const double* vecs, const double* vals, const double* rhs, double* dest, uint64_t d, uint64_t r) {
+  apply_lowrank_transform(Vec(vecs, vecs + r * d), Vec(vals, vals + r), rhs, dest, d);
+}
 void orc_ham_update_diag_draw_grad(void* h, const double* draw_mean, const double* grad_mean, const double* draw_var,
                                    const double* grad_var, int has_fill, double fill, double lo, double hi) {
   auto& H = ((Ham*)h)->h;
