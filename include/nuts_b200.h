@@ -318,6 +318,24 @@ typedef struct {
 int nuts_sampler_get_chain_state(nuts_sampler_t*, const nuts_chain_state_t* out);
 int nuts_sampler_set_chain_state(nuts_sampler_t*, const nuts_chain_state_t* in);
 
+/* ---- Low-rank mass matrix in whole draws (reference src/transform/low_rank.rs + src/transform/adapt/low_rank.rs).
+ * nuts_sampler_create_lowrank builds the sampler on an engine with the low-rank transformation compiled in (dim <= 1024): every
+ * leapfrog applies x = sigma * ((I + U (sqrt(lambda) - 1) U^T) z + mu_lr) + mean and grad_z = (I + U (sqrt(lambda) - 1) U^T)(sigma * grad_x),
+ * i.e. two skinny products with the chain's U [rank x dim] and two team-wide reductions of `rank` values on top of the diagonal path.
+ * The estimator (thin SVDs, pivoted QR and three eigendecompositions per update and chain, adapt/low_rank.rs:73-262) stays on the
+ * host: the caller collects draws (nuts_draw) and gradients (nuts_sampler_set_grads_out), computes (stds, mean, vals, vecs,
+ * mean_low_rank) and installs them with nuts_sampler_set_lowrank_transform == LowRankMassMatrix::update (low_rank.rs:158-190) for
+ * every chain (arguments as nuts_set_lowrank_transform).  The first update of a run re-runs the step size search from the current
+ * point (adapt_strategy.rs:204-214).  The device-side adaptation of such a sampler should be limited to the step size: set
+ * mass_matrix_update_freq / early_mass_matrix_switch_freq / mass_matrix_switch_freq beyond num_tune (nuts_rs_b200/lowrank.py does). */
+int nuts_sampler_create_lowrank(nuts_ctx_t*, nuts_sampler_t** sampler, const nuts_settings_t* settings, uint64_t seed, uint64_t chain_id_offset,
+                                uint64_t rank_max);
+int nuts_sampler_set_lowrank_transform(nuts_sampler_t*, const double* stds, const double* mean, uint64_t rank_max, const double* vals,
+                                       const double* vecs, const int32_t* rank, const double* mean_low_rank, uint8_t* accepted);
+/* gradient of logp at every draw of the following nuts_draw / nuts_draw_device calls: [n_draws][nchains][dim], device memory or
+ * page-locked host memory (nuts_host_alloc); NULL switches it off again */
+int nuts_sampler_set_grads_out(nuts_sampler_t*, double* grads);
+
 /* ===================== Multi-GPU: gather of the draws (the only exchange of the path) ====================
  * Chains are independent (reference src/sampler.rs:1094-1126: one Math / RNG stream / adaptation per chain), so a job is split
  * into contiguous blocks of chains, one sampler per GPU, with chain_id_offset = first global chain id of the block; nothing is

@@ -36,6 +36,11 @@ NB_DECL(32, 2, 21)
 NB_DECL(32, 4, 21)
 NB_DECL(32, 8, 21)
 NB_DECL(32, 16, 21)
+// SM_LOWRANK (tag 31): the engines of nuts_sampler_create_lowrank
+NB_DECL(32, 1, 31)
+NB_DECL(32, 4, 31)
+NB_DECL(32, 16, 31)
+NB_DECL(64, 16, 31)
 NB_DECL(64, 16, 44)   // SM_EXACT + SM_ALIGN: the 4 resident 64-thread teams of an SM in one 256-thread CTA
 NB_DECL(64, 16, 54)  // SM_EXACT variant of 64x16x4 (rows padded to 1024)
 NB_DECL(64, 16, 58)  // SM_EXACT + SM_STAGE, model parameters through the read-only path (no shared-memory copy)
@@ -122,6 +127,8 @@ const EngineConfig kClusterLarge = NB_CFG(1024, 10, 41);
 // SM_ALIGN variants of the warp tilings (tag 21): the default unless the target's tree depths vary wildly (funnel) or
 // NUTS_B200_ALIGN=0
 const EngineConfig kAlignedConfigs[] = {NB_CFG(32, 1, 21), NB_CFG(32, 2, 21), NB_CFG(32, 4, 21), NB_CFG(32, 8, 21), NB_CFG(32, 16, 21)};
+// engines with the low-rank transformation compiled in (nuts_sampler_create_lowrank)
+const EngineConfig kLowRankConfigs[] = {NB_CFG(32, 1, 31), NB_CFG(32, 4, 31), NB_CFG(32, 16, 31), NB_CFG(64, 16, 31)};
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
@@ -196,6 +203,10 @@ struct nuts_sampler {
   uint64_t draws_done = 0;
   bool positioned = false;
   bool last_direct = false;  // the last nuts_draw wrote its draws straight into the caller's buffer
+  // low-rank sampler (nuts_sampler_create_lowrank)
+  uint64_t lowrank_rmax = 0;
+  double *lr_vecs = nullptr, *lr_vals_sqrt = nullptr, *lr_vals_sqrt_inv = nullptr, *lr_mu = nullptr;
+  int* lr_rank = nullptr;
 };
 
 namespace {
@@ -946,7 +957,8 @@ static ChainState fresh_chain_state(const SettingsDev& S) {
   return c;
 }
 
-int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settings_t* st, uint64_t seed, uint64_t chain_id_offset) {
+static int sampler_create_impl(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settings_t* st, uint64_t seed, uint64_t chain_id_offset,
+                               uint64_t lowrank_rmax) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (!st) return fail(NUTS_ERR_INVALID, "nuts_sampler_create: settings is NULL");
   if (st->trajectory_kind != NUTS_KINETIC_EUCLIDEAN) return fail(NUTS_ERR_UNSUPPORTED, "only KineticEnergyKind::Euclidean is supported");
@@ -958,6 +970,16 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   if (st->adapt_options.mass_matrix_window_growth < 1.0) return fail(NUTS_ERR_INVALID, "mass_matrix_window_growth must be >= 1");
   const EngineConfig* cfg = nullptr;
   const int s_variant = ctx->model.kind == NUTS_LOGP_GAUSS_RANK1 ? 1 : ctx->model.kind == NUTS_LOGP_FUNNEL ? 2 : ctx->model.kind == NUTS_LOGP_USER ? 3 : 0;
+  if (lowrank_rmax > 0) {
+    // low-rank mass matrix (SM_LOWRANK builds): the general two-pass leapfrog with the eigenvector reductions
+    if (lowrank_rmax > (uint64_t)LR_MAX_RANK) return fail(NUTS_ERR_INVALID, "low-rank sampler: rank_max must be <= %d", LR_MAX_RANK);
+    for (const EngineConfig& c : kLowRankConfigs)
+      if ((uint64_t)c.max_d >= ctx->d && c.launch[s_variant]) {
+        cfg = &c;
+        break;
+      }
+    if (!cfg) return fail(NUTS_ERR_UNSUPPORTED, "no low-rank engine build covers dim %llu (built: up to 1024)", (unsigned long long)ctx->d);
+  } else {
   if (const char* env = std::getenv("NUTS_B200_ENGINE")) {
     int tpc = 0, ept = 0, minb = 0;
     if (std::sscanf(env, "%d,%d,%d", &tpc, &ept, &minb) == 3) {
@@ -1004,6 +1026,7 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
       if (c.tpc == cfg->tpc && c.ept == cfg->ept && c.launch[0] && (uint64_t)c.max_d - ctx->d <= ctx->d * 7 / 100) cfg = &c;
   }
 
+  }
   nuts_sampler* s = new nuts_sampler();
   Guard<nuts_sampler, nuts_sampler_destroy> guard(s);  // every early return below releases what was allocated so far
   s->ctx = ctx;
@@ -1115,7 +1138,24 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   A((void**)&s->d_init, ctx->N * ctx->d * sizeof(double));
   A((void**)&s->d_status, ctx->N * sizeof(int));
   A((void**)&P.phase_clocks, 16 * sizeof(unsigned long long));
+  if (lowrank_rmax > 0) {
+    A((void**)&s->lr_vecs, ctx->N * lowrank_rmax * (size_t)P.ld * sizeof(double));
+    A((void**)&s->lr_vals_sqrt, ctx->N * lowrank_rmax * sizeof(double));
+    A((void**)&s->lr_vals_sqrt_inv, ctx->N * lowrank_rmax * sizeof(double));
+    A((void**)&s->lr_mu, plane);
+    A((void**)&s->lr_rank, ctx->N * sizeof(int));
+  }
   if (r != NUTS_OK) return r;
+  if (lowrank_rmax > 0) {
+    CUDA_TRY(cudaMemset(s->lr_rank, 0xff, ctx->N * sizeof(int)));  // -1: no low-rank part until the first update
+    P.lr_vecs = s->lr_vecs;
+    P.lr_vals_sqrt = s->lr_vals_sqrt;
+    P.lr_vals_sqrt_inv = s->lr_vals_sqrt_inv;
+    P.lr_mu = s->lr_mu;
+    P.lr_rank = s->lr_rank;
+    P.lr_rmax = (int)lowrank_rmax;
+    s->lowrank_rmax = lowrank_rmax;
+  }
   std::vector<ChainState> cs(ctx->N, fresh_chain_state(S));
   CUDA_TRY(cudaMemcpy(P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice));
   {
@@ -1128,6 +1168,15 @@ int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settin
   guard.dismiss();
   *out = s;
   return NUTS_OK;
+}
+
+int nuts_sampler_create(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settings_t* st, uint64_t seed, uint64_t chain_id_offset) {
+  return sampler_create_impl(ctx, out, st, seed, chain_id_offset, 0);
+}
+int nuts_sampler_create_lowrank(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts_settings_t* st, uint64_t seed, uint64_t chain_id_offset,
+                                uint64_t rank_max) {
+  if (rank_max == 0) return fail(NUTS_ERR_INVALID, "nuts_sampler_create_lowrank: rank_max must be >= 1");
+  return sampler_create_impl(ctx, out, st, seed, chain_id_offset, rank_max);
 }
 
 int nuts_sampler_destroy(nuts_sampler_t* s) {
@@ -1694,6 +1743,99 @@ int nuts_sampler_set_step_size(nuts_sampler_t* s, const double* step_size) {
   TRY(sync(ctx));
   for (uint64_t c = 0; c < ctx->N; ++c) cs[c].step_size = step_size[c];
   CUDA_TRY(cudaMemcpyAsync(s->P.cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice, ctx->stream));
+  return sync(ctx);
+}
+
+// ---- low-rank sampler: the transformation comes from the host estimator (LowRankMassMatrixStrategy::update -> LowRankMassMatrix::update)
+int nuts_sampler_set_grads_out(nuts_sampler_t* s, double* grads) {
+  if (s->lowrank_rmax == 0) return fail(NUTS_ERR_INVALID, "nuts_sampler_set_grads_out: not a low-rank sampler");
+  if (grads) {
+    cudaPointerAttributes at{};
+    cudaError_t e = cudaPointerGetAttributes(&at, grads);
+    if (e != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged)) {
+      cudaGetLastError();
+      return fail(NUTS_ERR_INVALID, "nuts_sampler_set_grads_out: the buffer must be device or page-locked host memory (nuts_host_alloc)");
+    }
+    if (at.type == cudaMemoryTypeHost) {
+      void* dp = nullptr;
+      CUDA_TRY(cudaHostGetDevicePointer(&dp, grads, 0));
+      grads = (double*)dp;
+    }
+  }
+  s->P.grads_out = grads;
+  return NUTS_OK;
+}
+
+int nuts_sampler_set_lowrank_transform(nuts_sampler_t* s, const double* stds, const double* mean, uint64_t rank_max, const double* vals,
+                                       const double* vecs, const int32_t* rank, const double* mean_low_rank, uint8_t* accepted) {
+  nuts_ctx* ctx = s->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (s->lowrank_rmax == 0) return fail(NUTS_ERR_INVALID, "nuts_sampler_set_lowrank_transform: create the sampler with nuts_sampler_create_lowrank");
+  if (!s->positioned) return fail(NUTS_ERR_INVALID, "nuts_sampler_set_lowrank_transform: call nuts_set_position first");
+  if (!stds || !mean || !mean_low_rank) return fail(NUTS_ERR_INVALID, "nuts_sampler_set_lowrank_transform: NULL argument");
+  if (rank_max > s->lowrank_rmax) return fail(NUTS_ERR_INVALID, "nuts_sampler_set_lowrank_transform: rank_max %llu exceeds the sampler's %llu", (unsigned long long)rank_max, (unsigned long long)s->lowrank_rmax);
+  if (rank_max > 0 && (!vals || !vecs)) return fail(NUTS_ERR_INVALID, "nuts_sampler_set_lowrank_transform: vals / vecs are NULL");
+  const uint64_t N = ctx->N, d = ctx->d, RM = s->lowrank_rmax, ld = (uint64_t)s->P.ld;
+  auto finite = [](const double* p, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i)
+      if (!std::isfinite(p[i])) return false;
+    return true;
+  };
+  std::vector<ChainState> cs(N);
+  std::vector<int> rk(N);
+  std::vector<double> vs(N * RM), vi(N * RM);
+  CUDA_TRY(cudaMemcpyAsync(cs.data(), s->P.cs, N * sizeof(ChainState), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(rk.data(), s->lr_rank, N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(vs.data(), s->lr_vals_sqrt, N * RM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(vi.data(), s->lr_vals_sqrt_inv, N * RM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(sync(ctx));
+  std::vector<double> inv(d);
+  for (uint64_t c = 0; c < N; ++c) {
+    const int r = rank_max == 0 ? 0 : (rank ? rank[c] : (int)rank_max);
+    if (r < 0 || (uint64_t)r > rank_max) return fail(NUTS_ERR_INVALID, "nuts_sampler_set_lowrank_transform: rank[%llu] = %d outside 0 .. rank_max", (unsigned long long)c, r);
+    bool good = finite(stds + c * d, d) && finite(mean + c * d, d);  // low_rank.rs:168-173: otherwise the old transformation stays
+    if (r > 0) good = good && finite(vals + c * rank_max, (uint64_t)r) && finite(vecs + c * rank_max * d, (uint64_t)r * d);
+    if (accepted) accepted[c] = good ? 1 : 0;
+    if (!good || !cs[c].alive) continue;
+    // diag.set_transform (diagonal.rs:156-162) + InnerMatrix::new (low_rank.rs:55-71) + logdet (low_rank.rs:186-187)
+    double logdet = 0.0, contrib = 0.0;
+    for (uint64_t i = 0; i < d; ++i) {
+      inv[i] = 1.0 / stds[c * d + i];
+      logdet += std::log(inv[i]);
+    }
+    for (int k = 0; k < r; ++k) {
+      const double lam = vals[c * rank_max + k];
+      contrib += -0.5 * std::log(lam);
+      const double sq = std::sqrt(lam);
+      vs[c * RM + k] = sq;
+      vi[c * RM + k] = 1.0 / sq;
+    }
+    rk[c] = r;
+    cs[c].mm_logdet = contrib + logdet;
+    cs[c].mm_id += 1;
+    const size_t row = c * ld;
+    CUDA_TRY(cudaMemcpyAsync(s->P.stds + row, stds + c * d, d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->P.inv_stds + row, inv.data(), d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->P.mean + row, mean + c * d, d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->lr_mu + row, mean_low_rank + c * d, d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(s->lr_vecs + c * RM * ld, 0, RM * ld * sizeof(double), ctx->stream));
+    if (r > 0)
+      CUDA_TRY(cudaMemcpy2DAsync(s->lr_vecs + c * RM * ld, ld * sizeof(double), vecs + c * rank_max * d, d * sizeof(double), d * sizeof(double),
+                                 (size_t)r, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(sync(ctx));  // `inv` is reused by the next chain
+  }
+  CUDA_TRY(cudaMemcpyAsync(s->P.cs, cs.data(), N * sizeof(ChainState), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->lr_rank, rk.data(), N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->lr_vals_sqrt, vs.data(), N * RM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->lr_vals_sqrt_inv, vi.data(), N * RM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  // the first mass-matrix update of a run re-initialises the step size from the current point (adapt_strategy.rs:204-214)
+  s->P.mode = 2;
+  s->P.init_position = nullptr;
+  s->P.init_mask = nullptr;
+  s->P.status_out = s->d_status;
+  s->P.n_draws = 0;
+  s->P.draws_per_unit = 1;
+  TRY(launch_engine(s));
   return sync(ctx);
 }
 

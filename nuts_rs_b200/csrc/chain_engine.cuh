@@ -117,6 +117,14 @@ struct EngineParams {
   uint32_t draws_per_unit;          // work unit of a draw launch = this many consecutive draws of one chain (>= 1)
   uint32_t _pad2;
   double* draws_out;                // [n_draws][N][d] device (may be null)
+  double* grads_out;                // [n_draws][N][d] device (may be null): gradient of logp at every draw (low-rank estimator input)
+  // low-rank correction of the mass matrix (SM_LOWRANK engines; null otherwise): see plane_kernels.cuh TransformDev
+  const double* lr_vecs;            // [N][lr_rmax][ld]
+  const double* lr_vals_sqrt;       // [N][lr_rmax]
+  const double* lr_vals_sqrt_inv;   // [N][lr_rmax]
+  const double* lr_mu;              // [N][ld]
+  const int* lr_rank;               // [N]; -1 = no correction
+  int lr_rmax, _pad3;
   StatsDev stats;
   uint64_t stats_offset;            // unused draws before this call inside the stats arrays (always 0 for now)
   unsigned long long* phase_clocks; // [16] debug phase timing (NB_PHASE_TIMING / NB_PHASE_TIMING_COLD builds), else unused
@@ -288,7 +296,10 @@ static __device__ __noinline__ AccSums accept_batch(double mine, int n, double a
 // threads' elements of the shared-memory vectors, reductions go through distributed shared memory (TeamReduce, CL > 1).
 // SM_ALIGN: the warp teams of a CTA start their work units together (a CTA barrier per unit): warps that run the same code at
 // the same time share the 32 KB instruction cache of the SM - the engine's per-draw instruction working set is 80 - 140 KB.
-enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32, SM_STAGE = 64, SM_CL2 = 128, SM_CL4 = 256, SM_ALIGN = 512 };
+enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32, SM_STAGE = 64, SM_CL2 = 128, SM_CL4 = 256, SM_ALIGN = 512, SM_LOWRANK = 1024 };
+// SM_LOWRANK: the chain's transformation may carry the low-rank correction of LowRankMassMatrix (reference src/transform/low_rank.rs):
+// x = sigma * ((I + U (sqrt(lambda) - 1) U^T) z + mu_lr) + mean.  Every leapfrog then runs the general (two-pass) path with two more
+// team-wide reductions of r values (U^T z and U^T (sigma * grad_x)); the elementwise shortcuts of the diagonal Gaussian are off.
 template <int SMF>
 __host__ __device__ constexpr int cluster_size() {
   return (SMF & SM_CL4) ? 4 : ((SMF & SM_CL2) ? 2 : 1);
@@ -323,11 +334,14 @@ struct Engine {
 
   // ---- register-resident vectors ----
   static constexpr bool MMS = (SMF & SM_MASS) != 0, MODS = (SMF & SM_MODEL) != 0, GS = (SMF & SM_GRAD) != 0, EXACT = (SMF & SM_EXACT) != 0,
-                        NOG = (SMF & SM_NOGRAD) != 0 && MODEL == LOGP_GAUSS_DIAG,
+                        LR = (SMF & SM_LOWRANK) != 0,
+                        ELEMWISE = MODEL == LOGP_GAUSS_DIAG && !LR,  // grad_z of a leaf is an elementwise function of its z
+                        NOG = (SMF & SM_NOGRAD) != 0 && ELEMWISE,
                         MSH = MODS || (MULTI && (SMF & SM_MODEL_GLOBAL) == 0);  // model parameters are read from shared memory
   static constexpr bool STAGE = (SMF & SM_STAGE) != 0 && (EPT % 2) == 0 && !MULTI;
   // (capi.cu pads the global model parameter arrays with zeros up to the largest tile)
   static_assert(!EXACT || MMS, "SM_EXACT needs a zero-padded copy of the mass matrix");
+  static_assert(!LR || (!MULTI && !GS && !EXACT && CL == 1), "low-rank engines: plain register-resident tilings");
   __device__ __forceinline__ bool inb(int i) const { return EXACT || i < d; }  // element i exists (or is zero padding that may be touched)
   // Element -> thread mapping of every vector.  Even EPT: a thread owns PAIRS of adjacent elements (2*tid, 2*tid + 1, then the
   // same 2*TPC further on), so its accesses to planes, checkpoints and shared memory are 16-byte (double2: LDG.E.128 / STG.E.128 /
@@ -391,6 +405,10 @@ struct Engine {
         sm_g(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0)) * LT * EPT),
         sm_stage(team_smem + ((MMS ? 2 : 0) + (MODS ? 2 : 0) + (GS ? 1 : 0)) * LT * EPT), T(tables) {
     stream = p.chain_offset + (uint64_t)chain_ + 1;  // reference src/sampler.rs:1106 set_stream(chain_id + 1)
+    if (LR && p.lr_rank) {
+      const int r = p.lr_rank[chain_];
+      lr_r = r < p.lr_rmax ? r : p.lr_rmax;
+    }
     if (SUBT) {
       red.bar_id = 1 + (int)threadIdx.x / TPC;
       red.warp = ((int)threadIdx.x % TPC) >> 5;
@@ -896,6 +914,84 @@ struct Engine {
     }
   }
 
+  // ------------------------------------------------------------------ transformation: position / gradient maps
+  // (I + U (diag(vals) - I) U^T) a for a register vector (Math::apply_lowrank_transform_inplace, cpu_math.rs:380-425): the r dot
+  // products 8 at a time through the team reduction, the update fused behind each group (the dot products use the ORIGINAL a).
+  // U is read through the read-only path: it only changes between launches.
+  int lr_r = -1;  // eigenvectors of this chain; -1: its transformation has no low-rank part
+  __device__ __forceinline__ void lowrank_apply(double (&a)[EPT], const double* __restrict__ vals) {
+    if (!LR || lr_r <= 0) return;
+    const double* U = P.lr_vecs + (size_t)chain * P.lr_rmax * ld;
+    const double* lam = vals + (size_t)chain * P.lr_rmax;
+    double acc[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) acc[j] = a[j];
+    for (int k0 = 0; k0 < lr_r; k0 += 8) {
+      double part[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (k0 + q < lr_r) {
+          const double* u = U + (size_t)(k0 + q) * ld;
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) {
+            const int i = eidx(j);
+            if (i < d) part[q] = fma(__ldg(u + i), a[j], part[q]);
+          }
+        }
+      }
+      red.allreduce(part);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (k0 + q < lr_r) {
+          const double c = part[q] * (__ldg(lam + k0 + q) - 1.0);
+          const double* u = U + (size_t)(k0 + q) * ld;
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) {
+            const int i = eidx(j);
+            if (i < d) acc[j] = fma(__ldg(u + i), c, acc[j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) a[j] = acc[j];
+  }
+  // x = F(z): compute_untransformed_position (diagonal.rs:248-256; low_rank.rs:350-378)
+  __device__ __forceinline__ void untransform_position(const double (&zz)[EPT], double (&x)[EPT]) {
+    if (LR && lr_r >= 0) {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) x[j] = zz[j];
+      lowrank_apply(x, P.lr_vals_sqrt);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int i = eidx(j);
+        double t = fma(1.0, i < d ? __ldg(P.lr_mu + row + i) : 0.0, x[j]);  // axpy(mu_lr, x, 1)
+        t = t * sg(j);                                                       // array_mult_inplace(x, stds)
+        x[j] = fma(1.0, mn(j), t);                                           // axpy(mean, x, 1)
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        double t = zz[j] * sg(j);
+        x[j] = fma(1.0, mn(j), t);
+      }
+    }
+  }
+  // grad_z = J_F^T grad_x: compute_transformed_gradient (diagonal.rs:258-265; low_rank.rs:380-398) into the gradient vector
+  __device__ __forceinline__ void transform_gradient(const double (&gx)[EPT]) {
+    if (LR && lr_r > 0) {
+      double w[EPT];
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) w[j] = gx[j] * sg(j);
+      lowrank_apply(w, P.lr_vals_sqrt);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) G(j) = w[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) G(j) = gx[j] * sg(j);
+    }
+  }
+
   // ------------------------------------------------------------------ leapfrog (transformed_hamiltonian.rs:524-615, Euclidean)
   // (z, v, g) <- one velocity-Verlet step of size eps in the whitened space; returns logp' and kinetic energy'.
   // When `with_prev` is set it also returns the U-turn products of the pair (previous leaf, new leaf):
@@ -904,7 +1000,7 @@ struct Engine {
   __device__ __forceinline__ void leapfrog(double eps, double& logp_out, double& ke_out, bool with_prev, double& sP, double& sQ) {
     const double eps_half = eps / 2.;
     hs_total_lf += 1;
-    if (MODEL == LOGP_GAUSS_DIAG) {
+    if (ELEMWISE) {
       double part[4];
       leapfrog_partials(eps, part);
       if (TPC > 32 || with_prev) {
@@ -926,17 +1022,16 @@ struct Engine {
     for (int j = 0; j < EPT; ++j) {
       v[j] = fma(eps_half, G(j), v[j]);
       z[j] = fma(eps, v[j], z[j]);
-      double t = z[j] * sg(j);
-      x[j] = fma(1.0, mn(j), t);
     }
+    untransform_position(z, x);
     double a0, a1, ev;
     model_phase_a(x, a0, a1);
     double part[2];
     part[0] = model_phase_b(x, gx, a0, a1, ev);
     part[1] = 0.0;
+    transform_gradient(gx);
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      G(j) = gx[j] * sg(j);
       v[j] = fma(eps_half, G(j), v[j]);
       part[1] = fma(v[j], v[j], part[1]);
     }
@@ -954,7 +1049,7 @@ struct Engine {
     sQ = 0.0;
   }
   // whether leapfrog() delivers the products of (previous leaf, new leaf)
-  static constexpr bool kFusedPrevCheck = (MODEL == LOGP_GAUSS_DIAG);
+  static constexpr bool kFusedPrevCheck = ELEMWISE;
 
   // logp + gradient at the x plane -> gx plane; returns logp (Math::logp_array)
   __device__ __forceinline__ double eval_at_position(double (&x)[EPT], double (&gx)[EPT]) {
@@ -1044,7 +1139,14 @@ struct Engine {
       int i = eidx(j);
       double t = fma(-1.0, mn(j), x[j]);  // axpy_out(mean, x, -1)
       z[j] = is[j] * t;                   // multiply_inplace(z, inv_stds): out = x*out
-      G(j) = gx[j] * sg(j);
+      if (LR && lr_r >= 0) z[j] = fma(-1.0, i < d ? __ldg(P.lr_mu + row + i) : 0.0, z[j]);  // axpy(mu_lr, z, -1) (low_rank.rs:337-339)
+      if (i >= d) z[j] = 0.0;
+    }
+    if (LR) lowrank_apply(z, P.lr_vals_sqrt_inv);  // (low_rank.rs:340-345)
+    transform_gradient(gx);
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      int i = eidx(j);
       if (i < d) {
         bool ok = isfinite(z[j]) && isfinite(G(j)) && (G(j) != 0.0) && isfinite(gx[j]) && isfinite(x[j]);
         if (!ok) bad[0] = 1.0;
@@ -1122,7 +1224,7 @@ struct Engine {
   // checks of one merge: (Af, cur) always; when `full` also (Al, cur) and (Af, Bf).   cur = registers.
   __device__ __forceinline__ bool merge_turning(const double* Afz, const double* Afv, const double* Alz, const double* Alv,
                                                 const double* Bfz, const double* Bfv, bool full, int dir) {
-    if (!full && MODEL != LOGP_GAUSS_DIAG) {  // (the elementwise target takes the full path below and ignores the extra products)
+    if (!full && !ELEMWISE) {  // (the elementwise target takes the full path below and ignores the extra products)
       double s[2] = {0.0, 0.0};
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
@@ -1261,7 +1363,7 @@ struct Engine {
       }
       if (near_init) {
         load_g(P.gz + row, true);
-      } else if (MODEL == LOGP_GAUSS_DIAG) {
+      } else if (ELEMWISE) {
         // elementwise target: the gradient of a leaf is a function of its z (the leapfrog's own instruction sequence)
 #pragma unroll
         for (int j = 0; j < EPT; ++j) G(j) = grad_z_at(z[j], j, eidx(j));
@@ -1410,7 +1512,7 @@ struct Engine {
     }
     ls_main = total;
     depth += 1;
-    if (MODEL != LOGP_GAUSS_DIAG) store_g(end_ptr(dir, 2), true);  // gradient of the new end (not a cheap function of z here)
+    if (!ELEMWISE) store_g(end_ptr(dir, 2), true);  // gradient of the new end (not a cheap function of z here)
     if (dir) {
       idx_right = idx_cur;
       es_right = s_last;
@@ -1874,19 +1976,15 @@ struct Engine {
     } else if (draw_slot >= 0) {
       double x[EPT], gx[EPT];
       load_cg(slot_ptr(draw_slot, 0), z);
-#pragma unroll
-      for (int j = 0; j < EPT; ++j) {
-        double tt = z[j] * sg(j);
-        x[j] = fma(1.0, mn(j), tt);
-      }
+      untransform_position(z, x);
       hs_logp = eval_at_position(x, gx);
-#pragma unroll
-      for (int j = 0; j < EPT; ++j) G(j) = gx[j] * sg(j);
+      transform_gradient(gx);
       store(P.x + row, x);
       store(P.gx + row, gx);
       store(P.z + row, z);
       store_g(P.gz + row, false);
       if (P.draws_out) store_dense(P.draws_out + (t * N + chain) * (size_t)d, x);
+      if (LR && P.grads_out) store_dense(P.grads_out + (t * N + chain) * (size_t)d, gx);
     } else {
       load(P.z + row, z);
       load_g(P.gz + row, false);
@@ -1894,6 +1992,11 @@ struct Engine {
         double x[EPT];
         load(P.x + row, x);
         store_dense(P.draws_out + (t * N + chain) * (size_t)d, x);
+      }
+      if (LR && P.grads_out) {
+        double gx[EPT];
+        load(P.gx + row, gx);
+        store_dense(P.grads_out + (t * N + chain) * (size_t)d, gx);
       }
     }
     if (!ROLL) {
@@ -2501,6 +2604,28 @@ __device__ __noinline__ int cold_set_position(const EngineParams& Pg, int chain,
   return status;
 }
 
+// After the host replaced a chain's transformation (nuts_sampler_set_lowrank_transform): the first mass-matrix update of a run
+// re-initialises the step size from the current point (GlobalStrategy::adapt, adapt_strategy.rs:204-214 -> stepsize/adapt.rs:91-199);
+// the point itself is re-whitened by the next draw (transformation id changed).  Returns 0, or 3 when the search failed.
+template <int TPC, int EPT, int SMF, int MODEL, bool MULTI>
+__device__ __noinline__ int cold_retransform(const EngineParams& Pg, int chain, int tid, double* scratch, double* team_smem, const MultiCtx* mc) {
+  const ParamsCopy<!MULTI> pc(Pg);
+  const EngineParams& P = pc.P;
+  TreeTables& tables = *reinterpret_cast<TreeTables*>(reinterpret_cast<unsigned char*>(team_smem) + (smem_vectors<SMF>() * (size_t)(TPC / cluster_size<SMF>()) * EPT * sizeof(double)));
+  Engine<TPC, EPT, SMF, MODEL, MULTI> E(P, chain, tid, scratch, team_smem, tables, mc);
+  E.cold_load();
+  int status = 0;
+  if (E.hs_alive && E.cs.has_initial_mass_matrix != 0 && E.cs.tuning != 0) {
+    E.cs.has_initial_mass_matrix = 0;
+    if (!E.stepsize_search()) {
+      status = 3;
+      E.hs_alive = 0;
+    }
+  }
+  E.cold_store();
+  return status;
+}
+
 // Draws t0.. of this launch that a dead chain never produces: NaN positions, and statistics that say "nothing happened"
 // (0 leapfrogs, depth 0, NaN floats) instead of whatever the buffers held before.
 static __device__ __noinline__ void cold_fill_dead(const EngineParams& P, int chain, int tid, int tpc, uint64_t t0) {
@@ -2603,7 +2728,7 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
     E0.load_model_params();
   }
   const unsigned B = P.draws_per_unit;
-  const unsigned blocks = P.mode == 0 ? 1u : ((unsigned)P.n_draws + B - 1u) / B;
+  const unsigned blocks = P.mode != 1 ? 1u : ((unsigned)P.n_draws + B - 1u) / B;
   const unsigned total_units = (unsigned)P.N * blocks;
   bool active = true;
   for (;;) {
@@ -2636,6 +2761,9 @@ __global__ void NB_KERNEL_BOUNDS(CTA_THREADS, MIN_BLOCKS) nuts_chain_kernel(cons
         const int status = cold_set_position<TPC, EPT, SMF, MODEL, false>(P, chain, tid, scratch, team_smem, nullptr);
         if (tid == 0 && P.status_out) P.status_out[chain] = status;
       }
+    } else if (P.mode == 2) {
+      const int status = cold_retransform<TPC, EPT, SMF, MODEL, false>(P, chain, tid, scratch, team_smem, nullptr);
+      if (tid == 0 && P.status_out) P.status_out[chain] = status;
     } else {
       if (blk > 0) __threadfence();  // (thread 0 acquired the chain in unit_pop; the team barrier above ordered the others after it)
       const uint64_t t_end = min((uint64_t)(blk + 1u) * B, (uint64_t)P.n_draws);

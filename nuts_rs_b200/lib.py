@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "nuts_sampler_counters", "nuts_sampler_last_timing", "nuts_sampler_get_state", "nuts_sampler_set_step_size",
     "nuts_host_alloc", "nuts_host_free", "nuts_sampler_last_draw_direct",
     "nuts_sampler_get_chain_state", "nuts_sampler_set_chain_state",
+    "nuts_sampler_create_lowrank", "nuts_sampler_set_lowrank_transform", "nuts_sampler_set_grads_out",
     "nuts_eigs_create", "nuts_eigs_free", "nuts_apply_lowrank_transform", "nuts_apply_lowrank_transform_inplace", "nuts_set_lowrank_transform",
     "nuts_set_position_masked", "nuts_comm_unique_id", "nuts_comm_create", "nuts_comm_destroy", "nuts_gather_draws_begin", "nuts_gather_draws_end",
 ]
@@ -98,6 +99,9 @@ def load():
     L.nuts_set_transform.argtypes = [vp, dp, dp]
     L.nuts_get_transform.argtypes = [vp, dp, dp, dp, dp, _abi.c_i64_p]
     L.nuts_eigs_create.argtypes = [vp, C.POINTER(vp), C.c_uint64, dp, dp, _abi.c_i32_p]
+    L.nuts_sampler_create_lowrank.argtypes = [vp, C.POINTER(vp), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.nuts_sampler_set_lowrank_transform.argtypes = [vp, dp, dp, C.c_uint64, dp, dp, _abi.c_i32_p, dp, C.POINTER(C.c_uint8)]
+    L.nuts_sampler_set_grads_out.argtypes = [vp, C.c_void_p]
     L.nuts_eigs_free.argtypes = [vp, vp]
     L.nuts_apply_lowrank_transform.argtypes = [vp, vp, vp, vp]
     L.nuts_apply_lowrank_transform_inplace.argtypes = [vp, vp, vp]
@@ -492,14 +496,44 @@ def alloc_stats(n_draws, nchains, names=None):
 class Sampler:
     """All chains of one GPU: `settings.new_chain(...)` + `Chain::set_position` / `Chain::draw` for each of them."""
 
-    def __init__(self, math, settings, seed, chain_id_offset=0):
+    def __init__(self, math, settings, seed, chain_id_offset=0, lowrank_rank_max=0):
+        """lowrank_rank_max > 0: an engine with the low-rank transformation compiled in (nuts_sampler_create_lowrank); the
+        transformation is installed with set_lowrank_transform (see nuts_rs_b200/lowrank.py for the host-side estimator)."""
         self.math = math
         self.nchains, self.dim = math.nchains, math.dim
         self.settings = settings
         self.chain_id_offset = chain_id_offset
+        self.lowrank_rank_max = int(lowrank_rank_max)
+        self._grads = None
         h = C.c_void_p()
-        _check(load().nuts_sampler_create(math.h, C.byref(h), C.byref(settings), seed, chain_id_offset))
+        if lowrank_rank_max:
+            _check(load().nuts_sampler_create_lowrank(math.h, C.byref(h), C.cast(C.byref(settings), C.c_void_p), seed, chain_id_offset, int(lowrank_rank_max)))
+        else:
+            _check(load().nuts_sampler_create(math.h, C.byref(h), C.byref(settings), seed, chain_id_offset))
         self.h = h
+
+    def set_lowrank_transform(self, stds, mean, vals, vecs, mean_low_rank, rank=None):
+        """LowRankMassMatrix::update (reference src/transform/low_rank.rs:158-190) for every chain: vals [N, r], vecs [N, r, dim],
+        rank [N] (eigenvectors actually used per chain).  Returns the accepted flags (False: non-finite input, old transformation kept)."""
+        N, d = self.nchains, self.dim
+        stds, mean, mu = (_f64(np.broadcast_to(a, (N, d))) for a in (stds, mean, mean_low_rank))
+        vals = np.asarray(vals, dtype=np.float64)
+        r = vals.shape[-1] if vals.ndim else 0
+        vals = _f64(np.broadcast_to(vals.reshape((-1, r)) if vals.ndim < 2 else vals, (N, r)))
+        vecs = np.asarray(vecs, dtype=np.float64)
+        vecs = _f64(np.broadcast_to(vecs.reshape((-1, r, d)) if vecs.ndim < 3 else vecs, (N, r, d)))
+        rk = None if rank is None else np.ascontiguousarray(np.broadcast_to(rank, (N,)), dtype=np.int32)
+        ok = np.zeros(N, dtype=np.uint8)
+        _check(load().nuts_sampler_set_lowrank_transform(self.h, _p(stds), _p(mean), r, _p(vals) if r else None, _p(vecs) if r else None,
+                                                         None if rk is None else rk.ctypes.data_as(_abi.c_i32_p), _p(mu),
+                                                         ok.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return ok.astype(bool)
+
+    def set_grads_out(self, host_buffer):
+        """The gradient of logp at every draw of the following draw calls lands in `host_buffer` (a HostBuffer of shape
+        [n_draws, nchains, dim]); None switches it off."""
+        self._grads = host_buffer
+        _check(load().nuts_sampler_set_grads_out(self.h, None if host_buffer is None else host_buffer.ptr))
 
     def set_position(self, position):
         position = _f64(position).reshape(self.nchains, self.dim)

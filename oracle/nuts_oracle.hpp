@@ -1141,6 +1141,19 @@ struct NutsChain {  // chain.rs:44-61
     strategy.init(hamiltonian, position, rng);
     state = hamiltonian.init_state(position);
   }
+  // LowRankMassMatrixStrategy::update -> LowRankMassMatrix::update (adapt/low_rank.rs:54-71, low_rank.rs:158-190) with values the
+  // caller computed, followed by what GlobalStrategy::adapt does after a mass-matrix change (adapt_strategy.rs:204-214): the first
+  // change of a run re-initialises the step size from the current point.  The point is re-whitened by the next draw
+  // (initialize_trajectory, transformation id changed).
+  bool set_lowrank_transform(const Vec& stds, const Vec& mean, const Vec& vals, const Vec& vecs, const Vec& mean_low_rank) {
+    if (!hamiltonian.transformation.update_lowrank(stds, mean, vals, vecs, mean_low_rank)) return false;
+    if (strategy.has_initial_mass_matrix && strategy.tuning) {
+      strategy.has_initial_mass_matrix = false;
+      Vec position = state->untransformed_position;
+      strategy.step_size.init(hamiltonian, position.data(), rng);
+    }
+    return true;
+  }
   // chain.rs:151-188 (+ the stats of expanded_draw :190-204)
   DrawStats draw(double* position_out) {
     auto [st, info] = nuts_draw(state, rng, hamiltonian, options, collector);

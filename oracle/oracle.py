@@ -73,6 +73,8 @@ def lib():
         L.orc_ham_set_lowrank_transform.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, C.c_uint64]
         L.orc_ham_set_lowrank_transform.restype = C.c_int
         L.orc_apply_lowrank_transform.argtypes = [dp, dp, dp, dp, C.c_uint64, C.c_uint64]
+        L.orc_sampler_set_lowrank_transform.argtypes = [C.c_void_p, dp, dp, C.c_uint64, dp, dp, C.POINTER(C.c_int32), dp, C.POINTER(C.c_uint8)]
+        L.orc_sampler_set_lowrank_transform.restype = None
         L.orc_ham_update_diag_draw_grad.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_double]
         L.orc_ham_update_diag_grad.argtypes = [C.c_void_p, dp, dp, C.c_double, C.c_double, C.c_double]
         L.orc_ham_update_diag_draw.argtypes = [C.c_void_p, dp, dp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
@@ -368,6 +370,23 @@ class Sampler:
         ctr = np.empty(N, dtype=np.uint64)
         lib().orc_sampler_get_state(self.h, _p(pos), _p(eps), _p(stds), _p(mean), ctr.ctypes.data_as(_abi.c_u64_p))
         return dict(position=pos, step_size=eps, stds=stds, mean=mean, rng_counter=ctr)
+
+    def set_lowrank_transform(self, stds, mean, vals, vecs, mean_low_rank, rank=None):
+        """LowRankMassMatrix::update for every chain (vals [N, r], vecs [N, r, dim], rank [N]); the first update of a run re-runs the
+        step size search.  Returns the per-chain accepted flags."""
+        N, d = self.nchains, self.model.dim
+        stds, mean, mu = (_f64(np.broadcast_to(a, (N, d))) for a in (stds, mean, mean_low_rank))
+        vals = np.asarray(vals, dtype=np.float64)
+        r = vals.shape[-1] if vals.ndim else 0
+        vals = _f64(np.broadcast_to(vals.reshape((-1, r)) if vals.ndim < 2 else vals, (N, r)))
+        vecs = np.asarray(vecs, dtype=np.float64)
+        vecs = _f64(np.broadcast_to(vecs.reshape((-1, r, d)) if vecs.ndim < 3 else vecs, (N, r, d)))
+        rk = None if rank is None else np.ascontiguousarray(np.broadcast_to(rank, (N,)), dtype=np.int32)
+        ok = np.zeros(N, dtype=np.uint8)
+        lib().orc_sampler_set_lowrank_transform(self.h, _p(stds), _p(mean), r, _p(vals) if r else None, _p(vecs) if r else None,
+                                                None if rk is None else rk.ctypes.data_as(C.POINTER(C.c_int32)), _p(mu),
+                                                ok.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return ok.astype(bool)
 
     def set_step_size(self, eps):
         eps = _f64(np.broadcast_to(eps, (self.nchains,)))

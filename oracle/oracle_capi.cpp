@@ -501,6 +501,30 @@ void orc_sampler_set_chain_state(void* sp, const nuts_chain_state_t* in) {
     s->alive[c] = in->alive[c] ? 1 : 0;
   }
 }
+// per chain LowRankMassMatrix::update with caller-supplied values; layouts as nuts_sampler_set_lowrank_transform
+void orc_sampler_set_lowrank_transform(void* sp, const double* stds, const double* mean, uint64_t rank_max, const double* vals,
+                                       const double* vecs, const int32_t* rank, const double* mean_low_rank, uint8_t* accepted) {
+  auto* s = (Sampler*)sp;
+  const size_t d = s->dim;
+  for (uint64_t c = 0; c < s->nchains; ++c) {
+    if (!s->alive[c]) {
+      if (accepted) accepted[c] = 0;
+      continue;
+    }
+    const size_t r = rank_max == 0 ? 0 : (rank ? (size_t)rank[c] : (size_t)rank_max);
+    const double* vc = vals ? vals + c * rank_max : nullptr;
+    const double* uc = vecs ? vecs + c * rank_max * d : nullptr;
+    bool ok = false;
+    try {
+      ok = s->chains[c]->set_lowrank_transform(Vec(stds + c * d, stds + (c + 1) * d), Vec(mean + c * d, mean + (c + 1) * d),
+                                               r ? Vec(vc, vc + r) : Vec(), r ? Vec(uc, uc + r * d) : Vec(),
+                                               Vec(mean_low_rank + c * d, mean_low_rank + (c + 1) * d));
+    } catch (const BadInitGrad&) {
+      s->alive[c] = 0;
+    }
+    if (accepted) accepted[c] = ok ? 1 : 0;
+  }
+}
 void orc_sampler_set_step_size(void* sp, const double* step_size) {
   auto* s = (Sampler*)sp;
   for (uint64_t c = 0; c < s->nchains; ++c) s->chains[c]->hamiltonian.step_size = step_size[c];

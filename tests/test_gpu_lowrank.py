@@ -183,3 +183,69 @@ def test_non_finite_update_keeps_the_old_transformation_and_diag_update_drops_th
     z_diag = _point_from_x(m, x).vec(2)
     np.testing.assert_array_equal(z_diag, (x - mean) * (1.0 / stds))
     m.close()
+
+
+# ------------------------------------------------------------------------------------------------ tier 3: whole draws
+def _lr_settings(L, **kw):
+    s = L.DiagNutsSettings(**kw)
+    return s
+
+
+def _freeze_mass_matrix(s):
+    """device-side adaptation limited to the step size: no window ever switches, no update is ever due"""
+    big = 1 << 40
+    s.adapt_options.mass_matrix_update_freq = big
+    s.adapt_options.early_mass_matrix_switch_freq = big
+    s.adapt_options.mass_matrix_switch_freq = big
+    return s
+
+
+@pytest.mark.parametrize("kind,d,r,N", [(_abi.NUTS_LOGP_GAUSS_DIAG, 50, 4, 5), (_abi.NUTS_LOGP_GAUSS_RANK1, 100, 2, 4), (_abi.NUTS_LOGP_FUNNEL, 12, 3, 6),
+                                        (_abi.NUTS_LOGP_GAUSS_DIAG, 300, 9, 3), (_abi.NUTS_LOGP_GAUSS_DIAG, 1000, 6, 3)])
+@pytest.mark.parametrize("num_tune", [0, 30])
+def test_whole_draws_with_a_lowrank_transformation(L, orc, kind, d, r, N, num_tune):
+    """Chain::draw x n on an SM_LOWRANK engine against the oracle with the same per-chain transformation (installed after
+    set_position: the first update re-runs the step size search on both sides).  num_tune = 0: step size and transformation fixed,
+    every draw and statistic to 1e-9 with identical trees; num_tune = 30: dual averaging runs on top (exact-agreement prefix)."""
+    rng = np.random.default_rng(d * 7 + r + num_tune)
+    kw = {_abi.NUTS_LOGP_GAUSS_DIAG: dict(mu=0.3, sigma=np.exp(0.5 * rng.normal(size=d))), _abi.NUTS_LOGP_GAUSS_RANK1: dict(mu=0.0, rank1_scale=0.5),
+          _abi.NUTS_LOGP_FUNNEL: dict(funnel_scale=3.0)}[kind]
+    s = _freeze_mass_matrix(L.DiagNutsSettings(num_tune=num_tune, maxdepth=5))
+    m = L.CudaMath(N, d, kind, **kw)
+    smp = L.Sampler(m, s, seed=5, lowrank_rank_max=16)
+    om = orc.Model(kind, d, **kw)
+    osmp = orc.Sampler(om, s, seed=5, nchains=N, nthreads=4)
+    x0 = rng.normal(size=(N, d))
+    if kind == _abi.NUTS_LOGP_FUNNEL:
+        x0[:, 0] = 0.1
+    st, ost = smp.set_position(x0), osmp.set_position(x0)
+    np.testing.assert_array_equal(st, ost)
+    stds, mean = np.exp(0.2 * rng.normal(size=(N, d))), 0.1 * rng.normal(size=(N, d))
+    vecs = np.stack([_orthonormal(rng, d, r) for _ in range(N)])
+    vals = np.exp(0.6 * rng.normal(size=(N, r)))
+    mu_lr = 0.05 * rng.normal(size=(N, d))
+    rank = np.array([r, r - 1, 0] + [r] * (N - 3), dtype=np.int32)
+    ok = smp.set_lowrank_transform(stds, mean, vals, vecs, mu_lr, rank)
+    ook = osmp.set_lowrank_transform(stds, mean, vals, vecs, mu_lr, rank)
+    assert ok.all() and ook.all()
+    g0, o0 = smp.state(), osmp.state()
+    np.testing.assert_allclose(g0["step_size"], o0["step_size"], rtol=1e-9)  # the re-run step size search agrees
+    np.testing.assert_array_equal(g0["rng_counter"], o0["rng_counter"])
+    n = 14
+    draws, stats = smp.draw(n)
+    odraws, ostats = osmp.draw(n)
+    strict = n if num_tune == 0 and kind != _abi.NUTS_LOGP_FUNNEL else 3
+    for c in range(N):
+        same = np.ones(n, dtype=bool)
+        for name in ("depth", "n_steps", "diverging", "index_in_trajectory"):
+            same &= stats[name][:, c] == ostats[name][:, c]
+        common = n if same.all() else int(np.argmin(same))
+        assert common >= strict, f"chain {c}: tree shapes differ from draw {common}"
+        k = min(strict, common)
+        scale = np.maximum(1.0, np.abs(odraws[:k, c]))
+        assert np.max(np.abs(draws[:k, c] - odraws[:k, c]) / scale) < 1e-9, c
+        for name in ("logp", "energy", "step_size", "mean_tree_accept"):
+            a, b = stats[name][:k, c], ostats[name][:k, c]
+            assert np.all(np.abs(a - b) <= 1e-9 * np.maximum(1.0, np.abs(b))), (c, name)
+    smp.close()
+    m.close()
