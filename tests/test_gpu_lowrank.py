@@ -249,3 +249,61 @@ def test_whole_draws_with_a_lowrank_transformation(L, orc, kind, d, r, N, num_tu
             assert np.all(np.abs(a - b) <= 1e-9 * np.maximum(1.0, np.abs(b))), (c, name)
     smp.close()
     m.close()
+
+
+# ------------------------------------------------------------------------------------------------ adaptation (host estimator + GPU)
+def test_low_rank_exact_gaussian(L):
+    """The reference's end-to-end known-answer test tests/sample_normal.rs:320-356: 10-dim N(0, I + 0.5 11^T), LowRankNutsSettings with
+    num_tune = 500, eigval_cutoff = 1.00001, start at x = 1: after the warm-up the transformation whitens the target exactly, so on
+    EVERY post-warm-up draw fisher_distance = |z + grad_z|^2 < 1e-10.  Here with 6 chains (own windows, own transformations)."""
+    from nuts_rs_b200 import lowrank
+
+    N, d = 6, 10
+    m = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_RANK1, mu=0.0, rank1_scale=0.5)
+    s = L.DiagNutsSettings(num_tune=500, maxdepth=6)  # LowRankNutsSettings::default(): maxdepth 6 (sampler.rs:636-642)
+    smp = lowrank.LowRankSampler(m, s, seed=42, rank_max=10, eigval_cutoff=1.00001)
+    status = smp.set_position(np.ones((N, d)))
+    assert (status == 0).all()
+    draws, stats = smp.draw(600)
+    post = stats["tuning"] == 0
+    assert post[500:].all() and not post[:500].any()
+    fd = stats["fisher_distance"][500:]
+    assert np.isfinite(fd).all() and fd.max() < 1e-10, fd.max()
+    assert smp.updates >= N * 10 and (smp.last_ranks >= 1).all()
+    # and the draws are draws of the target: variance 1.5, covariance 0.5
+    x = draws[500:].reshape(-1, d)
+    cov = np.cov(x.T)
+    assert abs(np.mean(np.diag(cov)) - 1.5) < 0.25 and abs((cov.sum() - np.trace(cov)) / (d * d - d) - 0.5) < 0.25
+    assert stats["diverging"][500:].sum() == 0
+    # an exactly whitened Gaussian: every post-warm-up tree has the same shape
+    assert stats["depth"][500:].max() <= 3
+    smp.close()
+    m.close()
+
+
+def test_lowrank_adaptation_beats_diagonal_on_a_correlated_target(L):
+    """Config 5's target (rank-1 correlated Gaussian, here d = 100): diagonal adaptation cannot whiten it (fisher distance |z + grad_z|^2
+    of order dim), the low-rank transformation does (near zero) at no more leapfrogs per draw."""
+    from nuts_rs_b200 import lowrank
+
+    N, d = 8, 100
+    kw = dict(mu=0.0, rank1_scale=0.5)
+    s = L.DiagNutsSettings(num_tune=300, maxdepth=8)
+    m = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_RANK1, **kw)
+    lr = lowrank.LowRankSampler(m, s, seed=3, rank_max=16)
+    x0 = np.random.default_rng(0).normal(size=(N, d))
+    assert (lr.set_position(x0) == 0).all()
+    _, st_lr = lr.draw(400)
+    lr_ranks = lr.last_ranks.copy()
+    lr.close()
+    diag = L.Sampler(m, s, seed=3)
+    assert (diag.set_position(x0) == 0).all()
+    _, st_d = diag.draw(400)
+    diag.close()
+    m.close()
+    n_lr, n_d = st_lr["n_steps"][300:].mean(), st_d["n_steps"][300:].mean()
+    assert n_lr <= 1.05 * n_d, (n_lr, n_d)
+    # the estimator finds the one eigenvalue that is far from 1 (51 = 1 + 0.5 * dim in the target, rescaled by the diagonal part)
+    assert (lr_ranks == 1).all(), lr_ranks
+    f_lr, f_d = st_lr["fisher_distance"][300:], st_d["fisher_distance"][300:]
+    assert np.median(f_lr) < 0.5 * np.median(f_d) and f_lr.max() < 0.2 * f_d.max(), (np.median(f_lr), np.median(f_d), f_lr.max(), f_d.max())
