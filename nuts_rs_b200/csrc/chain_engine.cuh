@@ -2814,6 +2814,9 @@ __global__ void __launch_bounds__(TPC / cluster_size<SMF>(), 1) nuts_chain_kerne
   const unsigned B = P.draws_per_unit;
   const unsigned blocks = P.mode == 0 ? 1u : ((unsigned)P.n_draws + B - 1u) / B;
   const unsigned total_units = (unsigned)P.N * blocks;
+  // distributed shared memory may only be touched once every CTA of the cluster is running (racecheck: "block that might not have
+  // entered yet"); the exit side is covered by the two barriers of the last iteration
+  cluster_barrier();
   for (;;) {
     if (tid == 0) {
       unsigned b;

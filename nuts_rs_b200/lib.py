@@ -199,6 +199,13 @@ class Plane:
         _check(load().nuts_plane_read_from_host(self.math.h, self.h, _p(src)))
         return self
 
+    def device_ptr(self):
+        """(device address, row stride in doubles): rows are padded - chain c starts at address + 8 * c * stride
+        (nuts_plane_device_ptr; the way to share the plane with torch or another CUDA owner)."""
+        stride = C.c_uint64(0)
+        ptr = load().nuts_plane_device_ptr(self.h, C.byref(stride))
+        return int(ptr or 0), int(stride.value)
+
     def box_array(self):
         out = np.empty((self.math.nchains, self.math.dim))
         _check(load().nuts_plane_write_to_host(self.math.h, self.h, _p(out)))

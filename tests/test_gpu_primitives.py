@@ -333,3 +333,30 @@ def test_branch_free_division_and_sqrt_are_ieee_exact(L):
     with np.errstate(all="ignore"):
         assert np.array_equal(qr[d].view(np.uint64), (a[d] / b[d]).view(np.uint64))  # and the CPU's IEEE division
         assert np.array_equal(rr[s].view(np.uint64), np.sqrt(a[s]).view(np.uint64))
+
+
+@pytest.mark.parametrize("d", [10, 16, 1000, 1001])
+def test_plane_device_pointer_reports_the_padded_row_stride(L, d):
+    """nuts_plane_device_ptr: rows start on 128-byte lines (stride = dim rounded up to 16 doubles); a torch view built from the
+    pointer and the stride sees exactly what read_from_slice wrote, for dim % 16 != 0 too."""
+    import torch
+
+    N = 5
+    m = _math(L, N, d)
+    x = np.random.default_rng(d).normal(size=(N, d))
+    plane = m.new_array().read_from_slice(x)
+    ptr, stride = plane.device_ptr()
+    assert ptr != 0 and stride == (d + 15) // 16 * 16
+    # copy the padded rows out with torch (device-to-device memcpy from the raw address) and compare
+    import ctypes as C
+
+    torch.cuda.synchronize()
+    buf = torch.empty(N * stride, dtype=torch.float64, device="cuda")
+    cudart = C.CDLL("libcudart.so.12")  # (already loaded by torch / libnuts_b200.so)
+    cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    rc = cudart.cudaMemcpy(buf.data_ptr(), ptr, N * stride * 8, 3)  # cudaMemcpyDeviceToDevice
+    assert rc == 0
+    got = buf.cpu().numpy().reshape(N, stride)
+    np.testing.assert_array_equal(got[:, :d], x)
+    np.testing.assert_array_equal(got[:, d:], 0.0)  # the padding is zero
+    m.close()
