@@ -223,10 +223,30 @@ struct ChainState {
 // (random streams are keyed by the global chain id, src/sampler.rs:1105-1106, so shards reproduce the unsharded run).
 class Chains {
  public:
-  Chains(const CudaMath& math, const DiagNutsSettings& settings, uint64_t seed, uint64_t chain_id_offset = 0)
+  // lowrank_rank_max > 0: LowRankNutsSettings chains (src/sampler.rs:636-690) on an engine with the low-rank transformation
+  // compiled in; the caller's estimator installs transformations with set_lowrank_transform (nuts_rs_b200/lowrank.py is the
+  // reference's LowRankMassMatrixStrategy around this API)
+  Chains(const CudaMath& math, const DiagNutsSettings& settings, uint64_t seed, uint64_t chain_id_offset = 0, uint64_t lowrank_rank_max = 0)
       : nchains_(math.nchains()), dim_(math.dim()) {
-    check(nuts_sampler_create(math.handle(), &s_, &settings, seed, chain_id_offset));
+    if (lowrank_rank_max > 0) check(nuts_sampler_create_lowrank(math.handle(), &s_, &settings, seed, chain_id_offset, lowrank_rank_max));
+    else check(nuts_sampler_create(math.handle(), &s_, &settings, seed, chain_id_offset));
   }
+  // LowRankMassMatrix::update (src/transform/low_rank.rs:158-190) for every chain: stds / mean / mean_low_rank [nchains][dim],
+  // vals [nchains][rank_max], vecs [nchains][rank_max][dim], rank [nchains] (or empty: rank_max everywhere).  Returns the accepted
+  // flags (0: non-finite input, that chain keeps its transformation).
+  std::vector<uint8_t> set_lowrank_transform(const std::vector<double>& stds, const std::vector<double>& mean, uint64_t rank_max,
+                                             const std::vector<double>& vals, const std::vector<double>& vecs,
+                                             const std::vector<int32_t>& rank, const std::vector<double>& mean_low_rank) {
+    if (stds.size() != nchains_ * dim_ || mean.size() != stds.size() || mean_low_rank.size() != stds.size() ||
+        vals.size() != nchains_ * rank_max || vecs.size() != nchains_ * rank_max * dim_ || (!rank.empty() && rank.size() != nchains_))
+      throw Error(NUTS_ERR_INVALID, "set_lowrank_transform: array sizes do not match nchains / dim / rank_max");
+    std::vector<uint8_t> accepted(nchains_);
+    check(nuts_sampler_set_lowrank_transform(s_, stds.data(), mean.data(), rank_max, vals.data(), vecs.data(),
+                                             rank.empty() ? nullptr : rank.data(), mean_low_rank.data(), accepted.data()));
+    return accepted;
+  }
+  // gradients of the following draws into a device / page-locked buffer [n_draws][nchains][dim] (the estimator's input); nullptr: off
+  void set_grads_out(double* grads) { check(nuts_sampler_set_grads_out(s_, grads)); }
   Chains(const Chains&) = delete;
   Chains& operator=(const Chains&) = delete;
   ~Chains() {

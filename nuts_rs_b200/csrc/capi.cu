@@ -157,6 +157,7 @@ struct nuts_ctx {
   double *lr_vals_sqrt = nullptr, *lr_vals_sqrt_inv = nullptr, *lr_mu = nullptr;
   int* lr_rank = nullptr;
   int lr_rmax = 0;
+  bool lr_active = false;  // some chain may carry a low-rank correction (since the last diagonal nuts_set_transform)
   // scratch
   double* d_dense = nullptr;    // [N*d] staging for host <-> plane packing
   double* d_sc[4] = {nullptr, nullptr, nullptr, nullptr};  // [N] f64 scratch
@@ -699,6 +700,7 @@ int nuts_set_transform(nuts_ctx_t* ctx, const double* stds, const double* mean) 
   TRY(plane_from_host(ctx, ctx->T.stds, stds));
   TRY(plane_from_host(ctx, ctx->T.mean, mean));
   if (ctx->lr_rank) CUDA_TRY(cudaMemsetAsync(ctx->lr_rank, 0xff, ctx->N * sizeof(int), ctx->stream));  // inner = None (rank -1)
+  ctx->lr_active = false;
   k_set_transform<<<GRID>>>(ctx->row_args(), ctx->T, nullptr);
   CHECK_LAUNCH();
   return sync(ctx);
@@ -864,6 +866,7 @@ int nuts_set_lowrank_transform(nuts_ctx_t* ctx, const double* stds, const double
   ctx->T.lr_mu = ctx->lr_mu;
   ctx->T.lr_rank = ctx->lr_rank;
   ctx->T.lr_rmax = ctx->lr_rmax;
+  ctx->lr_active = true;
   k_set_transform<<<GRID>>>(ctx->row_args(), ctx->T, d_mask);  // diag.set_transform: inv_stds, sum ln(1 / sigma), id += 1
   CHECK_LAUNCH();
   k_add_logdet<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((int)N, ctx->T.logdet, ctx->d_sc[3]);
@@ -911,8 +914,12 @@ int nuts_leapfrog(nuts_ctx_t* ctx, const nuts_point_t* start, nuts_point_t* out,
     ddir = ctx->d_i8;
   }
   CUDA_TRY(cudaMemsetAsync(ctx->d_i32, 0, ctx->N * sizeof(int), ctx->stream));
-  k_leapfrog<<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, start->dev, out->dev, dstep, step_size_bcast, ddir, dbase, max_energy_error, dm,
-                       ctx->d_i32, ctx->d_sc[2]);
+  if (ctx->lr_active)
+    k_leapfrog<true><<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, start->dev, out->dev, dstep, step_size_bcast, ddir, dbase, max_energy_error,
+                               dm, ctx->d_i32, ctx->d_sc[2]);
+  else
+    k_leapfrog<false><<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, start->dev, out->dev, dstep, step_size_bcast, ddir, dbase, max_energy_error,
+                                dm, ctx->d_i32, ctx->d_sc[2]);
   CHECK_LAUNCH();
   if (status) CUDA_TRY(cudaMemcpyAsync(status, ctx->d_i32, ctx->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   TRY(download_f64(ctx, 2, energy_error));
@@ -1310,6 +1317,10 @@ static int run_draws(nuts_sampler* s, uint64_t n_draws, double* draws_dev, bool 
     // (measured: blocks of draws pay for tiny dims, where the hand-over is a large part of a draw: config 3 +4 % sampling, +10 %
     // tuning; config 5 shard (dim 100) -5 %; config 2 +-0)
     uint64_t b = ctx->N <= teams ? n_draws : (ctx->d <= 32 ? std::max<uint64_t>(1, std::min<uint64_t>(8, n_draws / 8)) : 1);
+    // aligned warp tilings after the warm-up: two draws per unit halve the fences / queue traffic / alignment barriers of the
+    // hand-over (config 5 sampling +7 %, dim 200 +4 %); during the warm-up one draw per unit stays better (-5 ... -9 % with two:
+    // the trees still differ in length and an aligned CTA waits for its longest unit)
+    if (b == 1 && ctx->N > teams && s->cfg->tpc == 32 && s->cfg->minb == 21 && s->draws_done >= s->settings.num_tune && n_draws >= 2) b = 2;
     if (const char* env = std::getenv("NUTS_B200_DRAWS_PER_UNIT")) b = std::max<uint64_t>(1, std::strtoull(env, nullptr, 10));
     s->P.draws_per_unit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(b, 1), std::max<uint64_t>(n_draws, 1));
   }

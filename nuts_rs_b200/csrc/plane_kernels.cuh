@@ -377,6 +377,9 @@ __global__ void __launch_bounds__(PK_THREADS) k_initialize_trajectory(RowArgs A,
 
 // Hamiltonian::leapfrog (transformed_hamiltonian.rs:524-615), Euclidean, all chains in one launch.
 // HBM traffic per chain: reads z, v, gz, stds, mean (40*d B) ; writes z', v', x', gx', gz' (40*d B).
+// (LRK = false: the low-rank branch is compiled out - 64 registers, 4 CTAs per SM; the host launches LRK = true only while some
+// chain carries a low-rank correction)
+template <bool LRK>
 __global__ void __launch_bounds__(PK_THREADS) k_leapfrog(RowArgs A, ModelDev m, TransformDev T, PointDev s, PointDev o,
                                                           const double* step_size, double step_bcast, const int8_t* dir,
                                                           const double* baseline, double max_energy_error, const uint8_t* active,
@@ -390,8 +393,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_leapfrog(RowArgs A, ModelDev m, 
   const double eps_half = eps / 2.;
   double part[2] = {0.0, 0.0};
   double lp;
-  __shared__ double coef[LR_MAX_RANK];
-  const int lr = lowrank_rank(T, c);
+  __shared__ double coef[LRK ? LR_MAX_RANK : 1];
+  const int lr = LRK ? lowrank_rank(T, c) : -1;
   const bool single_pass = ((m.kind == LOGP_GAUSS_ISO) | (m.kind == LOGP_GAUSS_DIAG)) && lr < 0;
   if (single_pass) {
     for (int i = threadIdx.x; i < d; i += PK_THREADS) {
