@@ -44,6 +44,7 @@ NB_DECL(64, 16, 31)
 NB_DECL(64, 16, 44)   // SM_EXACT + SM_ALIGN: the 4 resident 64-thread teams of an SM in one 256-thread CTA
 NB_DECL(64, 16, 54)  // SM_EXACT variant of 64x16x4 (rows padded to 1024)
 NB_DECL(64, 16, 58)  // SM_EXACT + SM_STAGE, model parameters through the read-only path (no shared-memory copy)
+NB_DECL(64, 16, 59)  // SM_EXACT + SM_STAGE + SM_STAGE1: one staging buffer, model parameters in shared memory, 4 CTAs per SM
 NB_DECL(64, 16, 55)  // + SM_NOGRAD, 5 resident CTAs per SM
 NB_DECL(64, 16, 57)  // SM_EXACT + gradient in shared memory, 200 registers: 5 resident CTAs per SM
 NB_DECL(64, 16, 56)  // + SM_NOGRAD, 6 resident CTAs per SM
@@ -132,7 +133,7 @@ const EngineConfig kLowRankConfigs[] = {NB_CFG(32, 1, 31), NB_CFG(32, 4, 31), NB
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
-const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 44), NB_CFG(32, 1, 21), NB_CFG(32, 2, 21), NB_CFG(32, 4, 21), NB_CFG(32, 8, 21), NB_CFG(32, 16, 21), NB_CFG(1024, 10, 41), NB_CFG1(768, 14, 42), NB_CFG(128, 8, 53), NB_CFG(128, 8, 52), NB_CFG(256, 4, 62), NB_CFG(256, 4, 61), NB_CFG(64, 16, 58), NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
+const EngineConfig kExtraConfigs[] = {NB_CFG(64, 16, 59), NB_CFG(64, 16, 44), NB_CFG(32, 1, 21), NB_CFG(32, 2, 21), NB_CFG(32, 4, 21), NB_CFG(32, 8, 21), NB_CFG(32, 16, 21), NB_CFG(1024, 10, 41), NB_CFG1(768, 14, 42), NB_CFG(128, 8, 53), NB_CFG(128, 8, 52), NB_CFG(256, 4, 62), NB_CFG(256, 4, 61), NB_CFG(64, 16, 58), NB_CFG(64, 16, 57), NB_CFG(64, 16, 55), NB_CFG(64, 16, 56), NB_CFG(64, 16, 54), NB_CFG1(64, 16, 107), NB_CFG1(64, 16, 117), NB_CFG1(64, 16, 127), NB_CFG1(64, 16, 144), NB_CFG1(512, 20, 161), NB_CFG1(480, 21, 171), NB_CFG1(480, 18, 181), NB_CFG1(64, 16, 155), NB_CFG(64, 16, 5), NB_CFG(64, 16, 6), NB_CFG(32, 32, 8), NB_CFG(32, 32, 7), NB_CFG(128, 8, 4), NB_CFG(64, 16, 7), NB_CFG(64, 16, 8), NB_CFG(128, 8, 5)};
 
 }  // namespace
 

@@ -296,7 +296,9 @@ static __device__ __noinline__ AccSums accept_batch(double mine, int n, double a
 // threads' elements of the shared-memory vectors, reductions go through distributed shared memory (TeamReduce, CL > 1).
 // SM_ALIGN: the warp teams of a CTA start their work units together (a CTA barrier per unit): warps that run the same code at
 // the same time share the 32 KB instruction cache of the SM - the engine's per-draw instruction working set is 80 - 140 KB.
-enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32, SM_STAGE = 64, SM_CL2 = 128, SM_CL4 = 256, SM_ALIGN = 512, SM_LOWRANK = 1024 };
+enum { SM_MASS = 1, SM_MODEL = 2, SM_GRAD = 4, SM_EXACT = 8, SM_NOGRAD = 16, SM_MODEL_GLOBAL = 32, SM_STAGE = 64, SM_CL2 = 128, SM_CL4 = 256, SM_ALIGN = 512, SM_LOWRANK = 1024, SM_STAGE1 = 2048 };
+// SM_STAGE1 (with SM_STAGE): ONE staging buffer pair instead of two (16 KB less shared memory per 1000-dim team: 4 CTAs per SM stay
+// resident next to the mass matrix and the model parameters); the end-of-tree buffer Y does not exist.
 // SM_LOWRANK: the chain's transformation may carry the low-rank correction of LowRankMassMatrix (reference src/transform/low_rank.rs):
 // x = sigma * ((I + U (sqrt(lambda) - 1) U^T) z + mu_lr) + mean.  Every leapfrog then runs the general (two-pass) path with two more
 // team-wide reductions of r values (U^T z and U^T (sigma * grad_x)); the elementwise shortcuts of the diagonal Gaussian are off.
@@ -306,7 +308,7 @@ __host__ __device__ constexpr int cluster_size() {
 }
 template <int SMF>
 __host__ __device__ constexpr int smem_vectors() {
-  return ((SMF & SM_MASS) ? 2 : 0) + ((SMF & SM_MODEL) ? 2 : 0) + ((SMF & SM_GRAD) ? 1 : 0) + ((SMF & SM_STAGE) ? 4 : 0);
+  return ((SMF & SM_MASS) ? 2 : 0) + ((SMF & SM_MODEL) ? 2 : 0) + ((SMF & SM_GRAD) ? 1 : 0) + ((SMF & SM_STAGE) ? ((SMF & 2048) ? 2 : 4) : 0);
 }
 template <int TPC, int EPT, int SMF>
 __host__ __device__ constexpr size_t team_smem_bytes() {
@@ -1185,7 +1187,7 @@ struct Engine {
   const double* stg_src[2] = {nullptr, nullptr};
   __device__ __forceinline__ const double* stage_buf(int b, int which) const { return sm_stage + (size_t)(2 * b + which) * (LT * EPT); }
   __device__ __forceinline__ void stage_pair(int b, const double* zsrc, const double* vsrc) {
-    if (!STAGE) return;
+    if (!STAGE || (b == 1 && (SMF & SM_STAGE1) != 0)) return;
     stg_src[b] = zsrc;
     const unsigned dz = (unsigned)__cvta_generic_to_shared(stage_buf(b, 0)), dv = (unsigned)__cvta_generic_to_shared(stage_buf(b, 1));
 #pragma unroll
