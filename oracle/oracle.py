@@ -75,6 +75,12 @@ def lib():
         L.orc_apply_lowrank_transform.argtypes = [dp, dp, dp, dp, C.c_uint64, C.c_uint64]
         L.orc_sampler_set_lowrank_transform.argtypes = [C.c_void_p, dp, dp, C.c_uint64, dp, dp, C.POINTER(C.c_int32), dp, C.POINTER(C.c_uint8)]
         L.orc_sampler_set_lowrank_transform.restype = None
+        L.orc_lowrank_spd_mean.argtypes = [dp, dp, C.c_uint64, dp]
+        L.orc_lowrank_spd_mean.restype = C.c_int
+        L.orc_lowrank_estimate_mass_matrix.argtypes = [dp, dp, C.c_uint64, C.c_uint64, C.c_double, dp, dp]
+        L.orc_lowrank_estimate_mass_matrix.restype = C.c_int
+        L.orc_lowrank_compute_update.argtypes = [dp, dp, C.c_uint64, C.c_uint64, C.c_double, C.c_double, dp, dp, dp, dp, dp]
+        L.orc_lowrank_compute_update.restype = C.c_int64
         L.orc_ham_update_diag_draw_grad.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_double]
         L.orc_ham_update_diag_grad.argtypes = [C.c_void_p, dp, dp, C.c_double, C.c_double, C.c_double]
         L.orc_ham_update_diag_draw.argtypes = [C.c_void_p, dp, dp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
@@ -152,6 +158,38 @@ def apply_lowrank_transform(vecs, vals, rhs):
     out = np.empty_like(rhs)
     lib().orc_apply_lowrank_transform(_p(vecs), _p(vals), _p(rhs), _p(out), len(rhs), len(vals))
     return out
+
+
+def lowrank_spd_mean(cov_draws, cov_grads):
+    """spd_mean (src/transform/adapt/low_rank.rs:241-268)."""
+    a, b = _f64(cov_draws), _f64(cov_grads)
+    out = np.empty_like(a)
+    ok = lib().orc_lowrank_spd_mean(_p(a), _p(b), a.shape[0], _p(out))
+    return out if ok else None
+
+
+def lowrank_estimate_mass_matrix(draws, grads, gamma):
+    """estimate_mass_matrix (adapt/low_rank.rs:210-239): draws, grads [k, n]; returns (vals ascending, vecs [k, k] with eigenvector j in
+    column j) or None."""
+    d, g = _f64(draws), _f64(grads)
+    k, n = d.shape
+    vals, vecs = np.empty(k), np.empty((k, k))
+    ok = lib().orc_lowrank_estimate_mass_matrix(_p(d), _p(g), k, n, gamma, _p(vals), _p(vecs))
+    return (vals, vecs) if ok else None
+
+
+def lowrank_compute_update(draws, grads, gamma=1e-5, eigval_cutoff=2.0):
+    """LowRankMassMatrixStrategy::compute_update (adapt/low_rank.rs:73-131): draws, grads [n, dim] (oldest first).  Returns
+    (stds, mean, vals [r], vecs [r, dim], mean_low_rank) or None."""
+    d_, g_ = _f64(draws), _f64(grads)
+    n, d = d_.shape
+    cap = 2 * min(n, d)
+    stds, mean, mu = np.empty(d), np.empty(d), np.empty(d)
+    vals, vecs = np.empty(cap), np.empty((cap, d))
+    r = lib().orc_lowrank_compute_update(_p(d_), _p(g_), n, d, gamma, eigval_cutoff, _p(stds), _p(mean), _p(vals), _p(vecs), _p(mu))
+    if r < 0:
+        return None
+    return stds, mean, vals[:r].copy(), vecs[:r].copy(), mu
 
 
 def vector_dot(a, b):

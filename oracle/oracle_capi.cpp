@@ -7,6 +7,7 @@
 
 #include "../include/nuts_b200.h"
 #include "nuts_oracle.hpp"
+#include "lowrank_estimator.hpp"
 
 using namespace oracle;
 
@@ -500,6 +501,41 @@ void orc_sampler_set_chain_state(void* sp, const nuts_chain_state_t* in) {
     ch.hamiltonian.n_leapfrogs = in->total_leapfrogs[c];
     s->alive[c] = in->alive[c] ? 1 : 0;
   }
+}
+// ---------------- low-rank estimator (src/transform/adapt/low_rank.rs:73-268)
+// spd_mean of two n x n matrices (row-major = column-major: symmetric); returns 0 on failure
+int orc_lowrank_spd_mean(const double* cov_draws, const double* cov_grads, uint64_t n, double* out) {
+  oracle::lowrank::Mat a(n, n), b(n, n), o;
+  std::copy(cov_draws, cov_draws + n * n, a.a.begin());
+  std::copy(cov_grads, cov_grads + n * n, b.a.begin());
+  if (!oracle::lowrank::spd_mean(a, b, o)) return 0;
+  std::copy(o.a.begin(), o.a.end(), out);
+  return 1;
+}
+// estimate_mass_matrix: draws, grads [k][n] row-major; vals [k] ascending, vecs [k][k] (eigenvector j = column j, row-major)
+int orc_lowrank_estimate_mass_matrix(const double* draws, const double* grads, uint64_t k, uint64_t n, double gamma, double* vals, double* vecs) {
+  oracle::lowrank::Mat d(k, n), g(k, n), v;
+  for (uint64_t i = 0; i < k; ++i)
+    for (uint64_t j = 0; j < n; ++j) d(i, j) = draws[i * n + j], g(i, j) = grads[i * n + j];
+  std::vector<double> w;
+  if (!oracle::lowrank::estimate_mass_matrix(d, g, gamma, w, v)) return 0;
+  for (uint64_t i = 0; i < k; ++i) {
+    vals[i] = w[i];
+    for (uint64_t j = 0; j < k; ++j) vecs[i * k + j] = v(i, j);
+  }
+  return 1;
+}
+// compute_update: draws, grads [n][d]; outputs stds / mean / mu [d], vals [<= 2 n], vecs [<= 2 n][d]; returns the rank or -1
+int64_t orc_lowrank_compute_update(const double* draws, const double* grads, uint64_t n, uint64_t d, double gamma, double cutoff, double* stds,
+                                   double* mean, double* vals, double* vecs, double* mu) {
+  oracle::lowrank::Update u;
+  if (!oracle::lowrank::compute_update(draws, grads, n, d, gamma, cutoff, u)) return -1;
+  std::copy(u.stds.begin(), u.stds.end(), stds);
+  std::copy(u.mean.begin(), u.mean.end(), mean);
+  std::copy(u.vals.begin(), u.vals.end(), vals);
+  std::copy(u.vecs.begin(), u.vecs.end(), vecs);
+  std::copy(u.mu.begin(), u.mu.end(), mu);
+  return (int64_t)u.vals.size();
 }
 // per chain LowRankMassMatrix::update with caller-supplied values; layouts as nuts_sampler_set_lowrank_transform
 void orc_sampler_set_lowrank_transform(void* sp, const double* stds, const double* mean, uint64_t rank_max, const double* vals,

@@ -1,6 +1,7 @@
 """Pins the oracle's low-rank mass matrix (oracle/nuts_oracle.hpp: apply_lowrank_transform, LowRankInner, DiagMassMatrix::inner)
 against the reference's known-answer tests: src/transform/low_rank.rs:437-533 (round trips) and src/transform/mod.rs:383-674
-(position / gradient / logdet / adapted density, rank-1 correction, non-zero mean), all to 1e-12."""
+(position / gradient / logdet / adapted density, rank-1 correction, non-zero mean), all to 1e-12; and the restated estimator
+(oracle/lowrank_estimator.hpp) against src/transform/adapt/low_rank.rs:354-407 and the product's numpy estimator."""
 import math
 
 import numpy as np
@@ -145,3 +146,69 @@ def test_non_finite_update_is_ignored_and_diag_update_drops_the_correction(orc):
     ham.init_from_untransformed(p)
     t = ham.transform()
     np.testing.assert_allclose(p.vec(p.Z), (np.array([2.0, 1.0, 1.0]) - t["mean"]) * t["inv_stds"], atol=1e-15, rtol=0)
+
+
+# ------------------------------------------------------------------------------------------------ the estimator
+def test_estimator_spd_mean_known_answer(orc):
+    # adapt/low_rank.rs:354-381
+    out = orc.lowrank_spd_mean(np.diag([1.0, 4.0, 8.0]), np.diag([1.0, 1.0, 0.5]))
+    np.testing.assert_allclose(out, np.diag([1.0, 2.0, 4.0]), rtol=1e-10, atol=1e-10)
+
+
+def test_estimator_estimate_mass_matrix_known_answer(orc):
+    # adapt/low_rank.rs:383-407: grads = -draws => every eigenvalue is 1 to 1e-5
+    rng = np.random.default_rng(1)
+    draws = rng.normal(size=(20, 3))
+    vals, vecs = orc.lowrank_estimate_mass_matrix(draws, -draws, 0.0001)
+    assert (vals > 0).all() and np.isfinite(vecs).all()
+    np.testing.assert_allclose(vals, np.ones(20), rtol=1e-5, atol=1e-5)
+
+
+def _lowrank_operator(vals, vecs, d):
+    return np.eye(d) + vecs.T @ np.diag(vals - 1.0) @ vecs
+
+
+def test_product_estimator_agrees_with_the_restatement(orc):
+    """nuts_rs_b200/lowrank.py (numpy / scipy factorisations) against the C++ restatement (own Jacobi factorisations): eigenvector
+    signs, order and the basis of degenerate eigenspaces are conventions, the transformation is not - compare sigma, mean, mu_lr,
+    the sorted eigenvalues and I + U (diag(vals) - I) U^T."""
+    from nuts_rs_b200 import lowrank
+
+    rng = np.random.default_rng(11)
+    for d, n, cutoff in [(10, 40, 1.00001), (30, 12, 2.0), (6, 6, 1.5), (50, 25, 2.0)]:
+        cov = np.eye(d) + 0.5 * np.ones((d, d)) + np.diag(rng.uniform(0.0, 3.0, size=d))
+        m = rng.normal(size=d)
+        x = m + rng.multivariate_normal(np.zeros(d), cov, size=n)
+        g = -(x - m) @ np.linalg.inv(cov) + (0.01 * rng.normal(size=(n, d)) if n < d else 0.0)
+        a = lowrank.compute_update(x, g, gamma=1e-5, eigval_cutoff=cutoff)
+        b = orc.lowrank_compute_update(x, g, gamma=1e-5, eigval_cutoff=cutoff)
+        assert a is not None and b is not None
+        np.testing.assert_allclose(a[0], b[0], rtol=1e-10)  # stds
+        np.testing.assert_allclose(a[1], b[1], rtol=1e-10, atol=1e-12)  # mean
+        assert len(a[2]) == len(b[2]), (d, n, a[2], b[2])
+        # A window that spans the space (n > d) determines everything: agreement to rounding.  With n <= d the centred window has
+        # rank n - 1 and the thin SVD returns one singular vector of singular value ~0 - an arbitrary direction of the null space
+        # (LAPACK, faer and the restatement each pick their own; the restatement drops it) - that enters the joint subspace, and the
+        # 1 / gamma = 1e5 regularisation gives the geometric mean a condition number of ~1e14: the estimate itself is only defined to
+        # ~1e-2 there.
+        tol = 1e-9 if n > d else 1e-2
+        np.testing.assert_allclose(np.sort(a[2]), np.sort(b[2]), rtol=tol)
+        np.testing.assert_allclose(_lowrank_operator(a[2], a[3], d), _lowrank_operator(b[2], b[3], d), rtol=tol, atol=tol)
+        np.testing.assert_allclose(a[4], b[4], rtol=tol, atol=tol)  # mean_low_rank
+
+
+def test_restated_estimator_whitens_an_exact_gaussian(orc):
+    # the property behind tests/sample_normal.rs:320-356 (see tests/test_lowrank_estimator.py for the product side)
+    rng = np.random.default_rng(2)
+    d, n = 10, 40
+    cov = np.eye(d) + 0.5 * np.ones((d, d))
+    prec = np.linalg.inv(cov)
+    x = rng.multivariate_normal(np.zeros(d), cov, size=n)
+    stds, mean, vals, vecs, mu = orc.lowrank_compute_update(x, -x @ prec, gamma=1e-5, eigval_cutoff=1.00001)
+    a_fwd = np.eye(d) + vecs.T @ np.diag(np.sqrt(vals) - 1.0) @ vecs
+    a_inv = np.eye(d) + vecs.T @ np.diag(1.0 / np.sqrt(vals) - 1.0) @ vecs
+    for _ in range(5):
+        xt = rng.multivariate_normal(np.zeros(d), cov)
+        z = a_inv @ ((xt - mean) / stds - mu)
+        gz = a_fwd @ ((-prec @ xt) * stds)
+        assert np.sum((z + gz) ** 2) < 1e-10
