@@ -130,6 +130,11 @@ const EngineConfig kClusterLarge = NB_CFG(1024, 10, 41);
 const EngineConfig kAlignedConfigs[] = {NB_CFG(32, 1, 21), NB_CFG(32, 2, 21), NB_CFG(32, 4, 21), NB_CFG(32, 8, 21), NB_CFG(32, 16, 21)};
 // engines with the low-rank transformation compiled in (nuts_sampler_create_lowrank)
 const EngineConfig kLowRankConfigs[] = {NB_CFG(32, 1, 31), NB_CFG(32, 4, 31), NB_CFG(32, 16, 31), NB_CFG(64, 16, 31)};
+// warm-up build of the exact 64x16 tiling: the four resident teams of an SM in ONE 256-thread CTA that starts its work units together
+// (SM_ALIGN, named barriers per team).  During the warm-up every draw ends in ~1500 instructions of adaptation code that sweep the
+// 32 KB instruction cache; teams in lock-step share those fetches: config 2's 400-draw warm-up 80.6 -> 73.1 ms with two draws per
+// unit.  After the warm-up the plain build is 1-4 % faster (no alignment barrier), so the choice is made per launch.
+const EngineConfig kExactTuneConfig = NB_CFG(64, 16, 44);
 // SM_EXACT variants of default tilings (tag = 50 + min blocks), chosen automatically when dim nearly fills the tile
 const EngineConfig kExactConfigs[] = {NB_CFG(64, 16, 54)};
 // alternatives selectable with NUTS_B200_ENGINE="tpc,ept,minb" (tuning experiments)
@@ -181,6 +186,9 @@ struct nuts_sampler {
   const EngineConfig* cfg = nullptr;
   int model_variant = 0;  // index into cfg->launch
   int grid = 0;
+  // launches that lie entirely inside the warm-up use this build when set (same tiling and memory layout, other CTA shape)
+  const EngineConfig* cfg_tune = nullptr;
+  int grid_tune = 0;
   int teams_per_cta = 1;
   uint64_t resident_teams = 1;
   std::vector<void*> allocations;
@@ -1115,6 +1123,19 @@ static int sampler_create_impl(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts
   }
   s->teams_per_cta = teams_per_cta;
   s->resident_teams = resident_teams;
+  if (cfg == &kExactConfigs[0] && lowrank_rmax == 0 && kExactTuneConfig.launch[s->model_variant] && !std::getenv("NUTS_B200_GRID") &&
+      !(std::getenv("NUTS_B200_TUNE_ENGINE") && std::atoi(std::getenv("NUTS_B200_TUNE_ENGINE")) == 0)) {
+    int b2 = 0, t2 = 0, f2 = 0;
+    CUDA_TRY(kExactTuneConfig.occupancy[s->model_variant](&b2, &t2, &f2));
+    const int teams2 = t2 / kExactTuneConfig.tpc;
+    const uint64_t ctas2 = (ctx->N + teams2 - 1) / teams2;
+    const int grid2 = (int)std::min<uint64_t>(ctas2, (uint64_t)std::max(b2, 0) * ctx->num_sms);
+    // same pools, same padded rows: only usable when it keeps exactly the resident teams the memory was sized for
+    if (b2 >= 1 && (f2 & SM_EXACT) && (uint64_t)grid2 * teams2 == resident_teams && ctx->N > resident_teams) {
+      s->cfg_tune = &kExactTuneConfig;
+      s->grid_tune = grid2;
+    }
+  }
   const size_t plane = ctx->N * (size_t)P.ld * sizeof(double);
   const size_t team_plane = resident_teams * (size_t)P.ld * sizeof(double);  // one row per resident team
   int r = NUTS_OK;
@@ -1205,13 +1226,14 @@ int nuts_sampler_destroy(nuts_sampler_t* s) {
   return NUTS_OK;
 }
 
-static int launch_engine(nuts_sampler* s) {
+static int launch_engine(nuts_sampler* s, bool tuning_build = false) {
   nuts_ctx* ctx = s->ctx;
   CUDA_TRY(cudaMemsetAsync(s->P.queue, 0, 2 * sizeof(unsigned int), ctx->stream));
   CUDA_TRY(cudaMemsetAsync(s->P.done, 0, ctx->N * sizeof(unsigned int), ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(s->P.ring_seq, s->d_ring_template, ((size_t)s->P.ring_mask + 1) * sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
   CUDA_TRY(cudaEventRecord(s->ev0, ctx->stream));
-  CUDA_TRY(s->cfg->launch[s->model_variant](&s->P, s->grid, ctx->stream));
+  if (tuning_build && s->cfg_tune) CUDA_TRY(s->cfg_tune->launch[s->model_variant](&s->P, s->grid_tune, ctx->stream));
+  else CUDA_TRY(s->cfg->launch[s->model_variant](&s->P, s->grid, ctx->stream));
   CUDA_TRY(cudaEventRecord(s->ev1, ctx->stream));
   s->last_launches += 1;
   return NUTS_OK;
@@ -1311,6 +1333,7 @@ static int run_draws(nuts_sampler* s, uint64_t n_draws, double* draws_dev, bool 
   s->P.init_position = nullptr;
   s->P.status_out = nullptr;
   s->P.n_draws = n_draws;
+  bool tuning_build = false;
   {
     // draws per work unit: the whole call when every chain has its own team (no hand-over at all), else one draw - or a few
     // for tiny dims; NUTS_B200_DRAWS_PER_UNIT overrides (experiments)
@@ -1322,12 +1345,15 @@ static int run_draws(nuts_sampler* s, uint64_t n_draws, double* draws_dev, bool 
     // hand-over (config 5 sampling +7 %, dim 200 +4 %); during the warm-up one draw per unit stays better (-5 ... -9 % with two:
     // the trees still differ in length and an aligned CTA waits for its longest unit)
     if (b == 1 && ctx->N > teams && s->cfg->tpc == 32 && s->cfg->minb == 21 && s->draws_done >= s->settings.num_tune && n_draws >= 2) b = 2;
+    // a launch inside the warm-up on the aligned warm-up build (kExactTuneConfig): two draws per unit there as well
+    tuning_build = s->cfg_tune != nullptr && s->draws_done + n_draws <= s->settings.num_tune;
+    if (tuning_build && b == 1 && n_draws >= 2) b = 2;
     if (const char* env = std::getenv("NUTS_B200_DRAWS_PER_UNIT")) b = std::max<uint64_t>(1, std::strtoull(env, nullptr, 10));
     s->P.draws_per_unit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(b, 1), std::max<uint64_t>(n_draws, 1));
   }
   s->P.draws_out = draws_dev;
   s->P.stats = want_stats ? s->d_stats : StatsDev{};
-  TRY(launch_engine(s));
+  TRY(launch_engine(s, tuning_build));
   s->draws_done += n_draws;
   (void)ctx;
   return NUTS_OK;

@@ -110,3 +110,38 @@ def test_aligned_warp_tilings_bit_identical(L, kind, d, N):
     assert np.array_equal(ref[1], got[1], equal_nan=True), "draws differ"
     for k in ref[2]:
         assert np.array_equal(ref[2][k], got[2][k], equal_nan=True), k
+
+
+def test_warm_up_build_is_bit_identical(L):
+    """dim ~ 1000 with more chains than resident teams: launches inside the warm-up run the aligned build of the exact 64x16 tiling
+    (four teams per CTA, named barriers, two draws per unit), everything else the plain one; NUTS_B200_TUNE_ENGINE=0 keeps the plain
+    build throughout.  Same arithmetic: draws, statistics and leapfrog counts agree bit for bit, across the hand-over between the
+    builds in the middle of the run."""
+    N, d = 1300, 1000
+
+    def run(flag):
+        old = os.environ.get("NUTS_B200_TUNE_ENGINE")
+        os.environ["NUTS_B200_TUNE_ENGINE"] = flag
+        try:
+            m = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_DIAG, mu=0.5, sigma=np.exp(np.linspace(-1, 1, d)))
+            s = L.Sampler(m, L.DiagNutsSettings(num_tune=24, maxdepth=6), seed=7)
+            status = s.set_position(np.random.default_rng(1).normal(size=(N, d)))
+            parts = [s.draw(k) for k in (10, 14, 3, 9)]  # two warm-up launches (aligned build), then sampling launches
+            lf, _ = s.counters()
+            s.close()
+            m.close()
+            draws = np.concatenate([p[0] for p in parts])
+            stats = {k: np.concatenate([p[1][k] for p in parts]) for k in parts[0][1]}
+            return status, draws, stats, lf
+        finally:
+            if old is None:
+                os.environ.pop("NUTS_B200_TUNE_ENGINE", None)
+            else:
+                os.environ["NUTS_B200_TUNE_ENGINE"] = old
+
+    ref, got = run("0"), run("1")
+    assert np.array_equal(ref[0], got[0]) and ref[3] == got[3]
+    assert np.array_equal(ref[1], got[1], equal_nan=True), "draws differ"
+    for k in ref[2]:
+        assert np.array_equal(ref[2][k], got[2][k], equal_nan=True), k
+    assert ref[2]["tuning"][:24].all() and not ref[2]["tuning"][24:].any()
