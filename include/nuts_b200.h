@@ -327,7 +327,9 @@ int nuts_sampler_set_chain_state(nuts_sampler_t*, const nuts_chain_state_t* in);
  * mean_low_rank) and installs them with nuts_sampler_set_lowrank_transform == LowRankMassMatrix::update (low_rank.rs:158-190) for
  * every chain (arguments as nuts_set_lowrank_transform).  The first update of a run re-runs the step size search from the current
  * point (adapt_strategy.rs:204-214).  The device-side adaptation of such a sampler should be limited to the step size: set
- * mass_matrix_update_freq / early_mass_matrix_switch_freq / mass_matrix_switch_freq beyond num_tune (nuts_rs_b200/lowrank.py does). */
+ * mass_matrix_update_freq / early_mass_matrix_switch_freq / mass_matrix_switch_freq beyond num_tune (nuts_rs_b200/lowrank.py does).
+ * Checkpoints: nuts_sampler_get/set_chain_state carry the diagonal part and all scalars; the caller keeps (vals, vecs, mean_low_rank) of
+ * its last update and re-installs them BEFORE nuts_sampler_set_chain_state when it restores a run. */
 int nuts_sampler_create_lowrank(nuts_ctx_t*, nuts_sampler_t** sampler, const nuts_settings_t* settings, uint64_t seed, uint64_t chain_id_offset,
                                 uint64_t rank_max);
 int nuts_sampler_set_lowrank_transform(nuts_sampler_t*, const double* stds, const double* mean, uint64_t rank_max, const double* vals,

@@ -4,7 +4,8 @@ reductions (double-buffered shared scratch, one barrier), the decoupled engine's
 
   compute-sanitizer --tool racecheck python tools/sanitize_run.py <case>
 cases: c1 (warp teams, 4 chains x d=10), migrate (d=1000, 64x16 CTA teams, more chains than one wave of teams via NUTS_B200_GRID),
-       large (large-dim engine, d=5000), funnel, rank1, cluster (rank-1 at d=4200: one chain on the 4 CTAs of a cluster, DSMEM reductions)"""
+       large (large-dim engine, d=5000), funnel, rank1, cluster (rank-1 at d=4200: one chain on the 4 CTAs of a cluster, DSMEM reductions),
+       tunebuild (640 chains x d=1000 on the full grid: aligned warm-up build, then the plain one), lowrank (SM_LOWRANK engine)"""
 import os
 import sys
 
@@ -21,13 +22,28 @@ shapes = {
     "funnel": (_abi.NUTS_LOGP_FUNNEL, 64, 10, dict(funnel_scale=3.0), 10, 6),
     "rank1": (_abi.NUTS_LOGP_GAUSS_RANK1, 24, 100, dict(mu=0.0, rank1_scale=0.5), 8, 5),
     "cluster": (_abi.NUTS_LOGP_GAUSS_RANK1, 3, 4200, dict(mu=0.0, rank1_scale=0.5), 4, 3),
+    # full grid (no NUTS_B200_GRID): more chains than the 592 resident teams, so the warm-up launch runs the aligned four-team build
+    # (named barriers per team + the CTA alignment barrier) and hands over to the plain build afterwards
+    "tunebuild": (_abi.NUTS_LOGP_GAUSS_DIAG, 640, 1000, dict(mu=0.5, sigma=np.exp(np.linspace(-1, 1, 1000))), 3, 3),
+    "lowrank": (_abi.NUTS_LOGP_GAUSS_RANK1, 12, 100, dict(mu=0.0, rank1_scale=0.5), 4, 4),
 }
 kind, N, d, mk, tune, maxdepth = shapes[case]
+if case == "tunebuild":
+    os.environ.pop("NUTS_B200_GRID", None)
 s = lib.DiagNutsSettings(num_tune=tune, maxdepth=maxdepth)
 m = lib.CudaMath(N, d, kind, **mk)
-S = lib.Sampler(m, s, seed=3)
+S = lib.Sampler(m, s, seed=3, lowrank_rank_max=4 if case == "lowrank" else 0)
 st = S.set_position(np.random.default_rng(3).normal(size=(N, d)))
-draws, stats = S.draw(tune + 4)
+if case == "lowrank":  # a rank-2 transformation on the SM_LOWRANK engine (eigenvector reductions inside the leapfrog, kernel mode 2)
+    rng = np.random.default_rng(4)
+    vecs = np.stack([np.ascontiguousarray(np.linalg.qr(rng.normal(size=(d, 2)))[0].T) for _ in range(N)])
+    S.set_lowrank_transform(np.ones((N, d)), np.zeros((N, d)), np.exp(rng.normal(size=(N, 2))), vecs, np.zeros((N, d)))
+if case == "tunebuild":
+    d1, s1 = S.draw(tune)       # the warm-up launch: aligned build
+    d2, s2 = S.draw(2)          # plain build
+    draws, stats = np.concatenate([d1, d2]), {k: np.concatenate([s1[k], s2[k]]) for k in s1}
+else:
+    draws, stats = S.draw(tune + 4)
 print(case, "ok: leapfrogs", int(stats["n_steps"].sum()), "finite", bool(np.isfinite(draws[:, st == 0]).all()))
 S.close()
 m.close()
