@@ -69,19 +69,24 @@ typedef struct {
 /* ---- settings: NutsSettings<EuclideanAdaptOptions<DiagAdaptExpSettings>> field for field --------------------
  * reference src/sampler.rs:199-239 (NutsSettings), src/adapt_strategy.rs:41-69 (EuclideanAdaptOptions),
  * src/stepsize/adapt.rs:308-329 (StepSizeSettings), :21-49 (StepSizeAdaptOptions / Method),
- * src/stepsize/dual_avg.rs:11-31 (DualAverageOptions), src/transform/adapt/diagonal.rs:93-106 (DiagAdaptExpSettings). */
-enum { NUTS_STEPSIZE_DUAL_AVERAGE = 0, NUTS_STEPSIZE_FIXED = 2 /* Adam (1) is out of scope */ };
+ * src/stepsize/dual_avg.rs:11-31 (DualAverageOptions), src/stepsize/adam.rs:13-34 (AdamOptions), src/transform/adapt/diagonal.rs:93-106 (DiagAdaptExpSettings). */
+enum { NUTS_STEPSIZE_DUAL_AVERAGE = 0, NUTS_STEPSIZE_ADAM = 1, NUTS_STEPSIZE_FIXED = 2 };
 enum { NUTS_KINETIC_EUCLIDEAN = 0 /* ExactNormal / Microcanonical are out of scope */ };
 
 typedef struct {
   double k, t0, gamma, max_step_size;
 } nuts_dual_average_options_t;
 
+typedef struct { /* AdamOptions (src/stepsize/adam.rs:13-34); defaults 0.9, 0.999, 1e-8, 0.05 */
+  double beta1, beta2, epsilon, learning_rate;
+} nuts_adam_options_t;
+
 typedef struct {
   int32_t method;    /* NUTS_STEPSIZE_* */
   int32_t _pad;
   double fixed_step; /* StepSizeAdaptMethod::Fixed(val) */
   nuts_dual_average_options_t dual_average;
+  nuts_adam_options_t adam;
 } nuts_step_size_adapt_options_t;
 
 typedef struct {

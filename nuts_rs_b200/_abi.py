@@ -14,6 +14,7 @@ NUTS_LOGP_FUNNEL = 3
 NUTS_LOGP_USER = 4
 
 NUTS_STEPSIZE_DUAL_AVERAGE = 0
+NUTS_STEPSIZE_ADAM = 1
 NUTS_STEPSIZE_FIXED = 2
 
 NUTS_STATUS_OK = 0
@@ -49,12 +50,17 @@ class DualAverageOptions(C.Structure):
     _fields_ = [("k", C.c_double), ("t0", C.c_double), ("gamma", C.c_double), ("max_step_size", C.c_double)]
 
 
+class AdamOptions(C.Structure):
+    _fields_ = [("beta1", C.c_double), ("beta2", C.c_double), ("epsilon", C.c_double), ("learning_rate", C.c_double)]
+
+
 class StepSizeAdaptOptions(C.Structure):
     _fields_ = [
         ("method", C.c_int32),
         ("_pad", C.c_int32),
         ("fixed_step", C.c_double),
         ("dual_average", DualAverageOptions),
+        ("adam", AdamOptions),
     ]
 
 
@@ -216,6 +222,8 @@ def default_settings() -> NutsSettings:
     ss.adapt_options.dual_average.t0 = 10.0
     ss.adapt_options.dual_average.gamma = 0.05
     ss.adapt_options.dual_average.max_step_size = 3.141592653589793
+    ss.adapt_options.adam.beta1, ss.adapt_options.adam.beta2 = 0.9, 0.999  # AdamOptions::default (src/stepsize/adam.rs:25-34)
+    ss.adapt_options.adam.epsilon, ss.adapt_options.adam.learning_rate = 1e-8, 0.05
     return s
 
 

@@ -331,6 +331,7 @@ void nuts_settings_default(nuts_settings_t* s) {
   a.step_size_settings.has_jitter = 1;
   a.step_size_settings.jitter = 0.1;
   a.step_size_settings.adapt_options.method = NUTS_STEPSIZE_DUAL_AVERAGE;
+  a.step_size_settings.adapt_options.adam = nuts_adam_options_t{0.9, 0.999, 1e-8, 0.05};  // AdamOptions::default (adam.rs:25-34)
   a.step_size_settings.adapt_options.dual_average = {0.75, 10., 0.05, 3.14159265358979323846};  // src/stepsize/dual_avg.rs:22-31
 }
 
@@ -963,8 +964,8 @@ static ChainState fresh_chain_state(const SettingsDev& S) {
   c.da_log_step = std::log(S.initial_step);
   c.da_log_step_adapted = std::log(S.initial_step);
   c.da_hbar = 0.0;
-  c.da_mu = std::log(10.0 * S.initial_step);
-  c.da_count = 1;
+  c.da_mu = S.method == 1 ? 0.0 : std::log(10.0 * S.initial_step);  // Adam::new (adam.rs:57-65): m = v = 0, t = 0
+  c.da_count = S.method == 1 ? 0 : 1;
   c.tuning = 1;
   c.has_initial_mass_matrix = 1;
   c.current_window_size = S.mm_switch_freq;
@@ -979,8 +980,8 @@ static int sampler_create_impl(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts
   if (!st) return fail(NUTS_ERR_INVALID, "nuts_sampler_create: settings is NULL");
   if (st->trajectory_kind != NUTS_KINETIC_EUCLIDEAN) return fail(NUTS_ERR_UNSUPPORTED, "only KineticEnergyKind::Euclidean is supported");
   const int method = st->adapt_options.step_size_settings.adapt_options.method;
-  if (method != NUTS_STEPSIZE_DUAL_AVERAGE && method != NUTS_STEPSIZE_FIXED)
-    return fail(NUTS_ERR_UNSUPPORTED, "step size method %d not supported (DualAverage and Fixed only)", method);
+  if (method != NUTS_STEPSIZE_DUAL_AVERAGE && method != NUTS_STEPSIZE_ADAM && method != NUTS_STEPSIZE_FIXED)
+    return fail(NUTS_ERR_INVALID, "unknown step size method %d", method);
   if (st->maxdepth + st->extra_doublings > (uint64_t)MAX_DOUBLING_DEPTH)
     return fail(NUTS_ERR_UNSUPPORTED, "maxdepth + extra_doublings must be <= %d", MAX_DOUBLING_DEPTH);
   if (st->adapt_options.mass_matrix_window_growth < 1.0) return fail(NUTS_ERR_INVALID, "mass_matrix_window_growth must be >= 1");
@@ -1086,6 +1087,10 @@ static int sampler_create_impl(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts
   S.has_jitter = a.step_size_settings.has_jitter;
   S.jitter = a.step_size_settings.jitter;
   S.method = method;
+  S.adam_beta1 = a.step_size_settings.adapt_options.adam.beta1;
+  S.adam_beta2 = a.step_size_settings.adapt_options.adam.beta2;
+  S.adam_epsilon = a.step_size_settings.adapt_options.adam.epsilon;
+  S.adam_lr = a.step_size_settings.adapt_options.adam.learning_rate;
   S.fixed_step = a.step_size_settings.adapt_options.fixed_step;
   S.da_k = a.step_size_settings.adapt_options.dual_average.k;
   S.da_t0 = a.step_size_settings.adapt_options.dual_average.t0;

@@ -45,7 +45,8 @@ struct SettingsDev {
   int check_turning, has_target_time;
   double target_time;
   double target_accept, initial_step;
-  int has_jitter, method;  // method: 0 dual average, 2 fixed
+  int has_jitter, method;  // method: 0 dual average, 1 Adam, 2 fixed
+  double adam_beta1, adam_beta2, adam_epsilon, adam_lr;
   double jitter, fixed_step;
   double da_k, da_t0, da_gamma, da_max_step;
   int use_grad_based, _pad;
@@ -1531,15 +1532,34 @@ struct Engine {
   }
 
   // ------------------------------------------------------------------ DualAverage (dual_avg.rs:33-81)
+  // (Adam, stepsize/adam.rs:55-115, lives in the same record: log_step, m = da_hbar, v = da_mu, t = da_count; log_step_adapted
+  // mirrors log_step, which is what step_size_bar and the post-warm-up step size are for Adam, stepsize/adapt.rs:256, 288)
   __device__ __forceinline__ void da_new(double initial_step) {
     cs.da_log_step = log(initial_step);
     cs.da_log_step_adapted = log(initial_step);
+    if (P.s.method == 1) {
+      cs.da_hbar = 0.;
+      cs.da_mu = 0.;
+      cs.da_count = 0;
+      return;
+    }
     cs.da_hbar = 0.;
     cs.da_mu = log(10. * initial_step);
     cs.da_count = 1;
   }
   __device__ __forceinline__ void da_advance(double accept_stat) {
-    if (P.s.method != 0) return;
+    if (P.s.method == 2) return;
+    if (P.s.method == 1) {  // Adam::advance
+      const double gradient = accept_stat - P.s.target_accept;
+      cs.da_count += 1;
+      cs.da_hbar = P.s.adam_beta1 * cs.da_hbar + (1.0 - P.s.adam_beta1) * gradient;
+      cs.da_mu = P.s.adam_beta2 * cs.da_mu + (1.0 - P.s.adam_beta2) * gradient * gradient;
+      const double m_hat = cs.da_hbar / (1.0 - powi_ref(P.s.adam_beta1, (int)cs.da_count));
+      const double v_hat = cs.da_mu / (1.0 - powi_ref(P.s.adam_beta2, (int)cs.da_count));
+      cs.da_log_step += P.s.adam_lr * m_hat / (sqrt(v_hat) + P.s.adam_epsilon);
+      cs.da_log_step_adapted = cs.da_log_step;
+      return;
+    }
     double cnt = (double)cs.da_count;
     double w = 1. / (cnt + P.s.da_t0);
     cs.da_hbar = (1. - w) * cs.da_hbar + w * (P.s.target_accept - accept_stat);
@@ -1551,7 +1571,7 @@ struct Engine {
   }
   // Strategy::update_stepsize (stepsize/adapt.rs:235-267)
   __device__ __forceinline__ void update_stepsize(bool use_best_guess) {
-    double step = P.s.method != 0 ? P.s.fixed_step : (use_best_guess ? exp(cs.da_log_step_adapted) : exp(cs.da_log_step));
+    double step = P.s.method == 2 ? P.s.fixed_step : (use_best_guess ? exp(cs.da_log_step_adapted) : exp(cs.da_log_step));
     if (P.s.has_jitter) {
       double lo = 1.0 - P.s.jitter, hi = 1.0 + P.s.jitter;
       double j = fma(hi - lo, rng_f64(), lo);
@@ -1565,7 +1585,7 @@ struct Engine {
   // Doubling / halving search from the chain's current position (x, gx planes, hs_logp).  Returns false when
   // init_state fails check_all (NutsError::BadInitGrad).  Uses the ends[0] buffers as scratch for the start state.
   __device__ __forceinline__ bool stepsize_search() {
-    if (P.s.method != 0) {
+    if (P.s.method == 2) {
       hs_step = P.s.fixed_step;
       return true;
     }
@@ -2012,7 +2032,7 @@ struct Engine {
     // ChainState through the cold function (same arithmetic, same random stream: bit-identical to the cold path)
     if (hs_draw_count >= P.s.num_tune) {
       const double mta = acc_sum / (double)acc_count, msa = acc_sym_sum / (double)acc_count;
-      const double step_bar = P.s.method != 0 ? P.s.fixed_step : exp(hs_da_lsa);
+      const double step_bar = P.s.method == 2 ? P.s.fixed_step : exp(hs_da_lsa);
       if (P.s.has_jitter) {
         const double lo = 1.0 - P.s.jitter, hi = 1.0 + P.s.jitter;
         hs_step = step_bar * fma(hi - lo, rng_f64(), lo);
@@ -2511,7 +2531,7 @@ struct Engine {
     hs_mm_logdet = ld[0];
     hs_mm_id += 1;
     // step_size.init
-    if (P.s.method == 0) {
+    if (P.s.method != 2) {
       if (!stepsize_search()) return 3;
     } else {
       hs_step = P.s.fixed_step;
@@ -2565,7 +2585,7 @@ __device__ __noinline__ int cold_adapt(const EngineParams& Pg, int chain, int ti
     if (st.energy_error) st.energy_error[k] = pt_energy_error;
     if (st.diverging) st.diverging[k] = diverging ? 1 : 0;
     if (st.step_size) st.step_size[k] = E.hs_step;
-    if (st.step_size_bar) st.step_size_bar[k] = P.s.method != 0 ? P.s.fixed_step : exp(E.cs.da_log_step_adapted);
+    if (st.step_size_bar) st.step_size_bar[k] = P.s.method == 2 ? P.s.fixed_step : exp(E.cs.da_log_step_adapted);
     if (st.mean_tree_accept) st.mean_tree_accept[k] = E.cs.last_mean_tree_accept;
     if (st.mean_tree_accept_sym) st.mean_tree_accept_sym[k] = E.cs.last_sym_mean_tree_accept;
     if (st.n_steps) st.n_steps[k] = E.cs.last_n_steps;

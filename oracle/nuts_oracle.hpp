@@ -873,22 +873,57 @@ struct DualAverage {
   double current_step_size_adapted() const { return std::exp(log_step_adapted); }
 };
 
-enum class StepSizeMethod { DualAverage = 0, Fixed = 2 };
+// src/stepsize/adam.rs
+struct AdamOptions {
+  double beta1 = 0.9, beta2 = 0.999, epsilon = 1e-8, learning_rate = 0.05;  // :25-34
+};
+inline double powi(double a, int b) {  // f64::powi -> llvm.powi -> compiler-rt __powidf2 (square and multiply)
+  const bool recip = b < 0;
+  double r = 1.0;
+  for (;;) {
+    if (b & 1) r *= a;
+    b /= 2;
+    if (b == 0) break;
+    a *= a;
+  }
+  return recip ? 1.0 / r : r;
+}
+struct Adam {
+  double log_step, m = 0., v = 0.;
+  uint64_t t = 0;
+  AdamOptions settings;
+  Adam(AdamOptions s, double initial_step) : log_step(std::log(initial_step)), settings(s) {}  // :57-65
+  void advance(double accept_stat, double target) {  // :71-97
+    double gradient = accept_stat - target;
+    t += 1;
+    m = settings.beta1 * m + (1.0 - settings.beta1) * gradient;
+    v = settings.beta2 * v + (1.0 - settings.beta2) * gradient * gradient;
+    double m_hat = m / (1.0 - powi(settings.beta1, (int)t));
+    double v_hat = v / (1.0 - powi(settings.beta2, (int)t));
+    log_step += settings.learning_rate * m_hat / (std::sqrt(v_hat) + settings.epsilon);
+  }
+  double current_step_size() const { return std::exp(log_step); }
+};
+
+enum class StepSizeMethod { DualAverage = 0, Adam = 1, Fixed = 2 };
 struct StepSizeSettings {  // adapt.rs:308-329
   double target_accept = 0.8, initial_step = 0.1;
   std::optional<double> jitter = 0.1;
   StepSizeMethod method = StepSizeMethod::DualAverage;
   double fixed_step = 0.;
   DualAverageOptions dual_average;
+  AdamOptions adam;
 };
 
 struct StepSizeStrategy {  // adapt.rs:52-267
   std::optional<DualAverage> adaptation;
+  std::optional<Adam> adam;  // Either::Right
   StepSizeSettings options;
   double last_mean_tree_accept = 0., last_sym_mean_tree_accept = 0., last_max_energy_error = 0.;
   uint64_t last_n_steps = 0;
   explicit StepSizeStrategy(StepSizeSettings o) : options(o) {  // :67-89
     if (o.method == StepSizeMethod::DualAverage) adaptation = DualAverage(o.dual_average, o.initial_step);
+    if (o.method == StepSizeMethod::Adam) adam = Adam(o.adam, o.initial_step);
   }
   // :91-199
   void init(TransformedHamiltonian& h, const double* position, Rng& rng) {
@@ -916,19 +951,23 @@ struct StepSizeStrategy {  // adapt.rs:52-267
       double acc = c.mean.current();
       if (dir == Direction::Forward) {
         if ((acc <= options.target_accept) | (h.step_size > 1e5)) {
-          adaptation = DualAverage(options.dual_average, h.step_size);
+          reset_adaptation(h.step_size);
           return;
         }
         h.step_size *= 2.;
       } else {
         if ((acc >= options.target_accept) | (h.step_size < 1e-10)) {
-          adaptation = DualAverage(options.dual_average, h.step_size);
+          reset_adaptation(h.step_size);
           return;
         }
         h.step_size /= 2.;
       }
     }
     h.step_size = options.initial_step;
+  }
+  void reset_adaptation(double step) {  // :155-171 / :177-193
+    if (options.method == StepSizeMethod::Adam) adam = Adam(options.adam, step);
+    else adaptation = DualAverage(options.dual_average, step);
   }
   void update(const AcceptanceRateCollector& c) {  // :201-209
     last_sym_mean_tree_accept = c.mean_sym.current();
@@ -938,13 +977,16 @@ struct StepSizeStrategy {  // adapt.rs:52-267
   }
   void update_estimator_early() {  // :211-221
     if (adaptation) adaptation->advance(last_mean_tree_accept, options.target_accept);
+    if (adam) adam->advance(last_mean_tree_accept, options.target_accept);
   }
   void update_estimator_late() {  // :223-233
     if (adaptation) adaptation->advance(last_sym_mean_tree_accept, options.target_accept);
+    if (adam) adam->advance(last_sym_mean_tree_accept, options.target_accept);
   }
   void update_stepsize(Rng& rng, TransformedHamiltonian& h, bool use_best_guess) {  // :235-267
     double step_size;
-    if (!adaptation) step_size = options.fixed_step;
+    if (adam) step_size = adam->current_step_size();  // :256
+    else if (!adaptation) step_size = options.fixed_step;
     else step_size = use_best_guess ? adaptation->current_step_size_adapted() : adaptation->current_step_size();
     if (options.jitter) {
       double j = rng.uniform(1.0 - *options.jitter, 1.0 + *options.jitter);
@@ -953,7 +995,10 @@ struct StepSizeStrategy {  // adapt.rs:52-267
       h.step_size = step_size;
     }
   }
-  double step_size_bar() const { return adaptation ? adaptation->current_step_size_adapted() : options.fixed_step; }  // :278-290
+  double step_size_bar() const {  // :278-290
+    if (adam) return adam->current_step_size();
+    return adaptation ? adaptation->current_step_size_adapted() : options.fixed_step;
+  }
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -73,7 +73,13 @@ NutsSettings convert_settings(const nuts_settings_t* s) {
   ss.initial_step = a.step_size_settings.initial_step;
   if (a.step_size_settings.has_jitter) ss.jitter = a.step_size_settings.jitter;
   else ss.jitter = std::nullopt;
-  ss.method = a.step_size_settings.adapt_options.method == NUTS_STEPSIZE_FIXED ? StepSizeMethod::Fixed : StepSizeMethod::DualAverage;
+  ss.method = a.step_size_settings.adapt_options.method == NUTS_STEPSIZE_FIXED  ? StepSizeMethod::Fixed
+              : a.step_size_settings.adapt_options.method == NUTS_STEPSIZE_ADAM ? StepSizeMethod::Adam
+                                                                                  : StepSizeMethod::DualAverage;
+  ss.adam.beta1 = a.step_size_settings.adapt_options.adam.beta1;
+  ss.adam.beta2 = a.step_size_settings.adapt_options.adam.beta2;
+  ss.adam.epsilon = a.step_size_settings.adapt_options.adam.epsilon;
+  ss.adam.learning_rate = a.step_size_settings.adapt_options.adam.learning_rate;
   ss.fixed_step = a.step_size_settings.adapt_options.fixed_step;
   ss.dual_average.k = a.step_size_settings.adapt_options.dual_average.k;
   ss.dual_average.t0 = a.step_size_settings.adapt_options.dual_average.t0;
@@ -428,11 +434,12 @@ void orc_sampler_get_chain_state(void* sp, const nuts_chain_state_t* o) {
     PUT(mass_matrix_id, m.id);
     PUT(step_size, ch.hamiltonian.step_size);
     const auto& da = ch.strategy.step_size.adaptation;
-    PUT(da_log_step, da ? da->log_step : 0.);
-    PUT(da_log_step_adapted, da ? da->log_step_adapted : 0.);
-    PUT(da_hbar, da ? da->hbar : 0.);
-    PUT(da_mu, da ? da->mu : 0.);
-    PUT(da_count, da ? da->count : 0);
+    const auto& ad = ch.strategy.step_size.adam;  // Adam shares the record: log_step, m, v, t (log_step_adapted mirrors log_step)
+    PUT(da_log_step, ad ? ad->log_step : da ? da->log_step : 0.);
+    PUT(da_log_step_adapted, ad ? ad->log_step : da ? da->log_step_adapted : 0.);
+    PUT(da_hbar, ad ? ad->m : da ? da->hbar : 0.);
+    PUT(da_mu, ad ? ad->v : da ? da->mu : 0.);
+    PUT(da_count, ad ? ad->t : da ? da->count : 0);
     PUT(foreground_count, a.exp_variance_draw.count);
     PUT(background_count, a.exp_variance_draw_bg.count);
     PUT(tuning, (uint8_t)ch.strategy.tuning);
@@ -481,6 +488,12 @@ void orc_sampler_set_chain_state(void* sp, const nuts_chain_state_t* in) {
       da->hbar = in->da_hbar[c];
       da->mu = in->da_mu[c];
       da->count = in->da_count[c];
+    }
+    if (auto& ad = ch.strategy.step_size.adam) {
+      ad->log_step = in->da_log_step[c];
+      ad->m = in->da_hbar[c];
+      ad->v = in->da_mu[c];
+      ad->t = in->da_count[c];
     }
     getv(a.exp_variance_draw.mean, in->draw_mean, c);
     getv(a.exp_variance_draw.variance, in->draw_var, c);
@@ -604,6 +617,7 @@ void orc_settings_default(nuts_settings_t* s) {
   a.step_size_settings.has_jitter = 1;
   a.step_size_settings.jitter = 0.1;
   a.step_size_settings.adapt_options.method = NUTS_STEPSIZE_DUAL_AVERAGE;
+  a.step_size_settings.adapt_options.adam = nuts_adam_options_t{0.9, 0.999, 1e-8, 0.05};
   a.step_size_settings.adapt_options.dual_average = {0.75, 10., 0.05, 3.14159265358979323846};
 }
 

@@ -396,3 +396,15 @@ def test_large_dim_cluster_engine_diag_with_adaptation(L, orc, monkeypatch, d, N
     compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_DIAG, N, d, s, draws, seed=d, strict=1, min_common=5, loose=1e-6)
     s = _no_adapt(L, maxdepth=6)
     compare_run(L, orc, _abi.NUTS_LOGP_GAUSS_DIAG, N, d, s, draws, seed=d + 1)
+
+
+@pytest.mark.parametrize("kind,d,N", [(_abi.NUTS_LOGP_GAUSS_ISO, 10, 6), (_abi.NUTS_LOGP_GAUSS_DIAG, 1000, 4), (_abi.NUTS_LOGP_GAUSS_RANK1, 100, 5)])
+def test_adam_step_size_adaptation_matches_the_oracle(L, orc, kind, d, N):
+    """StepSizeAdaptMethod::Adam (src/stepsize/adam.rs) instead of dual averaging, mass-matrix adaptation on: exact-agreement prefix
+    like every adaptive run, step size and step_size_bar included; the optimizer state travels in the dual-averaging record of the
+    chain state (log_step, m, v, t)."""
+    s = _settings(L, num_tune=60, maxdepth=6, step={"adapt_options.method": _abi.NUTS_STEPSIZE_ADAM})
+    stats, ostats = compare_run(L, orc, kind, N, d, s, 80, seed=21, strict=4, min_common=10, loose=1e-6)
+    assert stats["tuning"][:60].all() and not stats["tuning"][60:].any()
+    # after the warm-up the step size is exp(log_step) of the optimizer (jittered), not a dual-averaging average
+    np.testing.assert_allclose(stats["step_size_bar"][:4], ostats["step_size_bar"][:4], rtol=1e-9)

@@ -200,3 +200,41 @@ def test_chain_state_round_trip_continues_bit_identically(orc):
     for k in fa:
         assert np.array_equal(fa[k], fb[k]), k
     assert (fa["draw_count"] == 75).all() and (fa["tuning"] == 0).all()
+
+
+def test_adam_step_size_adaptation(orc):
+    """StepSizeAdaptMethod::Adam (reference src/stepsize/adam.rs:55-115, src/stepsize/adapt.rs:74-78, 162-166, 256, 288): the optimizer's
+    closed-form first steps, and a run that settles near the target acceptance rate."""
+    import math
+
+    from nuts_rs_b200 import _abi
+
+    # closed form: m_hat = g, v_hat = g^2 after bias correction at t = 1 => the first step moves log_step by lr * g / (|g| + eps)
+    s = _abi.default_settings()
+    ao = s.adapt_options.step_size_settings.adapt_options
+    ao.method = _abi.NUTS_STEPSIZE_ADAM
+    assert (ao.adam.beta1, ao.adam.beta2, ao.adam.epsilon, ao.adam.learning_rate) == (0.9, 0.999, 1e-8, 0.05)
+    s.num_tune, s.maxdepth = 300, 6
+    d, N = 20, 6
+    m = orc.Model(_abi.NUTS_LOGP_GAUSS_ISO, d, mu=0.0)
+    smp = orc.Sampler(m, s, seed=9, nchains=N, nthreads=2)
+    assert (smp.set_position(np.random.default_rng(0).normal(size=(N, d))) == 0).all()
+    st0 = smp.chain_state()
+    assert (st0["da_count"] == 0).all() and (st0["da_hbar"] == 0).all()  # Adam::new: t = 0, m = v = 0
+    np.testing.assert_allclose(st0["da_log_step"], np.log(st0["step_size"]), rtol=1e-12)  # reset to the searched step size
+    draws, stats = smp.draw(1)
+    st1 = smp.chain_state()
+    g = stats["mean_tree_accept_sym"][0] - 0.8  # num_tune small windows: draw 0 is already `late`? use whichever statistic was fed
+    g_early = stats["mean_tree_accept"][0] - 0.8
+    step = st1["da_log_step"] - st0["da_log_step"]
+    ok_late = np.allclose(step, 0.05 * g / (np.abs(g) + 1e-8), rtol=1e-9, atol=1e-12)
+    ok_early = np.allclose(step, 0.05 * g_early / (np.abs(g_early) + 1e-8), rtol=1e-9, atol=1e-12)
+    assert ok_late or ok_early
+    assert (st1["da_count"] == 1).all()
+    np.testing.assert_allclose(stats["step_size_bar"][0], np.exp(st1["da_log_step"]), rtol=1e-12)  # adapt.rs:288
+    # the run settles: acceptance near the target after the warm-up
+    draws, stats = smp.draw(500)
+    post = stats["tuning"] == 0
+    acc = stats["mean_tree_accept"][post].mean()
+    assert 0.6 < acc < 0.95, acc
+    assert math.isfinite(float(draws.sum()))
