@@ -15,6 +15,7 @@ The launch length follows the schedule: a launch ends exactly at the next draw a
 sees its new transformation at the same draw index as in the reference.
 """
 import collections
+import math
 
 import numpy as np
 import scipy.linalg
@@ -122,6 +123,33 @@ class _ChainWindow:
         return len(self.draws) - self.background_split
 
 
+def schedule_step(w, t, good, draw, grad, early_end, final_window, early_switch_freq, growth, update_freq):
+    """One draw of the mass-matrix half of GlobalStrategy::adapt (src/adapt_strategy.rs:139-203) for the window `w` of one chain: feed the
+    estimator (`good` = DrawGradCollector::is_good), switch windows when the background is full, and say whether an update of the
+    transformation is due after draw index `t` (forced by a switch, or every `update_freq` draws; needs three draws in the window)."""
+    is_early = t < early_end
+    if (not is_early) and t == early_end:
+        w.current_window_size = max(w.current_window_size, w.background_count())
+    switch_freq = early_switch_freq if is_early else w.current_window_size
+    if good:
+        w.add(draw, grad)
+    could_switch = w.background_count() >= switch_freq
+    # (f64::round rounds half away from zero; Python's round() rounds half to even)
+    nxt = early_switch_freq if is_early else max(w.current_window_size + 1, int(math.floor(w.current_window_size * growth + 0.5)))
+    is_late = nxt + t > final_window
+    force = False
+    if could_switch and not is_late:
+        w.switch()
+        force = True
+        if not is_early:
+            w.current_window_size = nxt
+    if force or (t - w.last_update >= update_freq):
+        if len(w.draws) >= 3:  # LowRankMassMatrixStrategy::adapt (adapt/low_rank.rs:340-348)
+            w.last_update = t
+            return True
+    return False
+
+
 class LowRankSampler:
     """`LowRankNutsSettings` chains on one GPU: lib.Sampler on a low-rank engine + the host-side adaptation above.
 
@@ -180,27 +208,8 @@ class LowRankSampler:
 
     def _adapt_chain(self, c, t, good, draw, grad):
         """the mass-matrix half of GlobalStrategy::adapt for draw index t of chain c; returns True when an update is due"""
-        w = self.windows[c]
-        is_early = t < self.early_end
-        if (not is_early) and t == self.early_end:
-            w.current_window_size = max(w.current_window_size, w.background_count())
-        switch_freq = self.early_switch_freq if is_early else w.current_window_size
-        if good:
-            w.add(draw, grad)
-        could_switch = w.background_count() >= switch_freq
-        nxt = self.early_switch_freq if is_early else max(w.current_window_size + 1, int(round(w.current_window_size * self.growth)))
-        is_late = nxt + t > self.final_window
-        force = False
-        if could_switch and not is_late:
-            w.switch()
-            force = True
-            if not is_early:
-                w.current_window_size = nxt
-        if force or (t - w.last_update >= self.update_freq):
-            if len(w.draws) >= 3:  # LowRankMassMatrixStrategy::adapt (adapt/low_rank.rs:340-348)
-                w.last_update = t
-                return True
-        return False
+        return schedule_step(self.windows[c], t, good, draw, grad, self.early_end, self.final_window, self.early_switch_freq, self.growth,
+                             self.update_freq)
 
     def draw(self, n_draws):
         """n_draws x Chain::draw for every chain; returns (draws [n, N, dim], stats dict) like lib.Sampler.draw."""

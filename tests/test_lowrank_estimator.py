@@ -66,3 +66,47 @@ def test_rescale_points():
     np.testing.assert_allclose(x2.mean(axis=1), 0.0, atol=1e-12)
     np.testing.assert_allclose(g2.mean(axis=1), 0.0, atol=1e-12)
     np.testing.assert_allclose(x2 + dm[:, None], (x - mu[:, None]) / sigma[:, None], rtol=1e-12, atol=1e-12)
+
+
+def test_window_schedule_matches_the_global_strategy(orc):
+    """lowrank.schedule_step (the mass-matrix half of GlobalStrategy::adapt, src/adapt_strategy.rs:139-203, around the deque of
+    LowRankMassMatrixStrategy) against the oracle's GlobalStrategy driving the diagonal strategy with the low-rank update frequency
+    (20): both keep a foreground window that contains the background window, so after every draw the counts, the window size, the
+    draw of the last update and whether the transformation changed must agree - on the funnel, where divergent draws are skipped."""
+    from nuts_rs_b200 import _abi
+
+    s = _abi.default_settings()
+    s.num_tune, s.maxdepth = 400, 6
+    s.adapt_options.mass_matrix_update_freq = 20
+    ao = s.adapt_options
+    early_end = int(ao.early_window * s.num_tune)
+    final_window = s.num_tune - int(ao.step_size_window * s.num_tune)
+    N, d = 4, 8
+    m = orc.Model(_abi.NUTS_LOGP_FUNNEL, d, funnel_scale=3.0)
+    smp = orc.Sampler(m, s, seed=3, nchains=N, nthreads=2)
+    x0 = np.random.default_rng(0).normal(size=(N, d))
+    x0[:, 0] = 0.1
+    assert (smp.set_position(x0) == 0).all()
+    windows = [lowrank._ChainWindow(int(ao.mass_matrix_switch_freq)) for _ in range(N)]
+    for w in windows:
+        w.add(None, None)  # LowRankMassMatrixStrategy::init adds the initial point
+    prev = smp.chain_state()
+    skipped = 0
+    for t in range(final_window + 5):
+        _, stats = smp.draw(1)
+        cur = smp.chain_state()
+        div, idx = stats["diverging"][0], stats["index_in_trajectory"][0]
+        good = np.where(div != 0, np.abs(idx) > 4, idx != 0)
+        skipped += int((~good).sum())
+        for c in range(N):
+            if t < final_window:
+                due = lowrank.schedule_step(windows[c], t, bool(good[c]), None, None, early_end, final_window,
+                                            int(ao.early_mass_matrix_switch_freq), float(ao.mass_matrix_window_growth), 20)
+            else:
+                due = False
+            w = windows[c]
+            assert due == (cur["mass_matrix_id"][c] != prev["mass_matrix_id"][c]), (t, c)
+            assert w.background_count() == cur["background_count"][c] and len(w.draws) == cur["foreground_count"][c], (t, c)
+            assert w.current_window_size == cur["current_window_size"][c] and w.last_update == cur["last_update"][c], (t, c)
+        prev = cur
+    assert skipped > 0  # the funnel produced draws that the estimators skip
