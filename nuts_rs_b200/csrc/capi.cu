@@ -788,9 +788,16 @@ int nuts_set_lowrank_transform(nuts_ctx_t* ctx, const double* stds, const double
   if (rank_max > 0 && (!vals || !vecs)) return fail(NUTS_ERR_INVALID, "nuts_set_lowrank_transform: vals / vecs are NULL");
   const uint64_t N = ctx->N, d = ctx->d, R = std::max<uint64_t>(rank_max, 1);
   if (!ctx->lr_rank || (uint64_t)ctx->lr_rmax < R) {  // (re)allocate for the larger rank
+    // (a larger rank than before: every chain falls back to its diagonal part until this call has installed the new correction)
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->lr_vecs), cudaFree(ctx->lr_vals_sqrt), cudaFree(ctx->lr_vals_sqrt_inv), cudaFree(ctx->lr_mu), cudaFree(ctx->lr_rank);
     ctx->lr_vecs = ctx->lr_vals_sqrt = ctx->lr_vals_sqrt_inv = ctx->lr_mu = nullptr;
     ctx->lr_rank = nullptr;
+    ctx->lr_rmax = 0;
+    ctx->lr_active = false;
+    ctx->T.lr_vecs = ctx->T.lr_vals_sqrt = ctx->T.lr_vals_sqrt_inv = ctx->T.lr_mu = nullptr;
+    ctx->T.lr_rank = nullptr;
+    ctx->T.lr_rmax = 0;
     TRY(dev_alloc(&ctx->lr_vecs, N * R * ctx->ld));
     TRY(dev_alloc(&ctx->lr_vals_sqrt, N * R));
     TRY(dev_alloc(&ctx->lr_vals_sqrt_inv, N * R));

@@ -307,3 +307,28 @@ def test_lowrank_adaptation_beats_diagonal_on_a_correlated_target(L):
     assert (lr_ranks == 1).all(), lr_ranks
     f_lr, f_d = st_lr["fisher_distance"][300:], st_d["fisher_distance"][300:]
     assert np.median(f_lr) < 0.5 * np.median(f_d) and f_lr.max() < 0.2 * f_d.max(), (np.median(f_lr), np.median(f_d), f_lr.max(), f_d.max())
+
+
+def test_rank_can_grow_between_updates(L, orc):
+    """A later update with more eigenvectors than any before (the window grew): the device buffers are re-allocated and the new
+    transformation is what the oracle computes; a smaller rank afterwards works too."""
+    N, d = 3, 40
+    rng = np.random.default_rng(8)
+    kw = dict(mu=0.1, sigma=np.exp(0.3 * rng.normal(size=d)))
+    m = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_DIAG, **kw)
+    om = orc.Model(_abi.NUTS_LOGP_GAUSS_DIAG, d, **kw)
+    x = rng.normal(size=(N, d))
+    for r in (2, 7, 3):
+        stds, mean = np.exp(0.2 * rng.normal(size=(N, d))), 0.1 * rng.normal(size=(N, d))
+        vecs = np.stack([_orthonormal(rng, d, r) for _ in range(N)])
+        vals, mu = np.exp(0.5 * rng.normal(size=(N, r))), 0.05 * rng.normal(size=(N, d))
+        assert m.set_lowrank_transform(stds, mean, vals, vecs, mu).all()
+        p, status = m.init_state(x)
+        assert (status == 0).all()
+        for c in range(N):
+            h = orc.Hamiltonian(om)
+            assert h.set_lowrank_transform(stds[c], mean[c], vals[c], vecs[c], mu[c])
+            op, ost = h.init_state(x[c])
+            assert rel_err(p.vec(p.Z)[c], op.vec(op.Z)) < 1e-12 and rel_err(p.vec(p.GZ)[c], op.vec(op.GZ)) < 1e-12
+            assert abs(m.transform()["logdet"][c] - h.transform()["logdet"]) < 1e-12 * max(1.0, abs(h.transform()["logdet"]))
+    m.close()
