@@ -21,7 +21,22 @@ CASES = {
     "diag_d100_noadapt": (_abi.NUTS_LOGP_GAUSS_DIAG, dict(mu=0.5, sigma="logspace"), 3, 100, dict(num_tune=0, maxdepth=6), 30, "normal"),
     "rank1_d20_noadapt": (_abi.NUTS_LOGP_GAUSS_RANK1, dict(mu=0.0, rank1_scale=0.5), 3, 20, dict(num_tune=0, maxdepth=6), 30, "normal"),
     "funnel_d10": (_abi.NUTS_LOGP_FUNNEL, dict(funnel_scale=3.0), 4, 10, dict(num_tune=20, maxdepth=8), 12, "normal"),
+    # low-rank mass matrix: a fixed rank-2 transformation per chain installed after set_position (see lowrank_transform())
+    "lowrank_rank1_d20_noadapt": (_abi.NUTS_LOGP_GAUSS_RANK1, dict(mu=0.0, rank1_scale=0.5), 3, 20, dict(num_tune=0, maxdepth=6), 30, "normal"),
 }
+
+
+def lowrank_transform(N, d, r=2):
+    """the transformation of the low-rank golden case: (stds, mean, vals [N, r], vecs [N, r, d], mean_low_rank).  Built from uniform
+    random numbers, +-1 patterns and one correctly rounded square root only, so that it is the same bits on every machine."""
+    assert d % 4 == 0 and r == 2 and N <= 3
+    rng = np.random.default_rng(321)
+    stds, mean = 0.75 + 0.5 * rng.random((N, d)), 0.2 * (rng.random((N, d)) - 0.5)
+    i = np.arange(d)
+    patterns = [np.ones(d), np.where(i % 2 == 0, 1.0, -1.0), np.where(i % 4 < 2, 1.0, -1.0)]  # mutually orthogonal for d % 4 == 0
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    vecs = np.stack([np.stack([patterns[a], patterns[b]]) / np.sqrt(float(d)) for a, b in pairs[:N]])
+    return stds, mean, 0.5 + 2.0 * rng.random((N, r)), vecs, 0.1 * (rng.random((N, d)) - 0.5)
 
 
 def build(name):
@@ -35,6 +50,8 @@ def build(name):
     x0 = np.full((N, d), 3.5) if x0kind == "const3.5" else np.random.default_rng(123).normal(size=(N, d))
     samp = O.Sampler(O.Model(kind, d, **mk), s, seed=2024, nchains=N)
     status = samp.set_position(x0)
+    if name.startswith("lowrank"):
+        assert samp.set_lowrank_transform(*lowrank_transform(N, d)).all()
     st0 = samp.state()
     draws, stats = samp.draw(n_draws)
     stats.pop("_total_leapfrogs")
