@@ -71,7 +71,9 @@ typedef struct {
  * src/stepsize/adapt.rs:308-329 (StepSizeSettings), :21-49 (StepSizeAdaptOptions / Method),
  * src/stepsize/dual_avg.rs:11-31 (DualAverageOptions), src/stepsize/adam.rs:13-34 (AdamOptions), src/transform/adapt/diagonal.rs:93-106 (DiagAdaptExpSettings). */
 enum { NUTS_STEPSIZE_DUAL_AVERAGE = 0, NUTS_STEPSIZE_ADAM = 1, NUTS_STEPSIZE_FIXED = 2 };
-enum { NUTS_KINETIC_EUCLIDEAN = 0 /* ExactNormal / Microcanonical are out of scope */ };
+/* KineticEnergyKind (dynamics/transformed_hamiltonian.rs:22-50).  Tier 1 / Tier 2 serve all three (nuts_std_norm_*, nuts_esh_momentum_update,
+ * nuts_leapfrog_kinetic, nuts_initialize_trajectory_kinetic); the Tier-3 whole-draw engines are Euclidean only. */
+enum { NUTS_KINETIC_EUCLIDEAN = 0, NUTS_KINETIC_EXACT_NORMAL = 1, NUTS_KINETIC_MICROCANONICAL = 2 };
 
 typedef struct {
   double k, t0, gamma, max_step_size;
@@ -182,6 +184,15 @@ double* nuts_plane_device_ptr(nuts_plane_t* plane, uint64_t* row_stride_elems);
  * `active` is an optional HOST uint8 [N] mask (NULL = all chains). Reductions write HOST arrays [N]. */
 int nuts_axpy(nuts_ctx_t*, const nuts_plane_t* x, nuts_plane_t* y, const double* a, double a_bcast, const uint8_t* active);                 /* :99  y = a*x + y (FMA) */
 int nuts_axpy_out(nuts_ctx_t*, const nuts_plane_t* x, const nuts_plane_t* y, const double* a, double a_bcast, nuts_plane_t* out, const uint8_t* active); /* :98 */
+/* geodesic / isokinetic integrator primitives (KineticEnergyKind::ExactNormal / Microcanonical); epsilon / step_size: HOST [N] or NULL + bcast.
+ * std_norm_flow (:155-161): pos_out = pos cos(eps) + vel sin(eps), vel = -pos sin(eps) + vel cos(eps) (sin / cos evaluated on the host);
+ * std_norm_grad_flow(_inplace) (:162-176): vel_out = vel + eps (pos + grad); array_normalize (:178-181): v /= |v|;
+ * esh_momentum_update (:183-210): momentum updated in place on the unit sphere, kinetic_energy_change HOST [N]. */
+int nuts_std_norm_flow(nuts_ctx_t*, const nuts_plane_t* pos, nuts_plane_t* pos_out, nuts_plane_t* vel, const double* epsilon, double epsilon_bcast, const uint8_t* active);
+int nuts_std_norm_grad_flow(nuts_ctx_t*, const nuts_plane_t* pos, const nuts_plane_t* grad, const nuts_plane_t* vel, nuts_plane_t* vel_out, const double* epsilon, double epsilon_bcast, const uint8_t* active);
+int nuts_std_norm_grad_flow_inplace(nuts_ctx_t*, const nuts_plane_t* pos, const nuts_plane_t* grad, nuts_plane_t* vel, const double* epsilon, double epsilon_bcast, const uint8_t* active);
+int nuts_array_normalize(nuts_ctx_t*, nuts_plane_t* v, const uint8_t* active);
+int nuts_esh_momentum_update(nuts_ctx_t*, const nuts_plane_t* gradient, nuts_plane_t* momentum, const double* step_size, double step_size_bcast, const uint8_t* active, double* kinetic_energy_change);
 int nuts_array_mult(nuts_ctx_t*, const nuts_plane_t* a1, const nuts_plane_t* a2, nuts_plane_t* dest);    /* :123 */
 int nuts_array_mult_inplace(nuts_ctx_t*, nuts_plane_t* a1, const nuts_plane_t* a2);                      /* :124 */
 int nuts_array_recip(nuts_ctx_t*, const nuts_plane_t* a, nuts_plane_t* dest);                            /* :125 */
@@ -256,6 +267,16 @@ int nuts_initialize_trajectory(nuts_ctx_t*, nuts_point_t* point, int resample_ve
 int nuts_leapfrog(nuts_ctx_t*, const nuts_point_t* start, nuts_point_t* out, const double* step_size, double step_size_bcast,
                   const int8_t* dir, const double* energy_baseline, double max_energy_error, const uint8_t* active,
                   int32_t* status, double* energy_error);
+/* Hamiltonian::leapfrog for the other KineticEnergyKinds (:160-258, :582-596).  kind = NUTS_KINETIC_*; EUCLIDEAN forwards to
+ * nuts_leapfrog.  EXACT_NORMAL: std_norm_grad_flow half-steps around the exact rotation std_norm_flow; MICROCANONICAL: ESH momentum
+ * updates with sqrt(dim)-scaled steps, point.kinetic_energy = the accumulated kinetic-energy change, divergence when
+ * |energy error| >= max_energy_error.  Diagonal transformation only (NUTS_ERR_UNSUPPORTED while a low-rank correction is set). */
+int nuts_leapfrog_kinetic(nuts_ctx_t*, int kind, const nuts_point_t* start, nuts_point_t* out, const double* step_size,
+                          double step_size_bcast, const int8_t* dir, const double* energy_baseline, double max_energy_error,
+                          const uint8_t* active, int32_t* status, double* energy_error);
+/* Hamiltonian::initialize_trajectory with the kind (:699-702 unit-sphere momentum, :720-729 kinetic_energy = 0 for MICROCANONICAL) */
+int nuts_initialize_trajectory_kinetic(nuts_ctx_t*, int kind, nuts_point_t* point, int resample_velocity, uint64_t seed,
+                                       uint64_t chain_offset, uint64_t counter);
 /* Hamiltonian::is_turning (:617-638) */
 int nuts_is_turning(nuts_ctx_t*, const nuts_point_t* state1, const nuts_point_t* state2, uint8_t* turning);
 

@@ -16,6 +16,9 @@ NUTS_LOGP_USER = 4
 NUTS_STEPSIZE_DUAL_AVERAGE = 0
 NUTS_STEPSIZE_ADAM = 1
 NUTS_STEPSIZE_FIXED = 2
+NUTS_KINETIC_EUCLIDEAN = 0
+NUTS_KINETIC_EXACT_NORMAL = 1
+NUTS_KINETIC_MICROCANONICAL = 2
 
 NUTS_STATUS_OK = 0
 NUTS_STATUS_DIVERGENT_ENERGY = 1

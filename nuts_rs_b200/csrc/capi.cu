@@ -166,7 +166,7 @@ struct nuts_ctx {
   bool lr_active = false;  // some chain may carry a low-rank correction (since the last diagonal nuts_set_transform)
   // scratch
   double* d_dense = nullptr;    // [N*d] staging for host <-> plane packing
-  double* d_sc[4] = {nullptr, nullptr, nullptr, nullptr};  // [N] f64 scratch
+  double* d_sc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [N] f64 scratch
   uint8_t* d_u8 = nullptr;      // [N]
   int8_t* d_i8 = nullptr;       // [N]
   int* d_i32 = nullptr;         // [N]
@@ -397,7 +397,7 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
   TRY(dev_alloc(&ctx->T.id, nchains));
   CUDA_TRY(cudaMemset(ctx->T.id, 0xff, nchains * sizeof(long long)));  // -1
   TRY(dev_alloc(&ctx->d_dense, nchains * dim));
-  for (int k = 0; k < 4; ++k) TRY(dev_alloc(&ctx->d_sc[k], nchains));
+  for (int k = 0; k < 6; ++k) TRY(dev_alloc(&ctx->d_sc[k], nchains));
   TRY(dev_alloc(&ctx->d_u8, nchains));
   TRY(dev_alloc(&ctx->d_i8, nchains));
   TRY(dev_alloc(&ctx->d_i32, nchains));
@@ -425,7 +425,7 @@ int nuts_ctx_destroy(nuts_ctx_t* ctx) {
   cudaFree(ctx->lr_mu);
   cudaFree(ctx->lr_rank);
   cudaFree(ctx->d_dense);
-  for (int k = 0; k < 4; ++k) cudaFree(ctx->d_sc[k]);
+  for (int k = 0; k < 6; ++k) cudaFree(ctx->d_sc[k]);
   cudaFree(ctx->d_u8);
   cudaFree(ctx->d_i8);
   cudaFree(ctx->d_i32);
@@ -508,6 +508,71 @@ int nuts_axpy_out(nuts_ctx_t* ctx, const nuts_plane_t* x, const nuts_plane_t* y,
   TRY(upload_mask(ctx, active, &dm));
   k_axpy_out<<<GRID>>>(ctx->row_args(), x->ptr, y->ptr, da, a_bcast, out->ptr, dm);
   CHECK_LAUNCH();
+  return sync(ctx);
+}
+// sine and cosine of the per-chain angles on the HOST (the reference calls f64::sin / f64::cos once per vector, util.rs:580-581) -> slots 4, 5
+static int upload_sincos(nuts_ctx* ctx, const double* angle, const double** dsn, const double** dcs) {
+  *dsn = *dcs = nullptr;
+  if (!angle) return NUTS_OK;
+  std::vector<double> sc(2 * ctx->N);
+  for (size_t c = 0; c < ctx->N; ++c) {
+    sc[c] = std::sin(angle[c]);
+    sc[ctx->N + c] = std::cos(angle[c]);
+  }
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_sc[4], sc.data(), ctx->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_sc[5], sc.data() + ctx->N, ctx->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // sc is pageable and leaves scope
+  *dsn = ctx->d_sc[4];
+  *dcs = ctx->d_sc[5];
+  return NUTS_OK;
+}
+int nuts_std_norm_flow(nuts_ctx_t* ctx, const nuts_plane_t* pos, nuts_plane_t* pos_out, nuts_plane_t* vel, const double* epsilon,
+                       double epsilon_bcast, const uint8_t* active) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (pos == pos_out || pos == vel || pos_out == vel) return fail(NUTS_ERR_INVALID, "nuts_std_norm_flow: the three planes must be distinct");
+  const double *dsn, *dcs;
+  const uint8_t* dm;
+  TRY(upload_sincos(ctx, epsilon, &dsn, &dcs));
+  TRY(upload_mask(ctx, active, &dm));
+  k_std_norm_flow<<<GRID>>>(ctx->row_args(), pos->ptr, pos_out->ptr, vel->ptr, dsn, dcs, std::sin(epsilon_bcast), std::cos(epsilon_bcast), dm);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_std_norm_grad_flow(nuts_ctx_t* ctx, const nuts_plane_t* pos, const nuts_plane_t* grad, const nuts_plane_t* vel,
+                            nuts_plane_t* vel_out, const double* epsilon, double epsilon_bcast, const uint8_t* active) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const double* de;
+  const uint8_t* dm;
+  TRY(upload_f64(ctx, epsilon, 0, &de));
+  TRY(upload_mask(ctx, active, &dm));
+  k_std_norm_grad_flow<<<GRID>>>(ctx->row_args(), pos->ptr, grad->ptr, vel->ptr, vel_out->ptr, de, epsilon_bcast, dm);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_std_norm_grad_flow_inplace(nuts_ctx_t* ctx, const nuts_plane_t* pos, const nuts_plane_t* grad, nuts_plane_t* vel,
+                                    const double* epsilon, double epsilon_bcast, const uint8_t* active) {
+  return nuts_std_norm_grad_flow(ctx, pos, grad, vel, vel, epsilon, epsilon_bcast, active);
+}
+int nuts_array_normalize(nuts_ctx_t* ctx, nuts_plane_t* v, const uint8_t* active) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const uint8_t* dm;
+  TRY(upload_mask(ctx, active, &dm));
+  k_normalize<<<GRID>>>(ctx->row_args(), v->ptr, dm);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
+int nuts_esh_momentum_update(nuts_ctx_t* ctx, const nuts_plane_t* gradient, nuts_plane_t* momentum, const double* step_size,
+                             double step_size_bcast, const uint8_t* active, double* kinetic_energy_change) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (ctx->d < 2) return fail(NUTS_ERR_INVALID, "nuts_esh_momentum_update: ESH dynamics requires at least 2 dimensions");  // cpu_math.rs:514
+  const double* ds;
+  const uint8_t* dm;
+  TRY(upload_f64(ctx, step_size, 0, &ds));
+  TRY(upload_mask(ctx, active, &dm));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_sc[2], 0, ctx->N * sizeof(double), ctx->stream));
+  k_esh_momentum_update<<<GRID>>>(ctx->row_args(), gradient->ptr, momentum->ptr, ds, step_size_bcast, dm, ctx->d_sc[2]);
+  CHECK_LAUNCH();
+  TRY(download_f64(ctx, 2, kinetic_energy_change));
   return sync(ctx);
 }
 int nuts_array_mult(nuts_ctx_t* ctx, const nuts_plane_t* a1, const nuts_plane_t* a2, nuts_plane_t* dest) {
@@ -908,11 +973,60 @@ int nuts_init_state(nuts_ctx_t* ctx, nuts_point_t* point, const double* position
   if (status) CUDA_TRY(cudaMemcpyAsync(status, ctx->d_i32, ctx->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   return sync(ctx);
 }
+static int check_kinetic_kind(nuts_ctx* ctx, int kind, const char* who) {
+  if (kind != NUTS_KINETIC_EUCLIDEAN && kind != NUTS_KINETIC_EXACT_NORMAL && kind != NUTS_KINETIC_MICROCANONICAL)
+    return fail(NUTS_ERR_INVALID, "%s: unknown kinetic energy kind %d", who, kind);
+  if (kind == NUTS_KINETIC_MICROCANONICAL && ctx->d < 2)
+    return fail(NUTS_ERR_INVALID, "%s: ESH dynamics requires at least 2 dimensions", who);
+  return NUTS_OK;
+}
+int nuts_initialize_trajectory_kinetic(nuts_ctx_t* ctx, int kind, nuts_point_t* point, int resample_velocity, uint64_t seed,
+                                       uint64_t chain_offset, uint64_t counter) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(check_kinetic_kind(ctx, kind, "nuts_initialize_trajectory_kinetic"));
+  k_initialize_trajectory<<<GRID>>>(ctx->row_args(), ctx->T, point->dev, resample_velocity, seed, chain_offset, counter, kind);
+  CHECK_LAUNCH();
+  return sync(ctx);
+}
 int nuts_initialize_trajectory(nuts_ctx_t* ctx, nuts_point_t* point, int resample_velocity, uint64_t seed, uint64_t chain_offset,
                                uint64_t counter) {
+  return nuts_initialize_trajectory_kinetic(ctx, NUTS_KINETIC_EUCLIDEAN, point, resample_velocity, seed, chain_offset, counter);
+}
+int nuts_leapfrog_kinetic(nuts_ctx_t* ctx, int kind, const nuts_point_t* start, nuts_point_t* out, const double* step_size,
+                          double step_size_bcast, const int8_t* dir, const double* energy_baseline, double max_energy_error,
+                          const uint8_t* active, int32_t* status, double* energy_error) {
   CUDA_TRY(cudaSetDevice(ctx->device));
-  k_initialize_trajectory<<<GRID>>>(ctx->row_args(), ctx->T, point->dev, resample_velocity, seed, chain_offset, counter);
+  TRY(check_kinetic_kind(ctx, kind, "nuts_leapfrog_kinetic"));
+  if (kind == NUTS_KINETIC_EUCLIDEAN)
+    return nuts_leapfrog(ctx, start, out, step_size, step_size_bcast, dir, energy_baseline, max_energy_error, active, status, energy_error);
+  if (start == out) return fail(NUTS_ERR_INVALID, "nuts_leapfrog_kinetic: out must not alias start");
+  if (ctx->lr_active)
+    return fail(NUTS_ERR_UNSUPPORTED, "nuts_leapfrog_kinetic: ExactNormal / Microcanonical run on the diagonal transformation only");
+  const double *dstep, *dbase, *dsn = nullptr, *dcs = nullptr;
+  const uint8_t* dm;
+  if (kind == NUTS_KINETIC_EXACT_NORMAL) {  // the signed step of every chain exactly as the kernel forms it, then f64::sin / cos on the host
+    std::vector<double> eps(ctx->N);
+    for (size_t c = 0; c < ctx->N; ++c) eps[c] = (double)(dir ? (int)dir[c] : 1) * (step_size ? step_size[c] : step_size_bcast) * 1.0;
+    TRY(upload_sincos(ctx, eps.data(), &dsn, &dcs));
+  }
+  TRY(upload_f64(ctx, step_size, 0, &dstep));
+  TRY(upload_f64(ctx, energy_baseline, 1, &dbase));
+  TRY(upload_mask(ctx, active, &dm));
+  const int8_t* ddir = nullptr;
+  if (dir) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_i8, dir, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    ddir = ctx->d_i8;
+  }
+  CUDA_TRY(cudaMemsetAsync(ctx->d_i32, 0, ctx->N * sizeof(int), ctx->stream));
+  if (kind == NUTS_KINETIC_EXACT_NORMAL)
+    k_leapfrog_kinetic<1><<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, start->dev, out->dev, dstep, step_size_bcast, ddir, dsn, dcs, dbase,
+                                    max_energy_error, dm, ctx->d_i32, ctx->d_sc[2]);
+  else
+    k_leapfrog_kinetic<2><<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, start->dev, out->dev, dstep, step_size_bcast, ddir, dsn, dcs, dbase,
+                                    max_energy_error, dm, ctx->d_i32, ctx->d_sc[2]);
   CHECK_LAUNCH();
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, ctx->d_i32, ctx->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(download_f64(ctx, 2, energy_error));
   return sync(ctx);
 }
 int nuts_leapfrog(nuts_ctx_t* ctx, const nuts_point_t* start, nuts_point_t* out, const double* step_size, double step_size_bcast,
@@ -985,7 +1099,7 @@ static int sampler_create_impl(nuts_ctx_t* ctx, nuts_sampler_t** out, const nuts
                                uint64_t lowrank_rmax) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (!st) return fail(NUTS_ERR_INVALID, "nuts_sampler_create: settings is NULL");
-  if (st->trajectory_kind != NUTS_KINETIC_EUCLIDEAN) return fail(NUTS_ERR_UNSUPPORTED, "only KineticEnergyKind::Euclidean is supported");
+  if (st->trajectory_kind != NUTS_KINETIC_EUCLIDEAN) return fail(NUTS_ERR_UNSUPPORTED, "the whole-draw engines support KineticEnergyKind::Euclidean only (ExactNormal / Microcanonical: Tier 1 / Tier 2, nuts_leapfrog_kinetic)");
   const int method = st->adapt_options.step_size_settings.adapt_options.method;
   if (method != NUTS_STEPSIZE_DUAL_AVERAGE && method != NUTS_STEPSIZE_ADAM && method != NUTS_STEPSIZE_FIXED)
     return fail(NUTS_ERR_INVALID, "unknown step size method %d", method);

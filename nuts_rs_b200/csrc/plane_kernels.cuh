@@ -346,8 +346,10 @@ __global__ void __launch_bounds__(PK_THREADS) k_init_state(RowArgs A, ModelDev m
 }
 
 // Hamiltonian::initialize_trajectory (transformed_hamiltonian.rs:687-736)
+// kind: KineticEnergyKind; Microcanonical (2) puts a resampled momentum on the unit sphere (:699-702) and starts the accumulated
+// kinetic-energy change at 0 (:720-729)
 __global__ void __launch_bounds__(PK_THREADS) k_initialize_trajectory(RowArgs A, TransformDev T, PointDev p, int resample, uint64_t seed,
-                                                                       uint64_t chain_offset, uint64_t counter) {
+                                                                       uint64_t chain_offset, uint64_t counter, int kind) {
   __shared__ double scratch[2 * 32 * REDUCE_MAXK];
   TeamReduce<PK_THREADS> red(scratch);
   const uint8_t* active = nullptr;
@@ -368,10 +370,14 @@ __global__ void __launch_bounds__(PK_THREADS) k_initialize_trajectory(RowArgs A,
       p.logdet[c] = T.logdet[c];
       p.tid[c] = T.id[c];
     }
-    double ke = 0.5 * s[0];
+    double ke = kind == 2 ? 0.0 : 0.5 * s[0];
     p.ke[c] = ke;
     p.idx[c] = 0;
     p.e0[c] = ke - (p.logp[c] + p.logdet[c]);
+  }
+  if (kind == 2 && resample) {  // Math::array_normalize (cpu_math.rs:496-503); every thread re-reads the elements it wrote
+    const double inv = 1.0 / sqrt(s[0]);
+    for (int i = threadIdx.x; i < A.d; i += PK_THREADS) p.v[row + i] *= inv;
   }
 }
 
@@ -527,6 +533,173 @@ __global__ void __launch_bounds__(PK_THREADS) k_is_turning(RowArgs A, PointDev s
   }
   red.allreduce(s);
   if (threadIdx.x == 0) turning[c] = ((s[0] < 0.) | (s[1] < 0.)) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------- KineticEnergyKind::ExactNormal / Microcanonical (Tier 1 + Tier 2)
+// The reference's SIMD kernels fuse the multiply-add in whole registers of 4 lanes and leave the last d % 4 elements to an unfused scalar
+// tail (util.rs:541-572, 625-647); `body` = (d / 4) * 4 keeps both roundings so the planes match the CPU bit for bit.
+// Math::std_norm_flow (math.rs:155-161, util.rs:507-590): sin / cos of epsilon are evaluated ON THE HOST (f64::sin / cos, like the reference)
+__global__ void __launch_bounds__(PK_THREADS) k_std_norm_flow(RowArgs A, const double* __restrict__ pos, double* __restrict__ pos_out,
+                                                               double* __restrict__ vel, const double* __restrict__ sn,
+                                                               const double* __restrict__ cs, double sn_bcast, double cs_bcast,
+                                                               const uint8_t* active) {
+  NB_ROW_PROLOGUE
+  const double es = sn ? sn[c] : sn_bcast, ec = cs ? cs[c] : cs_bcast;
+  const int body = (A.d / 4) * 4;
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
+    const double p = pos[row + i], v = vel[row + i];
+    double po, vo;
+    if (i < body) {
+      po = fma(p, ec, v * es);
+      vo = fma(p, -es, v * ec);
+    } else {
+      po = p * ec + v * es;
+      vo = p * (-es) + v * ec;
+    }
+    pos_out[row + i] = po;
+    vel[row + i] = vo;
+  }
+}
+// Math::std_norm_grad_flow / _inplace (math.rs:162-176, util.rs:592-742): vel_out = vel + eps * (pos + grad); vel_out may alias vel
+__global__ void __launch_bounds__(PK_THREADS) k_std_norm_grad_flow(RowArgs A, const double* pos, const double* grad, const double* vel,
+                                                                    double* vel_out, const double* eps, double eps_bcast,
+                                                                    const uint8_t* active) {
+  NB_ROW_PROLOGUE
+  const double e = eps ? eps[c] : eps_bcast;
+  const int body = (A.d / 4) * 4;
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) {
+    const double pg = pos[row + i] + grad[row + i], v = vel[row + i];
+    vel_out[row + i] = i < body ? fma(e, pg, v) : v + e * pg;
+  }
+}
+// Math::array_normalize (math.rs:178-181, cpu_math.rs:496-503)
+__global__ void __launch_bounds__(PK_THREADS) k_normalize(RowArgs A, double* v, const uint8_t* active) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  NB_ROW_PROLOGUE
+  double s[1] = {0.0};
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) s[0] += v[row + i] * v[row + i];
+  red.allreduce(s);
+  const double inv = 1.0 / sqrt(s[0]);
+  for (int i = threadIdx.x; i < A.d; i += PK_THREADS) v[row + i] *= inv;
+}
+// Math::esh_momentum_update (math.rs:183-210, cpu_math.rs:505-551) on one row: three team reductions (|g|^2, p.g, |p_raw|^2); every thread
+// only touches the elements tid + k * PK_THREADS, so no barrier is needed between the passes.  Returns the kinetic-energy change.
+__device__ __forceinline__ double esh_row(const double* g, double* mom, double step_size, int d, TeamReduce<PK_THREADS>& red) {
+  double s[1] = {0.0};
+  for (int i = threadIdx.x; i < d; i += PK_THREADS) s[0] += g[i] * g[i];
+  red.allreduce(s);
+  const double grad_norm = sqrt(s[0]);
+  const double inv_grad_norm = 1.0 / grad_norm;
+  s[0] = 0.0;
+  for (int i = threadIdx.x; i < d; i += PK_THREADS) s[0] += mom[i] * g[i] * inv_grad_norm;
+  red.allreduce(s);
+  const double momentum_proj = s[0];
+  const double dims_m1 = (double)(d - 1);
+  const double delta = step_size * grad_norm / dims_m1;
+  const double zeta = exp(-delta);
+  const double coeff_g = (1.0 - zeta) * (1.0 + zeta + momentum_proj * (1.0 - zeta));
+  const double coeff_p = 2.0 * zeta;
+  s[0] = 0.0;
+  for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+    const double pr = coeff_g * (g[i] * inv_grad_norm) + coeff_p * mom[i];
+    mom[i] = pr;
+    s[0] += pr * pr;
+  }
+  red.allreduce(s);
+  const double inv = 1.0 / sqrt(s[0]);
+  for (int i = threadIdx.x; i < d; i += PK_THREADS) mom[i] *= inv;
+  const double arg = momentum_proj + (1.0 - momentum_proj) * zeta * zeta;
+  return (delta - 0.6931471805599453094 + log1p(arg)) * dims_m1;
+}
+__global__ void __launch_bounds__(PK_THREADS) k_esh_momentum_update(RowArgs A, const double* grad, double* mom, const double* step,
+                                                                     double step_bcast, const uint8_t* active, double* dke) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  NB_ROW_PROLOGUE
+  const double r = esh_row(grad + row, mom + row, step ? step[c] : step_bcast, A.d, red);
+  if (threadIdx.x == 0) dke[c] = r;
+}
+
+// Hamiltonian::leapfrog (transformed_hamiltonian.rs:524-615) for KIND 1 = ExactNormal (:169-177, :206-213, :237-244: half-steps with the
+// gradient of the standard-normal part removed, exact rotation in between) and KIND 2 = Microcanonical (:186-198, :214-227, :248-256: ESH
+// momentum updates, step sizes scaled by sqrt(dim), kinetic_energy = accumulated change).  Diagonal transformation; sn / cs = sine and
+// cosine of the signed step dir[c] * step_size[c], evaluated on the host (KIND 1).  HBM traffic per chain like k_leapfrog's three-pass branch.
+template <int KIND>
+__global__ void __launch_bounds__(PK_THREADS) k_leapfrog_kinetic(RowArgs A, ModelDev m, TransformDev T, PointDev s, PointDev o,
+                                                                  const double* step_size, double step_bcast, const int8_t* dir,
+                                                                  const double* sn, const double* cs, const double* baseline,
+                                                                  double max_energy_error, const uint8_t* active, int* status,
+                                                                  double* energy_error_out) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  TeamReduce<PK_THREADS> red(scratch);
+  NB_ROW_PROLOGUE
+  const int d = A.d;
+  const int body = (d / 4) * 4;
+  const int sign = dir ? (int)dir[c] : 1;
+  const double eps = (double)sign * (step_size ? step_size[c] : step_bcast) * 1.0;
+  const double eps_half = eps / 2.;
+  const double sqrt_d = sqrt((double)d);
+  double ke = 0.0;
+  if (KIND == 1) {
+    const double es = sn[c], ec = cs[c];
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      const double z = s.z[row + i], pg = z + s.gz[row + i], v = s.v[row + i];
+      const double vh = i < body ? fma(eps_half, pg, v) : v + eps_half * pg;  // std_norm_grad_flow(z, grad_z, v, out.v, eps / 2)
+      double zn, vr;                                                            // std_norm_flow(z, out.z, out.v, eps)
+      if (i < body) {
+        zn = fma(z, ec, vh * es);
+        vr = fma(z, -es, vh * ec);
+      } else {
+        zn = z * ec + vh * es;
+        vr = z * (-es) + vh * ec;
+      }
+      o.z[row + i] = zn;
+      o.v[row + i] = vr;
+      o.x[row + i] = fma(1.0, T.mean[row + i], zn * T.stds[row + i]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) o.v[row + i] = s.v[row + i];
+    ke = s.ke[c] + esh_row(s.gz + row, o.v + row, sqrt_d * eps / 2., d, red);
+    const double e = eps * sqrt_d;
+    for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+      const double zn = fma(e, o.v[row + i], s.z[row + i]);
+      o.z[row + i] = zn;
+      o.x[row + i] = fma(1.0, T.mean[row + i], zn * T.stds[row + i]);
+    }
+  }
+  const double lp = model_eval_row(m, d, o.x + row, o.gx + row, red);
+  double part[1] = {0.0};
+  for (int i = threadIdx.x; i < d; i += PK_THREADS) {
+    const double gn = o.gx[row + i] * T.stds[row + i];
+    o.gz[row + i] = gn;
+    if (KIND == 1) {
+      const double pg = o.z[row + i] + gn, v = o.v[row + i];
+      const double vn = i < body ? fma(eps_half, pg, v) : v + eps_half * pg;  // std_norm_grad_flow_inplace(out.z, out.grad_z, out.v, eps / 2)
+      o.v[row + i] = vn;
+      part[0] = fma(vn, vn, part[0]);
+    }
+  }
+  if (KIND == 1) {
+    red.allreduce(part);
+    ke = 0.5 * part[0];
+  } else {
+    ke = ke + esh_row(o.gz + row, o.v + row, sqrt_d * eps / 2., d, red);
+  }
+  if (threadIdx.x == 0) {
+    const double logdet = T.logdet[c];
+    o.logp[c] = lp;
+    o.logdet[c] = logdet;
+    o.ke[c] = ke;
+    o.e0[c] = s.e0[c];
+    o.tid[c] = T.id[c];
+    o.idx[c] = s.idx[c] + sign;
+    const double base = baseline ? baseline[c] : s.e0[c];
+    const double ee = (ke - (lp + logdet)) - base;
+    if (energy_error_out) energy_error_out[c] = ee;
+    const bool bad = KIND == 2 ? fabs(ee) >= max_energy_error : ee > max_energy_error;  // :591-596
+    if (status) status[c] = (bad | !isfinite(ee)) ? 1 : 0;
+  }
 }
 
 }  // namespace nb

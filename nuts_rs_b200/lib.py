@@ -35,6 +35,8 @@ EXPORTED_SYMBOLS = [
     "nuts_sampler_get_chain_state", "nuts_sampler_set_chain_state",
     "nuts_sampler_create_lowrank", "nuts_sampler_set_lowrank_transform", "nuts_sampler_set_grads_out",
     "nuts_eigs_create", "nuts_eigs_free", "nuts_apply_lowrank_transform", "nuts_apply_lowrank_transform_inplace", "nuts_set_lowrank_transform",
+    "nuts_std_norm_flow", "nuts_std_norm_grad_flow", "nuts_std_norm_grad_flow_inplace", "nuts_array_normalize", "nuts_esh_momentum_update",
+    "nuts_leapfrog_kinetic", "nuts_initialize_trajectory_kinetic",
     "nuts_set_position_masked", "nuts_comm_unique_id", "nuts_comm_create", "nuts_comm_destroy", "nuts_gather_draws_begin", "nuts_gather_draws_end",
 ]
 
@@ -74,6 +76,13 @@ def load():
     L.nuts_axpy.argtypes = [vp, vp, vp, dp, C.c_double, _abi.c_u8_p]
     L.nuts_axpy_out.argtypes = [vp, vp, vp, dp, C.c_double, vp, _abi.c_u8_p]
     L.nuts_array_mult.argtypes = [vp, vp, vp, vp]
+    L.nuts_std_norm_flow.argtypes = [vp, vp, vp, vp, dp, C.c_double, _abi.c_u8_p]
+    L.nuts_std_norm_grad_flow.argtypes = [vp, vp, vp, vp, vp, dp, C.c_double, _abi.c_u8_p]
+    L.nuts_std_norm_grad_flow_inplace.argtypes = [vp, vp, vp, vp, dp, C.c_double, _abi.c_u8_p]
+    L.nuts_array_normalize.argtypes = [vp, vp, _abi.c_u8_p]
+    L.nuts_esh_momentum_update.argtypes = [vp, vp, vp, dp, C.c_double, _abi.c_u8_p, dp]
+    L.nuts_leapfrog_kinetic.argtypes = [vp, C.c_int, vp, vp, dp, C.c_double, _abi.c_i8_p, dp, C.c_double, _abi.c_u8_p, _abi.c_i32_p, dp]
+    L.nuts_initialize_trajectory_kinetic.argtypes = [vp, C.c_int, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]
     L.nuts_array_mult_inplace.argtypes = [vp, vp, vp]
     L.nuts_array_recip.argtypes = [vp, vp, vp]
     L.nuts_fill_array.argtypes = [vp, vp, C.c_double]
@@ -310,6 +319,35 @@ class CudaMath:
         m, mp = self._mask(active)
         _check(load().nuts_axpy_out(self.h, x.h, y.h, ap, ab, out.h, mp))
 
+    def std_norm_flow(self, pos, pos_out, vel, epsilon, active=None):
+        """Math::std_norm_flow (math.rs:155-161): pos_out = pos cos(eps) + vel sin(eps); vel = -pos sin(eps) + vel cos(eps)."""
+        keep, ep, eb = self._scal(epsilon)
+        m, mp = self._mask(active)
+        _check(load().nuts_std_norm_flow(self.h, pos.h, pos_out.h, vel.h, ep, eb, mp))
+
+    def std_norm_grad_flow(self, pos, grad, vel, vel_out, epsilon, active=None):
+        """Math::std_norm_grad_flow (math.rs:162-169): vel_out = vel + eps * (pos + grad)."""
+        keep, ep, eb = self._scal(epsilon)
+        m, mp = self._mask(active)
+        _check(load().nuts_std_norm_grad_flow(self.h, pos.h, grad.h, vel.h, vel_out.h, ep, eb, mp))
+
+    def std_norm_grad_flow_inplace(self, pos, grad, vel, epsilon, active=None):
+        keep, ep, eb = self._scal(epsilon)
+        m, mp = self._mask(active)
+        _check(load().nuts_std_norm_grad_flow_inplace(self.h, pos.h, grad.h, vel.h, ep, eb, mp))
+
+    def array_normalize(self, v, active=None):
+        m, mp = self._mask(active)
+        _check(load().nuts_array_normalize(self.h, v.h, mp))
+
+    def esh_momentum_update(self, gradient, momentum, step_size, active=None):
+        """Math::esh_momentum_update (math.rs:183-210): momentum updated in place; returns the kinetic-energy change per chain."""
+        keep, sp, sb = self._scal(step_size)
+        m, mp = self._mask(active)
+        out = np.zeros(self.nchains)
+        _check(load().nuts_esh_momentum_update(self.h, gradient.h, momentum.h, sp, sb, mp, _p(out)))
+        return out
+
     def array_mult(self, a1, a2, dest):
         _check(load().nuts_array_mult(self.h, a1.h, a2.h, dest.h))
 
@@ -437,10 +475,12 @@ class CudaMath:
         _check(load().nuts_init_state(self.h, p.h, _p(position), status.ctypes.data_as(_abi.c_i32_p)))
         return p, status
 
-    def initialize_trajectory(self, point, resample, seed, chain_offset, counter):
-        _check(load().nuts_initialize_trajectory(self.h, point.h, int(resample), seed, chain_offset, counter))
+    def initialize_trajectory(self, point, resample, seed, chain_offset, counter, kind=_abi.NUTS_KINETIC_EUCLIDEAN):
+        _check(load().nuts_initialize_trajectory_kinetic(self.h, int(kind), point.h, int(resample), seed, chain_offset, counter))
 
-    def leapfrog(self, start, step_size, direction=None, energy_baseline=None, max_energy_error=1000.0, active=None, out=None):
+    def leapfrog(self, start, step_size, direction=None, energy_baseline=None, max_energy_error=1000.0, active=None, out=None,
+                 kind=_abi.NUTS_KINETIC_EUCLIDEAN):
+        """Hamiltonian::leapfrog for every chain; kind = KineticEnergyKind (_abi.NUTS_KINETIC_*)."""
         out = out or Point(self)
         keep, sp, sb = self._scal(step_size)
         d8 = None if direction is None else np.ascontiguousarray(np.broadcast_to(direction, (self.nchains,)), dtype=np.int8)
@@ -448,8 +488,8 @@ class CudaMath:
         m, mp = self._mask(active)
         status = np.zeros(self.nchains, dtype=np.int32)
         ee = np.empty(self.nchains)
-        _check(load().nuts_leapfrog(self.h, start.h, out.h, sp, sb, None if d8 is None else d8.ctypes.data_as(_abi.c_i8_p), _p(base),
-                                    max_energy_error, mp, status.ctypes.data_as(_abi.c_i32_p), _p(ee)))
+        _check(load().nuts_leapfrog_kinetic(self.h, int(kind), start.h, out.h, sp, sb, None if d8 is None else d8.ctypes.data_as(_abi.c_i8_p),
+                                            _p(base), max_energy_error, mp, status.ctypes.data_as(_abi.c_i32_p), _p(ee)))
         return out, status, ee
 
     def is_turning(self, p1, p2):

@@ -63,6 +63,60 @@ inline void axpy_out(const double* x, const double* y, double a, double* out, si
   for (size_t i = 0; i < n; ++i) out[i] = std::fma(a, x[i], y[i]);
 }
 
+// util.rs:507-590  harmonic-oscillator flow of the standard normal: pos_out = p cos(eps) + v sin(eps), vel = -p sin(eps) + v cos(eps).
+// SIMD body (whole registers of LANES): mul_add(p, c, v * s) / mul_add(p, -s, v * c); scalar tail: unfused products.
+inline void std_norm_flow(const double* pos, double* pos_out, double* vel, double epsilon, size_t n) {
+  const double eps_sin = std::sin(epsilon), eps_cos = std::cos(epsilon);
+  const size_t body = (n / LANES) * LANES;
+  for (size_t i = 0; i < body; ++i) {
+    double p = pos[i], v = vel[i];
+    pos_out[i] = std::fma(p, eps_cos, v * eps_sin);
+    vel[i] = std::fma(p, -eps_sin, v * eps_cos);
+  }
+  for (size_t i = body; i < n; ++i) {
+    double p = pos[i], v = vel[i];
+    double new_po = p * eps_cos + v * eps_sin;
+    vel[i] = p * (-eps_sin) + v * eps_cos;
+    pos_out[i] = new_po;
+  }
+}
+// util.rs:592-671  vel_out = vel + eps * (pos + grad): mul_add(eps, p + g, v) in the SIMD body, `v + epsilon * (p + g)` (two roundings)
+// in the scalar tail
+inline void std_norm_grad_flow(const double* pos, const double* grad, const double* vel, double* vel_out, double epsilon, size_t n) {
+  const size_t body = (n / LANES) * LANES;
+  for (size_t i = 0; i < body; ++i) vel_out[i] = std::fma(epsilon, pos[i] + grad[i], vel[i]);
+  for (size_t i = body; i < n; ++i) vel_out[i] = vel[i] + epsilon * (pos[i] + grad[i]);
+}
+// util.rs:673-742
+inline void std_norm_grad_flow_inplace(const double* pos, const double* grad, double* vel, double epsilon, size_t n) {
+  std_norm_grad_flow(pos, grad, vel, vel, epsilon, n);
+}
+// cpu_math.rs:496-503  v := v / ||v||  (sequential sum of squares, one reciprocal, one product per element)
+inline void array_normalize(double* v, size_t n) {
+  double ss = 0.;
+  for (size_t i = 0; i < n; ++i) ss += v[i] * v[i];
+  const double inv = 1.0 / std::sqrt(ss);
+  for (size_t i = 0; i < n; ++i) v[i] *= inv;
+}
+// cpu_math.rs:505-551  ESH (isokinetic) momentum update of Microcanonical HMC; returns the kinetic-energy change
+inline double esh_momentum_update(const double* gradient, double* momentum, double step_size, size_t n) {
+  double gg = 0.;
+  for (size_t i = 0; i < n; ++i) gg += gradient[i] * gradient[i];
+  const double grad_norm = std::sqrt(gg);
+  const double inv_grad_norm = 1.0 / grad_norm;
+  double momentum_proj = 0.;
+  for (size_t i = 0; i < n; ++i) momentum_proj += momentum[i] * gradient[i] * inv_grad_norm;
+  const double dims_m1 = (double)(n - 1);
+  const double delta = step_size * grad_norm / dims_m1;
+  const double zeta = std::exp(-delta);
+  const double coeff_g = (1.0 - zeta) * (1.0 + zeta + momentum_proj * (1.0 - zeta));
+  const double coeff_p = 2.0 * zeta;
+  for (size_t i = 0; i < n; ++i) momentum[i] = coeff_g * (gradient[i] * inv_grad_norm) + coeff_p * momentum[i];
+  array_normalize(momentum, n);
+  const double arg = momentum_proj + (1.0 - momentum_proj) * zeta * zeta;
+  return (delta - 0.6931471805599453094 + std::log1p(arg)) * dims_m1;
+}
+
 // util.rs:349-400
 inline double vector_dot(const double* a, const double* b, size_t n) {
   size_t nsimd = n / LANES;  // whole SIMD registers
@@ -590,11 +644,14 @@ struct BadInitGrad : std::runtime_error {
   BadInitGrad() : std::runtime_error("Invalid initial point") {}
 };
 
+enum class KineticEnergyKind { Euclidean = 0, ExactNormal = 1, Microcanonical = 2 };  // :22-50
+
 struct TransformedHamiltonian {
   size_t dim;
   LogpFunc* logp_func;
   Vec ones, zeros;
   double step_size = 0.;
+  KineticEnergyKind kinetic_energy_kind = KineticEnergyKind::Euclidean;  // :381, default :434
   DiagMassMatrix transformation;
   StatePool pool;  // :427 StatePool::new(math, 10)
   uint64_t n_logp_evals = 0, n_leapfrogs = 0;
@@ -637,17 +694,39 @@ struct TransformedHamiltonian {
     int sign = dir == Direction::Forward ? 1 : -1;
     double epsilon = (double)sign * step_size * step_size_factor;
     o.step_size_factor = step_size_factor;
-    // first velocity half-step: v_out = (eps/2)*grad_z + v
-    axpy_out(s.transformed_gradient.data(), s.velocity.data(), epsilon / 2., o.velocity.data(), dim);
-    // position step: z_out = eps*v_out + z
-    axpy_out(o.velocity.data(), s.transformed_position.data(), epsilon, o.transformed_position.data(), dim);
+    const KineticEnergyKind kind = kinetic_energy_kind;
+    const double sqrt_d = std::sqrt((double)dim);
+    // first velocity half-step (:160-199)
+    if (kind == KineticEnergyKind::ExactNormal) {
+      std_norm_grad_flow(s.transformed_position.data(), s.transformed_gradient.data(), s.velocity.data(), o.velocity.data(),
+                         epsilon / 2., dim);
+    } else if (kind == KineticEnergyKind::Euclidean) {
+      axpy_out(s.transformed_gradient.data(), s.velocity.data(), epsilon / 2., o.velocity.data(), dim);  // v_out = (eps/2)*grad_z + v
+    } else {
+      o.velocity = s.velocity;
+      o.kinetic_energy = s.kinetic_energy + esh_momentum_update(s.transformed_gradient.data(), o.velocity.data(), sqrt_d * epsilon / 2., dim);
+    }
+    // position step (:201-228)
+    if (kind == KineticEnergyKind::ExactNormal) {
+      std_norm_flow(s.transformed_position.data(), o.transformed_position.data(), o.velocity.data(), epsilon, dim);
+    } else {
+      const double e = kind == KineticEnergyKind::Microcanonical ? epsilon * sqrt_d : epsilon;
+      axpy_out(o.velocity.data(), s.transformed_position.data(), e, o.transformed_position.data(), dim);  // z_out = eps*v_out + z
+    }
     init_from_transformed_position(o);
-    // second velocity half-step
-    axpy(o.transformed_gradient.data(), o.velocity.data(), epsilon / 2., dim);
-    o.update_kinetic_energy();
+    // second velocity half-step (:230-258); Microcanonical keeps the accumulated delta KE, the others recompute 1/2 |v|^2 (:582-586)
+    if (kind == KineticEnergyKind::ExactNormal) {
+      std_norm_grad_flow_inplace(o.transformed_position.data(), o.transformed_gradient.data(), o.velocity.data(), epsilon / 2., dim);
+    } else if (kind == KineticEnergyKind::Euclidean) {
+      axpy(o.transformed_gradient.data(), o.velocity.data(), epsilon / 2., dim);
+    } else {
+      o.kinetic_energy = o.kinetic_energy + esh_momentum_update(o.transformed_gradient.data(), o.velocity.data(), sqrt_d * epsilon / 2., dim);
+    }
+    if (kind != KineticEnergyKind::Microcanonical) o.update_kinetic_energy();
     o.index_in_trajectory = s.index_in_trajectory + sign;
     double energy_error = o.energy() - energy_baseline;
-    bool bad_energy = energy_error > max_energy_error;
+    bool bad_energy = kind == KineticEnergyKind::Microcanonical ? std::fabs(energy_error) >= max_energy_error  // :591-596
+                                                                : energy_error > max_energy_error;
     LeapfrogResult res;
     if (bad_energy | !std::isfinite(energy_error)) {
       res.kind = LeapfrogResult::Divergence;
@@ -700,6 +779,7 @@ struct TransformedHamiltonian {
       // cpu_math.rs:561-577 array_gaussian(rng, velocity, ones): v[i] = 1.0 * normal, sequential in i
       rng.fill_normal(p.velocity.data(), dim);
       for (size_t i = 0; i < dim; ++i) p.velocity[i] = ones[i] * p.velocity[i];
+      if (kinetic_energy_kind == KineticEnergyKind::Microcanonical) array_normalize(p.velocity.data(), dim);  // :699-702
     }
     if (transformation.id != p.transform_id) {
       // diagonal.rs:210-221 inv_transform_normalize: no logp evaluation
@@ -708,7 +788,8 @@ struct TransformedHamiltonian {
       p.logdet = transformation.logdet;
       p.transform_id = transformation.id;
     }
-    p.update_kinetic_energy();
+    if (kinetic_energy_kind == KineticEnergyKind::Microcanonical) p.kinetic_energy = 0.0;  // :720-729
+    else p.update_kinetic_energy();
     p.index_in_trajectory = 0;
     p.initial_energy = p.energy();
   }
@@ -1160,6 +1241,7 @@ struct NutsSettings {  // src/sampler.rs:199-239 + defaults :507-531,630-634
   bool check_turning = true;
   std::optional<double> target_integration_time;
   uint64_t num_chains = 6, seed = 0, extra_doublings = 0;
+  KineticEnergyKind trajectory_kind = KineticEnergyKind::Euclidean;  // sampler.rs:232, default :528
 };
 
 struct NutsChain {  // chain.rs:44-61
@@ -1179,6 +1261,7 @@ struct NutsChain {  // chain.rs:44-61
     options.target_integration_time = s.target_integration_time;
     options.extra_doublings = s.extra_doublings;
     options.max_energy_error = s.max_energy_error;
+    hamiltonian.kinetic_energy_kind = s.trajectory_kind;  // sampler.rs:757 TransformedHamiltonian::new(.., self.trajectory_kind)
     state = std::make_shared<TransformedPoint>(f->dim);
   }
   // chain.rs:137-149 ; throws BadInitGrad

@@ -34,6 +34,13 @@ def lib():
         L.orc_vector_dot.restype = C.c_double
         L.orc_vector_dot.argtypes = [dp, dp, C.c_size_t]
         L.orc_axpy.argtypes = [dp, dp, C.c_double, C.c_size_t]
+        L.orc_std_norm_flow.argtypes = [dp, dp, dp, C.c_double, C.c_size_t]
+        L.orc_std_norm_grad_flow.argtypes = [dp, dp, dp, dp, C.c_double, C.c_size_t]
+        L.orc_std_norm_grad_flow_inplace.argtypes = [dp, dp, dp, C.c_double, C.c_size_t]
+        L.orc_array_normalize.argtypes = [dp, C.c_size_t]
+        L.orc_esh_momentum_update.restype = C.c_double
+        L.orc_esh_momentum_update.argtypes = [dp, dp, C.c_double, C.c_size_t]
+        L.orc_ham_set_kinetic_energy_kind.argtypes = [C.c_void_p, C.c_int]
         L.orc_axpy_out.argtypes = [dp, dp, C.c_double, dp, C.c_size_t]
         L.orc_multiply.argtypes = [dp, dp, dp, C.c_size_t]
         L.orc_multiply_inplace.argtypes = [dp, dp, C.c_size_t]
@@ -192,6 +199,39 @@ def lowrank_compute_update(draws, grads, gamma=1e-5, eigval_cutoff=2.0):
     return stds, mean, vals[:r].copy(), vecs[:r].copy(), mu
 
 
+def std_norm_flow(pos, vel, epsilon):
+    """util.rs:575 std_norm_flow: returns (pos_out, vel')."""
+    pos, vel = _f64(pos), _f64(vel).copy()
+    out = np.empty_like(pos)
+    lib().orc_std_norm_flow(_p(pos), _p(out), _p(vel), epsilon, pos.size)
+    return out, vel
+
+
+def std_norm_grad_flow(pos, grad, vel, epsilon, inplace=False):
+    """util.rs:650 / :726 std_norm_grad_flow(_inplace): returns vel + eps * (pos + grad)."""
+    pos, grad, vel = _f64(pos), _f64(grad), _f64(vel)
+    if inplace:
+        v = vel.copy()
+        lib().orc_std_norm_grad_flow_inplace(_p(pos), _p(grad), _p(v), epsilon, pos.size)
+        return v
+    out = np.empty_like(pos)
+    lib().orc_std_norm_grad_flow(_p(pos), _p(grad), _p(vel), _p(out), epsilon, pos.size)
+    return out
+
+
+def array_normalize(v):
+    v = _f64(v).copy()
+    lib().orc_array_normalize(_p(v), v.size)
+    return v
+
+
+def esh_momentum_update(gradient, momentum, step_size):
+    """cpu_math.rs:505-551: returns (momentum', kinetic energy change)."""
+    g, m = _f64(gradient), _f64(momentum).copy()
+    dke = lib().orc_esh_momentum_update(_p(g), _p(m), step_size, g.size)
+    return m, dke
+
+
 def vector_dot(a, b):
     a = _f64(a)
     b = _f64(b)
@@ -300,6 +340,10 @@ class Hamiltonian:
         self.model = model
         self.dim = model.dim
         self.h = lib().orc_ham_create(model.h)
+
+    def set_kinetic_energy_kind(self, kind):
+        """KineticEnergyKind (transformed_hamiltonian.rs:22-50): _abi.NUTS_KINETIC_*."""
+        lib().orc_ham_set_kinetic_energy_kind(self.h, int(kind))
 
     def set_transform(self, stds, mean):
         stds, mean = _f64(stds), _f64(mean)

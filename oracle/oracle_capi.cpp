@@ -60,6 +60,9 @@ NutsSettings convert_settings(const nuts_settings_t* s) {
   o.num_chains = s->num_chains;
   o.seed = s->seed;
   o.extra_doublings = s->extra_doublings;
+  o.trajectory_kind = s->trajectory_kind == NUTS_KINETIC_EXACT_NORMAL     ? KineticEnergyKind::ExactNormal
+                      : s->trajectory_kind == NUTS_KINETIC_MICROCANONICAL ? KineticEnergyKind::Microcanonical
+                                                                          : KineticEnergyKind::Euclidean;
   const auto& a = s->adapt_options;
   o.adapt_options.early_window = a.early_window;
   o.adapt_options.step_size_window = a.step_size_window;
@@ -135,6 +138,17 @@ void orc_multiply_inplace(double* out, const double* x, size_t n) { multiply_inp
 void orc_axpy(const double* x, double* y, double a, size_t n) { axpy(x, y, a, n); }
 void orc_axpy_out(const double* x, const double* y, double a, double* out, size_t n) { axpy_out(x, y, a, out, n); }
 double orc_vector_dot(const double* a, const double* b, size_t n) { return vector_dot(a, b, n); }
+void orc_std_norm_flow(const double* pos, double* pos_out, double* vel, double epsilon, size_t n) { std_norm_flow(pos, pos_out, vel, epsilon, n); }
+void orc_std_norm_grad_flow(const double* pos, const double* grad, const double* vel, double* vel_out, double epsilon, size_t n) {
+  std_norm_grad_flow(pos, grad, vel, vel_out, epsilon, n);
+}
+void orc_std_norm_grad_flow_inplace(const double* pos, const double* grad, double* vel, double epsilon, size_t n) {
+  std_norm_grad_flow_inplace(pos, grad, vel, epsilon, n);
+}
+void orc_array_normalize(double* v, size_t n) { array_normalize(v, n); }
+double orc_esh_momentum_update(const double* gradient, double* momentum, double step_size, size_t n) {
+  return esh_momentum_update(gradient, momentum, step_size, n);
+}
 void orc_scalar_prods3(const double* p1, const double* n1, const double* p2, const double* x, const double* y, size_t n,
                        double* o1, double* o2) {
   scalar_prods3(p1, n1, p2, x, y, n, o1, o2);
@@ -206,6 +220,7 @@ double orc_model_logp(void* m, const double* x, double* grad) { return ((LogpFun
 void* orc_ham_create(void* model) { return new Ham((LogpFunc*)model); }
 void orc_ham_destroy(void* h) { delete (Ham*)h; }
 void orc_ham_set_step_size(void* h, double eps) { ((Ham*)h)->h.step_size = eps; }
+void orc_ham_set_kinetic_energy_kind(void* h, int kind) { ((Ham*)h)->h.kinetic_energy_kind = (KineticEnergyKind)kind; }
 void orc_ham_set_transform(void* h, const double* stds, const double* mean) {
   auto& H = ((Ham*)h)->h;
   H.transformation.set_transform(Vec(stds, stds + H.dim), Vec(mean, mean + H.dim));
