@@ -1045,7 +1045,14 @@ int nuts_leapfrog(nuts_ctx_t* ctx, const nuts_point_t* start, nuts_point_t* out,
     ddir = ctx->d_i8;
   }
   CUDA_TRY(cudaMemsetAsync(ctx->d_i32, 0, ctx->N * sizeof(int), ctx->stream));
-  if (ctx->lr_active)
+  // elementwise targets on the diagonal transformation: input rows staged by the TMA (bit-identical to the register path;
+  // NUTS_B200_PLANE_TMA=0 selects the register path)
+  const char* tma_env = std::getenv("NUTS_B200_PLANE_TMA");
+  const bool tma = !(tma_env && tma_env[0] == '0') && !ctx->lr_active && (ctx->model.kind == LOGP_GAUSS_ISO || ctx->model.kind == LOGP_GAUSS_DIAG);
+  if (tma)
+    k_leapfrog_tma<<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, start->dev, out->dev, dstep, step_size_bcast, ddir, dbase, max_energy_error, dm,
+                             ctx->d_i32, ctx->d_sc[2]);
+  else if (ctx->lr_active)
     k_leapfrog<true><<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, start->dev, out->dev, dstep, step_size_bcast, ddir, dbase, max_energy_error,
                                dm, ctx->d_i32, ctx->d_sc[2]);
   else

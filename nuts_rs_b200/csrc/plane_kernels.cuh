@@ -494,6 +494,139 @@ __global__ void __launch_bounds__(PK_THREADS) k_leapfrog(RowArgs A, ModelDev m, 
   }
 }
 
+// ---------------------------------------------------------------- TMA bulk copies (cp.async.bulk + mbarrier; SASS UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); completion is counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (int spin = 0; !ok; ++spin) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    if (spin > (1 << 22)) __trap();  // a byte count that never completes must not hang the GPU
+  }
+}
+
+// Hamiltonian::leapfrog for the elementwise targets (isotropic / diagonal Gaussian, diagonal transformation) with the five input rows
+// (z, v, grad_z, sigma, mean) staged through shared memory by the TMA: one thread arms an mbarrier per stage and issues five
+// cp.async.bulk copies of a TMA_CH-element chunk each (4 KB per vector, 20 KB per stage, two stages: a d <= 1024 row is completely in
+// flight before the first wait - 40 KB per CTA, 160 KB per SM at 4 resident CTAs, against ~40 KB for k_leapfrog's register loads); the
+// 256 threads wait on the stage, compute from shared memory and store the five output rows straight from registers.  Element ->
+// thread mapping and the order of every thread's partial sums are those of k_leapfrog's single-pass branch, so the results are
+// bit-identical to it (tests/test_gpu_primitives.py::test_leapfrog_tma_matches_register_path).
+// HBM traffic per chain: 40*d B in, 40*d B out (the model's mu / precision vectors are shared by all chains and stay in L2).
+constexpr int TMA_CH = 512;
+constexpr int TMA_NST = 2;
+__global__ void __launch_bounds__(PK_THREADS) k_leapfrog_tma(RowArgs A, ModelDev m, TransformDev T, PointDev s, PointDev o,
+                                                              const double* step_size, double step_bcast, const int8_t* dir,
+                                                              const double* baseline, double max_energy_error, const uint8_t* active,
+                                                              int* status, double* energy_error_out) {
+  __shared__ double scratch[2 * 32 * REDUCE_MAXK];
+  __shared__ alignas(128) double buf[TMA_NST][5][TMA_CH];
+  __shared__ alignas(8) uint64_t full[TMA_NST];
+  TeamReduce<PK_THREADS> red(scratch);
+  NB_ROW_PROLOGUE
+  const int d = A.d;
+  const int nch = (d + TMA_CH - 1) / TMA_CH;
+  const int sign = dir ? (int)dir[c] : 1;
+  const double eps = (double)sign * (step_size ? step_size[c] : step_bcast) * 1.0;
+  const double eps_half = eps / 2.;
+  const bool diag = m.kind == LOGP_GAUSS_DIAG;
+  const double* src[5] = {s.z + row, s.v + row, s.gz + row, T.stds + row, T.mean + row};
+  auto issue = [&](int k) {  // one thread: chunk k into stage k % TMA_NST
+    const int st = k % TMA_NST, c0 = k * TMA_CH;
+    const int len = min(TMA_CH, d - c0);
+    const uint32_t bytes = (uint32_t)((len + 1) & ~1) * 8u;  // rows are padded to a multiple of 16 doubles: the odd tail reads its neighbour
+    mbar_expect_tx(&full[st], 5u * bytes);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) bulk_g2s(&buf[st][q][0], src[q] + c0, bytes, &full[st]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int st = 0; st < TMA_NST; ++st) mbar_init(&full[st], 1);
+    mbar_fence_init();
+    for (int k = 0; k < nch && k < TMA_NST; ++k) issue(k);
+  }
+  __syncthreads();  // the barriers are initialised before anybody waits on them
+  double part[2] = {0.0, 0.0};
+  for (int k = 0; k < nch; ++k) {
+    const int st = k % TMA_NST, c0 = k * TMA_CH;
+    const int len = min(TMA_CH, d - c0);
+    // this thread's model parameters first: L2 hits that are in flight while the bulk copy lands
+    double mu_[TMA_CH / PK_THREADS], pr_[TMA_CH / PK_THREADS];
+#pragma unroll
+    for (int e = 0; e < TMA_CH / PK_THREADS; ++e) {
+      const int li = threadIdx.x + e * PK_THREADS;
+      mu_[e] = li < len ? m.mu[c0 + li] : 0.0;
+      pr_[e] = (diag && li < len) ? m.prec[c0 + li] : 0.0;
+    }
+    mbar_wait(&full[st], (uint32_t)((k / TMA_NST) & 1));
+#pragma unroll
+    for (int e = 0; e < TMA_CH / PK_THREADS; ++e) {
+      const int li = threadIdx.x + e * PK_THREADS;
+      if (li < len) {
+        const size_t gi = row + c0 + li;
+        const double sg = buf[st][3][li];
+        const double vh = fma(eps_half, buf[st][2][li], buf[st][1][li]);
+        const double zn = fma(eps, vh, buf[st][0][li]);
+        const double t = zn * sg;
+        const double xn = fma(1.0, buf[st][4][li], t);
+        const double diff = xn - mu_[e];
+        double gxn;
+        if (!diag) {
+          part[0] -= diff * diff / 2.;
+          gxn = -diff;
+        } else {
+          const double pd = diff * pr_[e];
+          part[0] -= diff * pd / 2.;
+          gxn = -pd;
+        }
+        const double gn = gxn * sg;
+        const double vn = fma(eps_half, gn, vh);
+        part[1] = fma(vn, vn, part[1]);
+        o.z[gi] = zn;
+        o.x[gi] = xn;
+        o.gx[gi] = gxn;
+        o.gz[gi] = gn;
+        o.v[gi] = vn;
+      }
+    }
+    if (k + TMA_NST < nch) {  // refill the stage once every thread has read it
+      __syncthreads();
+      if (threadIdx.x == 0) issue(k + TMA_NST);
+    }
+  }
+  red.allreduce(part);
+  if (threadIdx.x == 0) {
+    const double lp = part[0];
+    const double ke = 0.5 * part[1];
+    const double logdet = T.logdet[c];
+    o.logp[c] = lp;
+    o.logdet[c] = logdet;
+    o.ke[c] = ke;
+    o.e0[c] = s.e0[c];
+    o.tid[c] = T.id[c];
+    o.idx[c] = s.idx[c] + sign;
+    const double base = baseline ? baseline[c] : s.e0[c];
+    const double ee = (ke - (lp + logdet)) - base;
+    if (energy_error_out) energy_error_out[c] = ee;
+    if (status) status[c] = ((ee > max_energy_error) | !isfinite(ee)) ? 1 : 0;
+  }
+}
+
 // Math::apply_lowrank_transform / _inplace for every chain (Tier 1)
 __global__ void __launch_bounds__(PK_THREADS) k_lowrank_apply(RowArgs A, const double* vecs, const double* vals, const int* rank, int rmax,
                                                                const double* in, double* out) {

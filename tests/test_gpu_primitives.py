@@ -273,6 +273,49 @@ def test_leapfrog_parity(L, orc, name, spec, d):
     m.close()
 
 
+@pytest.mark.parametrize("kind", [_abi.NUTS_LOGP_GAUSS_ISO, _abi.NUTS_LOGP_GAUSS_DIAG])
+@pytest.mark.parametrize("d", [1, 3, 255, 511, 512, 513, 1000, 1024, 1025, 1537, 2000, 4567])
+def test_leapfrog_tma_matches_register_path(L, kind, d, monkeypatch):
+    """k_leapfrog_tma (input rows staged through shared memory by cp.async.bulk + mbarrier, the default for the elementwise targets)
+    against k_leapfrog's register path (NUTS_B200_PLANE_TMA=0): every plane and scalar bit-identical, over chunk boundaries (512
+    elements per stage), stage refills (d > 1024), odd tails, per-chain steps, both directions and a mask."""
+    N = 6
+    rng = np.random.default_rng(3 * d + kind)
+    kw = dict(mu=0.5)
+    if kind == _abi.NUTS_LOGP_GAUSS_DIAG:
+        kw["sigma"] = np.exp(np.linspace(-1, 1, d))
+    m = L.CudaMath(N, d, kind, **kw)
+    m.set_transform(np.exp(0.3 * rng.normal(size=(N, d))), 0.1 * rng.normal(size=(N, d)))
+    p, status = m.init_state(rng.normal(size=(N, d)))
+    assert (status == 0).all()
+    m.initialize_trajectory(p, True, seed=11, chain_offset=0, counter=0)
+    eps = 0.05 + 0.02 * rng.random(N)
+    direction = np.array([1, -1, 1, -1, -1, 1], dtype=np.int8)
+    active = np.array([1, 1, 0, 1, 1, 1], dtype=np.uint8)
+    results = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NUTS_B200_PLANE_TMA", flag)
+        cur, outs = p, []
+        for step in range(3):
+            nxt = m.new_point()
+            nxt.set_vec(nxt.Z, np.full((N, d), -7.0))
+            nxt, st, ee = m.leapfrog(cur, eps, direction=direction, active=active if step == 1 else None, out=nxt)
+            outs.append(([nxt.vec(w) for w in range(5)], nxt.scalars(), st.copy(), ee.copy()))
+            if step == 1:  # the masked chain keeps whatever the output point held
+                assert (nxt.vec(nxt.Z)[2] == -7.0).all()
+                nxt.set_vec(nxt.Z, np.where(active[:, None] != 0, nxt.vec(nxt.Z), cur.vec(cur.Z)))
+            cur = nxt
+        results[flag] = outs
+    for a, b in zip(results["1"], results["0"]):
+        for va, vb in zip(a[0], b[0]):
+            np.testing.assert_array_equal(va, vb)
+        for key in a[1]:
+            np.testing.assert_array_equal(np.asarray(a[1][key])[active != 0], np.asarray(b[1][key])[active != 0], err_msg=key)
+        np.testing.assert_array_equal(a[2], b[2])
+        np.testing.assert_array_equal(a[3][active != 0], b[3][active != 0])
+    m.close()
+
+
 def test_leapfrog_divergence_and_mask(L, orc):
     N, d = 4, 10
     m = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_ISO, mu=0.0)
