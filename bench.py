@@ -258,6 +258,40 @@ def microbench_fixed_depth(lib, _abi, device, chain_offset, depth=6, draws=8):
             "algorithmic_GBps": rate * 48 * DIM / 1e9}
 
 
+def microbench_plane_leapfrog(lib, _abi, device, nchains=16384, steps=10, warmup=3):
+    """The Tier-2 fused leapfrog `nuts_leapfrog` (plane kernel k_leapfrog_tma: rows staged by cp.async.bulk + mbarrier) at an
+    HBM-resident size: 16384 chains x 1000 dims = 131 MB per plane, 10 planes per step (read z, v, grad_z, sigma, mean; write z', v',
+    x', grad_x', grad_z' = 80 * dim bytes per chain).  Device time of the kernel from CUDA events on the context's stream
+    (nuts_ctx_last_kernel_ms); the two points ping-pong, so every step streams 1.3 GB that the previous step did not leave in L2
+    in a usable order (planes >> 126 MB L2)."""
+    try:
+        math = lib.CudaMath(nchains, DIM, _abi.NUTS_LOGP_GAUSS_DIAG, mu=0.5, sigma=model_sigma(), device=device)
+        math.set_transform(np.exp(np.linspace(-0.5, 0.5, DIM)), 0.1)
+        p, st = math.init_state(np.random.default_rng(0).normal(size=(nchains, DIM)))
+        math.initialize_trajectory(p, True, SEED, 0, 0)
+        q = lib.Point(math)
+        out = {}
+        for name, flag in (("tma", "1"), ("register_path", "0")):
+            os.environ["NUTS_B200_PLANE_TMA"] = flag
+            ms = []
+            for i in range(warmup + steps):
+                q, status, ee = math.leapfrog(p, 0.1, out=q)
+                p, q = q, p
+                if i >= warmup:
+                    ms.append(math.last_kernel_ms())
+            mean_ms = sum(ms) / len(ms)
+            gbps = 80.0 * DIM * nchains / (mean_ms * 1e-3) / 1e9
+            out[name] = {"kernel_ms": mean_ms, "kernel_ms_min": min(ms), "algorithmic_GBps": gbps, "diverged": int((status != 0).sum())}
+        os.environ.pop("NUTS_B200_PLANE_TMA", None)
+        math.close()
+        return {"what": "nuts_leapfrog (Tier 2) on %d chains x %d dims, diagonal Gaussian, CUDA events around the kernel; "
+                        "algorithmic bytes = 80 * dim per chain and step" % (nchains, DIM),
+                "chains": nchains, "dim": DIM, "steps": steps, "algorithmic_bytes_per_launch": 80 * DIM * nchains, **out}
+    except Exception as e:  # a measurement extra must never take the bench line down
+        os.environ.pop("NUTS_B200_PLANE_TMA", None)
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def cpu_oracle_throughput(max_seconds, nthreads):
     """The oracle (C++ restatement of nuts-rs's CPU path, one chain per thread like the reference's rayon pool,
     src/sampler.rs:1287-1326) on a bounded sample of the same workload: `4 x cores` chains, 400 tuning draws (untimed),
@@ -538,6 +572,7 @@ def main():
     clocks.__exit__(None, None, None)
 
     micro = microbench_fixed_depth(lib, _abi, local_rank, chain_offset) if rank == 0 else None
+    plane = microbench_plane_leapfrog(lib, _abi, local_rank) if rank == 0 else None
 
     # ---------------- reduce over ranks: max time, summed work
     names = sorted(other)
@@ -669,6 +704,12 @@ def main():
         elif gather is not None:
             line["config"]["draw_gather"] = gather
         line["config"]["microbench_fixed_step_no_turn_checks_rank0"] = micro
+        if plane is not None:
+            peak = line["roofline"]["peak"]
+            for k in ("tma", "register_path"):
+                if isinstance(plane.get(k), dict):
+                    plane[k]["frac_of_hbm_peak"] = plane[k]["algorithmic_GBps"] / peak
+            line["config"]["plane_leapfrog_rank0"] = plane
         line["config"]["other_configs"] = other_out
         if whole:
             k = 4 + 2 * len(names)

@@ -173,6 +173,8 @@ int nuts_ctx_synchronize(nuts_ctx_t* ctx);
 uint64_t nuts_ctx_nchains(const nuts_ctx_t* ctx);
 uint64_t nuts_ctx_dim(const nuts_ctx_t* ctx); /* Math::dim, math.rs:69 */
 void* nuts_ctx_stream(nuts_ctx_t* ctx);       /* the cudaStream_t every call on this ctx is ordered on */
+/* device time (CUDA events on the ctx stream, ms) of the kernel of the last nuts_leapfrog call: measurement hook of bench.py */
+int nuts_ctx_last_kernel_ms(nuts_ctx_t* ctx, float* ms);
 int nuts_plane_alloc(nuts_ctx_t* ctx, nuts_plane_t** plane);                     /* new_array (zero filled) */
 int nuts_plane_free(nuts_ctx_t* ctx, nuts_plane_t* plane);
 int nuts_plane_read_from_host(nuts_ctx_t* ctx, nuts_plane_t* dst, const double* src /*[N*d]*/); /* read_from_slice */

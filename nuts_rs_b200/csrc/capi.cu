@@ -171,6 +171,8 @@ struct nuts_ctx {
   int8_t* d_i8 = nullptr;       // [N]
   int* d_i32 = nullptr;         // [N]
   long long* d_i64 = nullptr;   // [N]
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the kernel of the last nuts_leapfrog (nuts_ctx_last_kernel_ms)
+  bool ev_valid = false;
   RowArgs row_args() const { return RowArgs{(int)N, (int)d, (int)ld}; }
 };
 
@@ -402,6 +404,8 @@ int nuts_ctx_create(nuts_ctx_t** out, int device_id, uint64_t nchains, uint64_t 
   TRY(dev_alloc(&ctx->d_i8, nchains));
   TRY(dev_alloc(&ctx->d_i32, nchains));
   TRY(dev_alloc(&ctx->d_i64, nchains));
+  CUDA_TRY(cudaEventCreate(&ctx->ev_k0));
+  CUDA_TRY(cudaEventCreate(&ctx->ev_k1));
   guard.dismiss();
   *out = ctx;
   return NUTS_OK;
@@ -430,6 +434,8 @@ int nuts_ctx_destroy(nuts_ctx_t* ctx) {
   cudaFree(ctx->d_i8);
   cudaFree(ctx->d_i32);
   cudaFree(ctx->d_i64);
+  if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+  if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return NUTS_OK;
@@ -438,6 +444,13 @@ int nuts_ctx_synchronize(nuts_ctx_t* ctx) { return sync(ctx); }
 uint64_t nuts_ctx_nchains(const nuts_ctx_t* ctx) { return ctx->N; }
 uint64_t nuts_ctx_dim(const nuts_ctx_t* ctx) { return ctx->d; }
 void* nuts_ctx_stream(nuts_ctx_t* ctx) { return (void*)ctx->stream; }
+int nuts_ctx_last_kernel_ms(nuts_ctx_t* ctx, float* ms) {
+  if (!ctx || !ms) return fail(NUTS_ERR_INVALID, "nuts_ctx_last_kernel_ms: NULL argument");
+  if (!ctx->ev_valid) return fail(NUTS_ERR_INVALID, "nuts_ctx_last_kernel_ms: no nuts_leapfrog call on this context yet");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+  return NUTS_OK;
+}
 
 int nuts_plane_alloc(nuts_ctx_t* ctx, nuts_plane_t** plane) {
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1049,6 +1062,7 @@ int nuts_leapfrog(nuts_ctx_t* ctx, const nuts_point_t* start, nuts_point_t* out,
   // NUTS_B200_PLANE_TMA=0 selects the register path)
   const char* tma_env = std::getenv("NUTS_B200_PLANE_TMA");
   const bool tma = !(tma_env && tma_env[0] == '0') && !ctx->lr_active && (ctx->model.kind == LOGP_GAUSS_ISO || ctx->model.kind == LOGP_GAUSS_DIAG);
+  CUDA_TRY(cudaEventRecord(ctx->ev_k0, ctx->stream));
   if (tma)
     k_leapfrog_tma<<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, start->dev, out->dev, dstep, step_size_bcast, ddir, dbase, max_energy_error, dm,
                              ctx->d_i32, ctx->d_sc[2]);
@@ -1059,6 +1073,8 @@ int nuts_leapfrog(nuts_ctx_t* ctx, const nuts_point_t* start, nuts_point_t* out,
     k_leapfrog<false><<<GRID>>>(ctx->row_args(), ctx->model, ctx->T, start->dev, out->dev, dstep, step_size_bcast, ddir, dbase, max_energy_error,
                                 dm, ctx->d_i32, ctx->d_sc[2]);
   CHECK_LAUNCH();
+  CUDA_TRY(cudaEventRecord(ctx->ev_k1, ctx->stream));
+  ctx->ev_valid = true;
   if (status) CUDA_TRY(cudaMemcpyAsync(status, ctx->d_i32, ctx->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   TRY(download_f64(ctx, 2, energy_error));
   return sync(ctx);

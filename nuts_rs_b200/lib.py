@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "nuts_sampler_create_lowrank", "nuts_sampler_set_lowrank_transform", "nuts_sampler_set_grads_out",
     "nuts_eigs_create", "nuts_eigs_free", "nuts_apply_lowrank_transform", "nuts_apply_lowrank_transform_inplace", "nuts_set_lowrank_transform",
     "nuts_std_norm_flow", "nuts_std_norm_grad_flow", "nuts_std_norm_grad_flow_inplace", "nuts_array_normalize", "nuts_esh_momentum_update",
-    "nuts_leapfrog_kinetic", "nuts_initialize_trajectory_kinetic",
+    "nuts_leapfrog_kinetic", "nuts_initialize_trajectory_kinetic", "nuts_ctx_last_kernel_ms",
     "nuts_set_position_masked", "nuts_comm_unique_id", "nuts_comm_create", "nuts_comm_destroy", "nuts_gather_draws_begin", "nuts_gather_draws_end",
 ]
 
@@ -81,6 +81,7 @@ def load():
     L.nuts_std_norm_grad_flow_inplace.argtypes = [vp, vp, vp, vp, dp, C.c_double, _abi.c_u8_p]
     L.nuts_array_normalize.argtypes = [vp, vp, _abi.c_u8_p]
     L.nuts_esh_momentum_update.argtypes = [vp, vp, vp, dp, C.c_double, _abi.c_u8_p, dp]
+    L.nuts_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.nuts_leapfrog_kinetic.argtypes = [vp, C.c_int, vp, vp, dp, C.c_double, _abi.c_i8_p, dp, C.c_double, _abi.c_u8_p, _abi.c_i32_p, dp]
     L.nuts_initialize_trajectory_kinetic.argtypes = [vp, C.c_int, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]
     L.nuts_array_mult_inplace.argtypes = [vp, vp, vp]
@@ -491,6 +492,12 @@ class CudaMath:
         _check(load().nuts_leapfrog_kinetic(self.h, int(kind), start.h, out.h, sp, sb, None if d8 is None else d8.ctypes.data_as(_abi.c_i8_p),
                                             _p(base), max_energy_error, mp, status.ctypes.data_as(_abi.c_i32_p), _p(ee)))
         return out, status, ee
+
+    def last_kernel_ms(self):
+        """Device time of the kernel of the last leapfrog() call (CUDA events on the context's stream)."""
+        ms = C.c_float()
+        _check(load().nuts_ctx_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
 
     def is_turning(self, p1, p2):
         out = np.zeros(self.nchains, dtype=np.uint8)

@@ -15,12 +15,25 @@ The launch length follows the schedule: a launch ends exactly at the next draw a
 sees its new transformation at the same draw index as in the reference.
 """
 import collections
+import concurrent.futures
 import math
+import os
 
 import numpy as np
 import scipy.linalg
 
 from . import lib as _lib
+
+
+def _blas_single_threaded():
+    try:
+        from threadpoolctl import threadpool_limits
+
+        return threadpool_limits(limits=1)
+    except ImportError:  # without threadpoolctl the estimator still works, only slower
+        import contextlib
+
+        return contextlib.nullcontext()
 
 
 # ------------------------------------------------------------------------------------------------ the estimator (host)
@@ -178,6 +191,8 @@ class LowRankSampler:
         self.updates = 0          # transformations installed so far (summed over chains)
         self.last_ranks = np.zeros(self.N, dtype=np.int64)
         self._gbuf = None
+        nthreads = min(self.N, os.cpu_count() or 1, int(os.environ.get("NUTS_B200_ESTIMATOR_THREADS", "16")))
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=nthreads) if nthreads > 1 else None
 
     def set_position(self, position):
         status = self.sampler.set_position(position)
@@ -256,9 +271,19 @@ class LowRankSampler:
         stds, mean = cur["stds"].copy(), cur["mean"].copy()
         vals, vecs = np.ones((N, self.rank_max)), np.zeros((N, self.rank_max, d))
         mu, rank = np.zeros((N, d)), np.zeros(N, dtype=np.int32)
-        for c in np.nonzero(due)[0]:
-            w = self.windows[c]
-            upd = compute_update(np.array(w.draws), np.array(w.grads), self.gamma, self.cutoff)
+        # the estimators of the chains that are due are independent: one host thread each (LAPACK releases the GIL), like the
+        # reference's one-chain-per-rayon-task warm-up (src/sampler.rs:1287-1326)
+        todo = [int(c) for c in np.nonzero(due)[0]]
+        work = lambda c: compute_update(np.array(self.windows[c].draws), np.array(self.windows[c].grads), self.gamma, self.cutoff)
+        # (BLAS / LAPACK themselves run single-threaded meanwhile: on these small matrices - 2 * window <= a few hundred rows - their
+        # own threading costs 5x more than it gains, and one thread per chain makes every chain's result independent of the others)
+        with _blas_single_threaded():
+            if len(todo) > 1 and self._pool is not None:
+                updates = dict(zip(todo, self._pool.map(work, todo)))
+            else:
+                updates = {c: work(c) for c in todo}
+        for c in todo:
+            upd = updates[c]
             if upd is None:
                 stds[c, 0] = np.nan  # "return" of LowRankMassMatrixStrategy::update: nothing changes for this chain
                 continue
@@ -281,4 +306,7 @@ class LowRankSampler:
             self.sampler.set_grads_out(None)
             self._gbuf.close()
             self._gbuf = None
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         self.sampler.close()

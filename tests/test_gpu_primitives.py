@@ -316,6 +316,20 @@ def test_leapfrog_tma_matches_register_path(L, kind, d, monkeypatch):
     m.close()
 
 
+def test_last_kernel_ms(L):
+    """nuts_ctx_last_kernel_ms: CUDA-event time of the kernel of the last nuts_leapfrog (bench.py's plane microbench reads it)."""
+    m = L.CudaMath(64, 1000, _abi.NUTS_LOGP_GAUSS_ISO, mu=0.0)
+    with pytest.raises(L.NutsError):
+        m.last_kernel_ms()
+    m.set_transform(np.ones((64, 1000)), np.zeros((64, 1000)))
+    p, _ = m.init_state(np.ones((64, 1000)))
+    m.initialize_trajectory(p, True, 1, 0, 0)
+    m.leapfrog(p, 0.1)
+    ms = m.last_kernel_ms()
+    assert 0.0 < ms < 50.0
+    m.close()
+
+
 def test_leapfrog_divergence_and_mask(L, orc):
     N, d = 4, 10
     m = L.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_ISO, mu=0.0)
