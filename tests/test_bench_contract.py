@@ -67,5 +67,12 @@ def test_committed_bench_lines_follow_the_contract():
     # weak scaling of the sharded path: no collective in the timed region
     for n in (2, 4, 8):
         assert values[n] / (n * values[1]) > 0.95
+    # the last line of the round (final build) adds the Tier-2 plane-leapfrog sub-record: TMA-staged rows vs the register path
+    last = json.load(open(os.path.join(prof, "r5_bench_line.json")))
+    assert last["n_gpus"] == 1 and abs(last["value"] / values[1] - 1) < 0.1
+    pl = last["config"]["plane_leapfrog_rank0"]
+    assert pl["algorithmic_bytes_per_launch"] == 80 * pl["dim"] * pl["chains"]
+    assert pl["tma"]["frac_of_hbm_peak"] > 0.9 > pl["register_path"]["frac_of_hbm_peak"] > 0.5
+    assert pl["tma"]["diverged"] == 0 and pl["register_path"]["diverged"] == 0
     ref = json.load(open(os.path.join(prof, "r2_bench_reference_line.json")))
     assert ref["impl"] == "reference" and ref["unit"] == "leapfrog-steps/s" and 0 < ref["value"] < values[1]
