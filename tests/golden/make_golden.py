@@ -59,7 +59,51 @@ def build(name):
                 **{"stat_" + k: v for k, v in stats.items()})
 
 
+# KineticEnergyKind::ExactNormal / Microcanonical (Tier 2): a short trajectory of Hamiltonian::leapfrog per kind, and whole NUTS draws
+# of the oracle with trajectory_kind set (the device runs these kinds at Tier 1 / Tier 2 only)
+KINETIC_D, KINETIC_N, KINETIC_STEPS = 37, 3, 6
+
+
+def kinetic_inputs():
+    rng = np.random.default_rng(77)
+    d, N = KINETIC_D, KINETIC_N
+    return dict(sigma=np.exp(np.linspace(-1, 1, d)), stds=0.75 + 0.5 * rng.random((N, d)), mean=0.2 * (rng.random((N, d)) - 0.5),
+                x0=rng.normal(size=(N, d)), eps=0.05 + 0.02 * rng.random(N))
+
+
+def build_kinetic():
+    inp = kinetic_inputs()
+    d, N = KINETIC_D, KINETIC_N
+    om = O.Model(_abi.NUTS_LOGP_GAUSS_DIAG, d, mu=0.5, sigma=inp["sigma"])
+    out = {}
+    for kind, tag in ((_abi.NUTS_KINETIC_EXACT_NORMAL, "exact"), (_abi.NUTS_KINETIC_MICROCANONICAL, "micro")):
+        z, v, sc = np.zeros((KINETIC_STEPS, N, d)), np.zeros((KINETIC_STEPS, N, d)), np.zeros((KINETIC_STEPS, N, 3))
+        for c in range(N):
+            h = O.Hamiltonian(om)
+            h.set_kinetic_energy_kind(kind)
+            h.set_transform(inp["stds"][c], inp["mean"][c])
+            p, st = h.init_state(inp["x0"][c])
+            h.initialize_trajectory(p, True, 9, c + 1, 3)
+            eps = inp["eps"][c] / (np.sqrt(float(d)) if kind == _abi.NUTS_KINETIC_MICROCANONICAL else 1.0)
+            for k in range(KINETIC_STEPS):
+                p, st, ee = h.leapfrog(p, eps, 1 if c != 1 else -1)
+                z[k, c], v[k, c] = p.vec(p.Z), p.vec(p.V)
+                s_ = p.scalars()
+                sc[k, c] = s_["logp"], s_["kinetic_energy"], ee
+        out.update({tag + "_z": z, tag + "_v": v, tag + "_scalars": sc})
+    s = _abi.default_settings()
+    s.num_tune, s.maxdepth, s.trajectory_kind = 30, 6, _abi.NUTS_KINETIC_EXACT_NORMAL
+    samp = O.Sampler(O.Model(_abi.NUTS_LOGP_GAUSS_ISO, 10, mu=3.0), s, seed=2024, nchains=4)
+    samp.set_position(np.full((4, 10), 3.5))
+    draws, stats = samp.draw(40)
+    out.update(nuts_exact_draws=draws, nuts_exact_depth=stats["depth"], nuts_exact_step_size=stats["step_size"],
+               nuts_exact_energy_error=stats["energy_error"])
+    return out
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "kinetic_kinds.npz"), **build_kinetic())
+    print("wrote kinetic_kinds")
     for name in CASES:
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **build(name))
         print("wrote", name)
