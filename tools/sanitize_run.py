@@ -5,7 +5,8 @@ reductions (double-buffered shared scratch, one barrier), the decoupled engine's
   compute-sanitizer --tool racecheck python tools/sanitize_run.py <case>
 cases: c1 (warp teams, 4 chains x d=10), migrate (d=1000, 64x16 CTA teams, more chains than one wave of teams via NUTS_B200_GRID),
        large (large-dim engine, d=5000), funnel, rank1, cluster (rank-1 at d=4200: one chain on the 4 CTAs of a cluster, DSMEM reductions),
-       tunebuild (640 chains x d=1000 on the full grid: aligned warm-up build, then the plain one), lowrank (SM_LOWRANK engine)"""
+       tunebuild (640 chains x d=1000 on the full grid: aligned warm-up build, then the plain one), lowrank (SM_LOWRANK engine),
+       plane (Tier-2 plane kernels: TMA-staged leapfrog, ExactNormal / Microcanonical leapfrogs, ESH update, flows)"""
 import os
 import sys
 
@@ -15,6 +16,32 @@ import numpy as np
 from nuts_rs_b200 import _abi, lib
 
 case = sys.argv[1]
+if case == "plane":
+    # Tier 1 / Tier 2 plane kernels added last: the TMA-staged leapfrog (cp.async.bulk + mbarrier; one / two / four chunks, i.e. with
+    # stage refills and an odd tail) and the ExactNormal / Microcanonical kernels (ESH: three team reductions per update)
+    total = 0
+    for d in (3, 513, 1537):
+        N = 5
+        rng = np.random.default_rng(d)
+        m = lib.CudaMath(N, d, _abi.NUTS_LOGP_GAUSS_DIAG, mu=0.5, sigma=np.exp(np.linspace(-1, 1, d)))
+        m.set_transform(np.exp(0.3 * rng.normal(size=(N, d))), 0.1 * rng.normal(size=(N, d)))
+        p, st = m.init_state(rng.normal(size=(N, d)))
+        for kind in (_abi.NUTS_KINETIC_EUCLIDEAN, _abi.NUTS_KINETIC_EXACT_NORMAL, _abi.NUTS_KINETIC_MICROCANONICAL):
+            m.initialize_trajectory(p, True, 9, 0, 3, kind=kind)
+            cur = p
+            for step in range(3):
+                cur, status, ee = m.leapfrog(cur, 0.01, direction=np.array([1, -1, 1, -1, 1], dtype=np.int8), kind=kind,
+                                             active=np.array([1, 1, 0, 1, 1], dtype=np.uint8) if step == 1 else None)
+                total += int((status == 0).sum())
+        a, b, c = m.from_host(rng.normal(size=(N, d))), m.from_host(rng.normal(size=(N, d))), m.new_array()
+        m.std_norm_flow(a, c, b, 0.3)
+        m.std_norm_grad_flow(a, b, c, c, 0.1)
+        m.array_normalize(b)
+        dke = m.esh_momentum_update(a, b, 0.05)
+        assert np.isfinite(dke).all() and np.isfinite(b.box_array()).all()
+        m.close()
+    print("plane ok: leapfrogs", total, "finite True")
+    sys.exit(0)
 shapes = {
     "c1": (_abi.NUTS_LOGP_GAUSS_ISO, 4, 10, dict(mu=3.0), 12, 8),
     "migrate": (_abi.NUTS_LOGP_GAUSS_DIAG, 40, 1000, dict(mu=0.5, sigma=np.exp(np.linspace(-1, 1, 1000))), 6, 4),
